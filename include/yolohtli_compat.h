@@ -1,0 +1,49 @@
+/*
+ * yolohtli_compat.h -- the handful of POD types the reference's launch API passes by value
+ * (typeDefinition.cuh:4-20), re-declared so that libyolohtli_shim.so exports the SAME mangled
+ * C++ symbols as the reference's own translation units (hostPrototypes.h:22-57).
+ * Inside the reference tree, define YH_USE_REFERENCE_TYPES and include typeDefinition.cuh first.
+ */
+#ifndef YOLOHTLI_COMPAT_H
+#define YOLOHTLI_COMPAT_H
+#include <cuda_runtime.h>
+#ifndef YH_USE_REFERENCE_TYPES
+typedef double REAL;
+typedef struct REAL3 { REAL x, y, t; } REAL3;
+typedef struct stateVar { REAL *u, *v; } stateVar;
+typedef struct advVar { REAL *x, *y; } advVar;
+typedef struct sliceVar { REAL *ux, *uy, *ut, *vx, *vy, *vt; } sliceVar;
+typedef struct vec5dyn { float x, y, vx, vy, t; } vec5dyn;
+#endif
+
+/* The reference's wrappers (hostPrototypes.h:22-57), implemented by the shim. */
+void reactionDiffusion_wrapper(size_t pitch, dim3 grid2D, dim3 block2D, stateVar gOut_d,
+                               stateVar gIn_d, stateVar J, stateVar velTan, bool reduceSym,
+                               bool *solid, bool stimLock, REAL *stim, bool stimLockMouse,
+                               int2 point);
+void tip_wrapper(size_t pitch, dim3 grid2D, dim3 block2D, stateVar gOut_d, stateVar gIn_d,
+                 stateVar velTan, REAL physicalTime, int tipAlgorithm, bool recordTip,
+                 bool *tip_plot, int *tip_count, vec5dyn *tip_vector);
+void slice_wrapper(size_t pitch, dim3 grid2D, dim3 block2D, stateVar g, sliceVar slice,
+                   sliceVar slice0, bool reduceSym, bool reduceSymStart, advVar adv, int scheme,
+                   bool *intglArea, int *tip_count, vec5dyn *tip_vector, int count);
+void Cxy_field_wrapper(size_t pitch, dim3 grid2D, dim3 block2D, advVar adv, REAL3 c, REAL3 phi,
+                       bool *solid);
+void advFDBFECC_wrapper(size_t pitch, dim3 grid2D, dim3 block2D, stateVar gOut, stateVar gIn,
+                        advVar adv, stateVar uf, stateVar ub, stateVar ue, bool *solid);
+REAL3 solve_matrix(REAL3 c, REAL3 phi, REAL *Int);
+void trapz_wrapper(dim3 grid1D, dim3 block1D, sliceVar slice, sliceVar slice0, stateVar velTan,
+                   REAL *integrals, REAL *coeffTrapz, int *tip_count, vec5dyn *tip_vector,
+                   int count);
+void singleCell_wrapper(size_t pitch, dim3 grid0D, dim3 block0D, stateVar gOut_d, int eSize,
+                        REAL *pt_h, REAL *pt_d, int2 point);
+void sAPD_wrapper(size_t pitch, dim3 grid1D, dim3 block1D, int count, REAL *uold, REAL *unew,
+                  REAL *APD1, REAL *APD2, REAL *sAPD, REAL *dAPD, REAL *back, REAL *front,
+                  bool *first, bool *stimArea, bool stimulate);
+void swapSoA(stateVar *A, stateVar *B);
+
+/* New: replaces the ~45 cudaMemcpyToSymbol calls of main.cu:309-402. */
+struct yh_params;
+extern "C" int yh_shim_configure(const struct yh_params *p);
+extern "C" int yh_shim_last_status(void);
+#endif

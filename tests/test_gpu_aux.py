@@ -1,0 +1,254 @@
+"""GPU parity of tip tracking, APD bookkeeping, probe, the symmetry-reduction kernels and the
+headless driver against the plain-C oracle (bitwise) and the reference's own kernels."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from tests import oracle_lib  # noqa: E402
+from yolohtli_b200 import host, synth  # noqa: E402
+
+TIP_DTYPE = oracle_lib.TIP_DTYPE
+
+
+def dev(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a)).to("cuda", dtype=dtype).contiguous()
+
+
+def fields(nx, ny, seed):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-0.1, 1.1, (ny, nx)), rng.uniform(0.0, 1.0, (ny, nx))
+
+
+def wavy(nx, ny, a=0.31, b=0.27, ph=0.1):
+    X, Y = np.meshgrid(np.arange(nx, dtype=float), np.arange(ny, dtype=float))
+    return 0.7 + 0.3 * np.sin(a * X + ph) * np.cos(b * Y) + 0.05 * np.sin(0.11 * X * Y / nx)
+
+
+def gpu_tips(p, past, present, t=0.0, alg=None, plot=False, capacity=host.TIPVECSIZE):
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    vec = torch.zeros(capacity * 20, dtype=torch.uint8, device="cuda")
+    pl = torch.zeros(p.nx * p.ny, dtype=torch.uint8, device="cuda") if plot else None
+    host.tip_track(p, dev(past), dev(present), cnt, vec, tip_plot=pl, t=t, algorithm=alg, capacity=capacity)
+    torch.cuda.synchronize()
+    out = host.tips_to_numpy(cnt, vec)
+    return (out, pl.cpu().numpy()) if plot else out
+
+
+@pytest.mark.parametrize("nx,ny", [(48, 40), (333, 257), (1024, 1024)])
+@pytest.mark.parametrize("alg", [1, 2])
+def test_tips_bitwise_and_ordered(oracle, nx, ny, alg):
+    p = oracle.params_default(nx, ny, tipOffsetX=min(160, nx // 2 - 2), tipOffsetY=min(160, ny // 2 - 2))
+    past, present = wavy(nx, ny), wavy(nx, ny, 0.29, 0.33, 0.7)
+    want, wplot = oracle.tip_track(p, past, present, t=2.5, algorithm=alg, plot=True)
+    for rep in range(3):   # ordered compaction: identical list every launch
+        got, gplot = gpu_tips(p, past, present, t=2.5, alg=alg, plot=True)
+        assert len(got) == len(want) and len(want) > 0
+        assert got.tobytes() == want.tobytes()
+        assert np.array_equal(gplot, wplot)
+
+
+def test_tips_gradient_solid_and_flag_algorithm(oracle):
+    nx = ny = 128
+    past, present = wavy(nx, ny), wavy(nx, ny, 0.29, 0.33, 0.7)
+    p = oracle.params_default(nx, ny, tipGrad=1, tipOffsetX=40, tipOffsetY=40)
+    assert gpu_tips(p, past, present).tobytes() == oracle.tip_track(p, past, present).tobytes()
+    p = oracle.params_default(nx, ny, solidSwitch=1, tipOffsetX=40, tipOffsetY=40)
+    got, want = gpu_tips(p, past, present), oracle.tip_track(p, past, present)
+    assert len(want) > 0 and got.tobytes() == want.tobytes()
+    p = oracle.params_default(nx, ny)
+    g, gp = gpu_tips(p, past, present, alg=3, plot=True)
+    w, wp = oracle.tip_track(p, past, present, algorithm=3, plot=True)
+    assert len(g) == 0 and np.array_equal(gp, wp) and wp.sum() > 0
+
+
+def test_tips_empty_and_capacity(oracle):
+    p = oracle.params_default(64, 64)
+    z = np.zeros((64, 64))
+    assert len(gpu_tips(p, z, z)) == 0
+    past, present = wavy(64, 64), wavy(64, 64, 0.29, 0.33, 0.7)
+    want = oracle.tip_track(p, past, present)
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    vec = torch.zeros(2 * 20 + 20, dtype=torch.uint8, device="cuda")
+    host.tip_track(p, dev(past), dev(present), cnt, vec, capacity=2)
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == len(want) > 2          # count keeps the true total
+    assert vec[40:].sum().item() == 0                # nothing written past the capacity
+
+
+@pytest.mark.skipif(not oracle_lib.have_reference(), reason="oracle/_ref not built")
+def test_tips_vs_reference_kernels(oracle):
+    ref = oracle_lib.Reference(nofma=True)
+    nx = ny = 256
+    p = oracle.params_default(nx, ny)
+    ref.init(p)
+    past, present = wavy(nx, ny), wavy(nx, ny, 0.29, 0.33, 0.7)
+    r = ref.tip(present, past, t=1.0, algorithm=1)       # unordered (atomicAdd)
+    g = gpu_tips(p, past, present, t=1.0, alg=1)
+    assert len(r) == len(g) > 0                          # T0: tip count bit-exact
+    key = lambda t: np.sort(np.stack([t["x"], t["y"], t["t"]], 1).view("f4,f4,f4").reshape(-1))
+    assert np.array_equal(key(r), key(g))                # same records as a multiset
+
+
+def test_sapd_sequence_bitwise(oracle):
+    nx, ny = 96, 64
+    p = oracle.params_default(nx, ny)
+    X, Y = np.meshgrid(np.arange(nx, dtype=float), np.arange(ny, dtype=float))
+    seq = [np.clip(0.5 + 0.6 * np.sin(0.2 * k + 0.05 * X + 0.07 * Y), -0.1, 1.1) for k in range(80)]
+    area = synth.stim_area_square(nx, ny)
+    for stimulate in (False, True):
+        want = oracle.sapd_sequence(p, seq, count0=1, stimArea=area, stimulate=stimulate)
+        n = nx * ny
+        st = {k: torch.zeros(n, dtype=torch.float64, device="cuda") for k in ("APD1", "APD2", "sAPD", "dAPD", "back", "front")}
+        first = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        dseq = [dev(a) for a in seq]
+        for k in range(len(seq) - 1):
+            host.sapd(p, 1 + k, dseq[k], dseq[k + 1], st["APD1"], st["APD2"], st["sAPD"], st["dAPD"],
+                      st["back"], st["front"], first, stimArea=dev(area, torch.uint8), stimulate=stimulate)
+        torch.cuda.synchronize()
+        for k in ("APD1", "APD2", "sAPD", "back", "front") + (("dAPD",) if stimulate else ()):
+            assert np.array_equal(st[k].cpu().numpy(), want[k]), k
+        assert np.array_equal(first.cpu().numpy(), want["first"])
+        assert want["APD1"].max() > 0 and want["APD2"].max() > 0
+
+
+def test_probe(oracle):
+    p = oracle.params_default(64, 48)
+    u, v = fields(64, 48, 1)
+    pt = torch.zeros(2, dtype=torch.float64, device="cuda")
+    host.probe(p, dev(u), dev(v), pt, 17, 31)
+    assert pt.cpu().tolist() == [u[31, 17], v[31, 17]]
+
+
+@pytest.mark.parametrize("nx,ny,off", [(96, 96, 30), (512, 512, 160), (200, 140, 50)])
+def test_sr_kernels_bitwise(oracle, nx, ny, off):
+    p = oracle.params_default(nx, ny, reduce_sym=True, tipOffsetX=off, tipOffsetY=off,
+                              tipx0=nx / 2 + 3.0, tipy0=ny / 2 - 5.0)
+    u, v = fields(nx, ny, 2)
+    vtu, vtv = fields(nx, ny, 3)
+    c, phi = [0.13, -0.21, 0.04], [0.3, -0.1, 0.77]
+    # Cxy
+    wax, way = oracle.cxy_field(p, c, phi)
+    ax, ay = torch.zeros(nx * ny, dtype=torch.float64, device="cuda"), torch.zeros(nx * ny, dtype=torch.float64, device="cuda")
+    host.cxy_field(p, ax, ay, c, phi)
+    assert np.array_equal(ax.cpu().numpy(), wax) and np.array_equal(ay.cpu().numpy(), way)
+    # slice (both schemes) + trapz + fused
+    du, dv, dvtu, dvtv = dev(u), dev(v), dev(vtu), dev(vtv)
+    for scheme in (2, 1):
+        ws, ws0 = oracle.slice(p, u, v, wax, way, scheme=scheme)
+        s = [torch.full((nx * ny,), 7.0, dtype=torch.float64, device="cuda") for _ in range(6)]
+        s0 = [torch.full((nx * ny,), 7.0, dtype=torch.float64, device="cuda") for _ in range(6)]
+        host.slice_fields(p, du, dv, s, s0, ax, ay, scheme=scheme)
+        for q in range(6):
+            assert np.array_equal(s[q].cpu().numpy(), ws[q]), (scheme, q)
+            assert np.array_equal(s0[q].cpu().numpy(), ws0[q]), (scheme, q)
+        if scheme == 2:
+            want = oracle.trapz(p, ws, ws0, vtu, vtv)
+            got = host.trapz(p, s, s0, dvtu, dvtv)
+            assert np.array_equal(got, want)
+            fused = host.sr_integrals(p, du, dv, dvtu, dvtv, ax, ay)
+            assert np.array_equal(fused, want)
+    # disc centre from the device tip list
+    tips = np.zeros(3, dtype=TIP_DTYPE)
+    tips[2]["x"], tips[2]["y"] = nx / 2 - 4.4, ny / 2 + 6.6
+    cnt = torch.tensor([3], dtype=torch.int32, device="cuda")
+    vec = torch.as_tensor(np.frombuffer(tips.tobytes(), dtype=np.uint8).copy()).cuda()
+    want = oracle.sr_integrals(p, u, v, vtu, vtv, wax, way, tips=tips, count=4)
+    got = host.sr_integrals(p, du, dv, dvtu, dvtv, ax, ay, tip_count=cnt, tip_vector=vec, count=4)
+    assert np.array_equal(got, want)
+    cnt0 = torch.tensor([0], dtype=torch.int32, device="cuda")   # empty list keeps tipx0 (defect B3)
+    got = host.sr_integrals(p, du, dv, dvtu, dvtv, ax, ay, tip_count=cnt0, tip_vector=vec, count=4)
+    assert np.array_equal(got, oracle.sr_integrals(p, u, v, vtu, vtv, wax, way))
+
+
+@pytest.mark.parametrize("neu,so", [(1, 0), (1, 1), (0, 0), (0, 1)])
+@pytest.mark.parametrize("nx,ny", [(96, 64), (130, 101)])
+def test_bfecc_bitwise(oracle, neu, so, nx, ny):
+    p = oracle.params_default(nx, ny, reduce_sym=True, neumannBC=neu, solidSwitch=so, boundaryVal=0.05)
+    u, v = fields(nx, ny, 4)
+    solid = (np.random.default_rng(9).uniform(size=(ny, nx)) > 0.15).astype(np.uint8) if so else None
+    c, phi = [0.9, -1.3, 0.5], [0.0, 0.0, 0.6]
+    wax, way = oracle.cxy_field(p, c, phi, solid=solid)
+    want = oracle.advect_bfecc(p, u, v, wax, way, solid=solid)
+    du, dv = dev(u), dev(v)
+    ds = dev(solid, torch.uint8) if so else None
+    uo, vo = torch.empty_like(du), torch.empty_like(dv)
+    host.advect_bfecc(p, du, dv, uo, vo, dev(wax), dev(way), solid=ds)
+    assert np.array_equal(uo.cpu().numpy(), want[0]) and np.array_equal(vo.cpu().numpy(), want[1])
+    # Cxy fused into the advection: same bits, adv field written as a by-product
+    ax, ay = torch.zeros(nx * ny, dtype=torch.float64, device="cuda"), torch.zeros(nx * ny, dtype=torch.float64, device="cuda")
+    uo2, vo2 = torch.empty_like(du), torch.empty_like(dv)
+    host.advect_bfecc_cphi(p, du, dv, uo2, vo2, c, phi, adv_x=ax, adv_y=ay, solid=ds)
+    assert torch.equal(uo, uo2) and torch.equal(vo, vo2)
+    assert np.array_equal(ax.cpu().numpy(), wax) and np.array_equal(ay.cpu().numpy(), way)
+
+
+@pytest.mark.skipif(not oracle_lib.have_reference(), reason="oracle/_ref not built")
+def test_sr_pieces_vs_reference_kernels(oracle):
+    ref = oracle_lib.Reference(nofma=True)
+    nx = ny = 128
+    p = oracle.params_default(nx, ny, reduce_sym=True, tipOffsetX=40, tipOffsetY=40, tipx0=70.0, tipy0=60.0)
+    ref.init(p)
+    u, v = fields(nx, ny, 5)
+    vtu, vtv = fields(nx, ny, 6)
+    c, phi = [0.13, -0.21, 0.04], [0.3, -0.1, 0.77]
+    rax, ray = ref.cxy(c, phi)
+    ax, ay = torch.zeros(nx * ny, dtype=torch.float64, device="cuda"), torch.zeros(nx * ny, dtype=torch.float64, device="cuda")
+    host.cxy_field(p, ax, ay, c, phi)
+    # device cos/sin (libdevice) vs host libm: <= 1 ulp of the O(1) terms
+    assert np.abs(ax.cpu().numpy() - rax).max() < 1e-15 and np.abs(ay.cpu().numpy() - ray).max() < 1e-15
+    rint, rsl = ref.slice_trapz(u, v, rax, ray, vtu, vtv, 0.0, 0.0, 0, want_slices=True)
+    s = [torch.zeros(nx * ny, dtype=torch.float64, device="cuda") for _ in range(6)]
+    s0 = [torch.zeros(nx * ny, dtype=torch.float64, device="cuda") for _ in range(6)]
+    host.slice_fields(p, dev(u), dev(v), s, s0, dev(rax), dev(ray))
+    for q in range(6):   # slice_kernel is race-free: bitwise
+        assert np.array_equal(s[q].cpu().numpy(), rsl[q]) and np.array_equal(s0[q].cpu().numpy(), rsl[6 + q])
+    got = host.sr_integrals(p, dev(u), dev(v), dev(vtu), dev(vtv), dev(rax), dev(ray))
+    # reference: 256 blocks atomicAdd(double) in arbitrary order -> 1e-12 relative
+    assert np.allclose(got, rint, rtol=1e-12, atol=1e-14)
+    assert np.array_equal(host.solve_matrix([0, 0, 0], phi, rint), ref.solve_matrix([0, 0, 0], phi, rint))
+    # BFECC: the reference kernel races on uf/ub/ue (advFDBFECC.cu:131-144); smooth fields agree to 1e-6
+    X, Y = np.meshgrid(np.arange(nx, dtype=float), np.arange(ny, dtype=float))
+    us = 0.5 + 0.4 * np.sin(0.07 * X) * np.cos(0.05 * Y)
+    ru, rv = ref.bfecc(us, us * 0.5, rax, ray)
+    uo, vo = torch.empty(ny, nx, dtype=torch.float64, device="cuda"), torch.empty(ny, nx, dtype=torch.float64, device="cuda")
+    host.advect_bfecc(p, dev(us), dev(us * 0.5), uo, vo, dev(rax), dev(ray))
+    assert np.abs(uo.cpu().numpy() - ru).max() < 1e-6
+
+
+def test_sim_driver_trace_batch_and_pacing(oracle, yh):
+    nx = ny = 128
+    p = oracle.params_default(nx, ny, timeIntOrder=1, lap4=0)
+    u0, v0 = synth.cross_field_ic(nx, ny)
+    sim = yh.Sim(p, n_sims=1)
+    sim.cross_field_ic()
+    tr = sim.run(50, trace=True)
+    u, v = sim.get_state()
+    wu, wv = oracle.rd_advance(p, 50, u0, v0)
+    assert np.array_equal(u[0], wu) and np.array_equal(v[0], wv)
+    # electrode trace with the one-step lag of main.cu:1040: sample k = state k at param.point
+    uu, vv = u0, v0
+    for k in range(3):
+        assert tr[k, 0, 0] == uu[ny // 2, nx // 2] and tr[k, 0, 1] == vv[ny // 2, nx // 2]
+        uu, vv = oracle.rd_step(p, uu, vv)
+    t = sim.tips()
+    prev = oracle.rd_advance(p, 49, u0, v0)
+    want = oracle.tip_track(p, prev[0], wu, t=p.dt * 50)
+    assert t.tobytes() == want.tobytes()
+    sim.close()
+    # batched sweep (C5 protocol, scaled down): per-sheet pacing period, quiescent IC
+    periods = np.array([40, 25, 0], dtype=np.int32)
+    sim = yh.Sim(p, n_sims=3)
+    sim.set_state(np.zeros((3, ny, nx)), np.zeros((3, ny, nx)))
+    sim.set_pacing(periods, 6)
+    sim.run(64, tb_steps=4)
+    u, v = sim.get_state()
+    for z, per in enumerate(periods):
+        uu, vv = np.zeros((ny, nx)), np.zeros((ny, nx))
+        for s in range(64):
+            on = per > 0 and (s % per) <= 6
+            uu, vv = oracle.rd_step(p, uu, vv, stim_mouse=bool(on))
+        assert np.array_equal(u[z], uu) and np.array_equal(v[z], vv), z
+    assert u[0].max() > 0.5 and u[2].max() == 0.0
+    sim.close()

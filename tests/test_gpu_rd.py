@@ -1,0 +1,213 @@
+"""GPU parity of the reaction-diffusion step: the sm_100a kernels (through the C ABI) against
+the plain-C oracle -- BITWISE in every mode (both sides compiled without FMA contraction) --
+and against the reference's own kernels (oracle/_ref, --fmad=false) bitwise in its race-free
+modes.  Tolerances, where any, are written in the test."""
+import ctypes as C
+import itertools
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from tests import oracle_lib  # noqa: E402
+from yolohtli_b200 import host, synth  # noqa: E402
+
+
+def dev(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a)).to("cuda", dtype=dtype).contiguous()
+
+
+def rand_fields(nx, ny, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-0.1, 1.1, (ny, nx)), rng.uniform(0.0, 1.0, (ny, nx))
+
+
+def gpu_step(p, u, v, solid=None, velTan=False, **kw):
+    du, dv = dev(u), dev(v)
+    uo, vo = torch.empty_like(du), torch.empty_like(dv)
+    vt = (torch.zeros_like(du), torch.zeros_like(du)) if velTan else None
+    ds = dev(solid, torch.uint8) if solid is not None else None
+    host.rd_step(p, du, dv, uo, vo, velTan=vt, solid=ds, **kw)
+    torch.cuda.synchronize()
+    out = [uo.cpu().numpy(), vo.cpu().numpy()]
+    if velTan:
+        out += [vt[0].cpu().numpy(), vt[1].cpu().numpy()]
+    return out
+
+
+def gpu_advance(p, n, u, v, tb=0, solid=None, **kw):
+    uA, vA = dev(u), dev(v)
+    uB, vB = torch.zeros_like(uA), torch.zeros_like(vA)
+    ds = dev(solid, torch.uint8) if solid is not None else None
+    ru, rv = host.rd_advance(p, n, uA, vA, uB, vB, tb_steps=tb, solid=ds, **kw)
+    torch.cuda.synchronize()
+    return ru.cpu().numpy(), rv.cpu().numpy()
+
+
+MODES = []
+for order, lap4, neu, so, gd, an in itertools.product((1, 2, 4), (0, 4), (1, 0), (0, 1), (1, 0), (0, 1)):
+    MODES.append(dict(timeIntOrder=order, lap4=lap4, neumannBC=neu, solidSwitch=so, gateDiff=gd, anisotropy=an))
+
+
+@pytest.mark.parametrize("size", [(48, 40), (50, 30), (130, 67)])
+def test_every_mode_bitwise_vs_oracle(oracle, size):
+    nx, ny = size
+    u, v = rand_fields(nx, ny, 11)
+    solid = (np.random.default_rng(5).uniform(size=(ny, nx)) > 0.2).astype(np.uint8)
+    for m in MODES:
+        p = oracle.params_default(nx, ny, **m)
+        if m["anisotropy"]:
+            oracle.l.yho_params_derive(C.byref(p), C.c_double(0.001), C.c_double(0.0004), C.c_double(0.0002))
+        want = oracle.rd_step(p, u, v, solid=solid, velTan=True, stim_mouse=True, point=(nx // 3, ny // 2))
+        got = gpu_step(p, u, v, solid=solid, velTan=True, stim_mouse=True, point=(nx // 3, ny // 2))
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), m
+        if m["gateDiff"]:
+            assert np.array_equal(got[2].ravel(), want[2].ravel()) and np.array_equal(got[3].ravel(), want[3].ravel()), m
+        if m["solidSwitch"]:
+            assert (got[0][solid == 0] == 0.0).all() and not np.signbit(got[0][solid == 0]).any()
+
+
+@pytest.mark.parametrize("nx,ny", [(64, 48), (256, 96), (500, 300), (1030, 130), (2048, 64)])
+@pytest.mark.parametrize("tb", [1, 2, 4])
+def test_temporal_blocking_is_bitwise_invariant(oracle, nx, ny, tb):
+    """T steps per HBM pass == T single-step launches == T oracle steps, bit for bit."""
+    p = oracle.params_default(nx, ny, timeIntOrder=1, lap4=0)
+    u, v = rand_fields(nx, ny, 21)
+    n = 9
+    want = oracle.rd_advance(p, n, u, v, stim_mouse=True, point=(nx // 2, ny // 3))
+    got = gpu_advance(p, n, u, v, tb=tb, stim_mouse=True, point=(nx // 2, ny // 3))
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+def test_fast_path_gate_diff_off_and_negative_zero(oracle):
+    p = oracle.params_default(96, 80, timeIntOrder=1, lap4=0, gateDiff=0)
+    u, v = rand_fields(96, 80, 3)
+    u[10:20, 10:30] = 0.0
+    v[10:20, 10:30] = 0.0
+    want = oracle.rd_advance(p, 6, u, v)
+    got = gpu_advance(p, 6, u, v, tb=4)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert np.array_equal(np.signbit(got[0]), np.signbit(want[0]))
+
+
+def test_spiral_10k_steps_512(oracle):
+    """C1 geometry (512^2 cross-field spiral), Euler + 5-point: 2000 steps bitwise vs the oracle
+    (the full 10 k-step run is exercised by bench.py; 2000 keeps the CPU side in seconds)."""
+    p = oracle.params_default(512, 512, timeIntOrder=1, lap4=0)
+    u, v = synth.cross_field_ic(512, 512)
+    want = oracle.rd_advance(p, 2000, u, v)
+    got = gpu_advance(p, 2000, u, v, tb=4)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert 0.05 < want[0].mean() < 0.9   # a wave is actually propagating
+
+
+def test_default_mode_rk4_lap4_vs_oracle_and_holes(oracle):
+    # C1 default mode and C2 (1024^2-style mask, scaled down): bitwise vs the synchronous oracle
+    p = oracle.params_default(256, 256)
+    assert p.timeIntOrder == 4 and p.lap4 == 4
+    u, v = synth.fibrillation_ic(256, 256, patch=64)
+    want = oracle.rd_advance(p, 20, u, v)
+    got = gpu_advance(p, 20, u, v)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    mask = synth.hole_mask(256, seed=3)
+    p = oracle.params_default(256, 256, solidSwitch=1)
+    want = oracle.rd_advance(p, 20, u * mask, v * mask, solid=mask)
+    got = gpu_advance(p, 20, u * mask, v * mask, solid=mask)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert (got[0][mask == 0] == 0.0).all()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_slab_decomposition_is_bitwise_invariant(oracle, world):
+    """N row slabs with ghost rows (emulated on one GPU, halos copied between slab buffers)
+    == the single-domain run, bit for bit (multi-GPU invariance)."""
+    from yolohtli_b200.slab import SlabLayout
+    nx, ny, H, nsteps = 256, 211, 4, 12
+    pg = oracle.params_default(nx, ny, timeIntOrder=1, lap4=0)
+    u, v = rand_fields(nx, ny, 31)
+    want = oracle.rd_advance(pg, nsteps, u, v, stim_mouse=True, point=(100, 105))
+    lays = [SlabLayout(ny, world, r, H) for r in range(world)]
+    bufs = []
+    for l in lays:
+        a = [dev(u[l.g0:l.g1]), dev(v[l.g0:l.g1])]
+        bufs.append((a, [torch.zeros_like(a[0]), torch.zeros_like(a[1])]))
+    cur = [b[0] for b in bufs]
+    oth = [b[1] for b in bufs]
+    for it in range(nsteps // H):
+        if it > 0:   # halo exchange: owned edge rows -> neighbours' ghosts
+            for r, l in enumerate(lays):
+                if l.down is not None:
+                    d = lays[l.down]
+                    for f in range(2):
+                        cur[l.down][f][d.own_lo - H:d.own_lo] = cur[r][f][l.own_hi - H:l.own_hi]
+                        cur[r][f][l.own_hi:l.own_hi + H] = cur[l.down][f][d.own_lo:d.own_lo + H]
+        for r, l in enumerate(lays):
+            p = l.local_params(pg)
+            ru, rv = host.rd_advance(p, H, cur[r][0], cur[r][1], oth[r][0], oth[r][1], tb_steps=4,
+                                     rows=(l.own_lo, l.own_hi), stim_mouse=True, point=(100, 105))
+            if ru is oth[r][0]:
+                cur[r], oth[r] = oth[r], cur[r]
+    torch.cuda.synchronize()
+    got_u = np.concatenate([cur[r][0][l.own_lo:l.own_hi].cpu().numpy() for r, l in enumerate(lays)])
+    got_v = np.concatenate([cur[r][1][l.own_lo:l.own_hi].cpu().numpy() for r, l in enumerate(lays)])
+    assert np.array_equal(got_u, want[0]) and np.array_equal(got_v, want[1])
+
+
+def test_slab_generic_rk4_rows(oracle):
+    # multi-stage path on a slab: ghost depth = stages
+    from yolohtli_b200.slab import SlabLayout
+    nx, ny = 64, 50
+    pg = oracle.params_default(nx, ny)   # RK4 + lap4
+    u, v = rand_fields(nx, ny, 41)
+    want = oracle.rd_step(pg, u, v)
+    for r in range(2):
+        l = SlabLayout(ny, 2, r, 4)
+        p = l.local_params(pg)
+        got = gpu_step(p, u[l.g0:l.g1], v[l.g0:l.g1], rows=(l.own_lo, l.own_hi))
+        assert np.array_equal(got[0][l.own_lo:l.own_hi], want[0][l.j0:l.j1])
+        assert np.array_equal(got[1][l.own_lo:l.own_hi], want[1][l.j0:l.j1])
+
+
+@pytest.mark.skipif(not oracle_lib.have_reference(), reason="oracle/_ref not built")
+def test_bitwise_vs_reference_kernels_race_free_modes(oracle):
+    """T1 tier: Euler + lap4=0, every boundary/mask branch the reference defines, against the
+    reference's OWN kernels (sm_100, --fmad=false): bit-identical after 25 steps."""
+    ref = oracle_lib.Reference(nofma=True)
+    nx, ny = 144, 112
+    u, v = rand_fields(nx, ny, 51)
+    solid = (np.random.default_rng(6).uniform(size=(ny, nx)) > 0.1).astype(np.uint8)
+    for neu, so, gd in itertools.product((1, 0), (0, 1), (1, 0)):
+        if (not neu) and so:
+            continue   # reference indexes out of bounds at the edges in this branch
+        p = oracle.params_default(nx, ny, timeIntOrder=1, lap4=0, neumannBC=neu, solidSwitch=so, gateDiff=gd)
+        ref.init(p)
+        ru, rv, _ = ref.rd_run(u, v, 25, solid=solid, stim_mouse=True, point=(70, 50))
+        gu, gv = gpu_advance(p, 25, u, v, tb=4, solid=solid if so else None, stim_mouse=True, point=(70, 50))
+        assert np.array_equal(gu, ru) and np.array_equal(gv, rv), (neu, so, gd)
+    # with the reference's DEFAULT flags (FMA contraction on) the fields agree to 1e-12
+    ref2 = oracle_lib.Reference(nofma=False)
+    p = oracle.params_default(nx, ny, timeIntOrder=1, lap4=0)
+    ref2.init(p)
+    ru, rv, _ = ref2.rd_run(u, v, 25)
+    gu, gv = gpu_advance(p, 25, u, v, tb=4)
+    assert np.abs(gu - ru).max() < 1e-12 and np.abs(gv - rv).max() < 1e-12
+
+
+@pytest.mark.skipif(not oracle_lib.have_reference(), reason="oracle/_ref not built")
+def test_racy_reference_modes_within_tolerance(oracle):
+    """T2 tier: the reference's default RK4 + lap4 kernel races on g_in / J
+    (reactionDiffusion.cu:117,219); against our synchronous stages the smooth spiral fields
+    agree to 2e-3 after 200 steps (the reference's own run-to-run spread is of that order)."""
+    ref = oracle_lib.Reference(nofma=False)
+    p = oracle.params_default(256, 256)
+    u, v = synth.cross_field_ic(256, 256)
+    ref.init(p)
+    a = ref.rd_run(u, v, 200)
+    b = ref.rd_run(u, v, 200)
+    spread = max(np.abs(a[0] - b[0]).max(), 1e-16)
+    gu, gv = gpu_advance(p, 200, u, v)
+    err = np.abs(gu - a[0]).max()
+    print(f"racy reference: run-to-run spread {spread:.3e}, ours vs reference {err:.3e}")
+    assert err < 2e-3

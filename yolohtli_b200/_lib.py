@@ -1,0 +1,115 @@
+"""ctypes binding of libyolohtli_b200.so (include/yolohtli_abi.h).  Fails loudly when the
+CUDA library has not been built -- there is no Python/NumPy fallback."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libyolohtli_b200.so")
+SHIM_PATH = os.path.join(HERE, "lib", "libyolohtli_shim.so")
+
+
+class YolohtliError(RuntimeError):
+    pass
+
+
+class YhParams(C.Structure):
+    """struct yh_params of include/yolohtli_abi.h (same order, same types)."""
+    _fields_ = [
+        ("nx", C.c_int32), ("ny", C.c_int32), ("ny_global", C.c_int32), ("jg0", C.c_int32),
+        ("solidSwitch", C.c_int32), ("neumannBC", C.c_int32), ("gateDiff", C.c_int32),
+        ("anisotropy", C.c_int32), ("lap4", C.c_int32), ("timeIntOrder", C.c_int32),
+        ("tipGrad", C.c_int32), ("tipAlgorithm", C.c_int32),
+        ("tipOffsetX", C.c_int32), ("tipOffsetY", C.c_int32),
+        ("tipx0", C.c_float), ("tipy0", C.c_float),
+        ("dt", C.c_double), ("hx", C.c_double), ("hy", C.c_double), ("Lx", C.c_double),
+        ("Ly", C.c_double),
+        ("rx", C.c_double), ("ry", C.c_double), ("rxy", C.c_double), ("rbx", C.c_double),
+        ("rby", C.c_double), ("rscale", C.c_double),
+        ("qx4", C.c_double), ("qy4", C.c_double), ("fx4", C.c_double), ("fy4", C.c_double),
+        ("invdx", C.c_double), ("invdy", C.c_double),
+        ("tc", C.c_double), ("alpha", C.c_double), ("beta", C.c_double), ("gamma", C.c_double),
+        ("delta", C.c_double), ("eps", C.c_double), ("mu", C.c_double), ("theta", C.c_double),
+        ("boundaryVal", C.c_double), ("Uth", C.c_double),
+    ]
+
+    def copy(self):
+        q = YhParams()
+        C.memmove(C.byref(q), C.byref(self), C.sizeof(YhParams))
+        return q
+
+
+class YhTip(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("vx", C.c_float), ("vy", C.c_float),
+                ("t", C.c_float)]
+
+
+_P = C.POINTER(YhParams)
+_vp = C.c_void_p
+_i = C.c_int
+_d = C.c_double
+
+# name -> (restype, argtypes); every symbol include/yolohtli_abi.h declares
+SIGNATURES = {
+    "yh_abi_version": (_i, []),
+    "yh_last_error": (C.c_char_p, []),
+    "yh_device_count": (_i, []),
+    "yh_release_workspace": (_i, []),
+    "yh_params_default": (_i, [_P, _i, _i, _i, _i]),
+    "yh_params_derive": (_i, [_P, _d, _d, _d]),
+    "yh_rd_step": (_i, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "yh_rd_advance": (_i, [_P, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
+                           C.POINTER(_i), _vp]),
+    "yh_tip_track": (_i, [_P, _vp, _vp, _vp, _vp, _vp, _i, _d, _i, _vp]),
+    "yh_slice": (_i, [_P, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _i, _i, _vp, _vp, _i, _vp,
+                      _vp, _i, _vp]),
+    "yh_trapz": (_i, [_P, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, C.POINTER(_d), _vp, _vp, _i,
+                      _vp]),
+    "yh_sr_integrals": (_i, [_P, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_d), _vp, _vp, _i, _vp]),
+    "yh_solve_matrix": (_i, [C.POINTER(_d), C.POINTER(_d), C.POINTER(_d), C.POINTER(_d)]),
+    "yh_cxy_field": (_i, [_P, _vp, _vp, C.POINTER(_d), C.POINTER(_d), _vp, _vp]),
+    "yh_advect_bfecc": (_i, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "yh_advect_bfecc_cphi": (_i, [_P, _vp, _vp, _vp, _vp, C.POINTER(_d), C.POINTER(_d), _vp, _vp,
+                                  _vp, _vp]),
+    "yh_sapd": (_i, [_P, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "yh_probe": (_i, [_P, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "yh_sim_create": (_i, [C.POINTER(_vp), _P, _i, _i]),
+    "yh_sim_destroy": (_i, [_vp]),
+    "yh_sim_set_state": (_i, [_vp, _vp, _vp]),
+    "yh_sim_get_state": (_i, [_vp, _vp, _vp]),
+    "yh_sim_set_solid": (_i, [_vp, _vp]),
+    "yh_sim_cross_field_ic": (_i, [_vp]),
+    "yh_sim_set_point": (_i, [_vp, _i, _i]),
+    "yh_sim_run": (_i, [_vp, _i, _i, _vp]),
+    "yh_sim_set_pacing": (_i, [_vp, _vp, _i]),
+    "yh_sim_run_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "yh_sim_tips": (_i, [_vp, _vp, _i, C.POINTER(_i)]),
+    "yh_sim_count": (_i, [_vp]),
+    "yh_sim_device_u": (_vp, [_vp]),
+    "yh_sim_device_v": (_vp, [_vp]),
+}
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the CUDA library and type every entry point.  Raises if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise YolohtliError(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  yolohtli_b200 has no CPU fallback.")
+    lib_ = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib_, name)   # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib_
+    return lib_
+
+
+def lib():
+    return load_library()

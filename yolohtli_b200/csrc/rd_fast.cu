@@ -1,0 +1,238 @@
+// rd_fast.cu -- the HBM-roofline path of the monodomain step: Euler + 5-point Laplacian +
+// no-flux (mirror) boundaries, square domain, with TEMPORAL BLOCKING (T time steps per pass
+// over HBM).  Mode of reactionDiffusion.cu:186-199 + :498-513; same expression order, so the
+// result is bit-identical to T launches of the reference kernel built with --fmad=false.
+//
+// Design ("3.5-D streaming"): a CTA owns a strip of W columns (W - 2H of them are outputs)
+// and streams down RY rows.  Each time level l = 0..T-1 keeps a small ring of rows in shared
+// memory; warp group l (W/2 threads, two cells per thread, 16-byte smem/global accesses)
+// turns rows of level l-1 into one row of level l per iteration.  Level-0 rows arrive by
+// cp.async (LDGSTS) 4 rows ahead of use; level-T rows go straight to HBM.  Every cell is read
+// once and written once per T steps; the only redundancy is the 2H halo columns of a strip
+// (3 % at W=256, T=4) and the 3T-row pipeline fill of a chunk.  One __syncthreads per row.
+//
+//   level-l row m is produced in iteration  m - c0 + 2l   (c0 = first level-0 row of the chunk)
+//
+// Zero-sign note: the reference forms the stage state as u0 + (0.0*0.0) (reactionDiffusion.cu:
+// 117); x + 0.0 only changes -0.0 into +0.0.  Rows are stored canonicalised (+0.0) in the
+// rings, which is exact for tc > 0 ("zero signs").
+#include "yh_common.cuh"
+
+namespace {
+
+struct FastArgs {
+  const double *u_in, *v_in;
+  double *u_out, *v_out;
+  int RY;                 // output rows per chunk
+  long long sim_stride;   // elements between stacked independent sheets (blockIdx.z)
+  const int *period;      // per-sheet pacing period in steps (NULL: k.stim decides)
+  int duration, count0;   // stimulus on while (step % period) <= duration; step of level 1
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;   // src-size 0 => 16 bytes of zero fill, nothing read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// One Euler update of one cell (reactionDiffusion.cu:131-141,188-197,498-513).  Inputs are
+// canonical (already "+0.0").  rhs = 0.0 + 1.0*du is du for canonical u (see header note).
+__device__ __forceinline__ void euler_cell(const YhK &k, double u, double v, double uW, double uE,
+                                           double uN, double uS, double vW, double vE, double vN,
+                                           double vS, bool scs, double &un, double &vn) {
+  double I_sum = -(k.mu * u * (1.0 - u) * (u - k.alpha) - u * v);
+  if (scs) I_sum = I_sum - 24.7;   // x - 0.0 == x exactly, so the else arm is a no-op
+  const double I_v = -(k.eps * (k.delta * (u - k.gamma) * (k.beta - u) - v - k.theta));
+  double du = ((uW - 2.0 * u + uE) * k.rx + (uN - 2.0 * u + uS) * k.ry);
+  double dv = 0.0;
+  if (k.gateDiff) dv = ((vW - 2.0 * v + vE) * k.rx * k.rscale + (vN - 2.0 * v + vS) * k.ry * k.rscale);
+  du -= k.dt * I_sum;
+  dv -= k.dt * I_v;
+  un = u + k.tc * du;
+  vn = v + k.tc * dv;
+}
+
+template <int T, int W>
+__global__ void __launch_bounds__(T *(W / 2))
+rd_euler_stream(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a) {
+  constexpr int H = (T + 1) & ~1;        // halo columns each side (even: 16-byte alignment)
+  constexpr int BX = W - 2 * H;          // output columns per strip
+  constexpr int PITCH = W + 4;           // 2 pad doubles each side
+  constexpr int ROW = 2 * PITCH;         // u plane then v plane
+  constexpr int NR0 = 8, PF = 4, NRL = 4;
+  constexpr int NT = T * (W / 2);
+  extern __shared__ __align__(16) double sm[];
+
+  const int tid = threadIdx.x;
+  const int lev = tid / (W / 2) + 1;     // level this thread produces (warp-uniform)
+  const int c = 2 * (tid % (W / 2));     // window column of the thread's first cell
+  const int x0 = blockIdx.x * BX, wx0 = x0 - H;
+  const int gx = wx0 + c;
+  const int nx = k.nx;
+  const int y0 = k.row0 + blockIdx.y * a.RY;
+  const int RYe = min(a.RY, k.row1 - y0);
+  const int c0 = y0 - T;
+  const int dom_lo = -k.jg0, dom_hi = k.nyg - k.jg0;   // local rows that exist globally
+  const size_t zoff = (size_t)blockIdx.z * (size_t)a.sim_stride;
+  const double *__restrict__ u_in = a.u_in + zoff;
+  const double *__restrict__ v_in = a.v_in + zoff;
+  double *__restrict__ u_out = a.u_out + zoff;
+  double *__restrict__ v_out = a.v_out + zoff;
+
+  // rows this level must produce
+  const int lo_l = max(dom_lo, y0 - (T - lev));
+  const int hi_l = min(dom_hi, y0 + RYe + (T - lev));
+  const int ld_lo = max(dom_lo, c0), ld_hi = min(dom_hi, y0 + RYe + T);
+  const bool col_ok = (gx >= 0) && (gx < nx);
+  const bool out_col = col_ok && (c >= H) && (c < W - H);
+
+  // pacing (batched sweeps): level `lev` performs step count0 + lev - 1 of its sheet
+  bool stim_on = k.stim != 0;
+  if (a.period) {
+    const int per = a.period[blockIdx.z];
+    stim_on = per > 0 && ((a.count0 + lev - 1) % per) <= a.duration;
+  }
+
+  const double *src_ring = sm + (lev == 1 ? 0 : (NR0 + (lev - 2) * NRL) * ROW);
+  double *dst_ring = sm + (NR0 + (lev - 1) * NRL) * ROW;
+  const int src_mask = (lev == 1) ? (NR0 - 1) : (NRL - 1);
+
+  auto issue_row = [&](int q) {   // level-0 row q -> ring 0 (all threads help)
+    if (q >= ld_lo && q < ld_hi) {
+      double *dst = sm + ((q - c0) & (NR0 - 1)) * ROW;
+      for (int t = tid; t < W; t += NT) {
+        const int f = t / (W / 2), cc = 2 * (t % (W / 2));
+        const int ggx = wx0 + cc;
+        const bool ok = (ggx >= 0) && (ggx < nx);
+        const double *src = (f ? v_in : u_in) + (size_t)q * nx + (ok ? ggx : 0);
+        cp_async16(dst + f * PITCH + cc + 2, src, ok);
+      }
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int q = 0; q < PF; q++) issue_row(c0 + q);
+
+  const int n_it = RYe + 3 * T;
+  for (int it = 0; it < n_it; it++) {
+    issue_row(c0 + it + PF);
+    const int m = it + c0 - 2 * lev;
+    if (m >= lo_l && m < hi_l && col_ok) {
+      const int ms = (m - 1 < dom_lo) ? m + 1 : m - 1;   // mirror rows at the global edges
+      const int mn = (m + 1 >= dom_hi) ? m - 1 : m + 1;
+      const double *rc = src_ring + ((m - c0) & src_mask) * ROW + c + 2;
+      const double *rs = src_ring + ((ms - c0) & src_mask) * ROW + c + 2;
+      const double *rn = src_ring + ((mn - c0) & src_mask) * ROW + c + 2;
+      double2 uc = *reinterpret_cast<const double2 *>(rc);
+      double2 us = *reinterpret_cast<const double2 *>(rs);
+      double2 un = *reinterpret_cast<const double2 *>(rn);
+      double uw = rc[-1], ue = rc[2];
+      double2 vc = *reinterpret_cast<const double2 *>(rc + PITCH);
+      double2 vs = *reinterpret_cast<const double2 *>(rs + PITCH);
+      double2 vn = *reinterpret_cast<const double2 *>(rn + PITCH);
+      double vw = rc[PITCH - 1], ve = rc[PITCH + 2];
+      if (lev == 1) {   // level-0 data is raw: form u0 + (0.0*0.0) as the reference does
+        uc.x += 0.0; uc.y += 0.0; us.x += 0.0; us.y += 0.0; un.x += 0.0; un.y += 0.0;
+        uw += 0.0; ue += 0.0;
+        vc.x += 0.0; vc.y += 0.0; vs.x += 0.0; vs.y += 0.0; vn.x += 0.0; vn.y += 0.0;
+        vw += 0.0; ve += 0.0;
+      }
+      if (gx == 0) { uw = uc.y; vw = vc.y; }              // mirror: W of x=0 is x=1
+      if (gx + 2 == nx) { ue = uc.x; ve = vc.x; }          // mirror: E of x=nx-1 is x=nx-2
+      bool s0 = false, s1 = false;
+      if (stim_on) { s0 = yh_scs_on(k, gx, m + k.jg0); s1 = yh_scs_on(k, gx + 1, m + k.jg0); }
+      double2 uo, vo;
+      euler_cell(k, uc.x, vc.x, uw, uc.y, un.x, us.x, vw, vc.y, vn.x, vs.x, s0, uo.x, vo.x);
+      euler_cell(k, uc.y, vc.y, uc.x, ue, un.y, us.y, vc.x, ve, vn.y, vs.y, s1, uo.y, vo.y);
+      if (lev < T) {
+        uo.x += 0.0; uo.y += 0.0; vo.x += 0.0; vo.y += 0.0;   // next level's stage state
+        double *d = dst_ring + ((m - c0) & (NRL - 1)) * ROW + c + 2;
+        *reinterpret_cast<double2 *>(d) = uo;
+        *reinterpret_cast<double2 *>(d + PITCH) = vo;
+      } else if (out_col) {
+        const size_t o = (size_t)m * nx + gx;
+        *reinterpret_cast<double2 *>(u_out + o) = uo;
+        *reinterpret_cast<double2 *>(v_out + o) = vo;
+      }
+    }
+    cp_async_wait<PF>();
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+}
+
+template <int T, int W>
+int launch(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
+  constexpr int H = (T + 1) & ~1, BX = W - 2 * H, PITCH = W + 4, ROW = 2 * PITCH;
+  constexpr int NT = T * (W / 2);
+  const size_t smem = (size_t)(8 + (T - 1) * 4) * ROW * sizeof(double);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  YH_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    YH_CUDA(cudaFuncSetAttribute(rd_euler_stream<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    attr_set[dev & 63] = true;
+  }
+  const int rows = k.row1 - k.row0;
+  dim3 grd((k.nx + BX - 1) / BX, (rows + a.RY - 1) / a.RY, nsims);
+  rd_euler_stream<T, W><<<grd, NT, smem, st>>>(k, a);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
+
+}  // namespace
+
+int yh_rd_fast_supported(const YhK &k, int tb) {
+  if (k.timeIntOrder != 1 || k.lap4 || !k.neumannBC || k.solidSwitch || k.anisotropy)
+    return 0;
+  if (!(k.tc > 0.0)) return 0;            // zero-sign argument needs tc > 0
+  if ((k.nx & 1) || k.nx < 8) return 0;   // two cells per thread, 16-byte rows
+  if (tb != 1 && tb != 2 && tb != 4) return 0;
+  return 1;
+}
+
+// Chunk height: enough CTAs to fill 148 SMs a few times over, tall enough to amortise the
+// 3T-row pipeline fill.
+static int pick_ry(int rows, int strips, int nsims, int T) {
+  int ry = 512;
+  const int min_ry = 16 * T;
+  while (ry > min_ry && (long long)strips * ((rows + ry - 1) / ry) * nsims < 4 * 148) ry >>= 1;
+  return ry;
+}
+
+int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const double *v_in,
+                            double *u_out, double *v_out, int nsims, long long sim_stride,
+                            const int *period_d, int duration_it, int count0, cudaStream_t st) {
+  if (!yh_rd_fast_supported(k, tb)) return YH_ERR_UNSUPPORTED;
+  FastArgs a{u_in, v_in, u_out, v_out, 0, sim_stride, period_d, duration_it, count0};
+  const int rows = k.row1 - k.row0;
+  if (rows <= 0) return YH_OK;
+  const bool narrow = k.nx < 1024;   // small sheets: more, narrower strips
+  const int W = narrow ? 128 : 256;
+  const int H = (tb + 1) & ~1, BX = W - 2 * H;
+  a.RY = pick_ry(rows, (k.nx + BX - 1) / BX, nsims, tb);
+  if (narrow) {
+    switch (tb) {
+      case 1: return launch<1, 128>(k, a, nsims, st);
+      case 2: return launch<2, 128>(k, a, nsims, st);
+      default: return launch<4, 128>(k, a, nsims, st);
+    }
+  }
+  switch (tb) {
+    case 1: return launch<1, 256>(k, a, nsims, st);
+    case 2: return launch<2, 256>(k, a, nsims, st);
+    default: return launch<4, 256>(k, a, nsims, st);
+  }
+}
+
+int yh_launch_rd_fast(const YhK &k, int tb, const double *u_in, const double *v_in,
+                      double *u_out, double *v_out, const uint8_t *solid, cudaStream_t st) {
+  (void)solid;
+  return yh_launch_rd_fast_paced(k, tb, u_in, v_in, u_out, v_out, 1, 0, nullptr, 0, 0, st);
+}

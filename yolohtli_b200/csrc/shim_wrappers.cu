@@ -1,0 +1,126 @@
+// shim_wrappers.cu -> libyolohtli_shim.so: the reference's launch API (hostPrototypes.h:22-57)
+// with the reference's exact C++ signatures, forwarding to the C ABI of libyolohtli_b200.so.
+// pitch / grid / block arguments are hints and are ignored (the new kernels choose their own
+// launch shape); scalars come from yh_shim_configure() instead of __constant__ symbols.
+// Wrappers are `void` like the reference's; a failure is printed, latched in
+// yh_shim_last_status(), and -- like -DCUDA_ERROR_CHECK builds (common/CudaSafeCall.h:8-16) --
+// terminates the process when YH_SHIM_ABORT_ON_ERROR is set in the environment.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../../include/yolohtli_abi.h"
+#include "../../include/yolohtli_compat.h"
+
+static yh_params g_p;
+static bool g_configured = false;
+static int g_status = YH_OK;
+
+static void note(int rc, const char *what) {
+  if (rc == YH_OK) return;
+  g_status = rc;
+  fprintf(stderr, "yolohtli shim: %s failed (%d): %s\n", what, rc, yh_last_error());
+  if (getenv("YH_SHIM_ABORT_ON_ERROR")) exit(-1);
+}
+static bool ready(const char *what) {
+  if (g_configured) return true;
+  g_status = YH_ERR_INVALID_ARG;
+  fprintf(stderr, "yolohtli shim: %s called before yh_shim_configure()\n", what);
+  if (getenv("YH_SHIM_ABORT_ON_ERROR")) exit(-1);
+  return false;
+}
+
+extern "C" int yh_shim_configure(const yh_params *p) {
+  if (!p) return YH_ERR_INVALID_ARG;
+  g_p = *p;
+  g_configured = true;
+  g_status = YH_OK;
+  return YH_OK;
+}
+extern "C" int yh_shim_last_status(void) { return g_status; }
+
+void reactionDiffusion_wrapper(size_t, dim3, dim3, stateVar gOut_d, stateVar gIn_d, stateVar,
+                               stateVar velTan, bool, bool *solid, bool, REAL *, bool stimLockMouse,
+                               int2 point) {
+  if (!ready("reactionDiffusion_wrapper")) return;
+  // velTan is produced whenever gateDiff is on, as reactionDiffusion.cu:529-552 does; the J
+  // scratch array and the stim/stimLock arguments are unused (the latter as shipped, :132-133).
+  note(yh_rd_step(&g_p, gIn_d.u, gIn_d.v, gOut_d.u, gOut_d.v, g_p.gateDiff ? velTan.u : nullptr,
+                  g_p.gateDiff ? velTan.v : nullptr, reinterpret_cast<const uint8_t *>(solid),
+                  stimLockMouse, point.x, point.y, 0, g_p.ny, nullptr),
+       "reactionDiffusion_wrapper");
+}
+
+void tip_wrapper(size_t, dim3, dim3, stateVar gOut_d, stateVar gIn_d, stateVar, REAL physicalTime,
+                 int tipAlgorithm, bool, bool *tip_plot, int *tip_count, vec5dyn *tip_vector) {
+  if (!ready("tip_wrapper")) return;
+  // tipTracker.cu:586: kernel(g_past = gIn_d.u, g_present = gOut_d.u)
+  note(yh_tip_track(&g_p, gIn_d.u, gOut_d.u, reinterpret_cast<uint8_t *>(tip_plot), tip_count,
+                    reinterpret_cast<yh_tip *>(tip_vector), YH_TIPVECSIZE, physicalTime,
+                    tipAlgorithm, nullptr),
+       "tip_wrapper");
+}
+
+void slice_wrapper(size_t, dim3, dim3, stateVar g, sliceVar slice, sliceVar slice0, bool reduceSym,
+                   bool reduceSymStart, advVar adv, int scheme, bool *, int *tip_count,
+                   vec5dyn *tip_vector, int count) {
+  if (!ready("slice_wrapper")) return;
+  double *s[6] = {slice.ux, slice.uy, slice.ut, slice.vx, slice.vy, slice.vt};
+  double *s0[6] = {slice0.ux, slice0.uy, slice0.ut, slice0.vx, slice0.vy, slice0.vt};
+  note(yh_slice(&g_p, g.u, g.v, s, s0, reduceSym, reduceSymStart, adv.x, adv.y, scheme, tip_count,
+                reinterpret_cast<const yh_tip *>(tip_vector), count, nullptr),
+       "slice_wrapper");
+}
+
+void Cxy_field_wrapper(size_t, dim3, dim3, advVar adv, REAL3 c, REAL3 phi, bool *solid) {
+  if (!ready("Cxy_field_wrapper")) return;
+  const double cc[3] = {c.x, c.y, c.t}, ph[3] = {phi.x, phi.y, phi.t};
+  note(yh_cxy_field(&g_p, adv.x, adv.y, cc, ph, reinterpret_cast<const uint8_t *>(solid), nullptr),
+       "Cxy_field_wrapper");
+}
+
+void advFDBFECC_wrapper(size_t, dim3, dim3, stateVar gOut, stateVar gIn, advVar adv, stateVar,
+                        stateVar, stateVar, bool *solid) {
+  if (!ready("advFDBFECC_wrapper")) return;   // uf / ub / ue scratch arrays are not needed
+  note(yh_advect_bfecc(&g_p, gIn.u, gIn.v, gOut.u, gOut.v, adv.x, adv.y,
+                       reinterpret_cast<const uint8_t *>(solid), nullptr),
+       "advFDBFECC_wrapper");
+}
+
+REAL3 solve_matrix(REAL3 c, REAL3 phi, REAL *Int) {
+  const double ci[3] = {c.x, c.y, c.t}, ph[3] = {phi.x, phi.y, phi.t};
+  double co[3] = {c.x, c.y, c.t};
+  note(yh_solve_matrix(ci, ph, Int, co), "solve_matrix");
+  REAL3 r = {co[0], co[1], co[2]};
+  return r;
+}
+
+void trapz_wrapper(dim3, dim3, sliceVar slice, sliceVar slice0, stateVar velTan, REAL *integrals,
+                   REAL *, int *tip_count, vec5dyn *tip_vector, int count) {
+  if (!ready("trapz_wrapper")) return;
+  const double *s[6] = {slice.ux, slice.uy, slice.ut, slice.vx, slice.vy, slice.vt};
+  const double *s0[6] = {slice0.ux, slice0.uy, slice0.ut, slice0.vx, slice0.vy, slice0.vt};
+  note(yh_trapz(&g_p, s, s0, velTan.u, velTan.v, integrals, tip_count,
+                reinterpret_cast<const yh_tip *>(tip_vector), count, nullptr),
+       "trapz_wrapper");
+}
+
+void singleCell_wrapper(size_t, dim3, dim3, stateVar gOut_d, int, REAL *pt_h, REAL *pt_d, int2 point) {
+  if (!ready("singleCell_wrapper")) return;
+  note(yh_probe(&g_p, gOut_d.u, gOut_d.v, pt_d, point.x, point.y, pt_h, nullptr), "singleCell_wrapper");
+}
+
+void sAPD_wrapper(size_t, dim3, dim3, int count, REAL *uold, REAL *unew, REAL *APD1, REAL *APD2,
+                  REAL *sAPD, REAL *dAPD, REAL *back, REAL *front, bool *first, bool *stimArea,
+                  bool stimulate) {
+  if (!ready("sAPD_wrapper")) return;
+  note(yh_sapd(&g_p, count, uold, unew, APD1, APD2, sAPD, dAPD, back, front,
+               reinterpret_cast<uint8_t *>(first), reinterpret_cast<const uint8_t *>(stimArea),
+               stimulate, nullptr),
+       "sAPD_wrapper");
+}
+
+void swapSoA(stateVar *A, stateVar *B) {
+  stateVar t = *A;
+  *A = *B;
+  *B = t;
+}

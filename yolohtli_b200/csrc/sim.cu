@@ -1,0 +1,266 @@
+// sim.cu -- headless driver: the display() step loop of the reference (main.cu:862-1043)
+// without GLUT/OpenGL, for one sheet or a batch of independent sheets (parameter sweeps).
+// State lives in HBM for the whole run; the per-step blocking 16-byte D2H of
+// singleCell_wrapper (singleCell.cu:28) becomes a device-side trace buffer drained once.
+#include <string.h>
+#include <vector>
+
+#include "yh_common.cuh"
+
+int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const double *v_in,
+                            double *u_out, double *v_out, int nsims, long long sim_stride,
+                            const int *period_d, int duration_it, int count0, cudaStream_t st);
+
+struct yh_sim {
+  yh_params p;
+  int n_sims, device;
+  size_t n;              // cells per sheet
+  double *u[2], *v[2];
+  int cur;
+  uint8_t *solid;
+  double *trace_d;
+  size_t trace_cap;
+  int *tip_count_d;
+  yh_tip *tip_vec_d;
+  int *period_d;
+  std::vector<int> period_h;
+  int duration_it;
+  int px, py;
+  int count;
+  int have_prev;         // other buffer holds the state exactly one step back
+  cudaStream_t st;
+};
+
+namespace {
+
+__global__ void probe_batch_kernel(const double *u, const double *v, double *out, long long idx,
+                                   long long stride, int nsims) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsims) return;
+  out[2 * s] = u[idx + stride * s];
+  out[2 * s + 1] = v[idx + stride * s];
+}
+
+struct DevGuard {
+  int prev;
+  explicit DevGuard(int d) { cudaGetDevice(&prev); cudaSetDevice(d); }
+  ~DevGuard() { cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int yh_sim_create(yh_sim **out, const yh_params *p, int n_sims, int device) {
+  int rc = yh_check_device();
+  if (rc != YH_OK) return rc;
+  YH_REQUIRE(out && p && n_sims >= 1, "bad arguments");
+  YH_REQUIRE(p->jg0 == 0 && p->ny_global == p->ny, "yh_sim drives whole sheets");
+  YH_REQUIRE(device >= 0 && device < yh_device_count(), "no such device");
+  DevGuard g(device);
+  yh_sim *s = new yh_sim();
+  memset(&s->p, 0, sizeof(s->p));
+  s->p = *p;
+  s->n_sims = n_sims; s->device = device;
+  s->n = (size_t)p->nx * p->ny;
+  s->cur = 0; s->solid = nullptr; s->trace_d = nullptr; s->trace_cap = 0;
+  s->period_d = nullptr; s->duration_it = 0; s->count = 0; s->have_prev = 0;
+  s->px = p->nx / 2; s->py = p->ny / 2;   // param.point, saveFiles.cu:180
+  const size_t bytes = s->n * n_sims * sizeof(double);
+  for (int b = 0; b < 2; b++) {
+    YH_CUDA(cudaMalloc(&s->u[b], bytes));
+    YH_CUDA(cudaMalloc(&s->v[b], bytes));
+    YH_CUDA(cudaMemset(s->u[b], 0, bytes));
+    YH_CUDA(cudaMemset(s->v[b], 0, bytes));
+  }
+  YH_CUDA(cudaMalloc(&s->tip_count_d, sizeof(int)));
+  YH_CUDA(cudaMemset(s->tip_count_d, 0, sizeof(int)));
+  YH_CUDA(cudaMalloc(&s->tip_vec_d, sizeof(yh_tip) * (size_t)YH_TIPVECSIZE));
+  YH_CUDA(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+  *out = s;
+  return YH_OK;
+}
+
+int yh_sim_destroy(yh_sim *s) {
+  if (!s) return YH_OK;
+  DevGuard g(s->device);
+  cudaStreamSynchronize(s->st);
+  for (int b = 0; b < 2; b++) { cudaFree(s->u[b]); cudaFree(s->v[b]); }
+  cudaFree(s->solid); cudaFree(s->trace_d); cudaFree(s->tip_count_d); cudaFree(s->tip_vec_d);
+  cudaFree(s->period_d);
+  cudaStreamDestroy(s->st);
+  delete s;
+  return YH_OK;
+}
+
+int yh_sim_set_state(yh_sim *s, const double *u_h, const double *v_h) {
+  YH_REQUIRE(s && u_h && v_h, "null pointer");
+  DevGuard g(s->device);
+  const size_t bytes = s->n * s->n_sims * sizeof(double);
+  YH_CUDA(cudaMemcpyAsync(s->u[s->cur], u_h, bytes, cudaMemcpyHostToDevice, s->st));
+  YH_CUDA(cudaMemcpyAsync(s->v[s->cur], v_h, bytes, cudaMemcpyHostToDevice, s->st));
+  YH_CUDA(cudaStreamSynchronize(s->st));
+  s->have_prev = 0;
+  return YH_OK;
+}
+
+int yh_sim_get_state(yh_sim *s, double *u_h, double *v_h) {
+  YH_REQUIRE(s && u_h && v_h, "null pointer");
+  DevGuard g(s->device);
+  const size_t bytes = s->n * s->n_sims * sizeof(double);
+  YH_CUDA(cudaMemcpyAsync(u_h, s->u[s->cur], bytes, cudaMemcpyDeviceToHost, s->st));
+  YH_CUDA(cudaMemcpyAsync(v_h, s->v[s->cur], bytes, cudaMemcpyDeviceToHost, s->st));
+  YH_CUDA(cudaStreamSynchronize(s->st));
+  return YH_OK;
+}
+
+int yh_sim_set_solid(yh_sim *s, const uint8_t *solid_h) {
+  YH_REQUIRE(s && solid_h, "null pointer");
+  DevGuard g(s->device);
+  if (!s->solid) YH_CUDA(cudaMalloc(&s->solid, s->n));
+  YH_CUDA(cudaMemcpy(s->solid, solid_h, s->n, cudaMemcpyHostToDevice));
+  return YH_OK;
+}
+
+// initGates, main.cu:606-618: u = 1 for i < nx/8, v = 1 for j >= ny/2 (every sheet)
+int yh_sim_cross_field_ic(yh_sim *s) {
+  YH_REQUIRE(s != nullptr, "null sim");
+  const int nx = s->p.nx, ny = s->p.ny;
+  std::vector<double> u(s->n * s->n_sims, 0.0), v(s->n * s->n_sims, 0.0);
+  for (int z = 0; z < s->n_sims; z++) {
+    double *uz = u.data() + s->n * z, *vz = v.data() + s->n * z;
+    for (int j = 0; j < ny; j++)
+      for (int i = 0; i < nx / 8; i++) uz[i + (size_t)nx * j] = 1.0;
+    for (int j = ny / 2; j < ny; j++)
+      for (int i = 0; i < nx; i++) vz[i + (size_t)nx * j] = 1.0;
+  }
+  s->count = 0;
+  return yh_sim_set_state(s, u.data(), v.data());
+}
+
+int yh_sim_set_point(yh_sim *s, int x, int y) {
+  YH_REQUIRE(s && x >= 0 && x < s->p.nx && y >= 0 && y < s->p.ny, "bad point");
+  s->px = x; s->py = y;
+  return YH_OK;
+}
+
+int yh_sim_set_pacing(yh_sim *s, const int *period_it, int duration_it) {
+  YH_REQUIRE(s != nullptr, "null sim");
+  DevGuard g(s->device);
+  if (!period_it) {   // pacing off
+    cudaFree(s->period_d); s->period_d = nullptr; s->period_h.clear();
+    return YH_OK;
+  }
+  YH_REQUIRE(duration_it >= 0, "negative duration");
+  s->period_h.assign(period_it, period_it + s->n_sims);
+  if (!s->period_d) YH_CUDA(cudaMalloc(&s->period_d, sizeof(int) * s->n_sims));
+  YH_CUDA(cudaMemcpy(s->period_d, period_it, sizeof(int) * s->n_sims, cudaMemcpyHostToDevice));
+  s->duration_it = duration_it;
+  return YH_OK;
+}
+
+// nsteps x { reactionDiffusion ; swap ; probe }  (main.cu:869-885, 1040)
+int yh_sim_run(yh_sim *s, int nsteps, int tb_steps, double *trace_h) {
+  YH_REQUIRE(s && nsteps >= 0, "bad arguments");
+  YH_REQUIRE(tb_steps >= 0 && tb_steps <= 4 && tb_steps != 3, "tb_steps must be 0 (auto), 1, 2 or 4");
+  DevGuard g(s->device);
+  YhK k = yh_make_k(&s->p);
+  k.px = s->px; k.py = s->py;
+  const bool pacing = s->period_d != nullptr;
+  const long long stride = (long long)s->n;
+  int tb = tb_steps ? tb_steps : 4;
+  if (trace_h) {
+    tb = 1;   // one probe sample per step, taken BEFORE the step (one-step lag of main.cu:1040)
+    const size_t need = (size_t)2 * nsteps * s->n_sims;
+    if (s->trace_cap < need) {
+      cudaFree(s->trace_d); s->trace_d = nullptr; s->trace_cap = 0;
+      YH_CUDA(cudaMalloc(&s->trace_d, need * sizeof(double)));
+      s->trace_cap = need;
+    }
+  }
+  const bool fast1 = yh_rd_fast_supported(k, 1) != 0;
+  int left = nsteps, step = 0;
+  while (left > 0) {
+    int T = 1;
+    if (fast1) { T = tb; while (T > left) T >>= 1; }
+    const int c = s->cur, o = c ^ 1;
+    if (trace_h) {
+      probe_batch_kernel<<<(s->n_sims + 127) / 128, 128, 0, s->st>>>(
+          s->u[c], s->v[c], s->trace_d + (size_t)2 * step * s->n_sims,
+          (long long)s->px + (long long)s->p.nx * s->py, stride, s->n_sims);
+      YH_LAUNCH_CHECK();
+    }
+    int rc;
+    if (fast1) {
+      rc = yh_launch_rd_fast_paced(k, T, s->u[c], s->v[c], s->u[o], s->v[o], s->n_sims, stride,
+                                   s->period_d, s->duration_it, s->count, s->st);
+    } else {
+      rc = YH_OK;
+      for (int z = 0; z < s->n_sims && rc == YH_OK; z++) {
+        YhK kz = k;
+        if (pacing) {
+          const int per = s->period_h[z];
+          kz.stim = per > 0 && (s->count % per) <= s->duration_it;
+        }
+        rc = yh_launch_rd_generic(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
+                                  s->v[o] + s->n * z, nullptr, nullptr, s->solid, s->st);
+      }
+    }
+    if (rc != YH_OK) return rc;
+    s->cur = o;
+    s->have_prev = (T == 1);
+    s->count += T;
+    left -= T; step += T;
+  }
+  if (trace_h && nsteps > 0) {
+    YH_CUDA(cudaMemcpyAsync(trace_h, s->trace_d, sizeof(double) * 2 * nsteps * s->n_sims,
+                            cudaMemcpyDeviceToHost, s->st));
+  }
+  YH_CUDA(cudaStreamSynchronize(s->st));
+  return YH_OK;
+}
+
+int yh_sim_run_host(yh_sim *s, const double *u_in_h, const double *v_in_h, double *u_out_h,
+                    double *v_out_h, int nsteps, int tb_steps) {
+  YH_REQUIRE(s && u_in_h && v_in_h && u_out_h && v_out_h, "null pointer");
+  DevGuard g(s->device);
+  const size_t bytes = s->n * s->n_sims * sizeof(double);
+  YH_CUDA(cudaMemcpyAsync(s->u[s->cur], u_in_h, bytes, cudaMemcpyHostToDevice, s->st));
+  YH_CUDA(cudaMemcpyAsync(s->v[s->cur], v_in_h, bytes, cudaMemcpyHostToDevice, s->st));
+  int rc = yh_sim_run(s, nsteps, tb_steps, nullptr);
+  if (rc != YH_OK) return rc;
+  YH_CUDA(cudaMemcpyAsync(u_out_h, s->u[s->cur], bytes, cudaMemcpyDeviceToHost, s->st));
+  YH_CUDA(cudaMemcpyAsync(v_out_h, s->v[s->cur], bytes, cudaMemcpyDeviceToHost, s->st));
+  YH_CUDA(cudaStreamSynchronize(s->st));
+  return YH_OK;
+}
+
+// Tips between the last two states (tip_wrapper as called at main.cu:963: present = newest).
+// Sheet 0 only.  Requires the last pass to have been a single step (run with tb_steps = 1, or
+// any run whose final pass has T = 1).
+int yh_sim_tips(yh_sim *s, yh_tip *tips_h, int capacity, int *count_out) {
+  YH_REQUIRE(s && tips_h && count_out && capacity >= 0, "bad arguments");
+  if (!s->have_prev) {
+    yh_set_error("yh_sim_tips: previous state not held (end the run with a single-step pass)");
+    return YH_ERR_UNSUPPORTED;
+  }
+  DevGuard g(s->device);
+  const double t = s->p.dt * (double)s->count;   // param.physicalTime, main.cu:885
+  int rc = yh_tip_track(&s->p, s->u[s->cur ^ 1], s->u[s->cur], nullptr, s->tip_count_d,
+                        s->tip_vec_d, YH_TIPVECSIZE, t, s->p.tipAlgorithm, s->st);
+  if (rc != YH_OK) return rc;
+  int n = 0;
+  YH_CUDA(cudaMemcpyAsync(&n, s->tip_count_d, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+  YH_CUDA(cudaStreamSynchronize(s->st));
+  *count_out = n;
+  if (n > YH_TIPVECSIZE) { yh_set_error("tip list overflow: %d > %d", n, YH_TIPVECSIZE); return YH_ERR_CAPACITY; }
+  const int m = n < capacity ? n : capacity;
+  if (m > 0) YH_CUDA(cudaMemcpy(tips_h, s->tip_vec_d, sizeof(yh_tip) * (size_t)m, cudaMemcpyDeviceToHost));
+  return YH_OK;
+}
+
+int yh_sim_count(const yh_sim *s) { return s ? s->count : -1; }
+void *yh_sim_device_u(yh_sim *s) { return s ? s->u[s->cur] : nullptr; }
+void *yh_sim_device_v(yh_sim *s) { return s ? s->v[s->cur] : nullptr; }
+
+}  // extern "C"

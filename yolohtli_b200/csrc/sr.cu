@@ -1,0 +1,605 @@
+// sr.cu -- symmetry-reduction (co-moving frame) pieces of the step (main.cu:894-954):
+//   yh_slice          slice_kernel                symmetryReduction.cu:72-222
+//   yh_trapz          trapz_kernel x 12           integralTrapz.cu:17-184   (one pass, one D2H)
+//   yh_sr_integrals   slice + trapz fused: tangent fields formed in registers, the 12
+//                     nx*ny slice arrays (96 B/cell of writes that only trapz re-reads) never exist
+//   yh_cxy_field      Cxy_field_kernel            symmetryReduction.cu:20-62
+//   yh_advect_bfecc*  advFDBFECC_kernel           advFDBFECC.cu:18-353, three SYNCHRONOUS
+//                     sweeps in a shared-memory tile with a 3-cell halo (no uf/ub/ue arrays)
+//
+// Reductions are warp-shuffle / fixed-order so the 12 integrals are deterministic: one warp
+// per grid row (lane l sums i = l, l+32, ...; xor-butterfly 16..1), rows added in ascending j.
+#include <math.h>
+
+#include "yh_common.cuh"
+
+namespace {
+
+// Disc centre (symmetryReduction.cu:98-104 / integralTrapz.cu:42-48).  An empty list keeps
+// (tipx0, tipy0) instead of reading tip_vector[-1] (defect B3).
+__device__ __forceinline__ void disc_centre(const YhK &k, float tipx0, float tipy0, const int *tip_count,
+                                            const yh_tip *tv, int count, int &cx, int &cy) {
+  float fx = tipx0, fy = tipy0;
+  if (count != 0 && tip_count) {
+    const int n = *tip_count;
+    if (n > 0) { fx = tv[n - 1].x; fy = tv[n - 1].y; }
+  }
+  cx = __float2int_rn(fx - (float)(k.nx / 2));
+  cy = __float2int_rn(fy - (float)(k.ny / 2));
+}
+
+__device__ __forceinline__ int IDX(const YhK &k, int i, int j) { return i + k.nx * j; }
+
+__device__ __forceinline__ double fb2x(const YhK &k, const double *f, int i, int j, int C, int E, int W, double ax) {
+  const int WW = IDX(k, yh_mir(i - 2, k.nx), j), EE = IDX(k, yh_mir(i + 2, k.nx), j);
+  return (ax > 0.0) ? (-3.0 * f[C] + 4.0 * f[E] - f[EE]) * k.invdx : (3.0 * f[C] - 4.0 * f[W] + f[WW]) * k.invdx;
+}
+__device__ __forceinline__ double fb2y(const YhK &k, const double *f, int i, int j, int C, int N, int S, double ay) {
+  const int SS = IDX(k, i, yh_mir(j - 2, k.ny)), NN = IDX(k, i, yh_mir(j + 2, k.ny));
+  return (ay > 0.0) ? (-3.0 * f[C] + 4.0 * f[N] - f[NN]) * k.invdy : (3.0 * f[C] - 4.0 * f[S] + f[SS]) * k.invdy;
+}
+__device__ __forceinline__ double cen2x(const YhK &k, const double *f, int i, int j, int E, int W) {
+  const int WW = IDX(k, yh_mir(i - 2, k.nx), j), EE = IDX(k, yh_mir(i + 2, k.nx), j);
+  return (f[EE] - 8.0 * f[E] + 8.0 * f[W] - f[WW]) * k.invdx * (1.0 / 6.0);
+}
+__device__ __forceinline__ double cen2y(const YhK &k, const double *f, int i, int j, int N, int S) {
+  const int SS = IDX(k, i, yh_mir(j - 2, k.ny)), NN = IDX(k, i, yh_mir(j + 2, k.ny));
+  return (f[NN] - 8.0 * f[N] + 8.0 * f[S] - f[SS]) * k.invdy * (1.0 / 6.0);
+}
+
+// tangent values of one cell: s = upwind (slice), s0 = template (slice0); order ux uy ut vx vy vt
+__device__ __forceinline__ void slice_cell(const YhK &k, const double *gu, const double *gv, const double *ax,
+                                           const double *ay, int scheme, bool sc, int i, int j, bool want0,
+                                           double s[6], double s0[6]) {
+  const int c = IDX(k, i, j);
+  const double x = (double)(c % k.nx);
+  const double y = (double)floorf((float)((c / k.nx) % k.nx));   // as shipped (:109-110)
+  const int S = IDX(k, i, yh_mir(j - 1, k.ny)), N = IDX(k, i, yh_mir(j + 1, k.ny));
+  const int W = IDX(k, yh_mir(i - 1, k.nx), j), E = IDX(k, yh_mir(i + 1, k.nx), j);
+  const bool on = (scheme == 1) ? true : sc;
+  if (on) {
+    const double axc = ax[c], ayc = ay[c];
+    s[0] = fb2x(k, gu, i, j, c, E, W, axc);
+    s[1] = fb2y(k, gu, i, j, c, N, S, ayc);
+    s[3] = fb2x(k, gv, i, j, c, E, W, axc);
+    s[4] = fb2y(k, gv, i, j, c, N, S, ayc);
+    s[2] = k.hx * x * s[1] - k.hy * y * s[0];
+    s[5] = k.hx * x * s[4] - k.hy * y * s[3];
+  } else {
+#pragma unroll
+    for (int q = 0; q < 6; q++) s[q] = 0.0;
+  }
+  if (!want0) return;
+  if (scheme == 1) {   // :151-157
+    s0[0] = s[0]; s0[1] = s[1]; s0[3] = s[3]; s0[4] = s[4];
+    s0[2] = k.hx * x * s[1] - k.hy * y * s[0];
+    s0[5] = k.hx * x * s[4] - k.hy * y * s[3];
+  } else if (sc) {     // :191-202
+    s0[0] = cen2x(k, gu, i, j, E, W);
+    s0[1] = cen2y(k, gu, i, j, N, S);
+    s0[3] = cen2x(k, gv, i, j, E, W);
+    s0[4] = cen2y(k, gv, i, j, N, S);
+    s0[2] = k.hx * x * s0[1] - k.hy * y * s0[0];
+    s0[5] = k.hx * x * s0[4] - k.hy * y * s0[3];
+  } else {
+#pragma unroll
+    for (int q = 0; q < 6; q++) s0[q] = 0.0;
+  }
+}
+
+struct P6 { double *p[6]; };
+struct CP6 { const double *p[6]; };
+
+struct SliceArgs {
+  const double *u, *v, *ax, *ay;
+  P6 s, s0;
+  int start, scheme, count;
+  const int *tip_count;
+  const yh_tip *tv;
+  float tipx0, tipy0;
+};
+
+__global__ void __launch_bounds__(256)
+slice_kernel(const __grid_constant__ YhK k, const __grid_constant__ SliceArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= k.nx || j >= k.ny) return;
+  int cx, cy;
+  disc_centre(k, a.tipx0, a.tipy0, a.tip_count, a.tv, a.count, cx, cy);
+  const int ic = i - k.nx / 2, jc = j - k.ny / 2;
+  const bool sc = ((ic - cx) * (ic - cx) + (jc - cy) * (jc - cy)) < k.tipOffX * k.tipOffY;
+  double s[6], s0[6];
+  slice_cell(k, a.u, a.v, a.ax, a.ay, a.scheme, sc, i, j, a.start != 0, s, s0);
+  const int c = IDX(k, i, j);
+#pragma unroll
+  for (int q = 0; q < 6; q++) a.s.p[q][c] = s[q];
+  if (a.start) {
+#pragma unroll
+    for (int q = 0; q < 6; q++) a.s0.p[q][c] = s0[q];
+  }
+}
+
+// ---- the 12 integrals -------------------------------------------------------------------
+struct IntArgs {
+  // FUSED: from u, v, adv; otherwise from the slice arrays
+  const double *u, *v, *ax, *ay;
+  CP6 s, s0;
+  const double *vtu, *vtv;
+  double *rows;        // [nrows_max][12] row sums
+  double *out;         // [12] device result
+  int count;
+  const int *tip_count;
+  const yh_tip *tv;
+  float tipx0, tipy0;
+  int R;               // ceil(sqrt(tipOffX*tipOffY)): rows cy-R .. cy+R can intersect the disc
+};
+
+template <bool FUSED>
+__global__ void __launch_bounds__(128)
+integrals_rows_kernel(const __grid_constant__ YhK k, const __grid_constant__ IntArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // row slot
+  const int lane = threadIdx.x & 31;
+  if (warp >= 2 * a.R + 1) return;
+  int cx, cy;
+  disc_centre(k, a.tipx0, a.tipy0, a.tip_count, a.tv, a.count, cx, cy);
+  const int j = cy + k.ny / 2 - a.R + warp;   // grid row of this slot
+  double acc[12];
+#pragma unroll
+  for (int q = 0; q < 12; q++) acc[q] = 0.0;
+  if (j >= 0 && j < k.ny) {
+    const int jc = j - k.ny / 2;
+    for (int i = lane; i < k.nx; i += 32) {
+      const int ic = i - k.nx / 2;
+      const bool sc = ((ic - cx) * (ic - cx) + (jc - cy) * (jc - cy)) < k.tipOffX * k.tipOffY;
+      if (!sc) continue;   // the reference adds exactly +0.0 here (integralTrapz.cu:55-57)
+      const int c = IDX(k, i, j);
+      double s[6], s0[6];
+      if (FUSED) {
+        slice_cell(k, a.u, a.v, a.ax, a.ay, 2, true, i, j, true, s, s0);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 6; q++) { s[q] = a.s.p[q][c]; s0[q] = a.s0.p[q][c]; }
+      }
+      const double vu = a.vtu[c], vv = a.vtv[c];
+#pragma unroll
+      for (int m = 0; m < 3; m++) {
+#pragma unroll
+        for (int b = 0; b < 3; b++) acc[3 * m + b] += 4.0 * (s0[m] * s[b] + s0[m + 3] * s[b + 3]);
+        acc[9 + m] += 4.0 * (s0[m] * vu + s0[m + 3] * vv);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 12; q++) {
+    double x = acc[q];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, m);
+    acc[q] = x;
+  }
+  if (lane < 12) {
+    double r = 0.0;
+#pragma unroll
+    for (int q = 0; q < 12; q++) if (lane == q) r = acc[q];
+    a.rows[(size_t)warp * 12 + lane] = r;
+  }
+}
+
+__global__ void integrals_final_kernel(const __grid_constant__ YhK k, const __grid_constant__ IntArgs a) {
+  const int q = threadIdx.x;
+  if (q >= 12) return;
+  double tot = 0.0;
+  for (int w = 0; w < 2 * a.R + 1; w++) tot += a.rows[(size_t)w * 12 + q];   // ascending j
+  a.out[q] = 0.25 * k.hx * k.hy * tot;   // integralTrapz.cu:79
+}
+
+int run_integrals(const yh_params *p, IntArgs &a, bool fused, double *integrals_host, cudaStream_t st) {
+  YhK k = yh_make_k(p);
+  const long long r2 = (long long)p->tipOffsetX * p->tipOffsetY;
+  int R = (int)ceil(sqrt((double)r2));
+  if (R > p->ny) R = p->ny;
+  a.R = R;
+  const int nrows = 2 * R + 1;
+  double *ws = nullptr;
+  int rc = yh_workspace(((size_t)nrows * 12 + 12) * sizeof(double), (void **)&ws, 2);
+  if (rc != YH_OK) return rc;
+  a.rows = ws; a.out = ws + (size_t)nrows * 12;
+  const int blocks = (nrows * 32 + 127) / 128;
+  if (fused) integrals_rows_kernel<true><<<blocks, 128, 0, st>>>(k, a);
+  else integrals_rows_kernel<false><<<blocks, 128, 0, st>>>(k, a);
+  YH_LAUNCH_CHECK();
+  integrals_final_kernel<<<1, 32, 0, st>>>(k, a);
+  YH_LAUNCH_CHECK();
+  static thread_local double *pinned = nullptr;
+  if (!pinned) YH_CUDA(cudaMallocHost(&pinned, 12 * sizeof(double)));
+  YH_CUDA(cudaMemcpyAsync(pinned, a.out, 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  YH_CUDA(cudaStreamSynchronize(st));   // the ONE host sync of the SR step (reference: 12 + malloc/free)
+  for (int q = 0; q < 12; q++) integrals_host[q] = pinned[q];
+  return YH_OK;
+}
+
+// ---- Cxy ----------------------------------------------------------------------------------
+struct CxyArgs { double *ax, *ay; const uint8_t *solid; double cx, cy, ct, cs, sn; };
+
+// adv of one cell (symmetryReduction.cu:45-56); cos/sin(phi.t) are computed on the HOST so the
+// field is reproducible by the plain-C oracle bit for bit.
+__device__ __forceinline__ void cxy_cell(const YhK &k, const CxyArgs &a, int i, int j, double &ax, double &ay) {
+  const int c = i + k.nx * j;
+  const double x = (double)(c % k.nx);
+  const double y = (double)floorf((float)((c / k.nx) % k.nx));
+  ax = k.hy * y * a.ct - a.cx * a.cs + a.cy * a.sn;
+  ay = -k.hx * x * a.ct - a.cx * a.sn - a.cy * a.cs;
+  if (k.solidSwitch && !a.solid[c]) { ax = 0.0; ay = 0.0; }
+}
+
+__global__ void __launch_bounds__(256)
+cxy_kernel(const __grid_constant__ YhK k, const __grid_constant__ CxyArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= k.nx || j >= k.ny) return;
+  double ax, ay;
+  cxy_cell(k, a, i, j, ax, ay);
+  a.ax[i + k.nx * j] = ax;
+  a.ay[i + k.nx * j] = ay;
+}
+
+// ---- BFECC --------------------------------------------------------------------------------
+constexpr int BT = 32;            // output tile edge
+constexpr int BH = 3;             // halo
+constexpr int BP = BT + 2 * BH;   // 38
+constexpr int BTHREADS = 256;
+
+struct BfArgs {
+  const double *u_in, *v_in;
+  double *u_out, *v_out;
+  const double *ax, *ay;   // adv arrays (when !from_c)
+  double *ax_out, *ay_out; // optional copy of the generated field (from_c)
+  const uint8_t *solid;
+  CxyArgs cxy;
+  int from_c;
+};
+
+__device__ __forceinline__ int sgn(double x) { int t = x < 0.0 ? -1 : 0; return x > 0.0 ? 1 : t; }
+
+// tile-local index of GLOBAL cell (gi, gj), mirrored into the domain first (defect B5)
+__device__ __forceinline__ int TL(const YhK &k, int gi, int gj, int ti0, int tj0) {
+  gi = yh_mir(gi, k.nx); gj = yh_mir(gj, k.ny);
+  return (gi - ti0) + BP * (gj - tj0);
+}
+
+struct NbrIdx { int W, E, S, N, i2dW, W2, i2dE, E2, i2dS, S2, i2dN, N2; bool sc; };
+
+// index selection of the Neumann branches (advFDBFECC.cu:44-66 solid, :112-126 square)
+__device__ __forceinline__ NbrIdx neumann_idx(const YhK &k, const uint8_t *msk, int gi, int gj, int ti0, int tj0) {
+  NbrIdx x;
+  const int C = (gi - ti0) + BP * (gj - tj0);
+  bool sw, se, sn, ss;
+  if (k.solidSwitch) {
+    x.sc = msk[C];
+    sw = (gi > 0) && msk[C - 1];
+    se = (gi < k.nx - 1) && msk[C + 1];
+    sn = (gj > 0) && msk[C - BP];            // "sn" is the mask at j-1 (:47)
+    ss = (gj < k.ny - 1) && msk[C + BP];     // "ss" is the mask at j+1 (:48)
+  } else {
+    x.sc = true;
+    sw = gi > 0; se = gi < (k.nx - 1);
+    ss = gj > 0;            // square branch tests the index itself: S uses (j>0), N uses (j<ny-1)
+    sn = gj < (k.ny - 1);
+  }
+  if (k.solidSwitch) {
+    const int Wm = TL(k, gi - 1, gj, ti0, tj0), Em = TL(k, gi + 1, gj, ti0, tj0);
+    const int Sm = TL(k, gi, gj - 1, ti0, tj0), Nm = TL(k, gi, gj + 1, ti0, tj0);
+    x.W = x.sc ? (sw ? Wm : Em) : C;
+    x.E = x.sc ? (se ? Em : Wm) : C;
+    x.S = x.sc ? (ss ? Sm : Nm) : C;
+    x.N = x.sc ? (sn ? Nm : Sm) : C;
+    x.i2dW = x.sc ? (sw ? C : Em) : C;  x.W2 = x.sc ? (sw ? Wm : C) : C;
+    x.i2dE = x.sc ? (se ? C : Wm) : C;  x.E2 = x.sc ? (se ? Em : C) : C;
+    x.i2dS = x.sc ? (ss ? C : Nm) : C;  x.S2 = x.sc ? (ss ? Sm : C) : C;
+    x.i2dN = x.sc ? (sn ? C : Sm) : C;  x.N2 = x.sc ? (sn ? Nm : C) : C;
+  } else {
+    x.W = sw ? C - 1 : C + 1;   x.E = se ? C + 1 : C - 1;
+    x.S = ss ? C - BP : C + BP; x.N = sn ? C + BP : C - BP;
+    x.i2dW = sw ? C : C + 1;    x.W2 = sw ? C - 1 : C;
+    x.i2dE = se ? C : C - 1;    x.E2 = se ? C + 1 : C;
+    x.i2dS = ss ? C : C + BP;   x.S2 = ss ? C - BP : C;
+    x.i2dN = sn ? C : C - BP;   x.N2 = sn ? C + BP : C;
+  }
+  return x;
+}
+
+// Dirichlet neighbour values (advFDBFECC.cu:171-183 solid, :265-269 square).
+// bnd = value used where the neighbour is missing (boundaryVal, or the centre value in the
+// backward sweep :193-196,:279-282).
+struct DirMask { bool sc, sw, se, sS, sN; };
+__device__ __forceinline__ DirMask dir_mask(const YhK &k, const uint8_t *msk, int gi, int gj, int C) {
+  DirMask d;
+  if (k.solidSwitch) {
+    d.sc = msk[C];
+    d.sw = (gi > 0) && msk[C - 1];
+    d.se = (gi < k.nx - 1) && msk[C + 1];
+    const bool sn = (gj > 0) && msk[C - BP];           // mask at j-1
+    const bool ss = (gj < k.ny - 1) && msk[C + BP];    // mask at j+1
+    d.sS = ss;   // the shipped code gates the (j-1) read by ss and the (j+1) read by sn (:182-183)
+    d.sN = sn;
+  } else {
+    d.sc = true; d.sw = gi > 0; d.se = gi < (k.nx - 1); d.sS = gj > 0; d.sN = gj < (k.ny - 1);
+  }
+  return d;
+}
+
+__global__ void __launch_bounds__(BTHREADS)
+bfecc_kernel(const __grid_constant__ YhK k, const __grid_constant__ BfArgs a) {
+  extern __shared__ __align__(16) double bsm[];
+  double *g = bsm, *uf = bsm + BP * BP, *ue = bsm + 2 * BP * BP;
+  double *sRx = bsm + 3 * BP * BP, *sRy = bsm + 4 * BP * BP;   // |c| dt / h, upwind direction in the sign bit
+  uint8_t *msk = reinterpret_cast<uint8_t *>(bsm + 5 * BP * BP);
+  const int ti0 = blockIdx.x * BT - BH, tj0 = blockIdx.y * BT - BH;
+  const int tid = threadIdx.x;
+  const bool neu = k.neumannBC != 0;
+  const double tc = k.tc, bv = k.boundaryVal;
+
+  // per-cell Courant numbers, once for the three sweeps and both fields (advFDBFECC.cu:30-34)
+  for (int t = tid; t < BP * BP; t += BTHREADS) {
+    const int gi = ti0 + t % BP, gj = tj0 + t / BP;
+    double rx = 0.0, ry = 0.0;
+    uint8_t m = 0;
+    if (gi >= 0 && gi < k.nx && gj >= 0 && gj < k.ny) {
+      const int c = gi + k.nx * gj;
+      double ax, ay;
+      if (a.from_c) {
+        cxy_cell(k, a.cxy, gi, gj, ax, ay);
+        const bool own = (t % BP >= BH) && (t % BP < BH + BT) && (t / BP >= BH) && (t / BP < BH + BT);
+        if (own && a.ax_out) { a.ax_out[c] = ax; a.ay_out[c] = ay; }
+      } else { ax = a.ax[c]; ay = a.ay[c]; }
+      const double cx = -ax, cy = -ay;
+      const double Rx = sgn(cx) * cx * k.dt / k.hx, Ry = sgn(cy) * cy * k.dt / k.hy;
+      rx = (cx > 0.0) ? fabs(Rx) : -fabs(Rx);   // Rx >= 0 always; sign bit carries (cx > 0)
+      ry = (cy > 0.0) ? fabs(Ry) : -fabs(Ry);
+      if (k.solidSwitch) m = a.solid[c];
+    }
+    sRx[t] = rx; sRy[t] = ry; msk[t] = m;
+  }
+
+  for (int f = 0; f < 2; f++) {
+    const double *gin = f ? a.v_in : a.u_in;
+    double *gout = f ? a.v_out : a.u_out;
+    __syncthreads();
+    for (int t = tid; t < BP * BP; t += BTHREADS) {
+      const int gi = ti0 + t % BP, gj = tj0 + t / BP;
+      g[t] = (gi >= 0 && gi < k.nx && gj >= 0 && gj < k.ny) ? gin[gi + k.nx * gj] : 0.0;
+    }
+    __syncthreads();
+    // sweep 1 (forward) on the tile minus one ring
+    for (int t = tid; t < BP * BP; t += BTHREADS) {
+      const int li = t % BP, lj = t / BP, gi = ti0 + li, gj = tj0 + lj;
+      if (li < 1 || li >= BP - 1 || lj < 1 || lj >= BP - 1) continue;
+      if (gi < 0 || gi >= k.nx || gj < 0 || gj >= k.ny) continue;
+      const bool px = !signbit(sRx[t]), py = !signbit(sRy[t]);
+      const double Rx = fabs(sRx[t]), Ry = fabs(sRy[t]);
+      if (neu) {
+        const NbrIdx x = neumann_idx(k, msk, gi, gj, ti0, tj0);
+        const double FDx = px ? g[t] - g[x.W] : g[t] - g[x.E];
+        const double FDy = py ? g[t] - g[x.S] : g[t] - g[x.N];
+        uf[t] = g[t] - tc * (Rx * FDx + Ry * FDy);
+      } else {
+        const DirMask d = dir_mask(k, msk, gi, gj, t);
+        const double u = d.sc ? g[t] : 0.0;
+        const double W = d.sc && d.sw ? g[t - 1] : (d.sc ? bv : 0.0);
+        const double E = d.sc && d.se ? g[t + 1] : (d.sc ? bv : 0.0);
+        const double S = d.sc && d.sS ? g[TL(k, gi, gj - 1, ti0, tj0)] : (d.sc ? bv : 0.0);
+        const double N = d.sc && d.sN ? g[TL(k, gi, gj + 1, ti0, tj0)] : (d.sc ? bv : 0.0);
+        const double FDx = px ? u - W : u - E, FDy = py ? u - S : u - N;
+        uf[t] = u - tc * (Rx * FDx + Ry * FDy);
+      }
+    }
+    __syncthreads();
+    // sweep 2 (backward + error compensation) on the tile minus two rings
+    for (int t = tid; t < BP * BP; t += BTHREADS) {
+      const int li = t % BP, lj = t / BP, gi = ti0 + li, gj = tj0 + lj;
+      if (li < 2 || li >= BP - 2 || lj < 2 || lj >= BP - 2) continue;
+      if (gi < 0 || gi >= k.nx || gj < 0 || gj >= k.ny) continue;
+      const bool px = !signbit(sRx[t]), py = !signbit(sRy[t]);
+      const double Rx = fabs(sRx[t]), Ry = fabs(sRy[t]);
+      if (neu) {
+        const NbrIdx x = neumann_idx(k, msk, gi, gj, ti0, tj0);
+        const double FDx = px ? uf[x.i2dE] - uf[x.E2] : uf[x.i2dW] - uf[x.W2];
+        const double FDy = py ? uf[x.i2dN] - uf[x.N2] : uf[x.i2dS] - uf[x.S2];
+        const double ub = uf[t] - tc * (Rx * FDx + Ry * FDy);
+        ue[t] = g[t] - 0.5 * (ub - g[t]);
+      } else {
+        const DirMask d = dir_mask(k, msk, gi, gj, t);
+        const double u = d.sc ? g[t] : 0.0;
+        const double uuf = d.sc ? uf[t] : 0.0;
+        const double W = d.sc && d.sw ? uf[t - 1] : (d.sc ? uf[t] : 0.0);
+        const double E = d.sc && d.se ? uf[t + 1] : (d.sc ? uf[t] : 0.0);
+        const double S = d.sc && d.sS ? uf[TL(k, gi, gj - 1, ti0, tj0)] : (d.sc ? uf[t] : 0.0);
+        const double N = d.sc && d.sN ? uf[TL(k, gi, gj + 1, ti0, tj0)] : (d.sc ? uf[t] : 0.0);
+        const double FDx = px ? uuf - E : uuf - W, FDy = py ? uuf - N : uuf - S;
+        // advFDBFECC.cu:287 ships "Rx*FDx - Ry*FDy" for u in the Dirichlet-square branch (B8)
+        const double ub = (!k.solidSwitch && f == 0) ? uuf - tc * (Rx * FDx - Ry * FDy)
+                                                     : uuf - tc * (Rx * FDx + Ry * FDy);
+        ue[t] = u - 0.5 * (ub - u);
+      }
+    }
+    __syncthreads();
+    // sweep 3 (forward) on the 32 x 32 interior -> HBM
+    for (int t = tid; t < BT * BT; t += BTHREADS) {
+      const int li = BH + t % BT, lj = BH + t / BT, gi = ti0 + li, gj = tj0 + lj;
+      if (gi >= k.nx || gj >= k.ny) continue;
+      const int q = li + BP * lj;
+      const bool px = !signbit(sRx[q]), py = !signbit(sRy[q]);
+      const double Rx = fabs(sRx[q]), Ry = fabs(sRy[q]);
+      double r;
+      bool sc;
+      if (neu) {
+        const NbrIdx x = neumann_idx(k, msk, gi, gj, ti0, tj0);
+        const double FDx = px ? ue[q] - ue[x.W] : ue[q] - ue[x.E];
+        const double FDy = py ? ue[q] - ue[x.S] : ue[q] - ue[x.N];
+        r = ue[q] - tc * (Rx * FDx + Ry * FDy);
+        sc = x.sc;
+      } else {
+        const DirMask d = dir_mask(k, msk, gi, gj, q);
+        const double uue = d.sc ? ue[q] : 0.0;
+        const double W = d.sc && d.sw ? ue[q - 1] : (d.sc ? bv : 0.0);
+        const double E = d.sc && d.se ? ue[q + 1] : (d.sc ? bv : 0.0);
+        const double S = d.sc && d.sS ? ue[TL(k, gi, gj - 1, ti0, tj0)] : (d.sc ? bv : 0.0);
+        const double N = d.sc && d.sN ? ue[TL(k, gi, gj + 1, ti0, tj0)] : (d.sc ? bv : 0.0);
+        const double FDx = px ? uue - W : uue - E, FDy = py ? uue - S : uue - N;
+        r = uue - tc * (Rx * FDx + Ry * FDy);
+        sc = d.sc;
+      }
+      gout[gi + k.nx * gj] = sc ? r : 0.0;
+    }
+  }
+}
+
+int check_sheet(const yh_params *p) {
+  YH_REQUIRE(p != nullptr, "null params");
+  YH_REQUIRE(p->nx >= 8 && p->ny >= 8, "grid too small");
+  YH_REQUIRE(p->jg0 == 0 && p->ny_global == p->ny, "symmetry-reduction kernels work on a whole sheet");
+  return YH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yh_slice(const yh_params *p, const double *u, const double *v, double *const slice[6],
+             double *const slice0[6], int reduce_sym, int reduce_sym_start, const double *adv_x,
+             const double *adv_y, int scheme, const int *tip_count, const yh_tip *tip_vector,
+             int count, void *stream) {
+  int rc = yh_check_device();
+  if (rc != YH_OK) return rc;
+  if ((rc = check_sheet(p)) != YH_OK) return rc;
+  YH_REQUIRE(u && v && slice && adv_x && adv_y, "null pointer");
+  YH_REQUIRE(scheme == 1 || scheme == 2, "scheme must be 1 or 2");
+  YH_REQUIRE(!reduce_sym_start || slice0, "slice0 == NULL with reduce_sym_start");
+  YH_REQUIRE(count == 0 || (tip_count && tip_vector), "tip list required when count != 0");
+  if (!reduce_sym) return YH_OK;   // symmetryReduction.cu:127,:169: nothing is written
+  YhK k = yh_make_k(p);
+  SliceArgs a;
+  a.u = u; a.v = v; a.ax = adv_x; a.ay = adv_y;
+  for (int q = 0; q < 6; q++) {
+    YH_REQUIRE(slice[q] != nullptr, "null slice array");
+    a.s.p[q] = slice[q];
+    a.s0.p[q] = reduce_sym_start ? slice0[q] : nullptr;
+    YH_REQUIRE(!reduce_sym_start || slice0[q], "null slice0 array");
+  }
+  a.start = reduce_sym_start; a.scheme = scheme; a.count = count;
+  a.tip_count = tip_count; a.tv = tip_vector; a.tipx0 = p->tipx0; a.tipy0 = p->tipy0;
+  dim3 blk(32, 8), grd((p->nx + 31) / 32, (p->ny + 7) / 8);
+  slice_kernel<<<grd, blk, 0, (cudaStream_t)stream>>>(k, a);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
+
+int yh_trapz(const yh_params *p, const double *const slice[6], const double *const slice0[6],
+             const double *velTan_u, const double *velTan_v, double *integrals_host,
+             const int *tip_count, const yh_tip *tip_vector, int count, void *stream) {
+  int rc = yh_check_device();
+  if (rc != YH_OK) return rc;
+  if ((rc = check_sheet(p)) != YH_OK) return rc;
+  YH_REQUIRE(slice && slice0 && velTan_u && velTan_v && integrals_host, "null pointer");
+  YH_REQUIRE(count == 0 || (tip_count && tip_vector), "tip list required when count != 0");
+  IntArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int q = 0; q < 6; q++) {
+    YH_REQUIRE(slice[q] && slice0[q], "null slice array");
+    a.s.p[q] = slice[q]; a.s0.p[q] = slice0[q];
+  }
+  a.vtu = velTan_u; a.vtv = velTan_v; a.count = count; a.tip_count = tip_count; a.tv = tip_vector;
+  a.tipx0 = p->tipx0; a.tipy0 = p->tipy0;
+  return run_integrals(p, a, false, integrals_host, (cudaStream_t)stream);
+}
+
+int yh_sr_integrals(const yh_params *p, const double *u, const double *v, const double *velTan_u,
+                    const double *velTan_v, const double *adv_x, const double *adv_y,
+                    double *integrals_host, const int *tip_count, const yh_tip *tip_vector,
+                    int count, void *stream) {
+  int rc = yh_check_device();
+  if (rc != YH_OK) return rc;
+  if ((rc = check_sheet(p)) != YH_OK) return rc;
+  YH_REQUIRE(u && v && velTan_u && velTan_v && adv_x && adv_y && integrals_host, "null pointer");
+  YH_REQUIRE(count == 0 || (tip_count && tip_vector), "tip list required when count != 0");
+  IntArgs a;
+  memset(&a, 0, sizeof(a));
+  a.u = u; a.v = v; a.ax = adv_x; a.ay = adv_y;
+  a.vtu = velTan_u; a.vtv = velTan_v; a.count = count; a.tip_count = tip_count; a.tv = tip_vector;
+  a.tipx0 = p->tipx0; a.tipy0 = p->tipy0;
+  return run_integrals(p, a, true, integrals_host, (cudaStream_t)stream);
+}
+
+static CxyArgs make_cxy(double *ax, double *ay, const uint8_t *solid, const double c[3], const double phi[3]) {
+  CxyArgs a;
+  a.ax = ax; a.ay = ay; a.solid = solid;
+  a.cx = c[0]; a.cy = c[1]; a.ct = c[2];
+  a.cs = cos(phi[2]); a.sn = sin(phi[2]);   // host libm, as solve_matrix (symmetryReduction.cu:390)
+  return a;
+}
+
+int yh_cxy_field(const yh_params *p, double *adv_x, double *adv_y, const double c[3],
+                 const double phi[3], const uint8_t *solid, void *stream) {
+  int rc = yh_check_device();
+  if (rc != YH_OK) return rc;
+  if ((rc = check_sheet(p)) != YH_OK) return rc;
+  YH_REQUIRE(adv_x && adv_y && c && phi, "null pointer");
+  YH_REQUIRE(!p->solidSwitch || solid, "solidSwitch set but solid == NULL");
+  YhK k = yh_make_k(p);
+  CxyArgs a = make_cxy(adv_x, adv_y, solid, c, phi);
+  dim3 blk(32, 8), grd((p->nx + 31) / 32, (p->ny + 7) / 8);
+  cxy_kernel<<<grd, blk, 0, (cudaStream_t)stream>>>(k, a);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
+
+static int bfecc_common(const yh_params *p, BfArgs &a, void *stream) {
+  YhK k = yh_make_k(p);
+  dim3 grd((p->nx + BT - 1) / BT, (p->ny + BT - 1) / BT);
+  const size_t smem = (size_t)5 * BP * BP * sizeof(double) + BP * BP;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  YH_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    YH_CUDA(cudaFuncSetAttribute(bfecc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[dev & 63] = true;
+  }
+  bfecc_kernel<<<grd, BTHREADS, smem, (cudaStream_t)stream>>>(k, a);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
+
+int yh_advect_bfecc(const yh_params *p, const double *u_in, const double *v_in, double *u_out,
+                    double *v_out, const double *adv_x, const double *adv_y, const uint8_t *solid,
+                    void *stream) {
+  int rc = yh_check_device();
+  if (rc != YH_OK) return rc;
+  if ((rc = check_sheet(p)) != YH_OK) return rc;
+  YH_REQUIRE(u_in && v_in && u_out && v_out && adv_x && adv_y, "null pointer");
+  YH_REQUIRE(u_in != u_out && v_in != v_out, "in-place advection is not supported");
+  YH_REQUIRE(!p->solidSwitch || solid, "solidSwitch set but solid == NULL");
+  BfArgs a;
+  memset(&a, 0, sizeof(a));
+  a.u_in = u_in; a.v_in = v_in; a.u_out = u_out; a.v_out = v_out;
+  a.ax = adv_x; a.ay = adv_y; a.solid = solid; a.from_c = 0;
+  return bfecc_common(p, a, stream);
+}
+
+int yh_advect_bfecc_cphi(const yh_params *p, const double *u_in, const double *v_in,
+                         double *u_out, double *v_out, const double c[3], const double phi[3],
+                         double *adv_x, double *adv_y, const uint8_t *solid, void *stream) {
+  int rc = yh_check_device();
+  if (rc != YH_OK) return rc;
+  if ((rc = check_sheet(p)) != YH_OK) return rc;
+  YH_REQUIRE(u_in && v_in && u_out && v_out && c && phi, "null pointer");
+  YH_REQUIRE(u_in != u_out && v_in != v_out, "in-place advection is not supported");
+  YH_REQUIRE((adv_x == nullptr) == (adv_y == nullptr), "adv_x / adv_y must both be set or NULL");
+  YH_REQUIRE(!p->solidSwitch || solid, "solidSwitch set but solid == NULL");
+  BfArgs a;
+  memset(&a, 0, sizeof(a));
+  a.u_in = u_in; a.v_in = v_in; a.u_out = u_out; a.v_out = v_out;
+  a.ax_out = adv_x; a.ay_out = adv_y; a.solid = solid; a.from_c = 1;
+  a.cxy = make_cxy(nullptr, nullptr, solid, c, phi);
+  return bfecc_common(p, a, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,268 @@
+// tip.cu -- spiral-tip tracking (tipTracker.cu:20-611): intersection of the iso-lines
+// u(t) = Uth and u(t+dt) = Uth inside each grid cell, appended to a device list.
+//
+// The reference appends with one atomicAdd per hit, so list order (and therefore "the last
+// tip", which slice/trapz use as the disc centre) depends on scheduling.  Here the append is
+// an ORDERED atomic compaction: CTAs take a ticket (atomicAdd), handle the ticket-th run of
+// 1024 consecutive cells, and chain their hit counts by decoupled look-back, so the list
+// comes out in ascending linear cell index, '+' root before '-' root, in one launch, with no
+// sort and no host round trip.  Cost: 16 B per cell of reads -- HBM-bound.
+#include "yh_common.cuh"
+
+namespace {
+
+constexpr int TIP_THREADS = 256;
+constexpr int TIP_CPT = 4;                       // consecutive cells per thread
+constexpr int TIP_CHUNK = TIP_THREADS * TIP_CPT;
+
+struct TipArgs {
+  const double *past, *present;
+  uint8_t *plot;
+  int *count;
+  yh_tip *vec;
+  int capacity;
+  int algorithm;
+  float t;
+  unsigned long long *state;   // [0] ticket, [1 + b] look-back word of chunk b
+  unsigned epoch;              // distinguishes this launch's words from stale ones
+  int nchunks;
+};
+
+__device__ __forceinline__ bool equals_tol(double a, double b, double tol) {   // helper_functions.cu:58
+  return (a == b) || ((a <= (b + tol)) && (a >= (b - tol)));
+}
+
+// gradient(), tipTracker.cu:519-566 (indices as shipped)
+__device__ void tip_gradient(const YhK &k, int i, int j, double s, double t, const double *g,
+                             float &gx, float &gy) {
+  const int nx = k.nx, ny = k.ny;
+#define ID(a, b) ((a) + nx * (b))
+  int S = (j > 0) ? ID(i, j - 1) : ID(i, j + 1);
+  int Sx = ((j > 0) && (i < (nx - 1))) ? ID(i + 1, j - 1) : ID(i - 1, j + 1);
+  int Sy = ID(i, j);
+  int Sxy = (i < (nx - 1)) ? ID(i + 1, j) : ID(i - 1, j);
+  int N = (j < (ny - 1)) ? ID(i, j + 1) : ID(i, j - 1);
+  int Nx = ((i < (nx - 1)) && (j < (ny - 1))) ? ID(i + 1, j + 1) : ID(i - 1, j - 1);
+  int Ny = (j < (ny - 2)) ? ID(i, j + 2) : ((j == (ny - 2)) ? ID(i, j) : ID(i, j - 1));
+  int Nxy = ((i < (nx - 1)) && (j < (ny - 2))) ? ID(i + 1, j + 2)
+          : ((j == (ny - 2)) ? ID(i - 1, j) : ID(i - 1, j - 1));
+  int W = ID(i - 1, j);
+  int Wx = ID(i, j);
+  int Wy = ((i > 0) && (j < (ny - 1))) ? ID(i - 1, j + 1) : ID(i + 1, j - 1);
+  int Wxy = (j < (ny - 1)) ? ID(i, j + 1) : ID(i - 1, j);
+  int E = (i < (nx - 1)) ? ID(i + 1, j) : ID(i - 1, j);
+  int Ex = (i < (nx - 2)) ? ID(i + 2, j) : ((i == (nx - 2)) ? ID(i, j) : ID(i - 1, j));
+  int Ey = ((i < (nx - 1)) && (j < (ny - 1))) ? ID(i + 1, j + 1) : ID(i - 1, j - 1);
+  int Exy = ((i < (nx - 2)) && (j < (ny - 1))) ? ID(i + 2, j + 1)
+          : ((i == (nx - 2)) ? ID(i, j - 1) : ID(i - 1, j - 1));
+#undef ID
+  double gx1 = (g[E] - g[W]) * k.invdx, gy1 = (g[N] - g[S]) * k.invdy;
+  double gx2 = (g[Ex] - g[Wx]) * k.invdx, gy2 = (g[Nx] - g[Sx]) * k.invdy;
+  double gx3 = (g[Ey] - g[Wy]) * k.invdx, gy3 = (g[Ny] - g[Sy]) * k.invdy;
+  double gx4 = (g[Exy] - g[Wxy]) * k.invdx, gy4 = (g[Nxy] - g[Sxy]) * k.invdy;
+  gx = (float)((1.0 - s) * (1.0 - t) * gx1 + s * (1.0 - t) * gx2 + t * (1.0 - s) * gx3 + s * t * gx4);
+  gy = (float)((1.0 - s) * (1.0 - t) * gy1 + s * (1.0 - t) * gy2 + t * (1.0 - s) * gy3 + s * t * gy4);
+}
+
+// Up to two candidate roots of one cell; returns how many pass tipRecordPlane's test.
+__device__ int tip_cell(const YhK &k, const TipArgs &a, int i, int j, float2 *roots) {
+  const int nx = k.nx, ny = k.ny;
+  bool inside;
+  if (k.solidSwitch) {   // tipTracker.cu:49-51
+    int ic = i - nx / 2, jc = j - ny / 2;
+    inside = (ic * ic + jc * jc) < k.tipOffX * k.tipOffY;
+  } else if (a.algorithm == 2) {   // :347-348
+    inside = (i >= (nx / 2 - k.tipOffX)) && (i < (nx / 2 + k.tipOffX)) &&
+             (j >= (ny / 2 - k.tipOffY)) && (j < (ny / 2 + k.tipOffY));
+  } else {   // :126
+    inside = (i >= 1) && (i < (nx - 2)) && (j >= 1) && (j < (ny - 2));
+  }
+  if (!inside) return 0;
+  const int s0 = i + nx * j;
+  const int sx = (i < (nx - 1)) ? s0 + 1 : s0;
+  const int sy = (j < (ny - 1)) ? s0 + nx : s0;
+  const int sxy = ((j < (ny - 1)) && (i < (nx - 1))) ? s0 + nx + 1 : s0;
+  const double x1 = a.present[s0], x2 = a.present[sx], x4 = a.present[sy], x3 = a.present[sxy];
+  const double y1 = a.past[s0], y2 = a.past[sx], y4 = a.past[sy], y3 = a.past[sxy];
+  const double Uth = k.Uth;
+  int n = 0;
+  if (a.algorithm == 1) {   // :150-200
+    const double x3y1 = x3 * y1, x4y1 = x4 * y1, x3y2 = x3 * y2, x4y2 = x4 * y2;
+    const double x1y3 = x1 * y3, x2y3 = x2 * y3, x1y4 = x1 * y4, x2y4 = x2 * y4;
+    const double x2y1 = x2 * y1, x1y2 = x1 * y2, x4y3 = x4 * y3, x3y4 = x3 * y4;
+    const double den1 = 2.0 * (x3y1 - x4y1 - x3y2 + x4y2 - x1y3 + x2y3 + x1y4 - x2y4);
+    const double den2 = 2.0 * (x2y1 - x3y1 - x1y2 + x4y2 + x1y3 - x4y3 - x2y4 + x3y4);
+    const double ctn1 = x1 - x2 + x3 - x4 - y1 + y2 - y3 + y4;
+    const double ctn2 = x3y1 - 2.0 * x4y1 + x4y2 - x1y3 + 2.0 * x1y4 - x2y4;
+    const double disc = sqrt(4.0 * (x3y1 - x3y2 - x4y1 + x4y2 - x1y3 + x1y4 + x2y3 - x2y4)
+                                 * (x4y1 - x1y4 + Uth * (x1 - x4 - y1 + y4))
+                             + (-ctn2 + Uth * ctn1) * (-ctn2 + Uth * ctn1));
+    const double px = ctn2 - Uth * ctn1;
+    const double py = Uth * ctn1 - x3y1 + x4y2 + x1y3 - x2y4 + 2.0 * (x2y1 - x1y2);
+    const bool ok = k.solidSwitch ? true : (disc >= 0.0);
+    float2 r;
+    r.x = (float)((px + disc) / den1); r.y = (float)((py + disc) / den2);
+    if (ok && ((r.x > 0.0) && (r.x < 1.0)) && ((r.y > 0.0) && (r.y < 1.0))) roots[n++] = r;
+    r.x = (float)((px - disc) / den1); r.y = (float)((py - disc) / den2);
+    if (ok && ((r.x > 0.0) && (r.x < 1.0)) && ((r.y > 0.0) && (r.y < 1.0))) roots[n++] = r;
+  } else {   // Newton, :384-424
+    double s = 0.5, t = 0.5;
+    for (int it = 0; it < 4; it++) {
+      const double r1 = x1 * (1.0 - s) * (1.0 - t) + x2 * s * (1.0 - t) + x3 * s * t + x4 * (1.0 - s) * t - Uth;
+      const double r2 = y1 * (1.0 - s) * (1.0 - t) + y2 * s * (1.0 - t) + y3 * s * t + y4 * (1.0 - s) * t - Uth;
+      const double J11 = -x1 * (1.0 - t) + x2 * (1.0 - t) + x3 * t - x4 * t;
+      const double J21 = -y1 * (1.0 - t) + y2 * (1.0 - t) + y3 * t - y4 * t;
+      const double J12 = -x1 * (1.0 - s) - x2 * s + x3 * s + x4 * (1.0 - s);
+      const double J22 = -y1 * (1.0 - s) - y2 * s + y3 * s + y4 * (1.0 - s);
+      const double detJ = J11 * J22 - J12 * J21;
+      if (!equals_tol(detJ, 0.0, 1e-14)) {
+        const double sn = s - (J22 * r1 - J12 * r2) / detJ;
+        const double tn = t - (-J21 * r1 + J11 * r2) / detJ;
+        s = fmin(fmax(sn, 0.0), 1.0);
+        t = fmin(fmax(tn, 0.0), 1.0);
+      } else { s = -1.0; t = -1.0; }
+    }
+    const bool in01 = (s >= 0.0) && (s <= 1.0) && (t >= 0.0) && (t <= 1.0);
+    const double u1 = in01 ? x1 * (1 - s) * (1.0 - t) + x2 * s * (1.0 - t) + x3 * s * t + x4 * (1.0 - s) * t : 0.0;
+    const double u2 = in01 ? y1 * (1 - s) * (1.0 - t) + y2 * s * (1.0 - t) + y3 * s * t + y4 * (1.0 - s) * t : 0.0;
+    if (equals_tol(u1, Uth, 1e-15) && equals_tol(u2, Uth, 1e-15)) {
+      float2 r = make_float2((float)s, (float)t);
+      if (((r.x > 0.0) && (r.x < 1.0)) && ((r.y > 0.0) && (r.y < 1.0))) roots[n++] = r;
+    }
+  }
+  return n;
+}
+
+// look-back word: [63:40] epoch, [33:32] flag (1 = aggregate, 2 = inclusive prefix), [31:0] value
+__device__ __forceinline__ unsigned long long lb_pack(unsigned epoch, unsigned flag, unsigned v) {
+  return ((unsigned long long)(epoch & 0xFFFFFFu) << 40) | ((unsigned long long)flag << 32) | v;
+}
+
+__global__ void __launch_bounds__(TIP_THREADS)
+tip_kernel(const __grid_constant__ YhK k, const __grid_constant__ TipArgs a) {
+  __shared__ int s_chunk;
+  __shared__ int s_warp[TIP_THREADS / 32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_chunk = (int)atomicAdd(&a.state[0], 1ull);   // ticket = chunk, in launch order
+  __syncthreads();
+  const int chunk = s_chunk;
+  const long long ncell = (long long)k.nx * k.ny;
+
+  float2 roots[TIP_CPT][2];
+  int nr[TIP_CPT];
+  int mine = 0;
+#pragma unroll
+  for (int r = 0; r < TIP_CPT; r++) {
+    const long long cell = (long long)chunk * TIP_CHUNK + (long long)tid * TIP_CPT + r;
+    nr[r] = 0;
+    if (cell < ncell) {
+      const int i = (int)(cell % k.nx), j = (int)(cell / k.nx);
+      if (a.algorithm == 3) {   // abouzarTip_kernel, :434-517 -- raster only, no list
+        const int s0 = (int)cell;
+        const int sx = (i < (k.nx - 1)) ? s0 + 1 : s0;
+        const int sy = (j < (k.ny - 1)) ? s0 + k.nx : s0;
+        const int sxy = ((j < (k.ny - 1)) && (i < (k.nx - 1))) ? s0 + k.nx + 1 : s0;
+        const double v0 = a.present[s0], vx = a.present[sx], vy = a.present[sy], vxy = a.present[sxy];
+        int s = (0.0 >= v0 - k.Uth) + (0.0 >= vx - k.Uth) + (0.0 >= vy - k.Uth) + (0.0 >= vxy - k.Uth);
+        const bool bv = (s > 0) && (s < 4);
+        s = (0.0 >= v0 - a.past[s0]) + (0.0 >= vx - a.past[sx]) + (0.0 >= vy - a.past[sy]) +
+            (0.0 >= vxy - a.past[sxy]);
+        const bool bdv = (s > 0) && (s < 4);
+        if (a.plot && bdv && bv) a.plot[s0] = 1;
+      } else {
+        nr[r] = tip_cell(k, a, i, j, roots[r]);
+      }
+    }
+    mine += nr[r];
+  }
+
+  // block-wide exclusive scan of `mine` in thread order (= cell order)
+  const int lane = tid & 31, wid = tid >> 5;
+  int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  int woff = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < TIP_THREADS / 32; w++) {
+    if (w < wid) woff += s_warp[w];
+    total += s_warp[w];
+  }
+  const int excl = woff + incl - mine;
+
+  if (tid == 0) {
+    volatile unsigned long long *st = a.state + 1;
+    unsigned prefix = 0;
+    if (chunk > 0) {
+      st[chunk] = lb_pack(a.epoch, 1u, (unsigned)total);
+      __threadfence();
+      for (int b = chunk - 1; b >= 0; b--) {
+        unsigned long long w;
+        do { w = st[b]; } while ((unsigned)(w >> 40) != (a.epoch & 0xFFFFFFu) || ((w >> 32) & 3u) == 0u);
+        prefix += (unsigned)w;
+        if (((w >> 32) & 3u) == 2u) break;
+      }
+    }
+    st[chunk] = lb_pack(a.epoch, 2u, prefix + (unsigned)total);
+    __threadfence();
+    s_base = (int)prefix;
+    if (chunk == a.nchunks - 1) {
+      *a.count = (int)(prefix + (unsigned)total);   // replaces cudaMemset(tip_count) + atomicAdd
+      a.state[0] = 0ull;                            // every ticket has been taken: re-arm
+    }
+  }
+  __syncthreads();
+  if (mine == 0) return;
+
+  int pos = s_base + excl;
+#pragma unroll
+  for (int r = 0; r < TIP_CPT; r++) {
+    if (nr[r] == 0) continue;
+    const long long cell = (long long)chunk * TIP_CHUNK + (long long)tid * TIP_CPT + r;
+    const int i = (int)(cell % k.nx), j = (int)(cell / k.nx);
+    for (int q = 0; q < nr[r]; q++, pos++) {   // tipRecordPlane, :210-241
+      const float2 tip = roots[r][q];
+      float gx = 0.f, gy = 0.f;
+      if (k.tipGrad) tip_gradient(k, i, j, tip.x, tip.y, a.present, gx, gy);
+      yh_tip d;
+      d.x = (float)(i + tip.x); d.y = (float)(j + tip.y); d.vx = gx; d.vy = gy; d.t = a.t;
+      if (pos < a.capacity) a.vec[pos] = d;
+      if (a.plot) {   // plot_field, helper_functions.cu:45-51
+        const int xi = (int)floorf(d.x), yi = (int)floorf(d.y);
+        a.plot[xi + k.nx * yi] = 1;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int yh_tip_track(const yh_params *p, const double *u_past, const double *u_present,
+                            uint8_t *tip_plot, int *tip_count, yh_tip *tip_vector, int capacity,
+                            double physical_time, int algorithm, void *stream) {
+  int rc = yh_check_device();
+  if (rc != YH_OK) return rc;
+  YH_REQUIRE(p && u_past && u_present && tip_count && tip_vector, "null pointer");
+  YH_REQUIRE(algorithm >= 1 && algorithm <= 3, "tip algorithm must be 1, 2 or 3");
+  YH_REQUIRE(capacity >= 0, "negative capacity");
+  YH_REQUIRE(p->jg0 == 0 && p->ny_global == p->ny, "tip tracking works on a whole sheet");
+  static thread_local unsigned epoch = 0;
+  YhK k = yh_make_k(p);
+  const long long ncell = (long long)p->nx * p->ny;
+  const int nchunks = (int)((ncell + TIP_CHUNK - 1) / TIP_CHUNK);
+  unsigned long long *state = nullptr;
+  rc = yh_workspace(((size_t)nchunks + 1) * sizeof(unsigned long long), (void **)&state, 1);
+  if (rc != YH_OK) return rc;
+  epoch = (epoch + 1) & 0xFFFFFFu;
+  if (epoch == 0) epoch = 1;   // zero-initialised workspace must never look current
+  TipArgs a{u_past, u_present, tip_plot, tip_count, tip_vector, capacity, algorithm,
+            (float)physical_time, state, epoch, nchunks};
+  tip_kernel<<<nchunks, TIP_THREADS, 0, (cudaStream_t)stream>>>(k, a);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}

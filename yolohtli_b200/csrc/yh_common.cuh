@@ -1,0 +1,104 @@
+// yh_common.cuh -- shared device/host definitions of libyolohtli_b200 (sm_100a only).
+//
+// Parameters travel to every kernel BY VALUE in one __grid_constant__ block (YhK) instead
+// of the reference's ~45 __constant__ symbols resolved at device-link time
+// (main.cu:40-51, 309-402), so no -rdc and no global state: two simulations with different
+// parameters can be in flight on different streams.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/yolohtli_abi.h"
+
+// Kernel-side copy of yh_params (POD, passed by value).
+struct YhK {
+  int nx, ny, nyg, jg0;
+  int solidSwitch, neumannBC, gateDiff, anisotropy, lap4, timeIntOrder, tipGrad;
+  int tipOffX, tipOffY;
+  int stim, px, py;          // live disc stimulus (reactionDiffusion.cu:54-61)
+  int row0, row1;            // local rows to write
+  double dt, hx, hy, rx, ry, rxy, rbx, rby, rscale, qx4, qy4, fx4, fy4, invdx, invdy;
+  double tc, alpha, beta, gamma, delta, eps, mu, theta, boundaryVal, Uth;
+};
+
+static inline YhK yh_make_k(const yh_params *p) {
+  YhK k;
+  k.nx = p->nx; k.ny = p->ny; k.nyg = p->ny_global; k.jg0 = p->jg0;
+  k.solidSwitch = p->solidSwitch; k.neumannBC = p->neumannBC; k.gateDiff = p->gateDiff;
+  k.anisotropy = p->anisotropy; k.lap4 = p->lap4; k.timeIntOrder = p->timeIntOrder;
+  k.tipGrad = p->tipGrad; k.tipOffX = p->tipOffsetX; k.tipOffY = p->tipOffsetY;
+  k.stim = 0; k.px = 0; k.py = 0; k.row0 = 0; k.row1 = p->ny;
+  k.dt = p->dt; k.hx = p->hx; k.hy = p->hy; k.rx = p->rx; k.ry = p->ry; k.rxy = p->rxy;
+  k.rbx = p->rbx; k.rby = p->rby; k.rscale = p->rscale; k.qx4 = p->qx4; k.qy4 = p->qy4;
+  k.fx4 = p->fx4; k.fy4 = p->fy4; k.invdx = p->invdx; k.invdy = p->invdy;
+  k.tc = p->tc; k.alpha = p->alpha; k.beta = p->beta; k.gamma = p->gamma; k.delta = p->delta;
+  k.eps = p->eps; k.mu = p->mu; k.theta = p->theta; k.boundaryVal = p->boundaryVal;
+  k.Uth = p->Uth;
+  return k;
+}
+
+// ---- error plumbing (abi.cu) -----------------------------------------------------------
+void yh_set_error(const char *fmt, ...);
+int yh_check_device(void);   // YH_OK or YH_ERR_NO_DEVICE
+
+#define YH_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      yh_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return YH_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+#define YH_REQUIRE(cond, msg)                                  \
+  do {                                                         \
+    if (!(cond)) {                                             \
+      yh_set_error("%s: %s", __func__, msg);                   \
+      return YH_ERR_INVALID_ARG;                               \
+    }                                                          \
+  } while (0)
+
+#define YH_LAUNCH_CHECK() YH_CUDA(cudaGetLastError())
+
+// internal workspace (per device, grown on demand, abi.cu)
+int yh_workspace(size_t bytes, void **ptr, int slot);
+
+// ---- device helpers --------------------------------------------------------------------
+// Neumann mirror index (the rule of coord_i/coord_j, helper_functions.cu:69-79).
+__device__ __forceinline__ int yh_mir(int i, int n) {
+  return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i);
+}
+
+// The ionic model (reactionDiffusion.cu:131-141); scs = inside the live stimulus disc.
+__device__ __forceinline__ double yh_Isum(const YhK &k, double u, double v, bool scs) {
+  return -(k.mu * u * (1.0 - u) * (u - k.alpha) - u * v) - (scs ? 24.7 : 0.0);
+}
+__device__ __forceinline__ double yh_Iv(const YhK &k, double u, double v) {
+  return -(k.eps * (k.delta * (u - k.gamma) * (k.beta - u) - v - k.theta));
+}
+// i, j are GLOBAL cell coordinates.
+__device__ __forceinline__ bool yh_scs(const YhK &k, int i, int j) {
+  if (!k.stim) return false;
+  int ic = i - k.nx / 2, jc = j - k.nyg / 2;
+  int cx = k.px - k.nx / 2, cy = k.py - k.nyg / 2;
+  return ((ic - cx) * (ic - cx) + (jc - cy) * (jc - cy)) < 400;
+}
+
+// disc test only (caller already knows the stimulus is on)
+__device__ __forceinline__ bool yh_scs_on(const YhK &k, int i, int j) {
+  int ic = i - k.nx / 2, jc = j - k.nyg / 2;
+  int cx = k.px - k.nx / 2, cy = k.py - k.nyg / 2;
+  return ((ic - cx) * (ic - cx) + (jc - cy) * (jc - cy)) < 400;
+}
+
+// ---- kernel launchers (one per .cu) ------------------------------------------------------
+int yh_launch_rd_generic(const YhK &k, const double *u_in, const double *v_in, double *u_out,
+                         double *v_out, double *vtu, double *vtv, const uint8_t *solid,
+                         cudaStream_t st);
+// Temporally blocked Euler/5-point path; returns YH_ERR_UNSUPPORTED when the mode is not
+// covered so the caller can fall back to the generic kernels.
+int yh_rd_fast_supported(const YhK &k, int tb);
+int yh_launch_rd_fast(const YhK &k, int tb, const double *u_in, const double *v_in,
+                      double *u_out, double *v_out, const uint8_t *solid, cudaStream_t st);

@@ -1,0 +1,126 @@
+"""Row-slab multi-GPU driver: one process per GPU (torch.distributed for the plumbing), the
+nx x ny_global sheet cut into contiguous row slabs, H ghost rows per side refreshed by a
+neighbour exchange every H time steps (H = temporal-blocking depth).  The reference is
+single-GPU; this is the new multi-GPU layer of section 8e.
+
+Exchange volume per neighbour and direction: H * nx * 8 B * 2 fields every H steps -- at
+nx = 16384, H = 4 that is 1 MiB against ~0.5 ms of compute, so the exchange is latency-, not
+bandwidth-bound; it is issued on a side stream and overlapped with the interior rows.
+
+The stepping backend is injectable so the partition / exchange logic is testable on CPU with
+gloo (tests/test_slab_gloo.py, stand-in stepper); the product backend is the CUDA library.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import host
+from ._lib import YhParams
+
+
+def partition(ny, world, rank):
+    """Rows [j0, j1) owned by `rank`: as even as possible, remainder to the low ranks."""
+    base, rem = divmod(ny, world)
+    j0 = rank * base + min(rank, rem)
+    return j0, j0 + base + (1 if rank < rem else 0)
+
+
+class SlabLayout:
+    """Where a rank's rows live.  Local storage holds global rows [g0, g1) = the owned rows
+    [j0, j1) plus up to `halo` ghost rows on each side (none beyond the physical boundary,
+    where the no-flux mirror applies instead)."""
+
+    def __init__(self, ny_global, world, rank, halo):
+        self.ny_global, self.world, self.rank, self.halo = ny_global, world, rank, halo
+        self.j0, self.j1 = partition(ny_global, world, rank)
+        if world > 1 and (self.j1 - self.j0) < halo:
+            raise ValueError("slab thinner than the halo")
+        self.g0 = max(0, self.j0 - halo)
+        self.g1 = min(ny_global, self.j1 + halo)
+        self.ny_local = self.g1 - self.g0
+        self.own_lo = self.j0 - self.g0          # local row of the first owned row
+        self.own_hi = self.j1 - self.g0
+        self.up = rank - 1 if rank > 0 else None             # neighbour holding rows below j0
+        self.down = rank + 1 if rank < world - 1 else None   # neighbour holding rows from j1
+
+    def local_params(self, p_global):
+        p = YhParams()
+        C.memmove(C.byref(p), C.byref(p_global), C.sizeof(YhParams))
+        p.ny = self.ny_local
+        p.ny_global = self.ny_global
+        p.jg0 = self.g0
+        return p
+
+
+class SlabRunner:
+    def __init__(self, p_global, rank=None, world=None, halo=4, device=None, stepper=None):
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.lay = SlabLayout(p_global.ny, self.world, self.rank, halo)
+        self.p = self.lay.local_params(p_global)
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.halo = halo
+        self.K = max(1, p_global.timeIntOrder)   # stencil radius consumed per time step
+        self.nx = p_global.nx
+        shape = (self.lay.ny_local, self.nx)
+        self.u = [torch.zeros(shape, dtype=torch.float64, device=self.device) for _ in range(2)]
+        self.v = [torch.zeros(shape, dtype=torch.float64, device=self.device) for _ in range(2)]
+        self.cur = 0
+        self.stepper = stepper or self._cuda_stepper
+        self.count = 0
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+
+    # -- state ---------------------------------------------------------------------------
+    def load_global(self, u_glob, v_glob):
+        """Every rank slices its rows (ghosts included) out of the same global arrays."""
+        l = self.lay
+        self.u[self.cur].copy_(torch.as_tensor(u_glob[l.g0:l.g1]).to(self.device))
+        self.v[self.cur].copy_(torch.as_tensor(v_glob[l.g0:l.g1]).to(self.device))
+
+    def owned(self):
+        l = self.lay
+        return self.u[self.cur][l.own_lo:l.own_hi], self.v[self.cur][l.own_lo:l.own_hi]
+
+    # -- halo exchange -------------------------------------------------------------------
+    def _ops(self):
+        l, H = self.lay, self.halo
+        u, v = self.u[self.cur], self.v[self.cur]
+        ops = []
+        if l.up is not None:      # my first H owned rows -> up's lower ghosts; its last H -> mine
+            ops += [dist.P2POp(dist.isend, u[l.own_lo:l.own_lo + H], l.up),
+                    dist.P2POp(dist.isend, v[l.own_lo:l.own_lo + H], l.up),
+                    dist.P2POp(dist.irecv, u[l.own_lo - H:l.own_lo], l.up),
+                    dist.P2POp(dist.irecv, v[l.own_lo - H:l.own_lo], l.up)]
+        if l.down is not None:
+            ops += [dist.P2POp(dist.isend, u[l.own_hi - H:l.own_hi], l.down),
+                    dist.P2POp(dist.isend, v[l.own_hi - H:l.own_hi], l.down),
+                    dist.P2POp(dist.irecv, u[l.own_hi:l.own_hi + H], l.down),
+                    dist.P2POp(dist.irecv, v[l.own_hi:l.own_hi + H], l.down)]
+        return ops
+
+    def exchange(self):
+        ops = self._ops()
+        if not ops:
+            return
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    # -- stepping ------------------------------------------------------------------------
+    def _cuda_stepper(self, p, nsteps, uA, vA, uB, vB, rows, tb):
+        return host.rd_advance(p, nsteps, uA, vA, uB, vB, tb_steps=tb, rows=rows)
+
+    def advance(self, nsteps, tb=0):
+        """nsteps time steps: ghosts refreshed, then up to `halo` steps per exchange."""
+        l = self.lay
+        left = nsteps
+        while left > 0:
+            n = min(max(1, self.halo // self.K), left)
+            if self.world > 1:
+                self.exchange()
+            c, o = self.cur, self.cur ^ 1
+            ru, rv = self.stepper(self.p, n, self.u[c], self.v[c], self.u[o], self.v[o],
+                                  (l.own_lo, l.own_hi), tb)
+            self.cur = o if ru is self.u[o] else c
+            left -= n
+            self.count += n
