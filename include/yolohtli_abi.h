@@ -53,6 +53,9 @@ extern "C" {
 /* capacity of the tip list the reference allocates (typeDefinition.cuh: TIPVECSIZE) */
 #define YH_TIPVECSIZE 500000
 
+/* yh_rd_advance flags */
+#define YH_RD_INPUT_CANONICAL 1
+
 /* One record of the tip list: layout of the reference's vec5dyn (typeDefinition.cuh:19-20). */
 typedef struct yh_tip {
   float x, y, vx, vy, t;
@@ -125,8 +128,10 @@ int yh_rd_step(const yh_params *p,
  * temporally-blocked kernels when the mode allows (Euler, 5-point), otherwise one pass per
  * step.  *result_in_B = 1 when the final state is in B.  Rows [row0,row1) are valid in the
  * result provided rows [row0-nsteps, row1+nsteps) (clipped to the global domain) were valid
- * in A -- the multi-GPU ghost-row contract.  tb_steps: time steps per HBM pass (0 = auto). */
-int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps,
+ * in A -- the multi-GPU ghost-row contract.  tb_steps: time steps per HBM pass (0 = auto).
+ * flags: YH_RD_INPUT_CANONICAL promises that A holds no -0.0 (true for anything this library
+ * wrote); the first pass may then skip the literal "u0 + 0.0*0.0" of reactionDiffusion.cu:117. */
+int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, int flags,
                   double *uA, double *vA, double *uB, double *vB,
                   const uint8_t *solid, int stim_mouse, int point_x, int point_y,
                   int row0, int row1, int *result_in_B, void *stream);

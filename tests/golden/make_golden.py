@@ -81,8 +81,8 @@ def check_oracle(oracle, g):
         assert np.array_equal(oracle.solve_matrix([0, 0, 0], phi, g["integrals"]), g["csol"])
     elif kind == "bfecc":
         uo, vo = oracle.advect_bfecc(p, g["u"], g["v"], g["ax"], g["ay"])
-        # the reference kernel races (B2): compare away from nothing -- tolerance tier
-        assert np.abs(uo - g["uo"]).max() < float(g["tol"]) and np.abs(vo - g["vo"]).max() < float(g["tol"])
+        # reference kernel called 3x on the same buffers = its synchronous fixed point (see ref_harness.cu)
+        assert np.array_equal(uo, g["uo"]) and np.array_equal(vo, g["vo"])
     else:
         raise AssertionError(kind)
 
@@ -149,11 +149,8 @@ def main():
     csol = ref.solve_matrix([0, 0, 0], phi, integrals)
     np.savez_compressed(os.path.join(HERE, "sr_00.npz"), kind="sr", u=u0, v=v0, ax=ax, ay=ay, vtu=vtu, vtv=vtv,
                         c=c, phi=phi, integrals=integrals, slices=slices, csol=csol, **kw)
-    uo, vo = ref.bfecc(u0, v0, ax, ay)
-    so, svo = oracle.advect_bfecc(p, u0, v0, ax, ay)
-    tol = 10 * max(np.abs(uo - so).max(), np.abs(vo - svo).max(), 1e-15)
-    np.savez_compressed(os.path.join(HERE, "bfecc_00.npz"), kind="bfecc", u=u0, v=v0, ax=ax, ay=ay, uo=uo, vo=vo,
-                        tol=tol, **kw)
+    uo, vo = ref.bfecc(u0, v0, ax, ay, repeats=3)
+    np.savez_compressed(os.path.join(HERE, "bfecc_00.npz"), kind="bfecc", u=u0, v=v0, ax=ax, ay=ay, uo=uo, vo=vo, **kw)
     print("golden fixtures written:", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
     # self-check
     for f in sorted(os.listdir(HERE)):

@@ -221,12 +221,12 @@ class Reference:
         assert self.l.yref_cxy(_p(c), _p(phi), _p(s), _p(ax), _p(ay)) == 0
         return ax, ay
 
-    def bfecc(self, u, v, adv_x, adv_y, solid=None):
+    def bfecc(self, u, v, adv_x, adv_y, solid=None, repeats=1):
         p = self.p
         u, v, ax, ay = map(_np, (u, v, adv_x, adv_y))
         uo, vo = np.empty_like(u), np.empty_like(v)
         s = _np(solid, np.uint8) if solid is not None else np.ones(p.nx * p.ny, dtype=np.uint8)
-        assert self.l.yref_bfecc(_p(u), _p(v), _p(ax), _p(ay), _p(s), _p(uo), _p(vo)) == 0
+        assert self.l.yref_bfecc(_p(u), _p(v), _p(ax), _p(ay), _p(s), _p(uo), _p(vo), repeats) == 0
         return uo, vo
 
     def sapd_sequence(self, u_seq, count0=0, stimArea=None, stimulate=False):

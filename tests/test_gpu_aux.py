@@ -208,13 +208,16 @@ def test_sr_pieces_vs_reference_kernels(oracle):
     # reference: 256 blocks atomicAdd(double) in arbitrary order -> 1e-12 relative
     assert np.allclose(got, rint, rtol=1e-12, atol=1e-14)
     assert np.array_equal(host.solve_matrix([0, 0, 0], phi, rint), ref.solve_matrix([0, 0, 0], phi, rint))
-    # BFECC: the reference kernel races on uf/ub/ue (advFDBFECC.cu:131-144); smooth fields agree to 1e-6
-    X, Y = np.meshgrid(np.arange(nx, dtype=float), np.arange(ny, dtype=float))
-    us = 0.5 + 0.4 * np.sin(0.07 * X) * np.cos(0.05 * Y)
-    ru, rv = ref.bfecc(us, us * 0.5, rax, ray)
+    # BFECC: the reference kernel races on uf/ub/ue (advFDBFECC.cu:131-144): a single call reads
+    # stale scratch across warps.  Its uf is a pure function of g_in, so repeating the call on
+    # the same buffers converges (call 2: correct ub/ue, call 3: correct neighbours of ue) to
+    # the synchronous three-sweep result -- which must then equal ours BITWISE.
+    ru, rv = ref.bfecc(u, v, rax, ray, repeats=3)
     uo, vo = torch.empty(ny, nx, dtype=torch.float64, device="cuda"), torch.empty(ny, nx, dtype=torch.float64, device="cuda")
-    host.advect_bfecc(p, dev(us), dev(us * 0.5), uo, vo, dev(rax), dev(ray))
-    assert np.abs(uo.cpu().numpy() - ru).max() < 1e-6
+    host.advect_bfecc(p, dev(u), dev(v), uo, vo, dev(rax), dev(ray))
+    assert np.array_equal(uo.cpu().numpy(), ru) and np.array_equal(vo.cpu().numpy(), rv)
+    r1u, _ = ref.bfecc(u, v, rax, ray, repeats=1)
+    print("BFECC single racy reference call vs synchronous: max |diff| =", np.abs(r1u - ru).max())
 
 
 def test_sim_driver_trace_batch_and_pacing(oracle, yh):

@@ -86,6 +86,8 @@ def test_fast_path_gate_diff_off_and_negative_zero(oracle):
     u, v = rand_fields(96, 80, 3)
     u[10:20, 10:30] = 0.0
     v[10:20, 10:30] = 0.0
+    u[30:40, 50:70] = -0.0   # raw user data may hold -0.0: the first pass forms u0 + 0.0 literally
+    v[35:45, 40:60] = -0.0
     want = oracle.rd_advance(p, 6, u, v)
     got = gpu_advance(p, 6, u, v, tb=4)
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])

@@ -153,11 +153,11 @@ int yh_rd_step(const yh_params *p, const double *u_in, const double *v_in, doubl
   cudaStream_t st = (cudaStream_t)stream;
   // single steps that need no velTan take the streaming kernel (T = 1)
   if (!(velTan_u && k.gateDiff) && yh_rd_fast_supported(k, 1))
-    return yh_launch_rd_fast(k, 1, u_in, v_in, u_out, v_out, solid, st);
+    return yh_launch_rd_fast(k, 1, u_in, v_in, u_out, v_out, solid, 1, st);
   return yh_launch_rd_generic(k, u_in, v_in, u_out, v_out, velTan_u, velTan_v, solid, st);
 }
 
-int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, double *uA, double *vA,
+int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, int flags, double *uA, double *vA,
                   double *uB, double *vB, const uint8_t *solid, int stim_mouse, int point_x,
                   int point_y, int row0, int row1, int *result_in_B, void *stream) {
   int rc = yh_check_device();
@@ -176,6 +176,7 @@ int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, double *uA, doub
   const int dom_lo = -p->jg0, dom_hi = p->ny_global - p->jg0;
   int left = nsteps;
   int tb = tb_steps ? tb_steps : 4;
+  int canon = (flags & YH_RD_INPUT_CANONICAL) ? 0 : 1;   // only the first pass can see user data
   while (left > 0) {
     int T = 1;
     if (yh_rd_fast_supported(k, 1)) { T = tb; while (T > left) T >>= 1; }
@@ -185,7 +186,7 @@ int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, double *uA, doub
     k.row1 = row1 + ext < dom_hi ? row1 + ext : dom_hi;
     if (k.row0 < 0) k.row0 = 0;
     if (k.row1 > p->ny) k.row1 = p->ny;
-    if (yh_rd_fast_supported(k, T)) rc = yh_launch_rd_fast(k, T, cu, cv, nu, nv, solid, st);
+    if (yh_rd_fast_supported(k, T)) { rc = yh_launch_rd_fast(k, T, cu, cv, nu, nv, solid, canon, st); canon = 0; }
     else rc = yh_launch_rd_generic(k, cu, cv, nu, nv, nullptr, nullptr, solid, st);
     if (rc != YH_OK) return rc;
     double *t = cu; cu = nu; nu = t;   // swapSoA (helper_functions.cu:140)

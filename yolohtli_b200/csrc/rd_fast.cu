@@ -16,6 +16,8 @@
 // Zero-sign note: the reference forms the stage state as u0 + (0.0*0.0) (reactionDiffusion.cu:
 // 117); x + 0.0 only changes -0.0 into +0.0.  Rows are stored canonicalised (+0.0) in the
 // rings, which is exact for tc > 0 ("zero signs").
+#include <stdlib.h>
+
 #include "yh_common.cuh"
 
 namespace {
@@ -29,66 +31,115 @@ struct FastArgs {
   int duration, count0;   // stimulus on while (step % period) <= duration; step of level 1
 };
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+__device__ __forceinline__ void cp_async16(unsigned smem, const void *gmem, bool valid) {
   int sz = valid ? 16 : 0;   // src-size 0 => 16 bytes of zero fill, nothing read
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem), "l"(gmem), "r"(sz)
                : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// One Euler update of one cell (reactionDiffusion.cu:131-141,188-197,498-513).  Inputs are
-// canonical (already "+0.0").  rhs = 0.0 + 1.0*du is du for canonical u (see header note).
+// One Euler update of one cell (reactionDiffusion.cu:131-141,188-197,498-513) for CANONICAL
+// inputs (no -0.0).  With X = mu*u*(1-u)*(u-alpha) - u*v the reference computes
+// I_sum = -X - (scs ? 24.7 : 0.0) and du -= dt*I_sum; for !scs that is du + dt*X bit for bit
+// (negation commutes with IEEE rounding, x - 0.0 == x, a - (-b) == a + b).  Likewise
+// dv - dt*(-(eps*Y)) == dv + dt*(eps*Y), rhs = 0.0 + 1.0*du only differs from du in the sign
+// of a zero that u + tc*rhs cannot see, and x*1.0 == x.
+template <bool TC1>
 __device__ __forceinline__ void euler_cell(const YhK &k, double u, double v, double uW, double uE,
                                            double uN, double uS, double vW, double vE, double vN,
                                            double vS, bool scs, double &un, double &vn) {
-  double I_sum = -(k.mu * u * (1.0 - u) * (u - k.alpha) - u * v);
-  if (scs) I_sum = I_sum - 24.7;   // x - 0.0 == x exactly, so the else arm is a no-op
-  const double I_v = -(k.eps * (k.delta * (u - k.gamma) * (k.beta - u) - v - k.theta));
+  const double X = k.mu * u * (1.0 - u) * (u - k.alpha) - u * v;
+  const double Y = k.eps * (k.delta * (u - k.gamma) * (k.beta - u) - v - k.theta);
   double du = ((uW - 2.0 * u + uE) * k.rx + (uN - 2.0 * u + uS) * k.ry);
   double dv = 0.0;
   if (k.gateDiff) dv = ((vW - 2.0 * v + vE) * k.rx * k.rscale + (vN - 2.0 * v + vS) * k.ry * k.rscale);
-  du -= k.dt * I_sum;
-  dv -= k.dt * I_v;
-  un = u + k.tc * du;
-  vn = v + k.tc * dv;
+  if (!scs) {
+    du = du + k.dt * X;
+  } else {   // inside the stimulus disc: the literal expression
+    const double I_sum = -X - 24.7;
+    du = du - k.dt * I_sum;
+  }
+  dv = dv + k.dt * Y;
+  un = u + (TC1 ? du : k.tc * du);
+  vn = v + (TC1 ? dv : k.tc * dv);
 }
 
-template <int T, int W>
-__global__ void __launch_bounds__(T *(W / 2))
+// T time levels, strip of W columns, one extra warp that only feeds level 0.
+template <int T, int W, bool CANON, bool TC1>
+__global__ void __launch_bounds__(T *(W / 2) + 32)
 rd_euler_stream(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a) {
   constexpr int H = (T + 1) & ~1;        // halo columns each side (even: 16-byte alignment)
   constexpr int BX = W - 2 * H;          // output columns per strip
   constexpr int PITCH = W + 4;           // 2 pad doubles each side
   constexpr int ROW = 2 * PITCH;         // u plane then v plane
   constexpr int NR0 = 8, PF = 4, NRL = 4;
-  constexpr int NT = T * (W / 2);
+  constexpr int NTC = T * (W / 2);       // compute threads
   extern __shared__ __align__(16) double sm[];
 
   const int tid = threadIdx.x;
-  const int lev = tid / (W / 2) + 1;     // level this thread produces (warp-uniform)
-  const int c = 2 * (tid % (W / 2));     // window column of the thread's first cell
-  const int x0 = blockIdx.x * BX, wx0 = x0 - H;
-  const int gx = wx0 + c;
   const int nx = k.nx;
+  const int x0 = blockIdx.x * BX, wx0 = x0 - H;
   const int y0 = k.row0 + blockIdx.y * a.RY;
   const int RYe = min(a.RY, k.row1 - y0);
   const int c0 = y0 - T;
   const int dom_lo = -k.jg0, dom_hi = k.nyg - k.jg0;   // local rows that exist globally
   const size_t zoff = (size_t)blockIdx.z * (size_t)a.sim_stride;
-  const double *__restrict__ u_in = a.u_in + zoff;
-  const double *__restrict__ v_in = a.v_in + zoff;
-  double *__restrict__ u_out = a.u_out + zoff;
-  double *__restrict__ v_out = a.v_out + zoff;
+  const int n_it = RYe + 3 * T;
+
+  if (tid >= NTC) {
+    // ---------------- loader warp: level-0 rows, PF rows ahead of their first use ----------
+    const int lane = tid - NTC;
+    constexpr int PER = W / 64;          // 16-byte pieces per lane per field per row
+    const double *__restrict__ u_in = a.u_in + zoff;
+    const double *__restrict__ v_in = a.v_in + zoff;
+    const int ld_lo = max(dom_lo, c0), ld_hi = min(dom_hi, y0 + RYe + T);
+    int goff[PER];
+    bool ok[PER];
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      const int ggx = wx0 + 2 * (lane + 32 * q);
+      ok[q] = (ggx >= 0) && (ggx < nx);
+      goff[q] = ok[q] ? ggx : 0;
+    }
+    const unsigned sm0 = (unsigned)__cvta_generic_to_shared(sm) + (unsigned)(2 * lane + 2) * 8u;
+    auto issue_row = [&](int q) {
+      if (q >= ld_lo && q < ld_hi) {
+        const unsigned dst = sm0 + (unsigned)((q - c0) & (NR0 - 1)) * (ROW * 8u);
+        const double *ru = u_in + (size_t)q * nx;
+        const double *rv = v_in + (size_t)q * nx;
+#pragma unroll
+        for (int p = 0; p < PER; p++) {
+          cp_async16(dst + p * 512u, ru + goff[p], ok[p]);
+          cp_async16(dst + PITCH * 8u + p * 512u, rv + goff[p], ok[p]);
+        }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int q = 0; q < PF; q++) issue_row(c0 + q);
+    for (int it = 0; it < n_it; it++) {
+      issue_row(c0 + it + PF);
+      cp_async_wait<PF>();   // row c0 + it has landed
+      __syncthreads();
+    }
+    cp_async_wait<0>();
+    return;
+  }
+
+  // ---------------- compute warps: warp group `lev` turns level lev-1 rows into level lev ----
+  const int lev = tid / (W / 2) + 1;     // warp-uniform
+  const int c = 2 * (tid % (W / 2));     // window column of the thread's first cell
+  const int gx = wx0 + c;
+  const bool col_ok = (gx >= 0) && (gx < nx);
+  const bool out_col = col_ok && (c >= H) && (c < W - H);
+  const bool left_edge = (gx == 0), right_edge = (gx + 2 == nx);
+  const bool canon = CANON && (lev == 1);   // level-0 data is raw: form u0 + (0.0*0.0) literally
 
   // rows this level must produce
   const int lo_l = max(dom_lo, y0 - (T - lev));
   const int hi_l = min(dom_hi, y0 + RYe + (T - lev));
-  const int ld_lo = max(dom_lo, c0), ld_hi = min(dom_hi, y0 + RYe + T);
-  const bool col_ok = (gx >= 0) && (gx < nx);
-  const bool out_col = col_ok && (c >= H) && (c < W - H);
 
   // pacing (batched sweeps): level `lev` performs step count0 + lev - 1 of its sheet
   bool stim_on = k.stim != 0;
@@ -97,93 +148,84 @@ rd_euler_stream(const __grid_constant__ YhK k, const __grid_constant__ FastArgs 
     stim_on = per > 0 && ((a.count0 + lev - 1) % per) <= a.duration;
   }
 
-  const double *src_ring = sm + (lev == 1 ? 0 : (NR0 + (lev - 2) * NRL) * ROW);
-  double *dst_ring = sm + (NR0 + (lev - 1) * NRL) * ROW;
-  const int src_mask = (lev == 1) ? (NR0 - 1) : (NRL - 1);
+  const int src_nr = (lev == 1) ? NR0 : NRL;
+  const double *src_ring = sm + (lev == 1 ? 0 : (NR0 + (lev - 2) * NRL) * ROW) + c + 2;
+  double *dst_ring = sm + (NR0 + (lev - 1) * NRL) * ROW + c + 2;
+  double *gu = a.u_out + zoff + gx;
+  double *gv = a.v_out + zoff + gx;
 
-  auto issue_row = [&](int q) {   // level-0 row q -> ring 0 (all threads help)
-    if (q >= ld_lo && q < ld_hi) {
-      double *dst = sm + ((q - c0) & (NR0 - 1)) * ROW;
-      for (int t = tid; t < W; t += NT) {
-        const int f = t / (W / 2), cc = 2 * (t % (W / 2));
-        const int ggx = wx0 + cc;
-        const bool ok = (ggx >= 0) && (ggx < nx);
-        const double *src = (f ? v_in : u_in) + (size_t)q * nx + (ok ? ggx : 0);
-        cp_async16(dst + f * PITCH + cc + 2, src, ok);
-      }
-    }
-    cp_async_commit();
+  // register-resident rows of the source level: S = m-1, C = m, N = m+1 (pairs of cells)
+  double2 uS = make_double2(0, 0), uC = uS, uN = uS, vS = uS, vC = uS, vN = uS;
+
+  auto ld_pair = [&](int row, double2 &pu, double2 &pv) {
+    const double *r = src_ring + ((row - c0) & (src_nr - 1)) * ROW;
+    pu = *reinterpret_cast<const double2 *>(r);
+    pv = *reinterpret_cast<const double2 *>(r + PITCH);
+    if (canon) { pu.x += 0.0; pu.y += 0.0; pv.x += 0.0; pv.y += 0.0; }
   };
 
-#pragma unroll
-  for (int q = 0; q < PF; q++) issue_row(c0 + q);
-
-  const int n_it = RYe + 3 * T;
   for (int it = 0; it < n_it; it++) {
-    issue_row(c0 + it + PF);
     const int m = it + c0 - 2 * lev;
-    if (m >= lo_l && m < hi_l && col_ok) {
-      const int ms = (m - 1 < dom_lo) ? m + 1 : m - 1;   // mirror rows at the global edges
-      const int mn = (m + 1 >= dom_hi) ? m - 1 : m + 1;
-      const double *rc = src_ring + ((m - c0) & src_mask) * ROW + c + 2;
-      const double *rs = src_ring + ((ms - c0) & src_mask) * ROW + c + 2;
-      const double *rn = src_ring + ((mn - c0) & src_mask) * ROW + c + 2;
-      double2 uc = *reinterpret_cast<const double2 *>(rc);
-      double2 us = *reinterpret_cast<const double2 *>(rs);
-      double2 un = *reinterpret_cast<const double2 *>(rn);
-      double uw = rc[-1], ue = rc[2];
-      double2 vc = *reinterpret_cast<const double2 *>(rc + PITCH);
-      double2 vs = *reinterpret_cast<const double2 *>(rs + PITCH);
-      double2 vn = *reinterpret_cast<const double2 *>(rn + PITCH);
-      double vw = rc[PITCH - 1], ve = rc[PITCH + 2];
-      if (lev == 1) {   // level-0 data is raw: form u0 + (0.0*0.0) as the reference does
-        uc.x += 0.0; uc.y += 0.0; us.x += 0.0; us.y += 0.0; un.x += 0.0; un.y += 0.0;
-        uw += 0.0; ue += 0.0;
-        vc.x += 0.0; vc.y += 0.0; vs.x += 0.0; vs.y += 0.0; vn.x += 0.0; vn.y += 0.0;
-        vw += 0.0; ve += 0.0;
-      }
-      if (gx == 0) { uw = uc.y; vw = vc.y; }              // mirror: W of x=0 is x=1
-      if (gx + 2 == nx) { ue = uc.x; ve = vc.x; }          // mirror: E of x=nx-1 is x=nx-2
-      bool s0 = false, s1 = false;
-      if (stim_on) { s0 = yh_scs_on(k, gx, m + k.jg0); s1 = yh_scs_on(k, gx + 1, m + k.jg0); }
-      double2 uo, vo;
-      euler_cell(k, uc.x, vc.x, uw, uc.y, un.x, us.x, vw, vc.y, vn.x, vs.x, s0, uo.x, vo.x);
-      euler_cell(k, uc.y, vc.y, uc.x, ue, un.y, us.y, vc.x, ve, vn.y, vs.y, s1, uo.y, vo.y);
-      if (lev < T) {
-        uo.x += 0.0; uo.y += 0.0; vo.x += 0.0; vo.y += 0.0;   // next level's stage state
-        double *d = dst_ring + ((m - c0) & (NRL - 1)) * ROW + c + 2;
-        *reinterpret_cast<double2 *>(d) = uo;
-        *reinterpret_cast<double2 *>(d + PITCH) = vo;
-      } else if (out_col) {
-        const size_t o = (size_t)m * nx + gx;
-        *reinterpret_cast<double2 *>(u_out + o) = uo;
-        *reinterpret_cast<double2 *>(v_out + o) = vo;
+    if (m >= lo_l && m < hi_l) {           // warp-uniform
+      if (col_ok) {
+        if (m == lo_l) {                   // first row of this level: no history in registers yet
+          ld_pair(m, uC, vC);
+          if (m - 1 >= dom_lo) ld_pair(m - 1, uS, vS);
+        }
+        if (m + 1 < dom_hi) ld_pair(m + 1, uN, vN);
+        else { uN = uS; vN = vS; }         // no-flux mirror at the last row: N := S
+        if (m - 1 < dom_lo) { uS = uN; vS = vN; }   // ... and at the first row: S := N
+        const double *rc = src_ring + ((m - c0) & (src_nr - 1)) * ROW;
+        double uw = rc[-1], ue = rc[2], vw = rc[PITCH - 1], ve = rc[PITCH + 2];
+        if (canon) { uw += 0.0; ue += 0.0; vw += 0.0; ve += 0.0; }
+        if (left_edge) { uw = uC.y; vw = vC.y; }      // mirror: W of x=0 is x=1
+        if (right_edge) { ue = uC.x; ve = vC.x; }     // mirror: E of x=nx-1 is x=nx-2
+        bool s0 = false, s1 = false;
+        if (stim_on) { s0 = yh_scs_on(k, gx, m + k.jg0); s1 = yh_scs_on(k, gx + 1, m + k.jg0); }
+        double2 uo, vo;
+        euler_cell<TC1>(k, uC.x, vC.x, uw, uC.y, uN.x, uS.x, vw, vC.y, vN.x, vS.x, s0, uo.x, vo.x);
+        euler_cell<TC1>(k, uC.y, vC.y, uC.x, ue, uN.y, uS.y, vC.x, ve, vN.y, vS.y, s1, uo.y, vo.y);
+        if (lev < T) {
+          double *d = dst_ring + ((m - c0) & (NRL - 1)) * ROW;
+          *reinterpret_cast<double2 *>(d) = uo;
+          *reinterpret_cast<double2 *>(d + PITCH) = vo;
+        } else if (out_col) {
+          const size_t o = (size_t)m * nx;
+          *reinterpret_cast<double2 *>(gu + o) = uo;
+          *reinterpret_cast<double2 *>(gv + o) = vo;
+        }
+        uS = uC; vS = vC; uC = uN; vC = vN;
       }
     }
-    cp_async_wait<PF>();
     __syncthreads();
   }
-  cp_async_wait<0>();
 }
 
-template <int T, int W>
-int launch(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
+template <int T, int W, bool CANON, bool TC1>
+int launch2(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   constexpr int H = (T + 1) & ~1, BX = W - 2 * H, PITCH = W + 4, ROW = 2 * PITCH;
-  constexpr int NT = T * (W / 2);
+  constexpr int NT = T * (W / 2) + 32;
   const size_t smem = (size_t)(8 + (T - 1) * 4) * ROW * sizeof(double);
   static bool attr_set[64] = {false};
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    YH_CUDA(cudaFuncSetAttribute(rd_euler_stream<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
+    YH_CUDA(cudaFuncSetAttribute(rd_euler_stream<T, W, CANON, TC1>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[dev & 63] = true;
   }
   const int rows = k.row1 - k.row0;
   dim3 grd((k.nx + BX - 1) / BX, (rows + a.RY - 1) / a.RY, nsims);
-  rd_euler_stream<T, W><<<grd, NT, smem, st>>>(k, a);
+  rd_euler_stream<T, W, CANON, TC1><<<grd, NT, smem, st>>>(k, a);
   YH_LAUNCH_CHECK();
   return YH_OK;
+}
+
+template <int T, int W>
+int launch(const YhK &k, const FastArgs &a, int nsims, bool canon, cudaStream_t st) {
+  const bool tc1 = (k.tc == 1.0);
+  if (canon) return tc1 ? launch2<T, W, true, true>(k, a, nsims, st) : launch2<T, W, true, false>(k, a, nsims, st);
+  return tc1 ? launch2<T, W, false, true>(k, a, nsims, st) : launch2<T, W, false, false>(k, a, nsims, st);
 }
 
 }  // namespace
@@ -208,31 +250,36 @@ static int pick_ry(int rows, int strips, int nsims, int T) {
 
 int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const double *v_in,
                             double *u_out, double *v_out, int nsims, long long sim_stride,
-                            const int *period_d, int duration_it, int count0, cudaStream_t st) {
+                            const int *period_d, int duration_it, int count0, int canon_in,
+                            cudaStream_t st) {
   if (!yh_rd_fast_supported(k, tb)) return YH_ERR_UNSUPPORTED;
   FastArgs a{u_in, v_in, u_out, v_out, 0, sim_stride, period_d, duration_it, count0};
   const int rows = k.row1 - k.row0;
   if (rows <= 0) return YH_OK;
-  const bool narrow = k.nx < 1024;   // small sheets: more, narrower strips
+  static const char *force_w = getenv("YH_FAST_W");   // tuning hook
+  bool narrow = k.nx < 1024;   // small sheets: more, narrower strips
+  if (force_w) narrow = atoi(force_w) == 128;
   const int W = narrow ? 128 : 256;
+  const bool canon = canon_in != 0;
   const int H = (tb + 1) & ~1, BX = W - 2 * H;
   a.RY = pick_ry(rows, (k.nx + BX - 1) / BX, nsims, tb);
   if (narrow) {
     switch (tb) {
-      case 1: return launch<1, 128>(k, a, nsims, st);
-      case 2: return launch<2, 128>(k, a, nsims, st);
-      default: return launch<4, 128>(k, a, nsims, st);
+      case 1: return launch<1, 128>(k, a, nsims, canon, st);
+      case 2: return launch<2, 128>(k, a, nsims, canon, st);
+      default: return launch<4, 128>(k, a, nsims, canon, st);
     }
   }
   switch (tb) {
-    case 1: return launch<1, 256>(k, a, nsims, st);
-    case 2: return launch<2, 256>(k, a, nsims, st);
-    default: return launch<4, 256>(k, a, nsims, st);
+    case 1: return launch<1, 256>(k, a, nsims, canon, st);
+    case 2: return launch<2, 256>(k, a, nsims, canon, st);
+    default: return launch<4, 256>(k, a, nsims, canon, st);
   }
 }
 
 int yh_launch_rd_fast(const YhK &k, int tb, const double *u_in, const double *v_in,
-                      double *u_out, double *v_out, const uint8_t *solid, cudaStream_t st) {
+                      double *u_out, double *v_out, const uint8_t *solid, int canon_in,
+                      cudaStream_t st) {
   (void)solid;
-  return yh_launch_rd_fast_paced(k, tb, u_in, v_in, u_out, v_out, 1, 0, nullptr, 0, 0, st);
+  return yh_launch_rd_fast_paced(k, tb, u_in, v_in, u_out, v_out, 1, 0, nullptr, 0, 0, canon_in, st);
 }

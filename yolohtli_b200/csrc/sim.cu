@@ -7,10 +7,6 @@
 
 #include "yh_common.cuh"
 
-int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const double *v_in,
-                            double *u_out, double *v_out, int nsims, long long sim_stride,
-                            const int *period_d, int duration_it, int count0, cudaStream_t st);
-
 struct yh_sim {
   yh_params p;
   int n_sims, device;
@@ -28,6 +24,7 @@ struct yh_sim {
   int px, py;
   int count;
   int have_prev;         // other buffer holds the state exactly one step back
+  int raw_input;         // current state came from the host and may hold -0.0
   cudaStream_t st;
 };
 
@@ -64,7 +61,7 @@ int yh_sim_create(yh_sim **out, const yh_params *p, int n_sims, int device) {
   s->n_sims = n_sims; s->device = device;
   s->n = (size_t)p->nx * p->ny;
   s->cur = 0; s->solid = nullptr; s->trace_d = nullptr; s->trace_cap = 0;
-  s->period_d = nullptr; s->duration_it = 0; s->count = 0; s->have_prev = 0;
+  s->period_d = nullptr; s->duration_it = 0; s->count = 0; s->have_prev = 0; s->raw_input = 1;
   s->px = p->nx / 2; s->py = p->ny / 2;   // param.point, saveFiles.cu:180
   const size_t bytes = s->n * n_sims * sizeof(double);
   for (int b = 0; b < 2; b++) {
@@ -101,6 +98,7 @@ int yh_sim_set_state(yh_sim *s, const double *u_h, const double *v_h) {
   YH_CUDA(cudaMemcpyAsync(s->v[s->cur], v_h, bytes, cudaMemcpyHostToDevice, s->st));
   YH_CUDA(cudaStreamSynchronize(s->st));
   s->have_prev = 0;
+  s->raw_input = 1;
   return YH_OK;
 }
 
@@ -193,7 +191,7 @@ int yh_sim_run(yh_sim *s, int nsteps, int tb_steps, double *trace_h) {
     int rc;
     if (fast1) {
       rc = yh_launch_rd_fast_paced(k, T, s->u[c], s->v[c], s->u[o], s->v[o], s->n_sims, stride,
-                                   s->period_d, s->duration_it, s->count, s->st);
+                                   s->period_d, s->duration_it, s->count, s->raw_input, s->st);
     } else {
       rc = YH_OK;
       for (int z = 0; z < s->n_sims && rc == YH_OK; z++) {
@@ -208,6 +206,7 @@ int yh_sim_run(yh_sim *s, int nsteps, int tb_steps, double *trace_h) {
     }
     if (rc != YH_OK) return rc;
     s->cur = o;
+    s->raw_input = 0;
     s->have_prev = (T == 1);
     s->count += T;
     left -= T; step += T;
@@ -227,6 +226,7 @@ int yh_sim_run_host(yh_sim *s, const double *u_in_h, const double *v_in_h, doubl
   const size_t bytes = s->n * s->n_sims * sizeof(double);
   YH_CUDA(cudaMemcpyAsync(s->u[s->cur], u_in_h, bytes, cudaMemcpyHostToDevice, s->st));
   YH_CUDA(cudaMemcpyAsync(s->v[s->cur], v_in_h, bytes, cudaMemcpyHostToDevice, s->st));
+  s->raw_input = 1;
   int rc = yh_sim_run(s, nsteps, tb_steps, nullptr);
   if (rc != YH_OK) return rc;
   YH_CUDA(cudaMemcpyAsync(u_out_h, s->u[s->cur], bytes, cudaMemcpyDeviceToHost, s->st));

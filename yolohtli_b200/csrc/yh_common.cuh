@@ -100,5 +100,12 @@ int yh_launch_rd_generic(const YhK &k, const double *u_in, const double *v_in, d
 // Temporally blocked Euler/5-point path; returns YH_ERR_UNSUPPORTED when the mode is not
 // covered so the caller can fall back to the generic kernels.
 int yh_rd_fast_supported(const YhK &k, int tb);
+// canon_in: the input may hold -0.0 (user data) and must go through "u0 + 0.0" literally;
+// outputs of these kernels never hold -0.0, so later passes skip it (zero signs).
 int yh_launch_rd_fast(const YhK &k, int tb, const double *u_in, const double *v_in,
-                      double *u_out, double *v_out, const uint8_t *solid, cudaStream_t st);
+                      double *u_out, double *v_out, const uint8_t *solid, int canon_in,
+                      cudaStream_t st);
+int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const double *v_in,
+                            double *u_out, double *v_out, int nsims, long long sim_stride,
+                            const int *period_d, int duration_it, int count0, int canon_in,
+                            cudaStream_t st);

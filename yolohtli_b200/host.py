@@ -64,14 +64,17 @@ def rd_step(p, u_in, v_in, u_out, v_out, velTan=None, solid=None, stim_mouse=Fal
                            _ptr(vtv), _ptr(solid), int(stim_mouse), px, py, r0, r1, _stream()))
 
 
+RD_INPUT_CANONICAL = 1
+
+
 def rd_advance(p, nsteps, uA, vA, uB, vB, tb_steps=0, solid=None, stim_mouse=False, point=None,
-               rows=None):
+               rows=None, flags=0):
     """nsteps x {reactionDiffusion_wrapper; swapSoA} (main.cu:879-882).  Returns (u, v) tensors
     holding the result (either the A or the B pair)."""
     px, py = point if point is not None else (p.nx // 2, p.ny_global // 2)
     r0, r1 = rows if rows is not None else (0, p.ny)
     inB = C.c_int(0)
-    check(lib().yh_rd_advance(C.byref(p), nsteps, tb_steps, _ptr(uA), _ptr(vA), _ptr(uB), _ptr(vB),
+    check(lib().yh_rd_advance(C.byref(p), nsteps, tb_steps, flags, _ptr(uA), _ptr(vA), _ptr(uB), _ptr(vB),
                               _ptr(solid), int(stim_mouse), px, py, r0, r1, C.byref(inB), _stream()))
     return (uB, vB) if inB.value else (uA, vA)
 

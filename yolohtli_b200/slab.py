@@ -77,6 +77,7 @@ class SlabRunner:
         l = self.lay
         self.u[self.cur].copy_(torch.as_tensor(u_glob[l.g0:l.g1]).to(self.device))
         self.v[self.cur].copy_(torch.as_tensor(v_glob[l.g0:l.g1]).to(self.device))
+        self.count = 0   # fresh host data: the next pass treats it as raw
 
     def owned(self):
         l = self.lay
@@ -108,7 +109,9 @@ class SlabRunner:
 
     # -- stepping ------------------------------------------------------------------------
     def _cuda_stepper(self, p, nsteps, uA, vA, uB, vB, rows, tb):
-        return host.rd_advance(p, nsteps, uA, vA, uB, vB, tb_steps=tb, rows=rows)
+        # after the first pass every value was written by the library: no -0.0 can be present
+        flags = host.RD_INPUT_CANONICAL if self.count > 0 else 0
+        return host.rd_advance(p, nsteps, uA, vA, uB, vB, tb_steps=tb, rows=rows, flags=flags)
 
     def advance(self, nsteps, tb=0):
         """nsteps time steps: ghosts refreshed, then up to `halo` steps per exchange."""
