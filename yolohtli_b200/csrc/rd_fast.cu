@@ -67,7 +67,9 @@ __device__ __forceinline__ void euler_cell(const YhK &k, double u, double v, dou
 }
 
 // T time levels, strip of W columns, one extra warp that only feeds level 0.
-template <int T, int W, bool CANON, bool TC1>
+// The compute loop is unrolled by three so that the S / C / N row registers rotate by renaming
+// instead of by moves; every sub-iteration ends in the CTA-wide barrier.
+template <int T, int W, bool CANON, bool TC1, bool STIM>
 __global__ void __launch_bounds__(T *(W / 2) + 32)
 rd_euler_stream(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a) {
   constexpr int H = (T + 1) & ~1;        // halo columns each side (even: 16-byte alignment)
@@ -86,7 +88,7 @@ rd_euler_stream(const __grid_constant__ YhK k, const __grid_constant__ FastArgs 
   const int c0 = y0 - T;
   const int dom_lo = -k.jg0, dom_hi = k.nyg - k.jg0;   // local rows that exist globally
   const size_t zoff = (size_t)blockIdx.z * (size_t)a.sim_stride;
-  const int n_it = RYe + 3 * T;
+  const int n_it = ((RYe + 3 * T + 2) / 3) * 3;        // multiple of the unroll factor
 
   if (tid >= NTC) {
     // ---------------- loader warp: level-0 rows, PF rows ahead of their first use ----------
@@ -137,72 +139,99 @@ rd_euler_stream(const __grid_constant__ YhK k, const __grid_constant__ FastArgs 
   const bool left_edge = (gx == 0), right_edge = (gx + 2 == nx);
   const bool canon = CANON && (lev == 1);   // level-0 data is raw: form u0 + (0.0*0.0) literally
 
-  // rows this level must produce
+  // rows this level must produce (empty for threads outside the domain)
   const int lo_l = max(dom_lo, y0 - (T - lev));
-  const int hi_l = min(dom_hi, y0 + RYe + (T - lev));
+  const int hi_l = col_ok ? min(dom_hi, y0 + RYe + (T - lev)) : lo_l;
 
   // pacing (batched sweeps): level `lev` performs step count0 + lev - 1 of its sheet
-  bool stim_on = k.stim != 0;
-  if (a.period) {
-    const int per = a.period[blockIdx.z];
-    stim_on = per > 0 && ((a.count0 + lev - 1) % per) <= a.duration;
+  bool stim_on = false;
+  if (STIM) {
+    stim_on = k.stim != 0;
+    if (a.period) {
+      const int per = a.period[blockIdx.z];
+      stim_on = per > 0 && ((a.count0 + lev - 1) % per) <= a.duration;
+    }
   }
 
-  const int src_nr = (lev == 1) ? NR0 : NRL;
+  const int src_mask = (lev == 1) ? (NR0 - 1) : (NRL - 1);
   const double *src_ring = sm + (lev == 1 ? 0 : (NR0 + (lev - 2) * NRL) * ROW) + c + 2;
   double *dst_ring = sm + (NR0 + (lev - 1) * NRL) * ROW + c + 2;
   double *gu = a.u_out + zoff + gx;
   double *gv = a.v_out + zoff + gx;
-
-  // register-resident rows of the source level: S = m-1, C = m, N = m+1 (pairs of cells)
-  double2 uS = make_double2(0, 0), uC = uS, uN = uS, vS = uS, vC = uS, vN = uS;
+  const int m0 = c0 - 2 * lev;           // row handled in iteration 0
 
   auto ld_pair = [&](int row, double2 &pu, double2 &pv) {
-    const double *r = src_ring + ((row - c0) & (src_nr - 1)) * ROW;
+    const double *r = src_ring + ((row - c0) & src_mask) * ROW;
     pu = *reinterpret_cast<const double2 *>(r);
     pv = *reinterpret_cast<const double2 *>(r + PITCH);
     if (canon) { pu.x += 0.0; pu.y += 0.0; pv.x += 0.0; pv.y += 0.0; }
   };
 
-  for (int it = 0; it < n_it; it++) {
-    const int m = it + c0 - 2 * lev;
-    if (m >= lo_l && m < hi_l) {           // warp-uniform
-      if (col_ok) {
-        if (m == lo_l) {                   // first row of this level: no history in registers yet
-          ld_pair(m, uC, vC);
-          if (m - 1 >= dom_lo) ld_pair(m - 1, uS, vS);
-        }
-        if (m + 1 < dom_hi) ld_pair(m + 1, uN, vN);
-        else { uN = uS; vN = vS; }         // no-flux mirror at the last row: N := S
-        if (m - 1 < dom_lo) { uS = uN; vS = vN; }   // ... and at the first row: S := N
-        const double *rc = src_ring + ((m - c0) & (src_nr - 1)) * ROW;
-        double uw = rc[-1], ue = rc[2], vw = rc[PITCH - 1], ve = rc[PITCH + 2];
-        if (canon) { uw += 0.0; ue += 0.0; vw += 0.0; ve += 0.0; }
-        if (left_edge) { uw = uC.y; vw = vC.y; }      // mirror: W of x=0 is x=1
-        if (right_edge) { ue = uC.x; ve = vC.x; }     // mirror: E of x=nx-1 is x=nx-2
-        bool s0 = false, s1 = false;
-        if (stim_on) { s0 = yh_scs_on(k, gx, m + k.jg0); s1 = yh_scs_on(k, gx + 1, m + k.jg0); }
-        double2 uo, vo;
-        euler_cell<TC1>(k, uC.x, vC.x, uw, uC.y, uN.x, uS.x, vw, vC.y, vN.x, vS.x, s0, uo.x, vo.x);
-        euler_cell<TC1>(k, uC.y, vC.y, uC.x, ue, uN.y, uS.y, vC.x, ve, vN.y, vS.y, s1, uo.y, vo.y);
-        if (lev < T) {
-          double *d = dst_ring + ((m - c0) & (NRL - 1)) * ROW;
-          *reinterpret_cast<double2 *>(d) = uo;
-          *reinterpret_cast<double2 *>(d + PITCH) = vo;
-        } else if (out_col) {
-          const size_t o = (size_t)m * nx;
-          *reinterpret_cast<double2 *>(gu + o) = uo;
-          *reinterpret_cast<double2 *>(gv + o) = vo;
-        }
-        uS = uC; vS = vC; uC = uN; vC = vN;
+  // one row: S / C / N are the register-resident source rows m-1, m, m+1
+  auto row_step = [&](int m, double2 &uS, double2 &vS, double2 &uC, double2 &vC, double2 &uN,
+                      double2 &vN) {
+    if (m >= lo_l && m < hi_l) {
+      if (m == lo_l) {                   // first row of this level: nothing in registers yet
+        ld_pair(m, uC, vC);
+        ld_pair((m - 1 < dom_lo) ? m + 1 : m - 1, uS, vS);   // no-flux mirror at the first row
+      }
+      ld_pair((m + 1 >= dom_hi) ? m - 1 : m + 1, uN, vN);    // ... and at the last row
+      const double *rc = src_ring + ((m - c0) & src_mask) * ROW;
+      double uw = rc[-1], ue = rc[2], vw = rc[PITCH - 1], ve = rc[PITCH + 2];
+      if (canon) { uw += 0.0; ue += 0.0; vw += 0.0; ve += 0.0; }
+      if (left_edge) { uw = uC.y; vw = vC.y; }      // mirror: W of x=0 is x=1
+      if (right_edge) { ue = uC.x; ve = vC.x; }     // mirror: E of x=nx-1 is x=nx-2
+      bool s0 = false, s1 = false;
+      if (STIM && stim_on) { s0 = yh_scs_on(k, gx, m + k.jg0); s1 = yh_scs_on(k, gx + 1, m + k.jg0); }
+      double2 uo, vo;
+      euler_cell<TC1>(k, uC.x, vC.x, uw, uC.y, uN.x, uS.x, vw, vC.y, vN.x, vS.x, s0, uo.x, vo.x);
+      euler_cell<TC1>(k, uC.y, vC.y, uC.x, ue, uN.y, uS.y, vC.x, ve, vN.y, vS.y, s1, uo.y, vo.y);
+      if (lev < T) {
+        double *d = dst_ring + ((m - c0) & (NRL - 1)) * ROW;
+        *reinterpret_cast<double2 *>(d) = uo;
+        *reinterpret_cast<double2 *>(d + PITCH) = vo;
+      } else if (out_col) {
+        const size_t o = (size_t)m * nx;
+        *reinterpret_cast<double2 *>(gu + o) = uo;
+        *reinterpret_cast<double2 *>(gv + o) = vo;
       }
     }
     __syncthreads();
+  };
+
+  double2 uA = make_double2(0, 0), uB = uA, uC = uA, vA = uA, vB = uA, vC = uA;
+  for (int it = 0; it < n_it; it += 3) {
+    const int m = m0 + it;
+    row_step(m, uA, vA, uB, vB, uC, vC);
+    row_step(m + 1, uB, vB, uC, vC, uA, vA);
+    row_step(m + 2, uC, vC, uA, vA, uB, vB);
   }
 }
 
-template <int T, int W, bool CANON, bool TC1>
-int launch2(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
+// Chunk height.  Every CTA does the same work, so the grid should fill the machine in whole
+// waves: pick the number of row chunks C that maximises
+//     (CTAs / (waves * slots))  *  (RY / (RY + 3T))        [wave fill x pipeline-fill loss]
+// where slots = 148 SMs x resident CTAs per SM of this kernel variant.
+static int pick_ry(int rows, int strips, int nsims, int T, int slots) {
+  const int min_ry = 8 * T;
+  int best_ry = rows;
+  double best = -1.0;
+  const int cmax = rows / min_ry > 0 ? rows / min_ry : 1;
+  for (int C = 1; C <= cmax; C++) {
+    const int ry = (rows + C - 1) / C;
+    const int chunks = (rows + ry - 1) / ry;
+    const long long ctas = (long long)strips * chunks * nsims;
+    const long long waves = (ctas + slots - 1) / slots;
+    const double fill = (double)ctas / (double)(waves * slots);
+    const double eff = fill * (double)ry / (double)(ry + 3 * T);
+    if (eff > best + 1e-9) { best = eff; best_ry = ry; }
+    if (ry <= min_ry) break;
+  }
+  return best_ry;
+}
+
+template <int T, int W, bool CANON, bool TC1, bool STIM>
+int launch3(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   constexpr int H = (T + 1) & ~1, BX = W - 2 * H, PITCH = W + 4, ROW = 2 * PITCH;
   constexpr int NT = T * (W / 2) + 32;
   const size_t smem = (size_t)(8 + (T - 1) * 4) * ROW * sizeof(double);
@@ -210,15 +239,33 @@ int launch2(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    YH_CUDA(cudaFuncSetAttribute(rd_euler_stream<T, W, CANON, TC1>,
+    YH_CUDA(cudaFuncSetAttribute(rd_euler_stream<T, W, CANON, TC1, STIM>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[dev & 63] = true;
   }
+  static int slots[64] = {0};
+  if (!slots[dev & 63]) {
+    int per_sm = 1, sms = 148;
+    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_euler_stream<T, W, CANON, TC1, STIM>,
+                                                          NT, smem));
+    YH_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    slots[dev & 63] = (per_sm > 0 ? per_sm : 1) * sms;
+  }
   const int rows = k.row1 - k.row0;
-  dim3 grd((k.nx + BX - 1) / BX, (rows + a.RY - 1) / a.RY, nsims);
-  rd_euler_stream<T, W, CANON, TC1><<<grd, NT, smem, st>>>(k, a);
+  FastArgs b = a;
+  const int strips = (k.nx + BX - 1) / BX;
+  b.RY = a.RY > 0 ? a.RY : pick_ry(rows, strips, nsims, T, slots[dev & 63]);
+  dim3 grd(strips, (rows + b.RY - 1) / b.RY, nsims);
+  rd_euler_stream<T, W, CANON, TC1, STIM><<<grd, NT, smem, st>>>(k, b);
   YH_LAUNCH_CHECK();
   return YH_OK;
+}
+
+template <int T, int W, bool CANON, bool TC1>
+int launch2(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
+  const bool stim = k.stim != 0 || a.period != nullptr;
+  return stim ? launch3<T, W, CANON, TC1, true>(k, a, nsims, st)
+              : launch3<T, W, CANON, TC1, false>(k, a, nsims, st);
 }
 
 template <int T, int W>
@@ -239,15 +286,6 @@ int yh_rd_fast_supported(const YhK &k, int tb) {
   return 1;
 }
 
-// Chunk height: enough CTAs to fill 148 SMs a few times over, tall enough to amortise the
-// 3T-row pipeline fill.
-static int pick_ry(int rows, int strips, int nsims, int T) {
-  int ry = 512;
-  const int min_ry = 16 * T;
-  while (ry > min_ry && (long long)strips * ((rows + ry - 1) / ry) * nsims < 4 * 148) ry >>= 1;
-  return ry;
-}
-
 int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const double *v_in,
                             double *u_out, double *v_out, int nsims, long long sim_stride,
                             const int *period_d, int duration_it, int count0, int canon_in,
@@ -261,8 +299,8 @@ int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const doub
   if (force_w) narrow = atoi(force_w) == 128;
   const int W = narrow ? 128 : 256;
   const bool canon = canon_in != 0;
-  const int H = (tb + 1) & ~1, BX = W - 2 * H;
-  a.RY = pick_ry(rows, (k.nx + BX - 1) / BX, nsims, tb);
+  static const char *force_ry = getenv("YH_FAST_RY");   // tuning hook
+  a.RY = force_ry ? atoi(force_ry) : 0;                   // 0: chosen per kernel variant
   if (narrow) {
     switch (tb) {
       case 1: return launch<1, 128>(k, a, nsims, canon, st);
