@@ -1,0 +1,86 @@
+"""CPU, world_size 2 and 3 over gloo: the row-slab partition + halo-exchange logic of
+yolohtli_b200.slab (the host side of the multi-GPU path) reproduces the single-domain run bit
+for bit.  The CUDA stepper is replaced by a stand-in that runs the plain-C oracle on the
+rank's local rows: treating the local array as a whole sheet is wrong only within n rows of a
+slab-internal edge after n steps, i.e. inside the ghost rows, so owned rows stay exact."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nx, ny, halo, nsteps, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests import oracle_lib
+    from yolohtli_b200.slab import SlabRunner
+    oracle = oracle_lib.load()
+    oracle.set_threads(1)
+    pg = oracle.params_default(nx, ny, timeIntOrder=1, lap4=0)
+
+    def stepper(p, n, uA, vA, uB, vB, rows, tb):
+        q = p.copy()            # same physics constants; local rows taken as a whole sheet
+        q.ny_global, q.jg0 = p.ny, 0
+        u, v = oracle.rd_advance(q, n, uA.numpy(), vA.numpy())
+        uB.copy_(torch.from_numpy(u.reshape(uB.shape)))
+        vB.copy_(torch.from_numpy(v.reshape(vB.shape)))
+        return uB, vB
+
+    rng = np.random.default_rng(77)
+    u0 = rng.uniform(-0.1, 1.1, (ny, nx))
+    v0 = rng.uniform(0.0, 1.0, (ny, nx))
+    run = SlabRunner(pg, rank=rank, world=world, halo=halo, device=torch.device("cpu"), stepper=stepper)
+    run.load_global(u0, v0)
+    run.advance(nsteps)
+    u, v = run.owned()
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), u=u.numpy(), v=v.numpy(), j0=run.lay.j0, j1=run.lay.j1)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,halo,nsteps", [(2, 4, 12), (3, 2, 7)])
+def test_slab_exchange_matches_single_domain(oracle, tmp_path, world, halo, nsteps):
+    nx, ny = 40, 67
+    mp.spawn(_worker, args=(world, _free_port(), nx, ny, halo, nsteps, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(77)
+    u0 = rng.uniform(-0.1, 1.1, (ny, nx))
+    v0 = rng.uniform(0.0, 1.0, (ny, nx))
+    pg = oracle.params_default(nx, ny, timeIntOrder=1, lap4=0)
+    wu, wv = oracle.rd_advance(pg, nsteps, u0, v0)
+    rows = 0
+    for r in range(world):
+        g = np.load(os.path.join(str(tmp_path), f"r{r}.npz"))
+        j0, j1 = int(g["j0"]), int(g["j1"])
+        assert np.array_equal(g["u"], wu[j0:j1]) and np.array_equal(g["v"], wv[j0:j1]), r
+        rows += j1 - j0
+    assert rows == ny
+
+
+def test_partition_covers_domain():
+    from yolohtli_b200.slab import SlabLayout, partition
+    for ny, world in [(16384, 8), (67, 3), (1000, 7)]:
+        edges = [partition(ny, world, r) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == ny
+        assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+        for r in range(world):
+            l = SlabLayout(ny, world, r, 4)
+            assert l.g0 == max(0, l.j0 - 4) and l.g1 == min(ny, l.j1 + 4)
+            assert (l.up is None) == (r == 0) and (l.down is None) == (r == world - 1)

@@ -200,8 +200,12 @@ int yh_sim_run(yh_sim *s, int nsteps, int tb_steps, double *trace_h) {
           const int per = s->period_h[z];
           kz.stim = per > 0 && (s->count % per) <= s->duration_it;
         }
-        rc = yh_launch_rd_generic(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
-                                  s->v[o] + s->n * z, nullptr, nullptr, s->solid, s->st);
+        if (yh_rd_rk_supported(kz))
+          rc = yh_launch_rd_rk(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
+                               s->v[o] + s->n * z, nullptr, nullptr, s->st);
+        else
+          rc = yh_launch_rd_generic(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
+                                    s->v[o] + s->n * z, nullptr, nullptr, s->solid, s->st);
       }
     }
     if (rc != YH_OK) return rc;

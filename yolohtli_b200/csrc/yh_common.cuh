@@ -109,3 +109,8 @@ int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const doub
                             double *u_out, double *v_out, int nsims, long long sim_stride,
                             const int *period_d, int duration_it, int count0, int canon_in,
                             cudaStream_t st);
+
+// Fused Runge-Kutta (RK2/RK4, optional 4th-order Laplacian) step, one launch per time step.
+int yh_rd_rk_supported(const YhK &k);
+int yh_launch_rd_rk(const YhK &k, const double *u_in, const double *v_in, double *u_out,
+                    double *v_out, double *vtu, double *vtv, cudaStream_t st);

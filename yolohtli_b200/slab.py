@@ -69,7 +69,8 @@ class SlabRunner:
         self.cur = 0
         self.stepper = stepper or self._cuda_stepper
         self.count = 0
-        self.comm_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.comm_stream = (torch.cuda.Stream(device=self.device, priority=-1)
+                            if self.device.type == "cuda" else None)
 
     # -- state ---------------------------------------------------------------------------
     def load_global(self, u_glob, v_glob):
@@ -113,8 +114,14 @@ class SlabRunner:
         flags = host.RD_INPUT_CANONICAL if self.count > 0 else 0
         return host.rd_advance(p, nsteps, uA, vA, uB, vB, tb_steps=tb, rows=rows, flags=flags)
 
-    def advance(self, nsteps, tb=0):
-        """nsteps time steps: ghosts refreshed, then up to `halo` steps per exchange."""
+    def advance(self, nsteps, tb=0, overlap=None):
+        """nsteps time steps: ghosts refreshed, then up to `halo` steps per exchange.
+        overlap (default: on for CUDA runs with neighbours): the edge rows of a slab are stepped
+        first on a high-priority stream and sent while the interior rows are still computing."""
+        if overlap is None:
+            overlap = self.world > 1 and self.comm_stream is not None and self.stepper == self._cuda_stepper
+        if overlap and self.K == 1:
+            return self._advance_overlapped(nsteps, tb)
         l = self.lay
         left = nsteps
         while left > 0:
@@ -127,3 +134,53 @@ class SlabRunner:
             self.cur = o if ru is self.u[o] else c
             left -= n
             self.count += n
+
+    # -- overlapped schedule ----------------------------------------------------------------
+    #   edge stream (high priority):  wait ghosts(k), interior(k-1) -> step edge rows -> NCCL
+    #                                 send/recv of the fresh edge rows = ghosts(k+1)
+    #   main stream:                  wait edges(k-1)               -> step interior rows
+    # Interior rows are >= halo rows away from the slab edges, so they never read a ghost row
+    # and run concurrently with the exchange.  One HBM pass (n = halo steps) per block.
+    def _advance_overlapped(self, nsteps, tb):
+        l, H = self.lay, self.halo
+        B = max(H, min(128, (l.own_hi - l.own_lo) // 4))     # edge band height
+        main = torch.cuda.current_stream(self.device)
+        edge = self.comm_stream
+        top = (l.own_lo, l.own_lo + B) if l.up is not None else None
+        bot = (l.own_hi - B, l.own_hi) if l.down is not None else None
+        inner = (top[1] if top else l.own_lo, bot[0] if bot else l.own_hi)
+        ev_int, ev_edge = torch.cuda.Event(), torch.cuda.Event()
+        ev_int.record(main)
+        ev_edge.record(main)
+        left = nsteps
+        first = True
+        while left > 0:
+            n = max(t for t in (1, 2, 4) if t <= min(H, left, tb or 4))   # exactly one HBM pass
+            c, o = self.cur, self.cur ^ 1
+            flags = host.RD_INPUT_CANONICAL if self.count > 0 else 0
+            with torch.cuda.stream(edge):
+                edge.wait_event(ev_int)                      # interior(k-1) wrote rows the edges read
+                if first:                                    # ghosts of the initial state
+                    self.exchange()
+                    first = False
+                for rows in (top, bot):
+                    if rows is not None:
+                        host.rd_advance(self.p, n, self.u[c], self.v[c], self.u[o], self.v[o], tb_steps=n,
+                                        rows=rows, flags=flags)
+                ev_edge_next = torch.cuda.Event()
+                ev_edge_next.record(edge)
+            main.wait_event(ev_edge)                         # edges(k-1) wrote rows the interior reads
+            if inner[1] > inner[0]:
+                host.rd_advance(self.p, n, self.u[c], self.v[c], self.u[o], self.v[o], tb_steps=n,
+                                rows=inner, flags=flags)
+            ev_int = torch.cuda.Event()
+            ev_int.record(main)
+            ev_edge = ev_edge_next
+            self.cur = o
+            left -= n
+            self.count += n
+            if left > 0:
+                with torch.cuda.stream(edge):
+                    self.exchange()                          # fresh edge rows -> neighbours' ghosts
+        main.wait_event(ev_edge)
+        main.wait_stream(edge)
