@@ -220,6 +220,13 @@ int yh_sim_set_pacing(yh_sim *s, const int *period_it, int duration_it);
 int yh_sim_run_host(yh_sim *s, const double *u_in_h, const double *v_in_h,
                     double *u_out_h, double *v_out_h, int nsteps, int tb_steps);
 int yh_sim_tips(yh_sim *s, yh_tip *tips_h, int capacity, int *count_out);
+/* Symmetry-reduction (co-moving frame) steps, main.cu:894-954: RD -> tips -> phase-condition
+ * integrals -> host 3x3 solve -> (Cxy + BFECC advection) -> phi += c*dt.  One host sync per step
+ * (the 12 integrals).  c_phi_h (optional) receives 6 doubles per step: c then phi as pushed to
+ * clist/philist (main.cu:902-903).  Sheet 0 only; (tipx0,tipy0) of the params centre the disc
+ * while count == 0.  yh_sim_sr_state reads / sets (c, phi). */
+int yh_sim_run_sr(yh_sim *s, int nsteps, double *c_phi_h);
+int yh_sim_sr_state(yh_sim *s, double c[3], double phi[3], int set);
 int yh_sim_count(const yh_sim *s);             /* param.count */
 void *yh_sim_device_u(yh_sim *s);              /* current device pointers (for tests)     */
 void *yh_sim_device_v(yh_sim *s);

@@ -255,3 +255,73 @@ def test_sim_driver_trace_batch_and_pacing(oracle, yh):
         assert np.array_equal(u[z], uu) and np.array_equal(v[z], vv), z
     assert u[0].max() > 0.5 and u[2].max() == 0.0
     sim.close()
+
+
+def test_reference_launch_api_through_the_shim(oracle):
+    """The display()-style loop of tests/shim_driver.cu calls reactionDiffusion_wrapper / swapSoA /
+    singleCell_wrapper / tip_wrapper with the reference's signatures (hostPrototypes.h:22-57),
+    linked against libyolohtli_shim.so: fields, electrode trace, velTan and tips == oracle."""
+    import ctypes as C
+    import os
+    from yolohtli_b200 import _lib
+    so = os.path.join(os.path.dirname(_lib.LIB_PATH), "libyh_shimtest.so")
+    drv = C.CDLL(so)
+    for kw in (dict(timeIntOrder=1, lap4=0), dict()):   # Euler/5-pt and the default RK4+lap4
+        nx = ny = 128
+        p = oracle.params_default(nx, ny, **kw)
+        u0, v0 = synth.cross_field_ic(nx, ny)
+        u, v = u0.copy(), v0.copy()
+        nsteps = 30
+        trace = np.zeros((nsteps, 2))
+        vtu = np.zeros(nx * ny)
+        tips = np.zeros(4096, dtype=TIP_DTYPE)
+        nt = C.c_int(0)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = drv.yh_shimtest_run(C.byref(p), vp(u), vp(v), nsteps, vp(trace), vp(vtu), vp(tips), C.byref(nt))
+        assert rc == 0
+        wu, wv = oracle.rd_advance(p, nsteps, u0, v0)
+        assert np.array_equal(u, wu) and np.array_equal(v, wv)
+        pu, pv = oracle.rd_advance(p, nsteps - 1, u0, v0)
+        # singleCell_wrapper reads gateOut AFTER the swap = the previous state (main.cu:1040)
+        assert trace[-1, 0] == pu[ny // 2, nx // 2] and trace[0, 0] == u0[ny // 2, nx // 2]
+        _, _, wvtu, _ = oracle.rd_step(p, pu, pv, velTan=True)
+        assert np.array_equal(vtu, wvtu.ravel())
+        want = oracle.tip_track(p, pu, wu, t=p.dt * nsteps)
+        assert nt.value == len(want) and tips[:nt.value].tobytes() == want.tobytes()
+
+
+def test_symmetry_reduction_step_loop(oracle, yh):
+    """C3 (scaled down): the display() symmetry-reduction loop (main.cu:894-954) in the headless
+    driver == the same loop composed from oracle pieces, bit for bit: fields, (c, phi) history."""
+    nx = ny = 128
+    p = oracle.params_default(nx, ny, reduce_sym=True, tipOffsetX=40, tipOffsetY=40, tipx0=60.0, tipy0=66.0)
+    u0 = wavy(nx, ny) - 0.05
+    v0 = 0.3 * wavy(nx, ny, 0.21, 0.17, 1.3)
+    nsteps = 14
+    sim = yh.Sim(p)
+    sim.set_state(u0[None], v0[None])
+    rec = sim.run_sr(nsteps)
+    gu, gv = sim.get_state()
+    gc, gphi = sim.sr_state()
+    sim.close()
+    u, v = u0.copy(), v0.copy()
+    c, phi = np.zeros(3), np.zeros(3)
+    ax, ay = np.zeros(nx * ny), np.zeros(nx * ny)
+    tip_steps = 0
+    for count in range(nsteps):
+        us, vs, vtu, vtv = oracle.rd_step(p, u, v, velTan=True)
+        tips = oracle.tip_track(p, us, u, t=p.dt * count)
+        tip_steps += len(tips) > 0
+        assert np.array_equal(rec[count], np.concatenate([c, phi])), count
+        I = oracle.sr_integrals(p, u, v, vtu, vtv, ax, ay, tips=tips, count=count)
+        if count == 0:
+            c = oracle.solve_matrix(c, phi, I)
+            ax, ay = oracle.cxy_field(p, c, phi)
+            I = oracle.sr_integrals(p, u, v, vtu, vtv, ax, ay, tips=tips, count=count)
+        c = oracle.solve_matrix(c, phi, I)
+        ax, ay = oracle.cxy_field(p, c, phi)
+        u, v = oracle.advect_bfecc(p, us, vs, ax, ay)
+        phi = np.array([phi[q] + c[q] * p.dt for q in range(3)])
+    assert tip_steps > 0, "the test fields should produce tips so the tip-centred disc is exercised"
+    assert np.array_equal(gu[0], u) and np.array_equal(gv[0], v)
+    assert np.array_equal(gc, c) and np.array_equal(gphi, phi)

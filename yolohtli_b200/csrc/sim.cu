@@ -25,6 +25,8 @@ struct yh_sim {
   int count;
   int have_prev;         // other buffer holds the state exactly one step back
   int raw_input;         // current state came from the host and may hold -0.0
+  double *vt[2], *adv[2];   // velTan and advection field (symmetry reduction), lazily allocated
+  double c[3], phi[3];   // drift velocities and frame phase (main.cu:60-61)
   cudaStream_t st;
 };
 
@@ -63,6 +65,8 @@ int yh_sim_create(yh_sim **out, const yh_params *p, int n_sims, int device) {
   s->cur = 0; s->solid = nullptr; s->trace_d = nullptr; s->trace_cap = 0;
   s->period_d = nullptr; s->duration_it = 0; s->count = 0; s->have_prev = 0; s->raw_input = 1;
   s->px = p->nx / 2; s->py = p->ny / 2;   // param.point, saveFiles.cu:180
+  s->vt[0] = s->vt[1] = s->adv[0] = s->adv[1] = nullptr;
+  for (int q = 0; q < 3; q++) { s->c[q] = 0.0; s->phi[q] = 0.0; }
   const size_t bytes = s->n * n_sims * sizeof(double);
   for (int b = 0; b < 2; b++) {
     YH_CUDA(cudaMalloc(&s->u[b], bytes));
@@ -85,6 +89,7 @@ int yh_sim_destroy(yh_sim *s) {
   for (int b = 0; b < 2; b++) { cudaFree(s->u[b]); cudaFree(s->v[b]); }
   cudaFree(s->solid); cudaFree(s->trace_d); cudaFree(s->tip_count_d); cudaFree(s->tip_vec_d);
   cudaFree(s->period_d);
+  cudaFree(s->vt[0]); cudaFree(s->vt[1]); cudaFree(s->adv[0]); cudaFree(s->adv[1]);
   cudaStreamDestroy(s->st);
   delete s;
   return YH_OK;
@@ -260,6 +265,72 @@ int yh_sim_tips(yh_sim *s, yh_tip *tips_h, int capacity, int *count_out) {
   if (n > YH_TIPVECSIZE) { yh_set_error("tip list overflow: %d > %d", n, YH_TIPVECSIZE); return YH_ERR_CAPACITY; }
   const int m = n < capacity ? n : capacity;
   if (m > 0) YH_CUDA(cudaMemcpy(tips_h, s->tip_vec_d, sizeof(yh_tip) * (size_t)m, cudaMemcpyDeviceToHost));
+  return YH_OK;
+}
+
+// One symmetry-reduction step per iteration, as display() does when param.reduceSym
+// (main.cu:894-954), with slice+trapz fused and Cxy fused into the advection.
+int yh_sim_run_sr(yh_sim *s, int nsteps, double *c_phi_h) {
+  YH_REQUIRE(s && nsteps >= 0, "bad arguments");
+  YH_REQUIRE(s->n_sims == 1, "symmetry reduction drives a single sheet");
+  DevGuard g(s->device);
+  const size_t bytes = s->n * sizeof(double);
+  if (!s->vt[0]) {
+    for (int q = 0; q < 2; q++) {
+      YH_CUDA(cudaMalloc(&s->vt[q], bytes));
+      YH_CUDA(cudaMalloc(&s->adv[q], bytes));
+      YH_CUDA(cudaMemsetAsync(s->vt[q], 0, bytes, s->st));    // main.cu:431-434
+      YH_CUDA(cudaMemsetAsync(s->adv[q], 0, bytes, s->st));
+    }
+  }
+  const yh_params *p = &s->p;
+  double I[12];
+  for (int it = 0; it < nsteps; it++) {
+    const int c = s->cur, o = c ^ 1;
+    // u* = RD(u^n), velTan = rhs/dt                                       (main.cu:896)
+    int rc = yh_rd_step(p, s->u[c], s->v[c], s->u[o], s->v[o], s->vt[0], s->vt[1], s->solid, 0, s->px,
+                        s->py, 0, p->ny, s->st);
+    if (rc != YH_OK) return rc;
+    // tips between u^n (present) and u* (past), every step                 (main.cu:900)
+    rc = yh_tip_track(p, s->u[o], s->u[c], nullptr, s->tip_count_d, s->tip_vec_d, YH_TIPVECSIZE,
+                      p->dt * (double)s->count, p->tipAlgorithm, s->st);
+    if (rc != YH_OK) return rc;
+    if (c_phi_h) {                                                       // main.cu:902-903
+      for (int q = 0; q < 3; q++) { c_phi_h[6 * it + q] = s->c[q]; c_phi_h[6 * it + 3 + q] = s->phi[q]; }
+    }
+    // phase-condition integrals of the tangent fields of u^n              (main.cu:906-923)
+    rc = yh_sr_integrals(p, s->u[c], s->v[c], s->vt[0], s->vt[1], s->adv[0], s->adv[1], I, s->tip_count_d,
+                         s->tip_vec_d, s->count, s->st);
+    if (rc != YH_OK) return rc;
+    if (s->count == 0) {   // first step: solve, rebuild the frame velocity, slice again (main.cu:910-921)
+      yh_solve_matrix(s->c, s->phi, I, s->c);
+      rc = yh_cxy_field(p, s->adv[0], s->adv[1], s->c, s->phi, s->solid, s->st);
+      if (rc != YH_OK) return rc;
+      rc = yh_sr_integrals(p, s->u[c], s->v[c], s->vt[0], s->vt[1], s->adv[0], s->adv[1], I,
+                           s->tip_count_d, s->tip_vec_d, s->count, s->st);
+      if (rc != YH_OK) return rc;
+    }
+    yh_solve_matrix(s->c, s->phi, I, s->c);                               // main.cu:926
+    // u^{n+1} = BFECC(u*) in the frame moving with (c, phi); result lands in the `c` buffers,
+    // exactly the reference's ping-pong without swap                     (main.cu:930-932)
+    rc = yh_advect_bfecc_cphi(p, s->u[o], s->v[o], s->u[c], s->v[c], s->c, s->phi, s->adv[0], s->adv[1],
+                              s->solid, s->st);
+    if (rc != YH_OK) return rc;
+    for (int q = 0; q < 3; q++) s->phi[q] = s->phi[q] + s->c[q] * p->dt;   // main.cu:936-938 (sticky start)
+    s->count++;
+    s->have_prev = 0;
+    s->raw_input = 0;
+  }
+  YH_CUDA(cudaStreamSynchronize(s->st));
+  return YH_OK;
+}
+
+int yh_sim_sr_state(yh_sim *s, double c[3], double phi[3], int set) {
+  YH_REQUIRE(s && c && phi, "null pointer");
+  for (int q = 0; q < 3; q++) {
+    if (set) { s->c[q] = c[q]; s->phi[q] = phi[q]; }
+    else { c[q] = s->c[q]; phi[q] = s->phi[q]; }
+  }
   return YH_OK;
 }
 

@@ -232,6 +232,17 @@ class Sim:
             return C.c_void_p(a) if isinstance(a, int) else a.ctypes.data_as(C.c_void_p)
         check(lib().yh_sim_run_host(self._h, hp(u_in), hp(v_in), hp(u_out), hp(v_out), nsteps, tb_steps))
 
+    def run_sr(self, nsteps, record=True):
+        """Symmetry-reduction steps (main.cu:894-954); returns [nsteps, 6] = (c, phi) per step."""
+        out = np.zeros((nsteps, 6), dtype=np.float64) if record else None
+        check(lib().yh_sim_run_sr(self._h, nsteps, out.ctypes.data_as(C.c_void_p) if record else None))
+        return out
+
+    def sr_state(self):
+        c, phi = (C.c_double * 3)(), (C.c_double * 3)()
+        check(lib().yh_sim_sr_state(self._h, c, phi, 0))
+        return np.array(c[:]), np.array(phi[:])
+
     def tips(self, capacity=4096):
         buf = np.zeros(capacity, dtype=TIP_DTYPE)
         n = C.c_int(0)
