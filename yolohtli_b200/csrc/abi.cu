@@ -154,7 +154,7 @@ int yh_rd_step(const yh_params *p, const double *u_in, const double *v_in, doubl
   // single steps that need no velTan take the streaming kernel (T = 1)
   if (!(velTan_u && k.gateDiff) && yh_rd_fast_supported(k, 1))
     return yh_launch_rd_fast(k, 1, u_in, v_in, u_out, v_out, solid, 1, st);
-  if (yh_rd_rk_supported(k)) return yh_launch_rd_rk(k, u_in, v_in, u_out, v_out, velTan_u, velTan_v, st);
+  if (yh_rd_rk_supported(k)) return yh_launch_rd_rk(k, u_in, v_in, u_out, v_out, velTan_u, velTan_v, solid, st);
   return yh_launch_rd_generic(k, u_in, v_in, u_out, v_out, velTan_u, velTan_v, solid, st);
 }
 
@@ -188,7 +188,7 @@ int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, int flags, doubl
     if (k.row0 < 0) k.row0 = 0;
     if (k.row1 > p->ny) k.row1 = p->ny;
     if (yh_rd_fast_supported(k, T)) { rc = yh_launch_rd_fast(k, T, cu, cv, nu, nv, solid, canon, st); canon = 0; }
-    else if (yh_rd_rk_supported(k)) rc = yh_launch_rd_rk(k, cu, cv, nu, nv, nullptr, nullptr, st);
+    else if (yh_rd_rk_supported(k)) rc = yh_launch_rd_rk(k, cu, cv, nu, nv, nullptr, nullptr, solid, st);
     else rc = yh_launch_rd_generic(k, cu, cv, nu, nv, nullptr, nullptr, solid, st);
     if (rc != YH_OK) return rc;
     double *t = cu; cu = nu; nu = t;   // swapSoA (helper_functions.cu:140)

@@ -213,7 +213,7 @@ rd_euler_stream(const __grid_constant__ YhK k, const __grid_constant__ FastArgs 
 //     (CTAs / (waves * slots))  *  (RY / (RY + 3T))        [wave fill x pipeline-fill loss]
 // where slots = 148 SMs x resident CTAs per SM of this kernel variant.
 static int pick_ry(int rows, int strips, int nsims, int T, int slots) {
-  const int min_ry = 8 * T;
+  const int min_ry = 4;
   int best_ry = rows;
   double best = -1.0;
   const int cmax = rows / min_ry > 0 ? rows / min_ry : 1;
@@ -294,25 +294,25 @@ int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const doub
   FastArgs a{u_in, v_in, u_out, v_out, 0, sim_stride, period_d, duration_it, count0};
   const int rows = k.row1 - k.row0;
   if (rows <= 0) return YH_OK;
-  static const char *force_w = getenv("YH_FAST_W");   // tuning hook
-  bool narrow = k.nx < 1024;   // small sheets: more, narrower strips
-  if (force_w) narrow = atoi(force_w) == 128;
-  const int W = narrow ? 128 : 256;
+  const char *force_w = getenv("YH_FAST_W");   // tuning hook
+  const char *force_ry = getenv("YH_FAST_RY");  // tuning hook
+  a.RY = force_ry ? atoi(force_ry) : 0;                // 0: chosen per kernel variant
   const bool canon = canon_in != 0;
-  static const char *force_ry = getenv("YH_FAST_RY");   // tuning hook
-  a.RY = force_ry ? atoi(force_ry) : 0;                   // 0: chosen per kernel variant
-  if (narrow) {
-    switch (tb) {
-      case 1: return launch<1, 128>(k, a, nsims, canon, st);
-      case 2: return launch<2, 128>(k, a, nsims, canon, st);
-      default: return launch<4, 128>(k, a, nsims, canon, st);
-    }
+  // strip width: wide strips (less halo redundancy) for big sheets, narrow ones when the sheet
+  // is too small to fill 148 SMs otherwise (latency-bound regime)
+  const long long cells = (long long)k.nx * rows * nsims;
+  int W = cells >= (1ll << 24) ? 256 : (cells >= (1ll << 21) ? 128 : 64);
+  if (force_w) W = atoi(force_w);
+#define YH_FAST_DISPATCH(WW)                                     \
+  switch (tb) {                                                  \
+    case 1: return launch<1, WW>(k, a, nsims, canon, st);        \
+    case 2: return launch<2, WW>(k, a, nsims, canon, st);        \
+    default: return launch<4, WW>(k, a, nsims, canon, st);       \
   }
-  switch (tb) {
-    case 1: return launch<1, 256>(k, a, nsims, canon, st);
-    case 2: return launch<2, 256>(k, a, nsims, canon, st);
-    default: return launch<4, 256>(k, a, nsims, canon, st);
-  }
+  if (W == 64) { YH_FAST_DISPATCH(64) }
+  if (W == 128) { YH_FAST_DISPATCH(128) }
+  YH_FAST_DISPATCH(256)
+#undef YH_FAST_DISPATCH
 }
 
 int yh_launch_rd_fast(const YhK &k, int tb, const double *u_in, const double *v_in,

@@ -1,6 +1,6 @@
-// rd_rk.cu -- the reference's DEFAULT mode in one launch per time step: Runge-Kutta (RK2 / RK4)
-// with SYNCHRONOUS stages and the optional 4th-order (9-point + J correction) Laplacian
-// (reactionDiffusion.cu:71-93, 115-247, 498-513), no-flux boundaries, square domain.
+// rd_rk.cu -- the reference's DEFAULT mode in one launch per time step: Euler / RK2 / RK4 with
+// SYNCHRONOUS stages, the optional 4th-order (9-point + J correction) Laplacian and the obstacle
+// masks (reactionDiffusion.cu:71-93, 115-247, 154-184, 498-561), no-flux boundaries.
 //
 // Same 3.5-D streaming skeleton as rd_fast.cu, with the RK stages as pipeline levels: a CTA
 // owns a strip of W columns and streams down the rows; warp group P canonicalises a level-0 row
@@ -22,8 +22,28 @@ namespace {
 struct RkArgs {
   const double *u_in, *v_in;
   double *u_out, *v_out, *vtu, *vtv;
+  const uint8_t *solid;   // SOLID variants: 1 = tissue (main.cu:676-680), local rows
   int RY;
 };
+
+// Obstacle masks (reactionDiffusion.cu:154-184): the six stencil coefficients of a cell depend
+// only on the mask of the cell and its four (mirrored) neighbours, not on the stage, so group P
+// packs them once per cell into 13 bits -- cxx cxy cxz cyx cyy cyz (2 bits each, values 0/1/2)
+// and sc -- and the stage groups read the code of THEIR cell only: no mask halo in the pipeline.
+__device__ __forceinline__ unsigned solid_code(bool sc, bool sw, bool se, bool sn, bool ss) {
+  const unsigned cxx = (sw && se) && (sw && sc) ? 1u : ((sw && sc) ? 2u : 0u);
+  const unsigned cxy = sc ? ((sw || se) ? 2u : 0u) : 0u;
+  const unsigned cxz = (sw && se) && (sc && se) ? 1u : ((sc && se) ? 2u : 0u);
+  const unsigned cyx = (sn && ss) && (sn && sc) ? 1u : ((sn && sc) ? 2u : 0u);
+  const unsigned cyy = sc ? ((sn || ss) ? 2u : 0u) : 0u;
+  const unsigned cyz = (sn && ss) && (sc && ss) ? 1u : ((sc && ss) ? 2u : 0u);
+  return cxx | (cxy << 2) | (cxz << 4) | (cyx << 6) | (cyy << 8) | (cyz << 10) | ((sc ? 1u : 0u) << 12);
+}
+// 0 / 1 / 2 as an exact double without a conversion instruction
+__device__ __forceinline__ double coef(unsigned code, int shift) {
+  const unsigned c2 = (code >> shift) & 3u;
+  return __hiloint2double(c2 ? (int)(0x3FE00000u + (c2 << 20)) : 0, 0);
+}
 
 __device__ __forceinline__ void cp_async16(unsigned smem, const void *gmem, bool valid) {
   int sz = valid ? 16 : 0;
@@ -35,10 +55,10 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // K stages, strip of W columns.  Arrays of one ring row: U V Ju Jv ru rv (6 x PITCH doubles).
-template <int K, int W, bool LAP4>
+template <int K, int W, bool LAP4, bool SOLID>
 __global__ void __launch_bounds__((K + 1) * (W / 2) + 32)
 rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
-  constexpr int H = K;                   // halo columns each side (K even)
+  constexpr int H = (K + 1) & ~1;        // halo columns each side (even: 16-byte alignment)
   constexpr int BX = W - 2 * H;
   constexpr int PITCH = W + 4;
   constexpr int ROW0 = 2 * PITCH;        // level-0 ring row: u0 v0
@@ -48,6 +68,7 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
   extern __shared__ __align__(16) double sm[];
   double *R0 = sm;
   double *A = sm + NR0 * ROW0;           // A[kk] = A + kk * NRA * ROWA
+  unsigned short *Cr = reinterpret_cast<unsigned short *>(A + K * NRA * ROWA);   // [NR0][W] mask codes
 
   const int tid = threadIdx.x;
   const int nx = k.nx;
@@ -114,9 +135,11 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
     const double ki[5] = {0.0, 0.5, 0.5, 1.0, 0.0};
     const double ws[4] = {0.166666666666667, 0.333333333333333, 0.333333333333333, 0.166666666666667};
     if (st >= 0) { a_next = ki[st + 1]; w_k = ws[st]; }
-  } else {   // RK2
+  } else if (K == 2) {
     if (st == 0) { a_next = 0.5; w_k = 0.0; }
     if (st == 1) { a_next = 0.0; w_k = 1.0; }
+  } else {   // Euler
+    w_k = 1.0;
   }
 
   // rows each group handles (empty for out-of-domain columns)
@@ -152,6 +175,17 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
         *reinterpret_cast<double2 *>(d + PITCH) = v;
         *reinterpret_cast<double2 *>(d + 2 * PITCH) = ju;
         *reinterpret_cast<double2 *>(d + 3 * PITCH) = jv;
+        if (SOLID) {
+          const int ny = k.nyg;
+          const uint8_t *mc = a.solid + (size_t)m * nx;
+          const uint8_t *mS = a.solid + (size_t)(yh_mir(gj - 1, ny) - k.jg0) * nx;   // S = j-1 (:149)
+          const uint8_t *mN = a.solid + (size_t)(yh_mir(gj + 1, ny) - k.jg0) * nx;   // N = j+1 (:150)
+          const bool c0m = mc[gx] != 0, c1m = mc[gx + 1] != 0;
+          const bool w0 = mc[yh_mir(gx - 1, nx)] != 0, e1 = mc[yh_mir(gx + 2, nx)] != 0;
+          const unsigned code0 = solid_code(c0m, w0, c1m, mN[gx] != 0, mS[gx] != 0);
+          const unsigned code1 = solid_code(c1m, c0m, e1, mN[gx + 1] != 0, mS[gx + 1] != 0);
+          *reinterpret_cast<unsigned *>(Cr + ((m - c0) & (NR0 - 1)) * W + c) = code0 | (code1 << 16);
+        }
       } else {
         // ---- S_st: du of stage st for the pair (c, c+1) of row m ----
         const double *Ak = A + st * NRA * ROWA;
@@ -161,6 +195,8 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
         const double *rs = Ak + ((ms - c0) & (NRA - 1)) * ROWA + cc;
         const double *rn = Ak + ((mn - c0) & (NRA - 1)) * ROWA + cc;
         double du[2], dv[2];
+        unsigned codes = 0;
+        if (SOLID) codes = *reinterpret_cast<const unsigned *>(Cr + ((m - c0) & (NR0 - 1)) * W + c);
 #pragma unroll
         for (int f = 0; f < 2; f++) {   // f = 0: u with Ju, f = 1: v with Jv
           const double *pc = rc + f * PITCH, *ps = rs + f * PITCH, *pn = rn + f * PITCH;
@@ -171,7 +207,22 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
           if (left_edge) Wv = C.y;
           if (right_edge) Ev = C.x;
           double d0, d1;
-          if (f == 0) {
+          if (SOLID) {   // reactionDiffusion.cu:171-180
+            const unsigned k0 = codes & 0xFFFFu, k1 = codes >> 16;
+            if (f == 0) {
+              d0 = ((coef(k0, 0) * Wv - coef(k0, 2) * C.x + coef(k0, 4) * C.y) * k.rx +
+                    (coef(k0, 6) * N.x - coef(k0, 8) * C.x + coef(k0, 10) * S.x) * k.ry);
+              d1 = ((coef(k1, 0) * C.x - coef(k1, 2) * C.y + coef(k1, 4) * Ev) * k.rx +
+                    (coef(k1, 6) * N.y - coef(k1, 8) * C.y + coef(k1, 10) * S.y) * k.ry);
+            } else if (k.gateDiff) {
+              d0 = ((coef(k0, 0) * Wv - coef(k0, 2) * C.x + coef(k0, 4) * C.y) * k.rx * k.rscale +
+                    (coef(k0, 6) * N.x - coef(k0, 8) * C.x + coef(k0, 10) * S.x) * k.ry * k.rscale);
+              d1 = ((coef(k1, 0) * C.x - coef(k1, 2) * C.y + coef(k1, 4) * Ev) * k.rx * k.rscale +
+                    (coef(k1, 6) * N.y - coef(k1, 8) * C.y + coef(k1, 10) * S.y) * k.ry * k.rscale);
+            } else {
+              d0 = 0.0; d1 = 0.0;
+            }
+          } else if (f == 0) {
             d0 = ((Wv - 2.0 * C.x + C.y) * k.rx + (N.x - 2.0 * C.x + S.x) * k.ry);
             d1 = ((C.x - 2.0 * C.y + Ev) * k.rx + (N.y - 2.0 * C.y + S.y) * k.ry);
           } else if (k.gateDiff) {
@@ -240,13 +291,18 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
           double2 uo, vo;   // :512-513
           uo.x = u0.x + k.tc * ru.x; uo.y = u0.y + k.tc * ru.y;
           vo.x = v0.x + k.tc * rv.x; vo.y = v0.y + k.tc * rv.y;
+          const bool sc0 = !SOLID || ((codes >> 12) & 1u), sc1 = !SOLID || ((codes >> 28) & 1u);
+          if (SOLID) {   // :521-522 masked cells are exactly 0.0
+            uo.x = sc0 ? uo.x : 0.0; uo.y = sc1 ? uo.y : 0.0;
+            vo.x = sc0 ? vo.x : 0.0; vo.y = sc1 ? vo.y : 0.0;
+          }
           const size_t o = (size_t)m * nx + gx;
           *reinterpret_cast<double2 *>(a.u_out + o) = uo;
           *reinterpret_cast<double2 *>(a.v_out + o) = vo;
           if (a.vtu && k.gateDiff) {   // :551-552
             double2 tu, tv;
-            tu.x = ru.x / k.dt; tu.y = ru.y / k.dt;
-            tv.x = rv.x / k.dt; tv.y = rv.y / k.dt;
+            tu.x = sc0 ? ru.x / k.dt : 0.0; tu.y = sc1 ? ru.y / k.dt : 0.0;   // :529-530
+            tv.x = sc0 ? rv.x / k.dt : 0.0; tv.y = sc1 ? rv.y / k.dt : 0.0;
             *reinterpret_cast<double2 *>(a.vtu + o) = tu;
             *reinterpret_cast<double2 *>(a.vtv + o) = tv;
           }
@@ -258,7 +314,7 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
 }
 
 static int pick_ry_rk(int rows, int strips, int K, int slots) {
-  const int min_ry = 16 * K;
+  const int min_ry = 4;
   int best_ry = rows;
   double best = -1.0;
   const int cmax = rows / min_ry > 0 ? rows / min_ry : 1;
@@ -274,29 +330,30 @@ static int pick_ry_rk(int rows, int strips, int K, int slots) {
   return best_ry;
 }
 
-template <int K, int W, bool LAP4>
+template <int K, int W, bool LAP4, bool SOLID>
 int launch(const YhK &k, RkArgs a, cudaStream_t st) {
-  constexpr int PITCH = W + 4, BX = W - 2 * K;
+  constexpr int PITCH = W + 4, BX = W - 2 * ((K + 1) & ~1);
   constexpr int NT = (K + 1) * (W / 2) + 32;
-  const size_t smem = ((size_t)16 * 2 * PITCH + (size_t)K * 4 * 6 * PITCH) * sizeof(double);
+  const size_t smem = ((size_t)16 * 2 * PITCH + (size_t)K * 4 * 6 * PITCH) * sizeof(double) +
+                      (size_t)16 * W * sizeof(unsigned short);
   static bool attr_set[64] = {false};
   static int slots[64] = {0};
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    YH_CUDA(cudaFuncSetAttribute(rd_rk_stream<K, W, LAP4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    YH_CUDA(cudaFuncSetAttribute(rd_rk_stream<K, W, LAP4, SOLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1, sms = 148;
-    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_rk_stream<K, W, LAP4>, NT, smem));
+    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_rk_stream<K, W, LAP4, SOLID>, NT, smem));
     YH_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     slots[dev & 63] = (per_sm > 0 ? per_sm : 1) * sms;
     attr_set[dev & 63] = true;
   }
   const int rows = k.row1 - k.row0;
   const int strips = (k.nx + BX - 1) / BX;
-  static const char *force_ry = getenv("YH_RK_RY");
+  const char *force_ry = getenv("YH_RK_RY");
   a.RY = force_ry ? atoi(force_ry) : pick_ry_rk(rows, strips, K, slots[dev & 63]);
   dim3 grd(strips, (rows + a.RY - 1) / a.RY);
-  rd_rk_stream<K, W, LAP4><<<grd, NT, smem, st>>>(k, a);
+  rd_rk_stream<K, W, LAP4, SOLID><<<grd, NT, smem, st>>>(k, a);
   YH_LAUNCH_CHECK();
   return YH_OK;
 }
@@ -304,24 +361,35 @@ int launch(const YhK &k, RkArgs a, cudaStream_t st) {
 }  // namespace
 
 int yh_rd_rk_supported(const YhK &k) {
-  if (k.timeIntOrder != 2 && k.timeIntOrder != 4) return 0;
-  if (!k.neumannBC || k.solidSwitch || k.anisotropy) return 0;
+  if (k.timeIntOrder != 1 && k.timeIntOrder != 2 && k.timeIntOrder != 4) return 0;
+  if (!k.neumannBC || k.anisotropy) return 0;
   if ((k.nx & 1) || k.nx < 16) return 0;
   return 1;
 }
 
 int yh_launch_rd_rk(const YhK &k, const double *u_in, const double *v_in, double *u_out,
-                    double *v_out, double *vtu, double *vtv, cudaStream_t st) {
+                    double *v_out, double *vtu, double *vtv, const uint8_t *solid, cudaStream_t st) {
   if (!yh_rd_rk_supported(k)) return YH_ERR_UNSUPPORTED;
   if (k.row1 <= k.row0) return YH_OK;
-  RkArgs a{u_in, v_in, u_out, v_out, vtu, vtv, 0};
-  static const char *force_w = getenv("YH_RK_W");
-  const bool wide = force_w ? atoi(force_w) == 192 : (k.nx >= 1024);
-  const bool lap4 = k.lap4 != 0;
-  if (k.timeIntOrder == 4) {
-    if (wide) return lap4 ? launch<4, 192, true>(k, a, st) : launch<4, 192, false>(k, a, st);
-    return lap4 ? launch<4, 128, true>(k, a, st) : launch<4, 128, false>(k, a, st);
+  RkArgs a{u_in, v_in, u_out, v_out, vtu, vtv, solid, 0};
+  const char *force_w = getenv("YH_RK_W");
+  const long long cells = (long long)k.nx * (k.row1 - k.row0);
+  int W = cells >= (1ll << 23) ? 192 : (cells >= (1ll << 21) ? 128 : 64);
+  if (force_w) W = atoi(force_w);
+  const bool so = k.solidSwitch != 0;
+  const bool lap4 = k.lap4 != 0 && !so;   // the mask branch has no 4th-order terms (:184)
+#define YH_RK_W(KK, WW)                                                                       \
+  {                                                                                           \
+    if (so) return launch<KK, WW, false, true>(k, a, st);                                     \
+    return lap4 ? launch<KK, WW, true, false>(k, a, st) : launch<KK, WW, false, false>(k, a, st); \
   }
-  if (wide) return lap4 ? launch<2, 192, true>(k, a, st) : launch<2, 192, false>(k, a, st);
-  return lap4 ? launch<2, 128, true>(k, a, st) : launch<2, 128, false>(k, a, st);
+#define YH_RK_DISPATCH(KK)      \
+  if (W == 64) YH_RK_W(KK, 64)  \
+  if (W == 128) YH_RK_W(KK, 128) \
+  YH_RK_W(KK, 192)
+  if (k.timeIntOrder == 4) { YH_RK_DISPATCH(4) }
+  if (k.timeIntOrder == 2) { YH_RK_DISPATCH(2) }
+  YH_RK_DISPATCH(1)
+#undef YH_RK_DISPATCH
+#undef YH_RK_W
 }

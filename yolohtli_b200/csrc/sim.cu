@@ -207,7 +207,7 @@ int yh_sim_run(yh_sim *s, int nsteps, int tb_steps, double *trace_h) {
         }
         if (yh_rd_rk_supported(kz))
           rc = yh_launch_rd_rk(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
-                               s->v[o] + s->n * z, nullptr, nullptr, s->st);
+                               s->v[o] + s->n * z, nullptr, nullptr, s->solid, s->st);
         else
           rc = yh_launch_rd_generic(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
                                     s->v[o] + s->n * z, nullptr, nullptr, s->solid, s->st);

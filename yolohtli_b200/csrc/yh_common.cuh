@@ -113,4 +113,4 @@ int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const doub
 // Fused Runge-Kutta (RK2/RK4, optional 4th-order Laplacian) step, one launch per time step.
 int yh_rd_rk_supported(const YhK &k);
 int yh_launch_rd_rk(const YhK &k, const double *u_in, const double *v_in, double *u_out,
-                    double *v_out, double *vtu, double *vtv, cudaStream_t st);
+                    double *v_out, double *vtu, double *vtv, const uint8_t *solid, cudaStream_t st);
