@@ -226,6 +226,13 @@ int yh_sim_tips(yh_sim *s, yh_tip *tips_h, int capacity, int *count_out);
  * clist/philist (main.cu:902-903).  Sheet 0 only; (tipx0,tipy0) of the params centre the disc
  * while count == 0.  yh_sim_sr_state reads / sets (c, phi). */
 int yh_sim_run_sr(yh_sim *s, int nsteps, double *c_phi_h);
+/* contourMode == 1 loop (main.cu:879-885, 1035): every step RD, swap, then sAPD_wrapper with the
+ * reference's argument order (uold := gateIn = NEW state, unew := gateOut = OLD state) and
+ * stimulate = 1 masked by stim_area_h (nx*ny bytes; NULL: every cell, stimulate = 0).  All sheets
+ * of the batch are processed by the same launches.  APD state is zero-initialised (defect B12).
+ * yh_sim_get_apd copies APD1, APD2 (n_sims*nx*ny doubles each) to the host. */
+int yh_sim_run_apd(yh_sim *s, int nsteps, const uint8_t *stim_area_h);
+int yh_sim_get_apd(yh_sim *s, double *apd1_h, double *apd2_h);
 int yh_sim_sr_state(yh_sim *s, double c[3], double phi[3], int set);
 int yh_sim_count(const yh_sim *s);             /* param.count */
 void *yh_sim_device_u(yh_sim *s);              /* current device pointers (for tests)     */

@@ -297,4 +297,121 @@ int yref_sapd(const double *u_seq_h, int nframes, int count0, const uint8_t *sti
   return g_err ? -1 : 0;
 }
 
+// display() with param.reduceSym (main.cu:894-954), the reference's own wrappers and host solve,
+// exactly as shipped: 12 blocking D2H + cudaMalloc/cudaFree per trapz_wrapper call, sticky
+// reduceSymStart (B6), the extra solve/Cxy/slice at count == 0.  c_phi_h: 6 doubles per step
+// (clist/philist).  Returns elapsed ms of the loop (CUDA events) or <0.
+float yref_sr_run(double *u_h, double *v_h, int nsteps, double *c_phi_h, int copy_back) {
+  g_err = 0;
+  const size_t n = (size_t)param.nx * param.ny;
+  stateVar gateIn_d, gateOut_d, J_d, velTan, uf, ub, ue; advVar advect; sliceVar sl, sl0;
+  gateIn_d.u = dalloc(n, u_h); gateIn_d.v = dalloc(n, v_h);
+  gateOut_d.u = dalloc(n, nullptr); gateOut_d.v = dalloc(n, nullptr);
+  J_d.u = dalloc(n, nullptr); J_d.v = dalloc(n, nullptr);
+  velTan.u = dalloc(n, nullptr); velTan.v = dalloc(n, nullptr);
+  uf.u = dalloc(n, nullptr); uf.v = dalloc(n, nullptr); ub.u = dalloc(n, nullptr); ub.v = dalloc(n, nullptr);
+  ue.u = dalloc(n, nullptr); ue.v = dalloc(n, nullptr);
+  advect.x = dalloc(n, nullptr); advect.y = dalloc(n, nullptr);
+  REAL **sp[12] = {&sl.ux, &sl.uy, &sl.ut, &sl.vx, &sl.vy, &sl.vt, &sl0.ux, &sl0.uy, &sl0.ut, &sl0.vx, &sl0.vy, &sl0.vt};
+  for (int k = 0; k < 12; k++) *sp[k] = dalloc(n, nullptr);
+  bool *solid_d = balloc(n, nullptr), *tip_plot = balloc(n, nullptr), *area_d = balloc(n, nullptr);
+  CK(cudaMemset(solid_d, 1, n));
+  REAL *stim_d = dalloc(n, nullptr), *coeff_d = dalloc(n, nullptr);
+  int *tip_count_d = nullptr; vec5dyn *tip_vector_d = nullptr;
+  CK(cudaMalloc(&tip_count_d, sizeof(int))); CK(cudaMemset(tip_count_d, 0, sizeof(int)));
+  CK(cudaMalloc(&tip_vector_d, sizeof(vec5dyn) * (size_t)TIPVECSIZE));
+  CK(cudaMemset(tip_vector_d, 0, sizeof(vec5dyn) * (size_t)TIPVECSIZE));
+  REAL integrals[12];
+  REAL3 c = {0, 0, 0}, phi = {0, 0, 0};
+  param.reduceSym = true; param.reduceSymStart = true; param.count = 0; param.physicalTime = 0.0;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  for (int it = 0; it < nsteps; it++) {
+    reactionDiffusion_wrapper(pitch, grid2D, block2D, gateOut_d, gateIn_d, J_d, velTan, param.reduceSym, solid_d,
+                              false, stim_d, false, param.point);
+    tip_wrapper(pitch, grid2D, block2D, gateIn_d, gateOut_d, velTan, param.physicalTime, param.tipAlgorithm,
+                param.recordTip, tip_plot, tip_count_d, tip_vector_d);
+    if (c_phi_h) { REAL *o = c_phi_h + 6 * it; o[0] = c.x; o[1] = c.y; o[2] = c.t; o[3] = phi.x; o[4] = phi.y; o[5] = phi.t; }
+    slice_wrapper(pitch, grid2D, block2D, gateIn_d, sl, sl0, param.reduceSym, param.reduceSymStart, advect, 2,
+                  area_d, tip_count_d, tip_vector_d, param.count);
+    if (param.count == 0) {
+      trapz_wrapper(grid1D, block1D, sl, sl0, velTan, integrals, coeff_d, tip_count_d, tip_vector_d, param.count);
+      c = solve_matrix(c, phi, integrals);
+      Cxy_field_wrapper(pitch, grid2D, block2D, advect, c, phi, solid_d);
+      slice_wrapper(pitch, grid2D, block2D, gateIn_d, sl, sl0, param.reduceSym, param.reduceSymStart, advect, 2,
+                    area_d, tip_count_d, tip_vector_d, param.count);
+    }
+    trapz_wrapper(grid1D, block1D, sl, sl0, velTan, integrals, coeff_d, tip_count_d, tip_vector_d, param.count);
+    c = solve_matrix(c, phi, integrals);
+    Cxy_field_wrapper(pitch, grid2D, block2D, advect, c, phi, solid_d);
+    advFDBFECC_wrapper(pitch, grid2D, block2D, gateIn_d, gateOut_d, advect, uf, ub, ue, solid_d);
+    phi.x = phi.x + c.x * param.dt; phi.y = phi.y + c.y * param.dt; phi.t = phi.t + c.t * param.dt;
+    param.count++;
+    param.physicalTime = param.dt * (REAL)param.count;
+  }
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaGetLastError();
+  if (copy_back) {
+    CK(cudaMemcpy(u_h, gateIn_d.u, n * sizeof(REAL), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(v_h, gateIn_d.v, n * sizeof(REAL), cudaMemcpyDeviceToHost));
+  }
+  REAL *all[] = {gateIn_d.u, gateIn_d.v, gateOut_d.u, gateOut_d.v, J_d.u, J_d.v, velTan.u, velTan.v, uf.u, uf.v,
+                 ub.u, ub.v, ue.u, ue.v, advect.x, advect.y, stim_d, coeff_d};
+  for (REAL *q : all) cudaFree(q);
+  for (int k = 0; k < 12; k++) cudaFree(*sp[k]);
+  cudaFree(solid_d); cudaFree(tip_plot); cudaFree(area_d); cudaFree(tip_count_d); cudaFree(tip_vector_d);
+  param.reduceSym = false; param.reduceSymStart = false;
+  return g_err ? -1.f : ms;
+}
+
+// contourMode == 1 loop for ONE sheet (main.cu:879-885, 1035, 1040): RD with the paced disc
+// stimulus, swap, sAPD_wrapper(count, gateIn.u, gateOut.u, ..., stimulate = true), and (mode 1)
+// the per-step singleCell_wrapper.  apd_h: APD1 then APD2 (2*n doubles).
+float yref_apd_run(double *u_h, double *v_h, int nsteps, int period_it, int duration_it,
+                   const uint8_t *stimArea_h, double *apd_h, int mode) {
+  g_err = 0;
+  const size_t n = (size_t)param.nx * param.ny;
+  stateVar gin, gout, J, vt;
+  gin.u = dalloc(n, u_h); gin.v = dalloc(n, v_h); gout.u = dalloc(n, nullptr); gout.v = dalloc(n, nullptr);
+  J.u = dalloc(n, nullptr); J.v = dalloc(n, nullptr); vt.u = dalloc(n, nullptr); vt.v = dalloc(n, nullptr);
+  REAL *st[6]; for (int k = 0; k < 6; k++) st[k] = dalloc(n, nullptr);
+  bool *first_d = balloc(n, nullptr), *area_d = balloc(n, stimArea_h), *solid_d = balloc(n, nullptr);
+  REAL *stim_d = dalloc(n, nullptr), *pt_d = dalloc(2, nullptr);
+  REAL pt_h[2];
+  int count = 0;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  for (int s = 0; s < nsteps; s++) {
+    const bool on = period_it > 0 && (count % period_it) <= duration_it;
+    reactionDiffusion_wrapper(pitch, grid2D, block2D, gout, gin, J, vt, false, solid_d, false, stim_d, on, param.point);
+    swapSoA(&gin, &gout);
+    count++;
+    sAPD_wrapper(pitch, grid1D, block1D, count, gin.u, gout.u, st[0], st[1], st[2], st[3], st[4], st[5], first_d,
+                 area_d, true);
+    if (mode == 1) singleCell_wrapper(pitch, grid0D, block0D, gout, 2, pt_h, pt_d, param.point);
+  }
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  CK(cudaMemcpy(u_h, gin.u, n * sizeof(REAL), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(v_h, gin.v, n * sizeof(REAL), cudaMemcpyDeviceToHost));
+  if (apd_h) {
+    CK(cudaMemcpy(apd_h, st[0], n * sizeof(REAL), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(apd_h + n, st[1], n * sizeof(REAL), cudaMemcpyDeviceToHost));
+  }
+  REAL *all[] = {gin.u, gin.v, gout.u, gout.v, J.u, J.v, vt.u, vt.v, stim_d, pt_d};
+  for (REAL *q : all) cudaFree(q);
+  for (int k = 0; k < 6; k++) cudaFree(st[k]);
+  cudaFree(first_d); cudaFree(area_d); cudaFree(solid_d);
+  return g_err ? -1.f : ms;
+}
+
 }  // extern "C"

@@ -172,6 +172,8 @@ class Reference:
             raise FileNotFoundError(path)
         self.l = C.CDLL(path)
         self.l.yref_rd_run.restype = C.c_float
+        self.l.yref_sr_run.restype = C.c_float
+        self.l.yref_apd_run.restype = C.c_float
         self.p = None
 
     def init(self, p):
@@ -190,6 +192,22 @@ class Reference:
                                 mode, int(copy_back))
         assert ms >= 0, "reference harness failed"
         return (u, v, vtu, vtv, ms) if velTan else (u, v, ms)
+
+    def sr_run(self, u, v, nsteps):
+        """display() symmetry-reduction loop with the reference's own wrappers; -> u, v, c_phi, ms"""
+        u, v = _np(u).copy(), _np(v).copy()
+        rec = np.zeros((nsteps, 6))
+        ms = self.l.yref_sr_run(_p(u), _p(v), nsteps, _p(rec), 1)
+        assert ms >= 0
+        return u, v, rec, ms
+
+    def apd_run(self, u, v, nsteps, period_it, duration_it, stimArea, mode=0):
+        u, v = _np(u).copy(), _np(v).copy()
+        sa = _np(stimArea, np.uint8)
+        apd = np.zeros(2 * u.size)
+        ms = self.l.yref_apd_run(_p(u), _p(v), nsteps, period_it, duration_it, _p(sa), _p(apd), mode)
+        assert ms >= 0
+        return u, v, apd[:u.size].copy(), apd[u.size:].copy(), ms
 
     def tip(self, u_present, u_past, t=0.0, algorithm=1, capacity=65536):
         a, b = _np(u_present), _np(u_past)

@@ -325,3 +325,41 @@ def test_symmetry_reduction_step_loop(oracle, yh):
     assert tip_steps > 0, "the test fields should produce tips so the tip-centred disc is exercised"
     assert np.array_equal(gu[0], u) and np.array_equal(gv[0], v)
     assert np.array_equal(gc, c) and np.array_equal(gphi, phi)
+
+
+def test_apd_loop_batched_matches_oracle_and_reference(oracle, yh):
+    """C5 protocol (scaled down): paced sheets, sAPD every step with the reference's argument order
+    (main.cu:1035).  Batched driver == oracle composition == the reference's own loop, bitwise."""
+    nx = ny = 96
+    p = oracle.params_default(nx, ny, timeIntOrder=1, lap4=0, eps=0.2, beta=3.0)   # short action potentials
+    area = synth.stim_area_square(nx, ny)
+    periods = np.array([400, 260], dtype=np.int32)
+    nsteps, dur = 700, 10
+    sim = yh.Sim(p, n_sims=2)
+    sim.set_state(np.zeros((2, ny, nx)), np.zeros((2, ny, nx)))
+    sim.set_pacing(periods, dur)
+    sim.run_apd(nsteps, stim_area=area)
+    gu, gv = sim.get_state()
+    a1, a2 = sim.get_apd()
+    sim.close()
+    for z, per in enumerate(periods):
+        u, v = np.zeros((ny, nx)), np.zeros((ny, nx))
+        st = {k: np.zeros(nx * ny) for k in ("APD1", "APD2", "sAPD", "dAPD", "back", "front")}
+        first = np.zeros(nx * ny, dtype=np.uint8)
+        import ctypes as C
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        for s in range(nsteps):
+            un, vn = oracle.rd_step(p, u, v, stim_mouse=bool((s % per) <= dur))
+            # (uold, unew) := (gateIn = new, gateOut = old) after the swap, count = s + 1
+            rc = oracle.l.yho_sapd(C.byref(p), s + 1, vp(un), vp(u), vp(st["APD1"]), vp(st["APD2"]), vp(st["sAPD"]),
+                                   vp(st["dAPD"]), vp(st["back"]), vp(st["front"]), vp(first), vp(area.reshape(-1)), 1)
+            assert rc == 0
+            u, v = un, vn
+        assert np.array_equal(gu[z], u) and np.array_equal(gv[z], v), z
+        assert np.array_equal(a1[z].ravel(), st["APD1"]) and np.array_equal(a2[z].ravel(), st["APD2"]), z
+        if oracle_lib.have_reference():
+            ref = oracle_lib.Reference(nofma=True)
+            ref.init(p)
+            ru, rv, r1, r2, _ = ref.apd_run(np.zeros((ny, nx)), np.zeros((ny, nx)), nsteps, int(per), dur, area)
+            assert np.array_equal(ru, u) and np.array_equal(r1, st["APD1"]) and np.array_equal(r2, st["APD2"]), z
+    assert np.abs(a1).max() > 0, "an action potential should have completed so APD1 is exercised"

@@ -84,6 +84,8 @@ SIGNATURES = {
     "yh_sim_run_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
     "yh_sim_tips": (_i, [_vp, _vp, _i, C.POINTER(_i)]),
     "yh_sim_run_sr": (_i, [_vp, _i, _vp]),
+    "yh_sim_run_apd": (_i, [_vp, _i, _vp]),
+    "yh_sim_get_apd": (_i, [_vp, _vp, _vp]),
     "yh_sim_sr_state": (_i, [_vp, C.POINTER(_d), C.POINTER(_d), _i]),
     "yh_sim_count": (_i, [_vp]),
     "yh_sim_device_u": (_vp, [_vp]),

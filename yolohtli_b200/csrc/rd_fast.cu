@@ -17,6 +17,7 @@
 // 117); x + 0.0 only changes -0.0 into +0.0.  Rows are stored canonicalised (+0.0) in the
 // rings, which is exact for tc > 0 ("zero signs").
 #include <stdlib.h>
+#include <string.h>
 
 #include "yh_common.cuh"
 
@@ -29,7 +30,36 @@ struct FastArgs {
   long long sim_stride;   // elements between stacked independent sheets (blockIdx.z)
   const int *period;      // per-sheet pacing period in steps (NULL: k.stim decides)
   int duration, count0;   // stimulus on while (step % period) <= duration; step of level 1
+  YhApd apd;              // fused APD bookkeeping (STIM variants only); apd.APD1 == NULL: off
 };
+
+// The APD state machine of one cell (spaceAPD.cu:296-342), entered only when the step crossed
+// the 0.15 threshold there: without a crossing neither front nor back changes, so none of the
+// branches can fire and sAPD / dAPD keep their values (they must have been initialised by one
+// full yh_sapd pass).  Argument roles as the reference calls it after the swap (main.cu:1035):
+// "uold" := the NEW state, "unew" := the OLD state.
+__device__ __noinline__ void apd_event(const YhK &k, const YhApd &A, size_t c, double uo, double un, int count) {
+  const double apdTh = 0.15;
+  const bool sc = A.stimulate ? A.stimArea[c] != 0 : true;
+  double fr = A.front[c], bk = A.back[c];
+  if ((un > apdTh) && (uo < apdTh) && sc) fr = k.dt * (count - (un - apdTh) / (un - uo));
+  if ((un < apdTh) && (uo > apdTh) && sc) bk = k.dt * (count - (un - apdTh) / (un - uo));
+  bool first = A.first[c] != 0;
+  double apd1 = A.APD1[c], apd2 = A.APD2[c];
+  if ((bk > 0.0) && (fr > 0.0) && (first == false) && sc) { apd1 = bk - fr; A.APD1[c] = apd1; fr = 0.0; bk = 0.0; first = true; }
+  if ((bk > 0.0) && (fr > 0.0) && first && sc) { apd2 = bk - fr; A.APD2[c] = apd2; fr = 0.0; bk = 0.0; first = false; }
+  A.front[c] = fr; A.back[c] = bk; A.first[c] = first ? 1 : 0;
+  if (A.stimulate) {
+    double s = (apd1 - apd2 > 0.0) && sc ? 1.0 : -1.0;
+    s *= (double)sc;
+    A.sAPD[c] = s;
+    double d = apd2;
+    d *= (double)sc;
+    A.dAPD[c] = d;
+  } else {
+    A.sAPD[c] = (apd1 - apd2 > 0.0) ? 1.0 : -1.0;
+  }
+}
 
 __device__ __forceinline__ void cp_async16(unsigned smem, const void *gmem, bool valid) {
   int sz = valid ? 16 : 0;   // src-size 0 => 16 bytes of zero fill, nothing read
@@ -186,6 +216,16 @@ rd_euler_stream(const __grid_constant__ YhK k, const __grid_constant__ FastArgs 
       double2 uo, vo;
       euler_cell<TC1>(k, uC.x, vC.x, uw, uC.y, uN.x, uS.x, vw, vC.y, vN.x, vS.x, s0, uo.x, vo.x);
       euler_cell<TC1>(k, uC.y, vC.y, uC.x, ue, uN.y, uS.y, vC.x, ve, vN.y, vS.y, s1, uo.y, vo.y);
+      if (STIM && a.apd.APD1 && out_col && m >= y0 && m < y0 + RYe) {   // fused sAPD epilogue (owner cells)
+        const double th = 0.15;
+        const bool e0 = ((uC.x > th) && (uo.x < th)) || ((uC.x < th) && (uo.x > th));
+        const bool e1 = ((uC.y > th) && (uo.y < th)) || ((uC.y < th) && (uo.y > th));
+        if (e0 || e1) {
+          const size_t cidx = zoff + (size_t)m * nx + gx;
+          if (e0) apd_event(k, a.apd, cidx, uo.x, uC.x, a.count0 + lev);
+          if (e1) apd_event(k, a.apd, cidx + 1, uo.y, uC.y, a.count0 + lev);
+        }
+      }
       if (lev < T) {
         double *d = dst_ring + ((m - c0) & (NRL - 1)) * ROW;
         *reinterpret_cast<double2 *>(d) = uo;
@@ -263,7 +303,7 @@ int launch3(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
 
 template <int T, int W, bool CANON, bool TC1>
 int launch2(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
-  const bool stim = k.stim != 0 || a.period != nullptr;
+  const bool stim = k.stim != 0 || a.period != nullptr || a.apd.APD1 != nullptr;
   return stim ? launch3<T, W, CANON, TC1, true>(k, a, nsims, st)
               : launch3<T, W, CANON, TC1, false>(k, a, nsims, st);
 }
@@ -289,9 +329,10 @@ int yh_rd_fast_supported(const YhK &k, int tb) {
 int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const double *v_in,
                             double *u_out, double *v_out, int nsims, long long sim_stride,
                             const int *period_d, int duration_it, int count0, int canon_in,
-                            cudaStream_t st) {
+                            cudaStream_t st, const YhApd *apd) {
   if (!yh_rd_fast_supported(k, tb)) return YH_ERR_UNSUPPORTED;
-  FastArgs a{u_in, v_in, u_out, v_out, 0, sim_stride, period_d, duration_it, count0};
+  FastArgs a{u_in, v_in, u_out, v_out, 0, sim_stride, period_d, duration_it, count0, {}};
+  if (apd) a.apd = *apd; else memset(&a.apd, 0, sizeof(a.apd));
   const int rows = k.row1 - k.row0;
   if (rows <= 0) return YH_OK;
   const char *force_w = getenv("YH_FAST_W");   // tuning hook

@@ -27,6 +27,9 @@ struct yh_sim {
   int raw_input;         // current state came from the host and may hold -0.0
   double *vt[2], *adv[2];   // velTan and advection field (symmetry reduction), lazily allocated
   double c[3], phi[3];   // drift velocities and frame phase (main.cu:60-61)
+  double *apd[6];        // APD1 APD2 sAPD dAPD back front, n_sims sheets each (lazily allocated)
+  uint8_t *apd_first, *stim_area;
+  int apd_init;          // sAPD / dAPD hold values for every cell (one full pass done)
   cudaStream_t st;
 };
 
@@ -66,6 +69,9 @@ int yh_sim_create(yh_sim **out, const yh_params *p, int n_sims, int device) {
   s->period_d = nullptr; s->duration_it = 0; s->count = 0; s->have_prev = 0; s->raw_input = 1;
   s->px = p->nx / 2; s->py = p->ny / 2;   // param.point, saveFiles.cu:180
   s->vt[0] = s->vt[1] = s->adv[0] = s->adv[1] = nullptr;
+  for (int q = 0; q < 6; q++) s->apd[q] = nullptr;
+  s->apd_first = s->stim_area = nullptr;
+  s->apd_init = 0;
   for (int q = 0; q < 3; q++) { s->c[q] = 0.0; s->phi[q] = 0.0; }
   const size_t bytes = s->n * n_sims * sizeof(double);
   for (int b = 0; b < 2; b++) {
@@ -90,6 +96,8 @@ int yh_sim_destroy(yh_sim *s) {
   cudaFree(s->solid); cudaFree(s->trace_d); cudaFree(s->tip_count_d); cudaFree(s->tip_vec_d);
   cudaFree(s->period_d);
   cudaFree(s->vt[0]); cudaFree(s->vt[1]); cudaFree(s->adv[0]); cudaFree(s->adv[1]);
+  for (int q = 0; q < 6; q++) cudaFree(s->apd[q]);
+  cudaFree(s->apd_first); cudaFree(s->stim_area);
   cudaStreamDestroy(s->st);
   delete s;
   return YH_OK;
@@ -162,8 +170,14 @@ int yh_sim_set_pacing(yh_sim *s, const int *period_it, int duration_it) {
   return YH_OK;
 }
 
+static int sim_run_impl(yh_sim *s, int nsteps, int tb_steps, double *trace_h, bool sync);
+
 // nsteps x { reactionDiffusion ; swap ; probe }  (main.cu:869-885, 1040)
 int yh_sim_run(yh_sim *s, int nsteps, int tb_steps, double *trace_h) {
+  return sim_run_impl(s, nsteps, tb_steps, trace_h, true);
+}
+
+static int sim_run_impl(yh_sim *s, int nsteps, int tb_steps, double *trace_h, bool sync) {
   YH_REQUIRE(s && nsteps >= 0, "bad arguments");
   YH_REQUIRE(tb_steps >= 0 && tb_steps <= 4 && tb_steps != 3, "tb_steps must be 0 (auto), 1, 2 or 4");
   DevGuard g(s->device);
@@ -224,7 +238,7 @@ int yh_sim_run(yh_sim *s, int nsteps, int tb_steps, double *trace_h) {
     YH_CUDA(cudaMemcpyAsync(trace_h, s->trace_d, sizeof(double) * 2 * nsteps * s->n_sims,
                             cudaMemcpyDeviceToHost, s->st));
   }
-  YH_CUDA(cudaStreamSynchronize(s->st));
+  if (sync) YH_CUDA(cudaStreamSynchronize(s->st));
   return YH_OK;
 }
 
@@ -322,6 +336,67 @@ int yh_sim_run_sr(yh_sim *s, int nsteps, double *c_phi_h) {
     s->raw_input = 0;
   }
   YH_CUDA(cudaStreamSynchronize(s->st));
+  return YH_OK;
+}
+
+// contourMode == 1: RD, swap, sAPD every step (main.cu:879-885, 1035), whole batch per launch.
+int yh_sim_run_apd(yh_sim *s, int nsteps, const uint8_t *stim_area_h) {
+  YH_REQUIRE(s && nsteps >= 0, "bad arguments");
+  DevGuard g(s->device);
+  const size_t cells = s->n * s->n_sims;
+  if (!s->apd[0]) {
+    for (int q = 0; q < 6; q++) {
+      YH_CUDA(cudaMalloc(&s->apd[q], cells * sizeof(double)));
+      YH_CUDA(cudaMemsetAsync(s->apd[q], 0, cells * sizeof(double), s->st));
+    }
+    YH_CUDA(cudaMalloc(&s->apd_first, cells));
+    YH_CUDA(cudaMemsetAsync(s->apd_first, 0, cells, s->st));
+    YH_CUDA(cudaMalloc(&s->stim_area, cells));
+  }
+  if (stim_area_h)   // the same mask for every sheet
+    for (int z = 0; z < s->n_sims; z++)
+      YH_CUDA(cudaMemcpyAsync(s->stim_area + s->n * z, stim_area_h, s->n, cudaMemcpyHostToDevice, s->st));
+  yh_params pb = s->p;   // the whole batch as one tall array for the element-wise APD kernel
+  pb.ny = s->p.ny * s->n_sims; pb.ny_global = pb.ny;
+  YhK k = yh_make_k(&s->p);
+  k.px = s->px; k.py = s->py;
+  const bool fused_ok = yh_rd_fast_supported(k, 1) != 0;
+  YhApd A{s->apd[0], s->apd[1], s->apd[2], s->apd[3], s->apd[4], s->apd[5], s->apd_first,
+          stim_area_h ? s->stim_area : nullptr, stim_area_h != nullptr};
+  int left = nsteps;
+  while (left > 0) {
+    if (!s->apd_init || !fused_ok) {
+      // full pass: every cell's sAPD / dAPD written, as sAPD_wrapper does every step (main.cu:1035:
+      // sAPD_wrapper(..., param.count, gateIn_d.u, gateOut_d.u, ...) AFTER the swap)
+      int rc = sim_run_impl(s, 1, 1, nullptr, false);
+      if (rc != YH_OK) return rc;
+      rc = yh_sapd(&pb, s->count, s->u[s->cur], s->u[s->cur ^ 1], s->apd[0], s->apd[1], s->apd[2], s->apd[3],
+                   s->apd[4], s->apd[5], s->apd_first, A.stimArea, A.stimulate, s->st);
+      if (rc != YH_OK) return rc;
+      s->apd_init = 1;
+      left -= 1;
+      continue;
+    }
+    // fused: the state machine runs in the epilogue of the RD kernel, only where u crossed 0.15
+    int T = 4;
+    while (T > left) T >>= 1;
+    const int c = s->cur, o = c ^ 1;
+    int rc = yh_launch_rd_fast_paced(k, T, s->u[c], s->v[c], s->u[o], s->v[o], s->n_sims, (long long)s->n,
+                                     s->period_d, s->duration_it, s->count, s->raw_input, s->st, &A);
+    if (rc != YH_OK) return rc;
+    s->cur = o; s->raw_input = 0; s->have_prev = (T == 1); s->count += T; left -= T;
+  }
+  YH_CUDA(cudaStreamSynchronize(s->st));
+  return YH_OK;
+}
+
+int yh_sim_get_apd(yh_sim *s, double *apd1_h, double *apd2_h) {
+  YH_REQUIRE(s && apd1_h && apd2_h, "null pointer");
+  if (!s->apd[0]) { yh_set_error("yh_sim_get_apd: yh_sim_run_apd was never called"); return YH_ERR_UNSUPPORTED; }
+  DevGuard g(s->device);
+  const size_t bytes = s->n * s->n_sims * sizeof(double);
+  YH_CUDA(cudaMemcpy(apd1_h, s->apd[0], bytes, cudaMemcpyDeviceToHost));
+  YH_CUDA(cudaMemcpy(apd2_h, s->apd[1], bytes, cudaMemcpyDeviceToHost));
   return YH_OK;
 }
 

@@ -93,6 +93,15 @@ __device__ __forceinline__ bool yh_scs_on(const YhK &k, int i, int j) {
   return ((ic - cx) * (ic - cx) + (jc - cy) * (jc - cy)) < 400;
 }
 
+// APD bookkeeping state (sAPD_kernel, spaceAPD.cu:278-374) for the fused epilogue of the fast
+// kernel; all pointers NULL = off.  Arrays span the whole batch (sheet z at offset z*stride).
+struct YhApd {
+  double *APD1, *APD2, *sAPD, *dAPD, *back, *front;
+  uint8_t *first;
+  const uint8_t *stimArea;
+  int stimulate;
+};
+
 // ---- kernel launchers (one per .cu) ------------------------------------------------------
 int yh_launch_rd_generic(const YhK &k, const double *u_in, const double *v_in, double *u_out,
                          double *v_out, double *vtu, double *vtv, const uint8_t *solid,
@@ -108,7 +117,7 @@ int yh_launch_rd_fast(const YhK &k, int tb, const double *u_in, const double *v_
 int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const double *v_in,
                             double *u_out, double *v_out, int nsims, long long sim_stride,
                             const int *period_d, int duration_it, int count0, int canon_in,
-                            cudaStream_t st);
+                            cudaStream_t st, const YhApd *apd = nullptr);
 
 // Fused Runge-Kutta (RK2/RK4, optional 4th-order Laplacian) step, one launch per time step.
 int yh_rd_rk_supported(const YhK &k);

@@ -238,6 +238,21 @@ class Sim:
         check(lib().yh_sim_run_sr(self._h, nsteps, out.ctypes.data_as(C.c_void_p) if record else None))
         return out
 
+    def run_apd(self, nsteps, stim_area=None):
+        """contourMode == 1 loop: RD + sAPD every step (main.cu:1035) for every sheet."""
+        ptr = None
+        if stim_area is not None:
+            sa = np.ascontiguousarray(stim_area, dtype=np.uint8)
+            assert sa.size == self.p.nx * self.p.ny
+            ptr = sa.ctypes.data_as(C.c_void_p)
+        check(lib().yh_sim_run_apd(self._h, nsteps, ptr))
+
+    def get_apd(self):
+        a = np.empty(self.shape, dtype=np.float64)
+        b = np.empty(self.shape, dtype=np.float64)
+        check(lib().yh_sim_get_apd(self._h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))
+        return a, b
+
     def sr_state(self):
         c, phi = (C.c_double * 3)(), (C.c_double * 3)()
         check(lib().yh_sim_sr_state(self._h, c, phi, 0))
