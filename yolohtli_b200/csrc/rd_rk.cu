@@ -54,8 +54,24 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// Ionic currents (reactionDiffusion.cu:131-141).  DEF = the reference's default constants
+// mu = delta = 1, gamma = theta = 0: 1.0*x == x and x - 0.0 == x exactly, so those operations
+// are dropped without changing a bit.
+template <bool DEF>
+__device__ __forceinline__ double rk_Isum(const YhK &k, double u, double v, bool scs) {
+  const double mu_u = DEF ? u : k.mu * u;
+  const double I = -(mu_u * (1.0 - u) * (u - k.alpha) - u * v);
+  return scs ? I - 24.7 : I;   // x - 0.0 == x
+}
+template <bool DEF>
+__device__ __forceinline__ double rk_Iv(const YhK &k, double u, double v) {
+  const double ug = DEF ? u : k.delta * (u - k.gamma);
+  const double yv = ug * (k.beta - u) - v;
+  return -(k.eps * (DEF ? yv : yv - k.theta));
+}
+
 // K stages, strip of W columns.  Arrays of one ring row: U V Ju Jv ru rv (6 x PITCH doubles).
-template <int K, int W, bool LAP4, bool SOLID>
+template <int K, int W, bool LAP4, bool SOLID, bool DEF>
 __global__ void __launch_bounds__((K + 1) * (W / 2) + 32)
 rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
   constexpr int H = (K + 1) & ~1;        // halo columns each side (even: 16-byte alignment)
@@ -77,7 +93,7 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
   const int RYe = min(a.RY, k.row1 - y0);
   const int c0 = y0 - K;
   const int dom_lo = -k.jg0, dom_hi = k.nyg - k.jg0;
-  const int n_it = RYe + 3 * K + 1;
+  const int n_it = ((RYe + 3 * K + 1 + 2) / 3) * 3;   // multiple of the unroll factor
 
   if (tid >= NTC) {   // ---------------- loader warp ----------------
     const int lane = tid - NTC;
@@ -154,162 +170,192 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
   const double mrs2 = -k.rscale * 2.0;             // -rscale*2.0  (then *q4, :235)
   const double rsq = k.rscale * q4;                // rscale*( qx4+qy4 ) (:239)
 
-  for (int it = 0; it < n_it; it++) {
-    const int m = it + c0 - m_shift;
-    if (m >= lo_g && m < hi_g) {
-      const int slot = (m - c0) & (NRA - 1);
-      const int gj = m + k.jg0;
-      if (g == 0) {
-        // ---- P: stage-0 state u0 + (0.0*0.0) and its currents ----
-        const double *r0 = R0 + ((m - c0) & (NR0 - 1)) * ROW0 + cc;
-        double2 u = *reinterpret_cast<const double2 *>(r0);
-        double2 v = *reinterpret_cast<const double2 *>(r0 + PITCH);
-        u.x += 0.0; u.y += 0.0; v.x += 0.0; v.y += 0.0;
-        double2 ju, jv;
-        ju.x = yh_Isum(k, u.x, v.x, yh_scs(k, gx, gj));
-        ju.y = yh_Isum(k, u.y, v.y, yh_scs(k, gx + 1, gj));
-        jv.x = yh_Iv(k, u.x, v.x);
-        jv.y = yh_Iv(k, u.y, v.y);
-        double *d = A + slot * ROWA + cc;
-        *reinterpret_cast<double2 *>(d) = u;
-        *reinterpret_cast<double2 *>(d + PITCH) = v;
-        *reinterpret_cast<double2 *>(d + 2 * PITCH) = ju;
-        *reinterpret_cast<double2 *>(d + 3 * PITCH) = jv;
-        if (SOLID) {
-          const int ny = k.nyg;
-          const uint8_t *mc = a.solid + (size_t)m * nx;
-          const uint8_t *mS = a.solid + (size_t)(yh_mir(gj - 1, ny) - k.jg0) * nx;   // S = j-1 (:149)
-          const uint8_t *mN = a.solid + (size_t)(yh_mir(gj + 1, ny) - k.jg0) * nx;   // N = j+1 (:150)
-          const bool c0m = mc[gx] != 0, c1m = mc[gx + 1] != 0;
-          const bool w0 = mc[yh_mir(gx - 1, nx)] != 0, e1 = mc[yh_mir(gx + 2, nx)] != 0;
-          const unsigned code0 = solid_code(c0m, w0, c1m, mN[gx] != 0, mS[gx] != 0);
-          const unsigned code1 = solid_code(c1m, c0m, e1, mN[gx + 1] != 0, mS[gx + 1] != 0);
-          *reinterpret_cast<unsigned *>(Cr + ((m - c0) & (NR0 - 1)) * W + c) = code0 | (code1 << 16);
-        }
-      } else {
-        // ---- S_st: du of stage st for the pair (c, c+1) of row m ----
-        const double *Ak = A + st * NRA * ROWA;
-        const int ms = (m - 1 < dom_lo) ? m + 1 : m - 1;
-        const int mn = (m + 1 >= dom_hi) ? m - 1 : m + 1;
-        const double *rc = Ak + slot * ROWA + cc;
-        const double *rs = Ak + ((ms - c0) & (NRA - 1)) * ROWA + cc;
-        const double *rn = Ak + ((mn - c0) & (NRA - 1)) * ROWA + cc;
-        double du[2], dv[2];
-        unsigned codes = 0;
-        if (SOLID) codes = *reinterpret_cast<const unsigned *>(Cr + ((m - c0) & (NR0 - 1)) * W + c);
+  // Source rows m-1, m, m+1 of this group's stage live in registers and rotate by renaming (loop
+  // unrolled by three): per iteration only the new N row is read from shared memory -- the
+  // kernel was LSU-wavefront bound when it re-read all three rows (ncu: 83 % of the LSU data pipe).
+  struct RowRegs { double2 u, v, ju, jv; double uw, ue, vw, ve; };
+  const double *Ak = A + (st > 0 ? st : 0) * NRA * ROWA + cc;
+
+  auto load_row = [&](int row, RowRegs &R) {
+    const double *p = Ak + ((row - c0) & (NRA - 1)) * ROWA;
+    R.u = *reinterpret_cast<const double2 *>(p);
+    R.v = *reinterpret_cast<const double2 *>(p + PITCH);
+    R.uw = p[-1]; R.ue = p[2]; R.vw = p[PITCH - 1]; R.ve = p[PITCH + 2];
+    if (left_edge) { R.uw = R.u.y; R.vw = R.v.y; }      // mirror: W of x=0 is x=1
+    if (right_edge) { R.ue = R.u.x; R.ve = R.v.x; }     // mirror: E of x=nx-1 is x=nx-2
+    if (LAP4) {
+      R.ju = *reinterpret_cast<const double2 *>(p + 2 * PITCH);
+      R.jv = *reinterpret_cast<const double2 *>(p + 3 * PITCH);
+    }
+  };
+
+  auto p_step = [&](int m) {   // ---- P: stage-0 state u0 + (0.0*0.0) and its currents ----
+    const int gj = m + k.jg0;
+    const double *r0 = R0 + ((m - c0) & (NR0 - 1)) * ROW0 + cc;
+    double2 u = *reinterpret_cast<const double2 *>(r0);
+    double2 v = *reinterpret_cast<const double2 *>(r0 + PITCH);
+    u.x += 0.0; u.y += 0.0; v.x += 0.0; v.y += 0.0;
+    double2 ju, jv;
+    ju.x = rk_Isum<DEF>(k, u.x, v.x, yh_scs(k, gx, gj));
+    ju.y = rk_Isum<DEF>(k, u.y, v.y, yh_scs(k, gx + 1, gj));
+    jv.x = rk_Iv<DEF>(k, u.x, v.x);
+    jv.y = rk_Iv<DEF>(k, u.y, v.y);
+    double *d = A + ((m - c0) & (NRA - 1)) * ROWA + cc;
+    *reinterpret_cast<double2 *>(d) = u;
+    *reinterpret_cast<double2 *>(d + PITCH) = v;
+    *reinterpret_cast<double2 *>(d + 2 * PITCH) = ju;
+    *reinterpret_cast<double2 *>(d + 3 * PITCH) = jv;
+    if (SOLID) {
+      const int ny = k.nyg;
+      const uint8_t *mc = a.solid + (size_t)m * nx;
+      const uint8_t *mS = a.solid + (size_t)(yh_mir(gj - 1, ny) - k.jg0) * nx;   // S = j-1 (:149)
+      const uint8_t *mN = a.solid + (size_t)(yh_mir(gj + 1, ny) - k.jg0) * nx;   // N = j+1 (:150)
+      const bool c0m = mc[gx] != 0, c1m = mc[gx + 1] != 0;
+      const bool w0 = mc[yh_mir(gx - 1, nx)] != 0, e1 = mc[yh_mir(gx + 2, nx)] != 0;
+      const unsigned code0 = solid_code(c0m, w0, c1m, mN[gx] != 0, mS[gx] != 0);
+      const unsigned code1 = solid_code(c1m, c0m, e1, mN[gx + 1] != 0, mS[gx + 1] != 0);
+      *reinterpret_cast<unsigned *>(Cr + ((m - c0) & (NR0 - 1)) * W + c) = code0 | (code1 << 16);
+    }
+  };
+
+  // ---- S_st: du of stage st for the pair (c, c+1) of row m from rows S (m-1), C (m), N (m+1) ----
+  auto s_step = [&](int m, RowRegs &S, RowRegs &C, RowRegs &N) {
+    const int slot = (m - c0) & (NRA - 1);
+    const int gj = m + k.jg0;
+    if (m == lo_g) {                      // first row of this group: nothing in registers yet
+      load_row(m, C);
+      load_row((m - 1 < dom_lo) ? m + 1 : m - 1, S);     // no-flux mirror at the first row
+    }
+    load_row((m + 1 >= dom_hi) ? m - 1 : m + 1, N);      // ... and at the last row
+    const double *pc = Ak + slot * ROWA;
+    unsigned codes = 0;
+    if (SOLID) codes = *reinterpret_cast<const unsigned *>(Cr + ((m - c0) & (NR0 - 1)) * W + c);
+    double du[2], dv[2];
 #pragma unroll
-        for (int f = 0; f < 2; f++) {   // f = 0: u with Ju, f = 1: v with Jv
-          const double *pc = rc + f * PITCH, *ps = rs + f * PITCH, *pn = rn + f * PITCH;
-          const double2 C = *reinterpret_cast<const double2 *>(pc);
-          const double2 S = *reinterpret_cast<const double2 *>(ps);
-          const double2 N = *reinterpret_cast<const double2 *>(pn);
-          double Wv = pc[-1], Ev = pc[2];
-          if (left_edge) Wv = C.y;
-          if (right_edge) Ev = C.x;
-          double d0, d1;
-          if (SOLID) {   // reactionDiffusion.cu:171-180
-            const unsigned k0 = codes & 0xFFFFu, k1 = codes >> 16;
-            if (f == 0) {
-              d0 = ((coef(k0, 0) * Wv - coef(k0, 2) * C.x + coef(k0, 4) * C.y) * k.rx +
-                    (coef(k0, 6) * N.x - coef(k0, 8) * C.x + coef(k0, 10) * S.x) * k.ry);
-              d1 = ((coef(k1, 0) * C.x - coef(k1, 2) * C.y + coef(k1, 4) * Ev) * k.rx +
-                    (coef(k1, 6) * N.y - coef(k1, 8) * C.y + coef(k1, 10) * S.y) * k.ry);
-            } else if (k.gateDiff) {
-              d0 = ((coef(k0, 0) * Wv - coef(k0, 2) * C.x + coef(k0, 4) * C.y) * k.rx * k.rscale +
-                    (coef(k0, 6) * N.x - coef(k0, 8) * C.x + coef(k0, 10) * S.x) * k.ry * k.rscale);
-              d1 = ((coef(k1, 0) * C.x - coef(k1, 2) * C.y + coef(k1, 4) * Ev) * k.rx * k.rscale +
-                    (coef(k1, 6) * N.y - coef(k1, 8) * C.y + coef(k1, 10) * S.y) * k.ry * k.rscale);
-            } else {
-              d0 = 0.0; d1 = 0.0;
-            }
-          } else if (f == 0) {
-            d0 = ((Wv - 2.0 * C.x + C.y) * k.rx + (N.x - 2.0 * C.x + S.x) * k.ry);
-            d1 = ((C.x - 2.0 * C.y + Ev) * k.rx + (N.y - 2.0 * C.y + S.y) * k.ry);
-          } else if (k.gateDiff) {
-            d0 = ((Wv - 2.0 * C.x + C.y) * k.rx * k.rscale + (N.x - 2.0 * C.x + S.x) * k.ry * k.rscale);
-            d1 = ((C.x - 2.0 * C.y + Ev) * k.rx * k.rscale + (N.y - 2.0 * C.y + S.y) * k.ry * k.rscale);
-          } else {
-            d0 = 0.0; d1 = 0.0;
-          }
-          const double2 Jc = *reinterpret_cast<const double2 *>(pc + 2 * PITCH);
-          if (LAP4 && (f == 0 || k.gateDiff)) {
-            double SWv = ps[-1], SEv = ps[2], NWv = pn[-1], NEv = pn[2];
-            if (left_edge) { SWv = S.y; NWv = N.y; }
-            if (right_edge) { SEv = S.x; NEv = N.x; }
-            const double2 Js = *reinterpret_cast<const double2 *>(ps + 2 * PITCH);
-            const double2 Jn = *reinterpret_cast<const double2 *>(pn + 2 * PITCH);
-            double JW = pc[2 * PITCH - 1], JE = pc[2 * PITCH + 2];
-            if (left_edge) JW = Jc.y;
-            if (right_edge) JE = Jc.x;
-            if (f == 0) {   // reactionDiffusion.cu:221-229
-              d0 += m2q * (+(Wv - C.x + C.y) + (N.x - C.x + S.x));
-              d1 += m2q * (+(C.x - C.y + Ev) + (N.y - C.y + S.y));
-              d0 += q4 * (SWv + S.y + NWv + N.y);
-              d1 += q4 * (S.x + SEv + N.x + NEv);
-            } else {        // :235-239
-              d0 += mrs2 * q4 * (+(Wv - C.x + C.y) + (N.x - C.x + S.x));
-              d1 += mrs2 * q4 * (+(C.x - C.y + Ev) + (N.y - C.y + S.y));
-              d0 += rsq * (SWv + S.y + NWv + N.y);
-              d1 += rsq * (S.x + SEv + N.x + NEv);
-            }
-            d0 -= ((JW - 2.0 * Jc.x + Jc.y) * k.fx4 + (Jn.x - 2.0 * Jc.x + Js.x) * k.fy4);
-            d1 -= ((Jc.x - 2.0 * Jc.y + JE) * k.fx4 + (Jn.y - 2.0 * Jc.y + Js.y) * k.fy4);
-          }
-          d0 -= k.dt * Jc.x;   // :498-499
-          d1 -= k.dt * Jc.y;
-          if (f == 0) { du[0] = d0; du[1] = d1; }
-          else { dv[0] = d0; dv[1] = d1; }
+    for (int f = 0; f < 2; f++) {   // f = 0: u with Ju, f = 1: v with Jv
+      const double2 Cc = f ? C.v : C.u, Ss = f ? S.v : S.u, Nn = f ? N.v : N.u;
+      const double Wv = f ? C.vw : C.uw, Ev = f ? C.ve : C.ue;
+      double d0, d1;
+      if (SOLID) {   // reactionDiffusion.cu:171-180
+        const unsigned k0 = codes & 0xFFFFu, k1 = codes >> 16;
+        if (f == 0) {
+          d0 = ((coef(k0, 0) * Wv - coef(k0, 2) * Cc.x + coef(k0, 4) * Cc.y) * k.rx +
+                (coef(k0, 6) * Nn.x - coef(k0, 8) * Cc.x + coef(k0, 10) * Ss.x) * k.ry);
+          d1 = ((coef(k1, 0) * Cc.x - coef(k1, 2) * Cc.y + coef(k1, 4) * Ev) * k.rx +
+                (coef(k1, 6) * Nn.y - coef(k1, 8) * Cc.y + coef(k1, 10) * Ss.y) * k.ry);
+        } else if (k.gateDiff) {
+          d0 = ((coef(k0, 0) * Wv - coef(k0, 2) * Cc.x + coef(k0, 4) * Cc.y) * k.rx * k.rscale +
+                (coef(k0, 6) * Nn.x - coef(k0, 8) * Cc.x + coef(k0, 10) * Ss.x) * k.ry * k.rscale);
+          d1 = ((coef(k1, 0) * Cc.x - coef(k1, 2) * Cc.y + coef(k1, 4) * Ev) * k.rx * k.rscale +
+                (coef(k1, 6) * Nn.y - coef(k1, 8) * Cc.y + coef(k1, 10) * Ss.y) * k.ry * k.rscale);
+        } else {
+          d0 = 0.0; d1 = 0.0;
         }
-        // running rhs (:502-503)
-        double2 ru = make_double2(0.0, 0.0), rv = ru;
-        if (st > 0) {
-          ru = *reinterpret_cast<const double2 *>(rc + 4 * PITCH);
-          rv = *reinterpret_cast<const double2 *>(rc + 5 * PITCH);
+      } else if (f == 0) {
+        // 2.0*C is exact, so fma(-2.0, C, w) == w - 2.0*C bit for bit
+        d0 = ((fma(-2.0, Cc.x, Wv) + Cc.y) * k.rx + (fma(-2.0, Cc.x, Nn.x) + Ss.x) * k.ry);
+        d1 = ((fma(-2.0, Cc.y, Cc.x) + Ev) * k.rx + (fma(-2.0, Cc.y, Nn.y) + Ss.y) * k.ry);
+      } else if (k.gateDiff) {
+        d0 = ((fma(-2.0, Cc.x, Wv) + Cc.y) * k.rx * k.rscale + (fma(-2.0, Cc.x, Nn.x) + Ss.x) * k.ry * k.rscale);
+        d1 = ((fma(-2.0, Cc.y, Cc.x) + Ev) * k.rx * k.rscale + (fma(-2.0, Cc.y, Nn.y) + Ss.y) * k.ry * k.rscale);
+      } else {
+        d0 = 0.0; d1 = 0.0;
+      }
+      double2 Jc;
+      if (LAP4) Jc = f ? C.jv : C.ju;
+      else Jc = *reinterpret_cast<const double2 *>(pc + (2 + f) * PITCH);
+      if (LAP4 && (f == 0 || k.gateDiff)) {
+        const double SWv = f ? S.vw : S.uw, SEv = f ? S.ve : S.ue;
+        const double NWv = f ? N.vw : N.uw, NEv = f ? N.ve : N.ue;
+        const double2 Js = f ? S.jv : S.ju, Jn = f ? N.jv : N.ju;
+        double JW = pc[(2 + f) * PITCH - 1], JE = pc[(2 + f) * PITCH + 2];
+        if (left_edge) JW = Jc.y;
+        if (right_edge) JE = Jc.x;
+        if (f == 0) {   // reactionDiffusion.cu:221-229
+          d0 += m2q * (+(Wv - Cc.x + Cc.y) + (Nn.x - Cc.x + Ss.x));
+          d1 += m2q * (+(Cc.x - Cc.y + Ev) + (Nn.y - Cc.y + Ss.y));
+          d0 += q4 * (SWv + Ss.y + NWv + Nn.y);
+          d1 += q4 * (Ss.x + SEv + Nn.x + NEv);
+        } else {        // :235-239
+          d0 += mrs2 * q4 * (+(Wv - Cc.x + Cc.y) + (Nn.x - Cc.x + Ss.x));
+          d1 += mrs2 * q4 * (+(Cc.x - Cc.y + Ev) + (Nn.y - Cc.y + Ss.y));
+          d0 += rsq * (SWv + Ss.y + NWv + Nn.y);
+          d1 += rsq * (Ss.x + SEv + Nn.x + NEv);
         }
-        ru.x += (w_k * du[0]); ru.y += (w_k * du[1]);
-        rv.x += (w_k * dv[0]); rv.y += (w_k * dv[1]);
-        const double *r0 = R0 + ((m - c0) & (NR0 - 1)) * ROW0 + cc;
-        const double2 u0 = *reinterpret_cast<const double2 *>(r0);
-        const double2 v0 = *reinterpret_cast<const double2 *>(r0 + PITCH);
-        if (st < K - 1) {
-          // stage st+1 state (:117-118), its currents, and the rhs travel to the next group
-          double2 un, vn, ju, jv;
-          un.x = u0.x + (a_next * du[0]); un.y = u0.y + (a_next * du[1]);
-          vn.x = v0.x + (a_next * dv[0]); vn.y = v0.y + (a_next * dv[1]);
-          ju.x = yh_Isum(k, un.x, vn.x, yh_scs(k, gx, gj));
-          ju.y = yh_Isum(k, un.y, vn.y, yh_scs(k, gx + 1, gj));
-          jv.x = yh_Iv(k, un.x, vn.x);
-          jv.y = yh_Iv(k, un.y, vn.y);
-          double *d = A + (st + 1) * NRA * ROWA + slot * ROWA + cc;
-          *reinterpret_cast<double2 *>(d) = un;
-          *reinterpret_cast<double2 *>(d + PITCH) = vn;
-          *reinterpret_cast<double2 *>(d + 2 * PITCH) = ju;
-          *reinterpret_cast<double2 *>(d + 3 * PITCH) = jv;
-          *reinterpret_cast<double2 *>(d + 4 * PITCH) = ru;
-          *reinterpret_cast<double2 *>(d + 5 * PITCH) = rv;
-        } else if (out_col) {
-          double2 uo, vo;   // :512-513
-          uo.x = u0.x + k.tc * ru.x; uo.y = u0.y + k.tc * ru.y;
-          vo.x = v0.x + k.tc * rv.x; vo.y = v0.y + k.tc * rv.y;
-          const bool sc0 = !SOLID || ((codes >> 12) & 1u), sc1 = !SOLID || ((codes >> 28) & 1u);
-          if (SOLID) {   // :521-522 masked cells are exactly 0.0
-            uo.x = sc0 ? uo.x : 0.0; uo.y = sc1 ? uo.y : 0.0;
-            vo.x = sc0 ? vo.x : 0.0; vo.y = sc1 ? vo.y : 0.0;
-          }
-          const size_t o = (size_t)m * nx + gx;
-          *reinterpret_cast<double2 *>(a.u_out + o) = uo;
-          *reinterpret_cast<double2 *>(a.v_out + o) = vo;
-          if (a.vtu && k.gateDiff) {   // :551-552
-            double2 tu, tv;
-            tu.x = sc0 ? ru.x / k.dt : 0.0; tu.y = sc1 ? ru.y / k.dt : 0.0;   // :529-530
-            tv.x = sc0 ? rv.x / k.dt : 0.0; tv.y = sc1 ? rv.y / k.dt : 0.0;
-            *reinterpret_cast<double2 *>(a.vtu + o) = tu;
-            *reinterpret_cast<double2 *>(a.vtv + o) = tv;
-          }
-        }
+        d0 -= ((fma(-2.0, Jc.x, JW) + Jc.y) * k.fx4 + (fma(-2.0, Jc.x, Jn.x) + Js.x) * k.fy4);
+        d1 -= ((fma(-2.0, Jc.y, Jc.x) + JE) * k.fx4 + (fma(-2.0, Jc.y, Jn.y) + Js.y) * k.fy4);
+      }
+      d0 -= k.dt * Jc.x;   // :498-499
+      d1 -= k.dt * Jc.y;
+      if (f == 0) { du[0] = d0; du[1] = d1; }
+      else { dv[0] = d0; dv[1] = d1; }
+    }
+    // running rhs (:502-503)
+    double2 ru = make_double2(0.0, 0.0), rv = ru;
+    if (st > 0) {
+      ru = *reinterpret_cast<const double2 *>(pc + 4 * PITCH);
+      rv = *reinterpret_cast<const double2 *>(pc + 5 * PITCH);
+    }
+    ru.x += (w_k * du[0]); ru.y += (w_k * du[1]);
+    rv.x += (w_k * dv[0]); rv.y += (w_k * dv[1]);
+    const double *r0 = R0 + ((m - c0) & (NR0 - 1)) * ROW0 + cc;
+    const double2 u0 = *reinterpret_cast<const double2 *>(r0);
+    const double2 v0 = *reinterpret_cast<const double2 *>(r0 + PITCH);
+    if (st < K - 1) {
+      // stage st+1 state (:117-118), its currents, and the rhs travel to the next group
+      double2 un, vn, ju, jv;
+      un.x = u0.x + (a_next * du[0]); un.y = u0.y + (a_next * du[1]);
+      vn.x = v0.x + (a_next * dv[0]); vn.y = v0.y + (a_next * dv[1]);
+      ju.x = rk_Isum<DEF>(k, un.x, vn.x, yh_scs(k, gx, gj));
+      ju.y = rk_Isum<DEF>(k, un.y, vn.y, yh_scs(k, gx + 1, gj));
+      jv.x = rk_Iv<DEF>(k, un.x, vn.x);
+      jv.y = rk_Iv<DEF>(k, un.y, vn.y);
+      double *d = A + (st + 1) * NRA * ROWA + slot * ROWA + cc;
+      *reinterpret_cast<double2 *>(d) = un;
+      *reinterpret_cast<double2 *>(d + PITCH) = vn;
+      *reinterpret_cast<double2 *>(d + 2 * PITCH) = ju;
+      *reinterpret_cast<double2 *>(d + 3 * PITCH) = jv;
+      *reinterpret_cast<double2 *>(d + 4 * PITCH) = ru;
+      *reinterpret_cast<double2 *>(d + 5 * PITCH) = rv;
+    } else if (out_col) {
+      double2 uo, vo;   // :512-513
+      uo.x = u0.x + k.tc * ru.x; uo.y = u0.y + k.tc * ru.y;
+      vo.x = v0.x + k.tc * rv.x; vo.y = v0.y + k.tc * rv.y;
+      const bool sc0 = !SOLID || ((codes >> 12) & 1u), sc1 = !SOLID || ((codes >> 28) & 1u);
+      if (SOLID) {   // :521-522 masked cells are exactly 0.0
+        uo.x = sc0 ? uo.x : 0.0; uo.y = sc1 ? uo.y : 0.0;
+        vo.x = sc0 ? vo.x : 0.0; vo.y = sc1 ? vo.y : 0.0;
+      }
+      const size_t o = (size_t)m * nx + gx;
+      *reinterpret_cast<double2 *>(a.u_out + o) = uo;
+      *reinterpret_cast<double2 *>(a.v_out + o) = vo;
+      if (a.vtu && k.gateDiff) {   // :551-552
+        double2 tu, tv;
+        tu.x = sc0 ? ru.x / k.dt : 0.0; tu.y = sc1 ? ru.y / k.dt : 0.0;   // :529-530
+        tv.x = sc0 ? rv.x / k.dt : 0.0; tv.y = sc1 ? rv.y / k.dt : 0.0;
+        *reinterpret_cast<double2 *>(a.vtu + o) = tu;
+        *reinterpret_cast<double2 *>(a.vtv + o) = tv;
       }
     }
+  };
+
+  auto sub = [&](int it, RowRegs &S, RowRegs &C, RowRegs &N) {
+    const int m = it + c0 - m_shift;
+    if (m >= lo_g && m < hi_g) {
+      if (g == 0) p_step(m);
+      else s_step(m, S, C, N);
+    }
     __syncthreads();
+  };
+
+  RowRegs RA, RB, RC;
+  RA.u = RA.v = RA.ju = RA.jv = make_double2(0, 0);
+  RA.uw = RA.ue = RA.vw = RA.ve = 0.0;
+  RB = RA; RC = RA;
+  for (int it = 0; it < n_it; it += 3) {
+    sub(it, RA, RB, RC);
+    sub(it + 1, RB, RC, RA);
+    sub(it + 2, RC, RA, RB);
   }
 }
 
@@ -330,8 +376,8 @@ static int pick_ry_rk(int rows, int strips, int K, int slots) {
   return best_ry;
 }
 
-template <int K, int W, bool LAP4, bool SOLID>
-int launch(const YhK &k, RkArgs a, cudaStream_t st) {
+template <int K, int W, bool LAP4, bool SOLID, bool DEF>
+int launch2(const YhK &k, RkArgs a, cudaStream_t st) {
   constexpr int PITCH = W + 4, BX = W - 2 * ((K + 1) & ~1);
   constexpr int NT = (K + 1) * (W / 2) + 32;
   const size_t smem = ((size_t)16 * 2 * PITCH + (size_t)K * 4 * 6 * PITCH) * sizeof(double) +
@@ -341,9 +387,9 @@ int launch(const YhK &k, RkArgs a, cudaStream_t st) {
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    YH_CUDA(cudaFuncSetAttribute(rd_rk_stream<K, W, LAP4, SOLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    YH_CUDA(cudaFuncSetAttribute(rd_rk_stream<K, W, LAP4, SOLID, DEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1, sms = 148;
-    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_rk_stream<K, W, LAP4, SOLID>, NT, smem));
+    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_rk_stream<K, W, LAP4, SOLID, DEF>, NT, smem));
     YH_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     slots[dev & 63] = (per_sm > 0 ? per_sm : 1) * sms;
     attr_set[dev & 63] = true;
@@ -353,9 +399,15 @@ int launch(const YhK &k, RkArgs a, cudaStream_t st) {
   const char *force_ry = getenv("YH_RK_RY");
   a.RY = force_ry ? atoi(force_ry) : pick_ry_rk(rows, strips, K, slots[dev & 63]);
   dim3 grd(strips, (rows + a.RY - 1) / a.RY);
-  rd_rk_stream<K, W, LAP4, SOLID><<<grd, NT, smem, st>>>(k, a);
+  rd_rk_stream<K, W, LAP4, SOLID, DEF><<<grd, NT, smem, st>>>(k, a);
   YH_LAUNCH_CHECK();
   return YH_OK;
+}
+
+template <int K, int W, bool LAP4, bool SOLID>
+int launch(const YhK &k, RkArgs a, cudaStream_t st) {
+  const bool def = (k.mu == 1.0) && (k.delta == 1.0) && (k.gamma == 0.0) && (k.theta == 0.0);
+  return def ? launch2<K, W, LAP4, SOLID, true>(k, a, st) : launch2<K, W, LAP4, SOLID, false>(k, a, st);
 }
 
 }  // namespace
