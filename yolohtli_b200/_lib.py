@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libyolohtli_b200.so")
+LIB_PATH = os.environ.get("YH_LIB_PATH") or os.path.join(HERE, "lib", "libyolohtli_b200.so")   # override: experiments only
 SHIM_PATH = os.path.join(HERE, "lib", "libyolohtli_shim.so")
 
 
