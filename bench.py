@@ -171,7 +171,7 @@ def run_ours(a):
     p = make_params(yh, a)
     T = a.tb
     halo = T if a.mode == "euler5" else 4
-    run = SlabRunner(p, rank=rank, world=world, halo=halo, device=dev)
+    run = SlabRunner(p, rank=rank, world=world, halo=halo, device=dev, transport=a.transport)
     lay = run.lay
     u0, v0 = synth.fibrillation_ic(a.nx, a.ny, rows=(lay.g0, lay.g1))
     run.u[run.cur].copy_(torch.as_tensor(u0))
@@ -261,7 +261,7 @@ def run_ours(a):
                             f"model, standard PDE mode, {a.mode}, row-slab sharded over {world} GPU(s); "
                             f"{a.substeps} time steps per bench step, {T} time steps per HBM pass",
                 "mode": a.mode, "nx": a.nx, "ny": a.ny, "substeps": a.substeps, "tb_steps": T,
-                "parallelism": f"slab{world}", "halo_rows": halo,
+                "parallelism": f"slab{world}", "halo_rows": halo, "halo_transport": run.transport,
                 "l2": "inputs (>= 1 GiB per array per GPU) are larger than the 126 MB L2; no flush needed",
                 "arithmetic": "FP64, no FMA contraction (bit-identical to the plain-C oracle)",
                 "checksum_u": checksum,
@@ -284,6 +284,7 @@ def run_ours(a):
         if cb:
             out["cpu_baseline"] = cb
         print(json.dumps(out), flush=True)
+    run.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -300,6 +301,7 @@ def main():
     ap.add_argument("--tb", type=int, default=4, help="time steps per HBM pass (1, 2, 4)")
     ap.add_argument("--substeps", type=int, default=64, help="time steps per bench step")
     ap.add_argument("--e2e-substeps", type=int, default=1024, help="time steps per host->device->host call")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="halo exchange: NVLink peer stores (CUDA IPC) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup

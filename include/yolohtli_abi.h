@@ -238,6 +238,17 @@ int yh_sim_count(const yh_sim *s);             /* param.count */
 void *yh_sim_device_u(yh_sim *s);              /* current device pointers (for tests)     */
 void *yh_sim_device_v(yh_sim *s);
 
+/* ---- multi-GPU: flags for the NVLink peer-to-peer halo exchange (new) -----------
+ * yh_flag_set releases `value` into a flag word that may live in a PEER's memory (CUDA-IPC
+ * mapping), stream-ordered after the ghost-row copies; yh_flag_wait blocks the stream until the
+ * local flag reaches `value` (*status_local = 1 on a ~4 s timeout instead of hanging). */
+int yh_flag_set(int *flag_peer, int value, void *stream);
+int yh_flag_wait(int *flag_local, int value, int *status_local, void *stream);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault): dst may be a peer (CUDA-IPC) mapping. */
+int yh_memcpy_async(void *dst, const void *src, size_t bytes, void *stream);
+/* cudaDeviceEnablePeerAccess(peer_device) from the current device (already-enabled is not an error). */
+int yh_enable_peer_access(int peer_device);
+
 #ifdef __cplusplus
 }
 #endif

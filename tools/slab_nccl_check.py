@@ -19,7 +19,8 @@ dist.init_process_group("nccl", device_id=dev)
 nx, ny, nsteps = 2048, 1536, 40
 p = yh.default_params(nx, ny, scale_L=True, timeIntOrder=1, lap4=0)
 u0, v0 = synth.fibrillation_ic(nx, ny)
-run = SlabRunner(p, rank=rank, world=world, halo=4, device=dev)
+transport = os.environ.get("YH_TRANSPORT", "nccl")
+run = SlabRunner(p, rank=rank, world=world, halo=4, device=dev, transport=transport)
 run.load_global(u0, v0)
 run.advance(nsteps, tb=4)
 u, v = run.owned()
@@ -35,7 +36,9 @@ if rank == 0:
     ru, rv = host.rd_advance(p, nsteps, uA, vA, uB, vB, tb_steps=4)
     torch.cuda.synchronize()
     ok = torch.equal(gu, ru) and torch.equal(gv, rv)
-    print(f"slab_nccl_check world={world}: {'BITWISE OK' if ok else 'MISMATCH'} "
+    print(f"slab check transport={transport} world={world}: {'BITWISE OK' if ok else 'MISMATCH'} "
           f"(max |du| = {(gu - ru).abs().max().item():.3e})", flush=True)
     assert ok
+assert run.p2p_status() == 0, 'p2p flag wait timed out'
+run.close()
 dist.destroy_process_group()

@@ -87,6 +87,10 @@ SIGNATURES = {
     "yh_sim_run_apd": (_i, [_vp, _i, _vp]),
     "yh_sim_get_apd": (_i, [_vp, _vp, _vp]),
     "yh_sim_sr_state": (_i, [_vp, C.POINTER(_d), C.POINTER(_d), _i]),
+    "yh_flag_set": (_i, [_vp, _i, _vp]),
+    "yh_flag_wait": (_i, [_vp, _i, _vp, _vp]),
+    "yh_memcpy_async": (_i, [_vp, _vp, C.c_size_t, _vp]),
+    "yh_enable_peer_access": (_i, [_i]),
     "yh_sim_count": (_i, [_vp]),
     "yh_sim_device_u": (_vp, [_vp]),
     "yh_sim_device_v": (_vp, [_vp]),

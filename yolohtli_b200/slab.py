@@ -54,7 +54,7 @@ class SlabLayout:
 
 
 class SlabRunner:
-    def __init__(self, p_global, rank=None, world=None, halo=4, device=None, stepper=None):
+    def __init__(self, p_global, rank=None, world=None, halo=4, device=None, stepper=None, transport="nccl"):
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self.lay = SlabLayout(p_global.ny, self.world, self.rank, halo)
@@ -71,6 +71,10 @@ class SlabRunner:
         self.count = 0
         self.comm_stream = (torch.cuda.Stream(device=self.device, priority=-1)
                             if self.device.type == "cuda" else None)
+        self.transport = transport if (self.world > 1 and self.device.type == "cuda") else "nccl"
+        self.seq = 0
+        if self.transport == "p2p":
+            self._setup_p2p()
 
     # -- state ---------------------------------------------------------------------------
     def load_global(self, u_glob, v_glob):
@@ -101,7 +105,90 @@ class SlabRunner:
                     dist.P2POp(dist.irecv, v[l.own_hi:l.own_hi + H], l.down)]
         return ops
 
+    # -- NVLink peer-to-peer transport ------------------------------------------------------
+    # Every rank exports its four state arrays and a flag word through CUDA IPC (torch's own
+    # reduce_tensor machinery); a rank WRITES its fresh edge rows straight into the neighbours'
+    # ghost rows (cudaMemcpyAsync through the peer mapping = NVLink stores), then releases a
+    # sequence number into the neighbour's flag; the neighbour's stream acquires it
+    # (yh_flag_wait) before reading the ghosts.  Write-after-read safety follows from the same
+    # chain: a rank cannot reach exchange k before it consumed its neighbour's exchange k-1,
+    # which the neighbour issued after it had finished reading the ghosts that k overwrites.
+    def _setup_p2p(self):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.flags = torch.zeros(8, dtype=torch.int32, device=self.device)   # [0] from up, [1] from down, [4] status
+        mine = {}
+        for name, t in (("u0", self.u[0]), ("u1", self.u[1]), ("v0", self.v[0]), ("v1", self.v[1]),
+                        ("flags", self.flags)):
+            fn, args = reduce_tensor(t)
+            mine[name] = (fn, args)
+        mine["device"] = self.device.index
+        torch.cuda.synchronize(self.device)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine)
+        self.peer = {}
+        from ._lib import lib
+        for nb in (self.lay.up, self.lay.down):
+            if nb is None:
+                continue
+            # the IPC mapping is opened in a context of the exporter's device; kernels and copies of
+            # THIS device reach it over NVLink once peer access is enabled
+            with torch.cuda.device(self.device):
+                host.check(lib().yh_enable_peer_access(int(everyone[nb]["device"])))
+            d = {}
+            for name, val in everyone[nb].items():
+                if name == "device":
+                    continue
+                fn, args = val
+                args = list(args)
+                args[6] = self.device.index  # open the handle with THIS device current: the mapping is
+                d[name] = fn(*args)          # then peer-accessible from our kernels (lazy peer access)
+            self.peer[nb] = d
+        self._peer_lay = {nb: SlabLayout(self.lay.ny_global, self.world, nb, self.halo) for nb in self.peer}
+        dist.barrier()
+
+    def _exchange_p2p(self):
+        from ._lib import lib
+        l, H = self.lay, self.halo
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        self.seq += 1
+        row_bytes = self.nx * 8
+        cur = self.cur
+        for nb, my_rows, flag_idx_at_peer in ((l.up, (l.own_lo, l.own_lo + H), 1), (l.down, (l.own_hi - H, l.own_hi), 0)):
+            if nb is None:
+                continue
+            pl = self._peer_lay[nb]
+            # my first H owned rows are the peer's lower ghosts (rows own_hi..own_hi+H there); my last H
+            # owned rows are the peer's upper ghosts (rows own_lo-H..own_lo there)
+            dst_row = pl.own_hi if nb == l.up else pl.own_lo - H
+            for f in ("u", "v"):
+                src = (self.u if f == "u" else self.v)[cur]
+                dst = self.peer[nb][f + str(cur)]
+                host.check(lib().yh_memcpy_async(C.c_void_p(dst.data_ptr() + dst_row * row_bytes),
+                                                 C.c_void_p(src.data_ptr() + my_rows[0] * row_bytes),
+                                                 H * row_bytes, st))
+            host.check(lib().yh_flag_set(C.c_void_p(self.peer[nb]["flags"].data_ptr() + 4 * flag_idx_at_peer),
+                                         self.seq, st))
+        for nb, idx in ((l.up, 0), (l.down, 1)):
+            if nb is not None:
+                host.check(lib().yh_flag_wait(C.c_void_p(self.flags.data_ptr() + 4 * idx), self.seq,
+                                              C.c_void_p(self.flags.data_ptr() + 16), st))
+
+    def p2p_status(self):
+        return int(self.flags[4].item()) if self.transport == "p2p" else 0
+
+    def close(self):
+        if self.transport == "p2p" and getattr(self, "peer", None):
+            import gc
+            torch.cuda.synchronize(self.device)
+            dist.barrier()
+            self.peer = {}            # drop the IPC mappings before the exporters exit
+            gc.collect()
+            torch.cuda.ipc_collect()
+            dist.barrier()
+
     def exchange(self):
+        if self.transport == "p2p":
+            return self._exchange_p2p()
         ops = self._ops()
         if not ops:
             return
