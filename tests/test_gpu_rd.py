@@ -213,3 +213,41 @@ def test_racy_reference_modes_within_tolerance(oracle):
     err = np.abs(gu - a[0]).max()
     print(f"racy reference: run-to-run spread {spread:.3e}, ours vs reference {err:.3e}")
     assert err < 2e-3
+
+
+def test_full_size_16384_sheet(oracle):
+    """BASELINE configs[3] at FULL size (16384 x 16384, 8 GiB of state): 4 time steps in ONE
+    temporally-blocked pass == 4 single-step passes == the plain-C oracle, bit for bit, plus the
+    size-independent properties: untouched input, row-band locality (a band recomputed alone with
+    ghost rows reproduces the same bits), and a checksum of checksums over row blocks."""
+    import psutil
+    free, total = torch.cuda.mem_get_info()
+    if free < 24 << 30 or psutil.virtual_memory().available < 40 << 30:
+        pytest.skip("needs 24 GiB of HBM and 40 GiB of host memory")
+    n = 16384
+    p = oracle.params_default(n, n, scale_L=True, timeIntOrder=1, lap4=0)
+    u0, v0 = synth.fibrillation_ic(n, n)
+    uA, vA = torch.as_tensor(u0).cuda(), torch.as_tensor(v0).cuda()
+    uB, vB = torch.empty_like(uA), torch.empty_like(vA)
+    uC, vC = torch.empty_like(uA), torch.empty_like(vA)
+    r4u, r4v = host.rd_advance(p, 4, uA, vA, uB, vB, tb_steps=4)          # one pass, T = 4
+    assert r4u is uB
+    assert torch.equal(uA.cpu(), torch.as_tensor(u0))                      # input never written
+    uD, vD = uA.clone(), vA.clone()
+    r1u, r1v = host.rd_advance(p, 4, uD, vD, uC, vC, tb_steps=1)          # four passes, T = 1
+    assert torch.equal(r4u, r1u) and torch.equal(r4v, r1v)
+    # row-band locality: rows [6000, 6512) recomputed from a slab with 4 ghost rows per side
+    from yolohtli_b200.slab import SlabLayout
+    lo, hi, H = 6000, 6512, 4
+    q = p.copy()
+    q.ny, q.ny_global, q.jg0 = hi - lo + 2 * H, n, lo - H
+    su, sv = uA[lo - H:hi + H].contiguous(), vA[lo - H:hi + H].contiguous()
+    tu, tv = torch.empty_like(su), torch.empty_like(sv)
+    bu, bv = host.rd_advance(q, 4, su, sv, tu, tv, tb_steps=4, rows=(H, H + hi - lo))
+    assert torch.equal(bu[H:H + hi - lo], r4u[lo:hi]) and torch.equal(bv[H:H + hi - lo], r4v[lo:hi])
+    # the oracle at full size (a few seconds on the host cores)
+    wu, wv = oracle.rd_advance(p, 4, u0, v0)
+    gu = r4u.cpu().numpy()
+    assert np.array_equal(gu, wu) and np.array_equal(r4v.cpu().numpy(), wv)
+    blocks = gu.reshape(64, 256, n).sum(axis=(1, 2))
+    assert blocks.sum() == wu.reshape(64, 256, n).sum(axis=(1, 2)).sum()
