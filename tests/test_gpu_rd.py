@@ -15,6 +15,16 @@ from tests import oracle_lib  # noqa: E402
 from yolohtli_b200 import host, synth  # noqa: E402
 
 
+@pytest.fixture(params=["stream", "tile"], autouse=True)
+def rd_path(request):
+    """Every test of this module runs twice: forced through the streaming kernels (rd_fast.cu /
+    rd_rk.cu) and forced through the shared-memory tile kernels (rd_tile.cu) where they apply."""
+    import os
+    os.environ["YH_RD_PATH"] = request.param
+    yield request.param
+    os.environ.pop("YH_RD_PATH", None)
+
+
 def dev(a, dtype=torch.float64):
     return torch.as_tensor(np.ascontiguousarray(a)).to("cuda", dtype=dtype).contiguous()
 
@@ -215,12 +225,14 @@ def test_racy_reference_modes_within_tolerance(oracle):
     assert err < 2e-3
 
 
-def test_full_size_16384_sheet(oracle):
+def test_full_size_16384_sheet(oracle, rd_path):
     """BASELINE configs[3] at FULL size (16384 x 16384, 8 GiB of state): 4 time steps in ONE
     temporally-blocked pass == 4 single-step passes == the plain-C oracle, bit for bit, plus the
     size-independent properties: untouched input, row-band locality (a band recomputed alone with
     ghost rows reproduces the same bits), and a checksum of checksums over row blocks."""
     import psutil
+    if rd_path == "tile":
+        pytest.skip("full size is the streaming kernels' regime")
     free, total = torch.cuda.mem_get_info()
     if free < 24 << 30 or psutil.virtual_memory().available < 40 << 30:
         pytest.skip("needs 24 GiB of HBM and 40 GiB of host memory")

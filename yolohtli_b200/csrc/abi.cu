@@ -151,9 +151,14 @@ int yh_rd_step(const yh_params *p, const double *u_in, const double *v_in, doubl
   YhK k = yh_make_k(p);
   k.stim = stim_mouse != 0; k.px = point_x; k.py = point_y; k.row0 = row0; k.row1 = row1;
   cudaStream_t st = (cudaStream_t)stream;
-  // single steps that need no velTan take the streaming kernel (T = 1)
-  if (!(velTan_u && k.gateDiff) && yh_rd_fast_supported(k, 1))
+  const bool tile = yh_rd_prefer_tile((long long)k.nx * (row1 - row0)) != 0;   // small sheets
+  // single steps that need no velTan take the Euler kernels (T = 1)
+  if (!(velTan_u && k.gateDiff) && yh_rd_fast_supported(k, 1)) {
+    if (tile) return yh_launch_rd_tile_euler(k, 1, u_in, v_in, u_out, v_out, 1, 0, nullptr, 0, 0, st);
     return yh_launch_rd_fast(k, 1, u_in, v_in, u_out, v_out, solid, 1, st);
+  }
+  if (tile && yh_rd_tile_rk_supported(k))
+    return yh_launch_rd_tile_rk(k, u_in, v_in, u_out, v_out, velTan_u, velTan_v, st);
   if (yh_rd_rk_supported(k)) return yh_launch_rd_rk(k, u_in, v_in, u_out, v_out, velTan_u, velTan_v, solid, st);
   return yh_launch_rd_generic(k, u_in, v_in, u_out, v_out, velTan_u, velTan_v, solid, st);
 }
@@ -187,7 +192,12 @@ int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, int flags, doubl
     k.row1 = row1 + ext < dom_hi ? row1 + ext : dom_hi;
     if (k.row0 < 0) k.row0 = 0;
     if (k.row1 > p->ny) k.row1 = p->ny;
-    if (yh_rd_fast_supported(k, T)) { rc = yh_launch_rd_fast(k, T, cu, cv, nu, nv, solid, canon, st); canon = 0; }
+    const bool tile = yh_rd_prefer_tile((long long)k.nx * (k.row1 - k.row0)) != 0;
+    if (yh_rd_fast_supported(k, T)) {
+      if (tile) rc = yh_launch_rd_tile_euler(k, T, cu, cv, nu, nv, 1, 0, nullptr, 0, 0, st);
+      else rc = yh_launch_rd_fast(k, T, cu, cv, nu, nv, solid, canon, st);
+      canon = 0;
+    } else if (tile && yh_rd_tile_rk_supported(k)) rc = yh_launch_rd_tile_rk(k, cu, cv, nu, nv, nullptr, nullptr, st);
     else if (yh_rd_rk_supported(k)) rc = yh_launch_rd_rk(k, cu, cv, nu, nv, nullptr, nullptr, solid, st);
     else rc = yh_launch_rd_generic(k, cu, cv, nu, nv, nullptr, nullptr, solid, st);
     if (rc != YH_OK) return rc;

@@ -1,0 +1,401 @@
+// rd_tile.cu -- the monodomain step for SMALL sheets (the reference's own default case is a
+// single 512 x 512 sheet, saveFiles.cu:137-138): the streaming kernels of rd_fast.cu / rd_rk.cu
+// need hundreds of rows per CTA to amortise their pipeline fill, and a 512^2 sheet cannot give
+// 148 SMs that many.  Here a CTA owns a 32 x 32 output tile plus halo entirely in shared memory
+// and performs either T Euler steps or the K synchronous Runge-Kutta stages of ONE step with a
+// __syncthreads between them; latency per launch is a handful of stage times instead of
+// (rows + fill) pipeline iterations.  Same arithmetic, same bits as the streaming kernels.
+//
+//   rd_tile_rk<K,LAP4>   RK2 / RK4 (+4th-order Laplacian), no-flux, square domain
+//                        reactionDiffusion.cu:71-93,115-247,498-561
+//   rd_tile_euler<T>     T Euler + 5-point steps per launch (temporal blocking in the tile)
+//
+// Threads own PAIRS of cells (16-byte shared-memory accesses); the mapping cell -> (thread, slot)
+// is fixed for the whole launch so du / rhs of a cell stay in registers across stages.
+#include <stdlib.h>
+
+#include "yh_common.cuh"
+
+namespace {
+
+constexpr int TB = 32;          // output tile edge
+constexpr int NTHR = 256;
+
+template <bool DEF>
+__device__ __forceinline__ double t_Isum(const YhK &k, double u, double v, bool scs) {
+  const double mu_u = DEF ? u : k.mu * u;
+  const double I = -(mu_u * (1.0 - u) * (u - k.alpha) - u * v);
+  return scs ? I - 24.7 : I;   // x - 0.0 == x
+}
+template <bool DEF>
+__device__ __forceinline__ double t_Iv(const YhK &k, double u, double v) {
+  const double ug = DEF ? u : k.delta * (u - k.gamma);
+  const double yv = ug * (k.beta - u) - v;
+  return -(k.eps * (DEF ? yv : yv - k.theta));
+}
+
+// A pair (tx, tx+1) is computed at a level whose valid region is the tile minus `ring` outer
+// rings when AT LEAST ONE of its cells is inside that region: with odd rings the region's x
+// bounds are odd and the boundary cell shares its pair with an invalid one.
+__device__ __forceinline__ bool pair_in_ring(int tx, int ty, int ring, int TW) {
+  return tx + 1 >= ring && tx < TW - ring && ty >= ring && ty < TW - ring;
+}
+
+struct TileArgs {
+  const double *u_in, *v_in;
+  double *u_out, *v_out, *vtu, *vtv;
+  long long sim_stride;
+  const int *period;
+  int duration, count0;
+};
+
+// ------------------------------------------------------------------------------------------
+// Runge-Kutta tile kernel
+// ------------------------------------------------------------------------------------------
+template <int K, bool LAP4, bool DEF>
+__global__ void __launch_bounds__(NTHR)
+rd_tile_rk(const __grid_constant__ YhK k, const __grid_constant__ TileArgs a) {
+  constexpr int H = K;                       // halo (K = 2 or 4: even, keeps pairs 16-byte aligned)
+  constexpr int TW = TB + 2 * H;             // tile width / height in cells
+  constexpr int NP = TW / 2;                 // pairs per tile row
+  constexpr int NPAIR = NP * TW;             // pairs in the tile
+  constexpr int SLOTS = (NPAIR + NTHR - 1) / NTHR;
+  constexpr int PL = TW * TW;                // doubles per plane
+  extern __shared__ __align__(16) double sm[];
+  double *s_u0 = sm, *s_v0 = sm + PL, *s_U = sm + 2 * PL, *s_V = sm + 3 * PL;
+  double *s_Ju = sm + 4 * PL, *s_Jv = sm + 5 * PL;
+
+  const int tid = threadIdx.x;
+  const int nx = k.nx;
+  const int gx0 = blockIdx.x * TB - H;                 // global x of tile column 0
+  const int ly0 = k.row0 + blockIdx.y * TB - H;        // LOCAL row of tile row 0
+  const int dom_lo = -k.jg0, dom_hi = k.nyg - k.jg0;   // local rows that exist globally
+  const int out_hi = min(k.row1, k.row0 + (int)(blockIdx.y + 1) * TB);
+
+  double ki[5] = {0, 0, 0, 0, 0}, ws[4] = {0, 0, 0, 0};
+  if (K == 4) {
+    ki[1] = 0.5; ki[2] = 0.5; ki[3] = 1.0;
+    ws[0] = 0.166666666666667; ws[1] = 0.333333333333333; ws[2] = 0.333333333333333; ws[3] = 0.166666666666667;
+  } else { ki[1] = 0.5; ws[1] = 1.0; }
+
+  // ---- load u0, v0 and form the stage-0 state and currents --------------------------------
+  for (int t = tid; t < NPAIR; t += NTHR) {
+    const int ty = t / NP, tx = 2 * (t % NP);
+    const int gx = gx0 + tx, ly = ly0 + ty;
+    double2 u = make_double2(0, 0), v = u, ju = u, jv = u, U = u, V = u;
+    if (gx >= 0 && gx < nx && ly >= dom_lo && ly < dom_hi) {
+      const size_t o = (size_t)ly * nx + gx;
+      u = *reinterpret_cast<const double2 *>(a.u_in + o);
+      v = *reinterpret_cast<const double2 *>(a.v_in + o);
+      U.x = u.x + 0.0; U.y = u.y + 0.0; V.x = v.x + 0.0; V.y = v.y + 0.0;   // u0 + (0.0*0.0)
+      const int gj = ly + k.jg0;
+      ju.x = t_Isum<DEF>(k, U.x, V.x, yh_scs(k, gx, gj));
+      ju.y = t_Isum<DEF>(k, U.y, V.y, yh_scs(k, gx + 1, gj));
+      jv.x = t_Iv<DEF>(k, U.x, V.x);
+      jv.y = t_Iv<DEF>(k, U.y, V.y);
+    }
+    const int c = ty * TW + tx;
+    *reinterpret_cast<double2 *>(s_u0 + c) = u;
+    *reinterpret_cast<double2 *>(s_v0 + c) = v;
+    *reinterpret_cast<double2 *>(s_U + c) = U;
+    *reinterpret_cast<double2 *>(s_V + c) = V;
+    *reinterpret_cast<double2 *>(s_Ju + c) = ju;
+    *reinterpret_cast<double2 *>(s_Jv + c) = jv;
+  }
+  __syncthreads();
+
+  const double q4 = k.qx4 + k.qy4, m2q = -2.0 * q4, mrs2 = -k.rscale * 2.0, rsq = k.rscale * q4;
+  double2 ru[SLOTS], rv[SLOTS], du[SLOTS], dv[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; s++) ru[s] = rv[s] = du[s] = dv[s] = make_double2(0.0, 0.0);
+
+#pragma unroll
+  for (int st = 0; st < K; st++) {
+    const int ring = st + 1;   // cells whose du_st is needed: tile minus `ring` outer rings
+    // ---- phase A: du, dv of stage st into registers ----------------------------------------
+#pragma unroll
+    for (int s = 0; s < SLOTS; s++) {
+      const int t = tid + s * NTHR;
+      if (t >= NPAIR) continue;
+      const int ty = t / NP, tx = 2 * (t % NP);
+      const int gx = gx0 + tx, ly = ly0 + ty;
+      const bool in_dom = gx >= 0 && gx < nx && ly >= dom_lo && ly < dom_hi;
+      const bool in_ring = pair_in_ring(tx, ty, ring, TW);
+      if (!(in_dom && in_ring)) continue;
+      const int c = ty * TW + tx;
+      // no-flux mirror = index selection inside the tile (helper_functions.cu:69-79)
+      const int cs = (ly - 1 < dom_lo) ? c + TW : c - TW;
+      const int cn = (ly + 1 >= dom_hi) ? c - TW : c + TW;
+      // tile-edge pairs (tx == 0 / TW-2) hold one cell outside the ring: its value is never
+      // read by a valid cell, it only must not read outside the tile
+      const bool le = (gx == 0) || (tx == 0), re = (gx + 2 == nx) || (tx == TW - 2);
+      double d[2][2];
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        const double *P = f ? s_V : s_U, *J = f ? s_Jv : s_Ju;
+        const double2 C = *reinterpret_cast<const double2 *>(P + c);
+        const double2 S = *reinterpret_cast<const double2 *>(P + cs);
+        const double2 N = *reinterpret_cast<const double2 *>(P + cn);
+        const double Wv = le ? C.y : P[c - 1], Ev = re ? C.x : P[c + 2];
+        double d0, d1;
+        if (f == 0) {
+          d0 = ((fma(-2.0, C.x, Wv) + C.y) * k.rx + (fma(-2.0, C.x, N.x) + S.x) * k.ry);
+          d1 = ((fma(-2.0, C.y, C.x) + Ev) * k.rx + (fma(-2.0, C.y, N.y) + S.y) * k.ry);
+        } else if (k.gateDiff) {
+          d0 = ((fma(-2.0, C.x, Wv) + C.y) * k.rx * k.rscale + (fma(-2.0, C.x, N.x) + S.x) * k.ry * k.rscale);
+          d1 = ((fma(-2.0, C.y, C.x) + Ev) * k.rx * k.rscale + (fma(-2.0, C.y, N.y) + S.y) * k.ry * k.rscale);
+        } else { d0 = 0.0; d1 = 0.0; }
+        const double2 Jc = *reinterpret_cast<const double2 *>(J + c);
+        if (LAP4 && (f == 0 || k.gateDiff)) {
+          const double SWv = le ? S.y : P[cs - 1], SEv = re ? S.x : P[cs + 2];
+          const double NWv = le ? N.y : P[cn - 1], NEv = re ? N.x : P[cn + 2];
+          const double2 Js = *reinterpret_cast<const double2 *>(J + cs);
+          const double2 Jn = *reinterpret_cast<const double2 *>(J + cn);
+          const double JW = le ? Jc.y : J[c - 1], JE = re ? Jc.x : J[c + 2];
+          if (f == 0) {   // reactionDiffusion.cu:221-229
+            d0 += m2q * (+(Wv - C.x + C.y) + (N.x - C.x + S.x));
+            d1 += m2q * (+(C.x - C.y + Ev) + (N.y - C.y + S.y));
+            d0 += q4 * (SWv + S.y + NWv + N.y);
+            d1 += q4 * (S.x + SEv + N.x + NEv);
+          } else {        // :235-239
+            d0 += mrs2 * q4 * (+(Wv - C.x + C.y) + (N.x - C.x + S.x));
+            d1 += mrs2 * q4 * (+(C.x - C.y + Ev) + (N.y - C.y + S.y));
+            d0 += rsq * (SWv + S.y + NWv + N.y);
+            d1 += rsq * (S.x + SEv + N.x + NEv);
+          }
+          d0 -= ((fma(-2.0, Jc.x, JW) + Jc.y) * k.fx4 + (fma(-2.0, Jc.x, Jn.x) + Js.x) * k.fy4);
+          d1 -= ((fma(-2.0, Jc.y, Jc.x) + JE) * k.fx4 + (fma(-2.0, Jc.y, Jn.y) + Js.y) * k.fy4);
+        }
+        d[f][0] = d0 - k.dt * Jc.x;   // :498-499
+        d[f][1] = d1 - k.dt * Jc.y;
+      }
+      du[s] = make_double2(d[0][0], d[0][1]);
+      dv[s] = make_double2(d[1][0], d[1][1]);
+      ru[s].x += (ws[st] * du[s].x); ru[s].y += (ws[st] * du[s].y);   // :502-503
+      rv[s].x += (ws[st] * dv[s].x); rv[s].y += (ws[st] * dv[s].y);
+    }
+    __syncthreads();   // every read of the stage-st state is done
+    // ---- phase B: stage st+1 state and currents, or the final update -----------------------
+#pragma unroll
+    for (int s = 0; s < SLOTS; s++) {
+      const int t = tid + s * NTHR;
+      if (t >= NPAIR) continue;
+      const int ty = t / NP, tx = 2 * (t % NP);
+      const int gx = gx0 + tx, ly = ly0 + ty;
+      const bool in_dom = gx >= 0 && gx < nx && ly >= dom_lo && ly < dom_hi;
+      const bool in_ring = pair_in_ring(tx, ty, ring, TW);
+      if (!(in_dom && in_ring)) continue;
+      const int c = ty * TW + tx;
+      const double2 u0 = *reinterpret_cast<const double2 *>(s_u0 + c);
+      const double2 v0 = *reinterpret_cast<const double2 *>(s_v0 + c);
+      if (st < K - 1) {
+        double2 U, V, ju, jv;
+        U.x = u0.x + (ki[st + 1] * du[s].x); U.y = u0.y + (ki[st + 1] * du[s].y);   // :117-118
+        V.x = v0.x + (ki[st + 1] * dv[s].x); V.y = v0.y + (ki[st + 1] * dv[s].y);
+        const int gj = ly + k.jg0;
+        ju.x = t_Isum<DEF>(k, U.x, V.x, yh_scs(k, gx, gj));
+        ju.y = t_Isum<DEF>(k, U.y, V.y, yh_scs(k, gx + 1, gj));
+        jv.x = t_Iv<DEF>(k, U.x, V.x);
+        jv.y = t_Iv<DEF>(k, U.y, V.y);
+        *reinterpret_cast<double2 *>(s_U + c) = U;
+        *reinterpret_cast<double2 *>(s_V + c) = V;
+        *reinterpret_cast<double2 *>(s_Ju + c) = ju;
+        *reinterpret_cast<double2 *>(s_Jv + c) = jv;
+      } else if (ly >= k.row0 && ly < out_hi) {   // ring == H here: exactly the output tile
+        double2 uo, vo;   // :512-513
+        uo.x = u0.x + k.tc * ru[s].x; uo.y = u0.y + k.tc * ru[s].y;
+        vo.x = v0.x + k.tc * rv[s].x; vo.y = v0.y + k.tc * rv[s].y;
+        const size_t o = (size_t)ly * nx + gx;
+        *reinterpret_cast<double2 *>(a.u_out + o) = uo;
+        *reinterpret_cast<double2 *>(a.v_out + o) = vo;
+        if (a.vtu && k.gateDiff) {   // :551-552
+          *reinterpret_cast<double2 *>(a.vtu + o) = make_double2(ru[s].x / k.dt, ru[s].y / k.dt);
+          *reinterpret_cast<double2 *>(a.vtv + o) = make_double2(rv[s].x / k.dt, rv[s].y / k.dt);
+        }
+      }
+    }
+    if (st < K - 1) __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Euler tile kernel: T steps per launch, ping-pong planes in shared memory
+// ------------------------------------------------------------------------------------------
+template <int T, bool DEF>
+__global__ void __launch_bounds__(NTHR)
+rd_tile_euler(const __grid_constant__ YhK k, const __grid_constant__ TileArgs a) {
+  constexpr int H = (T + 1) & ~1;
+  constexpr int TW = TB + 2 * H;
+  constexpr int NP = TW / 2;
+  constexpr int NPAIR = NP * TW;
+  constexpr int PL = TW * TW;
+  extern __shared__ __align__(16) double sm[];
+
+  const int tid = threadIdx.x;
+  const int nx = k.nx;
+  const int gx0 = blockIdx.x * TB - H;
+  const int ly0 = k.row0 + blockIdx.y * TB - H;
+  const int dom_lo = -k.jg0, dom_hi = k.nyg - k.jg0;
+  const int out_hi = min(k.row1, k.row0 + (int)(blockIdx.y + 1) * TB);
+  const size_t zoff = (size_t)blockIdx.z * (size_t)a.sim_stride;
+  const double *u_in = a.u_in + zoff, *v_in = a.v_in + zoff;
+  double *u_out = a.u_out + zoff, *v_out = a.v_out + zoff;
+
+  for (int t = tid; t < NPAIR; t += NTHR) {
+    const int ty = t / NP, tx = 2 * (t % NP);
+    const int gx = gx0 + tx, ly = ly0 + ty;
+    double2 u = make_double2(0, 0), v = u;
+    if (gx >= 0 && gx < nx && ly >= dom_lo && ly < dom_hi) {
+      const size_t o = (size_t)ly * nx + gx;
+      u = *reinterpret_cast<const double2 *>(u_in + o);
+      v = *reinterpret_cast<const double2 *>(v_in + o);
+      u.x += 0.0; u.y += 0.0; v.x += 0.0; v.y += 0.0;   // the reference's u0 + (0.0*0.0)
+    }
+    *reinterpret_cast<double2 *>(sm + ty * TW + tx) = u;
+    *reinterpret_cast<double2 *>(sm + PL + ty * TW + tx) = v;
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int s = 1; s <= T; s++) {
+    const double *iu = sm + ((s - 1) & 1) * 2 * PL, *iv = iu + PL;
+    double *ou = sm + (s & 1) * 2 * PL, *ov = ou + PL;
+    const int ring = (H - T) + s;   // valid region shrinks by one ring per step
+    bool stim_on = k.stim != 0;
+    if (a.period) {
+      const int per = a.period[blockIdx.z];
+      stim_on = per > 0 && ((a.count0 + s - 1) % per) <= a.duration;
+    }
+    for (int t = tid; t < NPAIR; t += NTHR) {
+      const int ty = t / NP, tx = 2 * (t % NP);
+      const int gx = gx0 + tx, ly = ly0 + ty;
+      if (!(gx >= 0 && gx < nx && ly >= dom_lo && ly < dom_hi)) continue;
+      if (!pair_in_ring(tx, ty, ring, TW)) continue;
+      const int c = ty * TW + tx;
+      const int cs = (ly - 1 < dom_lo) ? c + TW : c - TW;
+      const int cn = (ly + 1 >= dom_hi) ? c - TW : c + TW;
+      const bool le = (gx == 0) || (tx == 0), re = (gx + 2 == nx) || (tx == TW - 2);
+      const double2 uC = *reinterpret_cast<const double2 *>(iu + c), vC = *reinterpret_cast<const double2 *>(iv + c);
+      const double2 uS = *reinterpret_cast<const double2 *>(iu + cs), vS = *reinterpret_cast<const double2 *>(iv + cs);
+      const double2 uN = *reinterpret_cast<const double2 *>(iu + cn), vN = *reinterpret_cast<const double2 *>(iv + cn);
+      const double uw = le ? uC.y : iu[c - 1], ue = re ? uC.x : iu[c + 2];
+      const double vw = le ? vC.y : iv[c - 1], ve = re ? vC.x : iv[c + 2];
+      double2 uo, vo;
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const double u = q ? uC.y : uC.x, v = q ? vC.y : vC.x;
+        const double W = q ? uC.x : uw, E = q ? ue : uC.y, N = q ? uN.y : uN.x, S = q ? uS.y : uS.x;
+        const double Wv = q ? vC.x : vw, Ev = q ? ve : vC.y, Nv = q ? vN.y : vN.x, Sv = q ? vS.y : vS.x;
+        const bool scs = stim_on && yh_scs_on(k, gx + q, ly + k.jg0);
+        // same rewrites as rd_fast.cu::euler_cell (bit-exact identities, see there)
+        const double mu_u = DEF ? u : k.mu * u;
+        const double X = mu_u * (1.0 - u) * (u - k.alpha) - u * v;
+        const double ug = DEF ? u : k.delta * (u - k.gamma);
+        const double yv = ug * (k.beta - u) - v;
+        const double Y = k.eps * (DEF ? yv : yv - k.theta);
+        double du = ((fma(-2.0, u, W) + E) * k.rx + (fma(-2.0, u, N) + S) * k.ry);
+        double dv = 0.0;
+        if (k.gateDiff)
+          dv = ((fma(-2.0, v, Wv) + Ev) * k.rx * k.rscale + (fma(-2.0, v, Nv) + Sv) * k.ry * k.rscale);
+        if (!scs) du = du + k.dt * X;
+        else { const double I_sum = -X - 24.7; du = du - k.dt * I_sum; }
+        dv = dv + k.dt * Y;
+        const double un = u + (DEF ? du : k.tc * du), vn = v + (DEF ? dv : k.tc * dv);
+        if (q) { uo.y = un; vo.y = vn; } else { uo.x = un; vo.x = vn; }
+      }
+      if (s < T) {
+        *reinterpret_cast<double2 *>(ou + c) = uo;
+        *reinterpret_cast<double2 *>(ov + c) = vo;
+      } else if (ly >= k.row0 && ly < out_hi) {
+        const size_t o = (size_t)ly * nx + gx;
+        *reinterpret_cast<double2 *>(u_out + o) = uo;
+        *reinterpret_cast<double2 *>(v_out + o) = vo;
+      }
+    }
+    if (s < T) __syncthreads();
+  }
+}
+
+template <typename KernelT>
+int set_smem(KernelT kern, size_t smem) {
+  YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return YH_OK;
+}
+
+template <int K, bool LAP4, bool DEF>
+int launch_rk(const YhK &k, const TileArgs &a, cudaStream_t st) {
+  constexpr int TW = TB + 2 * K;
+  const size_t smem = (size_t)6 * TW * TW * sizeof(double);
+  static bool done[64] = {false};
+  int dev = 0;
+  YH_CUDA(cudaGetDevice(&dev));
+  if (!done[dev & 63]) { int rc = set_smem(rd_tile_rk<K, LAP4, DEF>, smem); if (rc) return rc; done[dev & 63] = true; }
+  dim3 grd((k.nx + TB - 1) / TB, (k.row1 - k.row0 + TB - 1) / TB);
+  rd_tile_rk<K, LAP4, DEF><<<grd, NTHR, smem, st>>>(k, a);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
+
+template <int T, bool DEF>
+int launch_euler(const YhK &k, const TileArgs &a, int nsims, cudaStream_t st) {
+  constexpr int H = (T + 1) & ~1, TW = TB + 2 * H;
+  const size_t smem = (size_t)4 * TW * TW * sizeof(double);
+  static bool done[64] = {false};
+  int dev = 0;
+  YH_CUDA(cudaGetDevice(&dev));
+  if (!done[dev & 63]) { int rc = set_smem(rd_tile_euler<T, DEF>, smem); if (rc) return rc; done[dev & 63] = true; }
+  dim3 grd((k.nx + TB - 1) / TB, (k.row1 - k.row0 + TB - 1) / TB, nsims);
+  rd_tile_euler<T, DEF><<<grd, NTHR, smem, st>>>(k, a);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
+
+bool is_def(const YhK &k) {
+  return (k.mu == 1.0) && (k.delta == 1.0) && (k.gamma == 0.0) && (k.theta == 0.0);
+}
+
+}  // namespace
+
+// Policy: tiles win while the sheet cannot fill the streaming pipelines (measured crossover
+// between 1024^2 and 2048^2 cells per launch); YH_RD_PATH = tile | stream overrides (tests).
+int yh_rd_prefer_tile(long long cells) {
+  const char *f = getenv("YH_RD_PATH");
+  if (f && f[0] == 't') return 1;
+  if (f && f[0] == 's') return 0;
+  return cells <= (3ll << 20);
+}
+
+int yh_rd_tile_rk_supported(const YhK &k) {
+  if (k.timeIntOrder != 2 && k.timeIntOrder != 4) return 0;
+  if (!k.neumannBC || k.solidSwitch || k.anisotropy) return 0;
+  if ((k.nx & 1) || k.nx < 8) return 0;
+  return 1;
+}
+
+int yh_launch_rd_tile_rk(const YhK &k, const double *u_in, const double *v_in, double *u_out,
+                         double *v_out, double *vtu, double *vtv, cudaStream_t st) {
+  if (!yh_rd_tile_rk_supported(k)) return YH_ERR_UNSUPPORTED;
+  if (k.row1 <= k.row0) return YH_OK;
+  TileArgs a{u_in, v_in, u_out, v_out, vtu, vtv, 0, nullptr, 0, 0};
+  const bool lap4 = k.lap4 != 0, def = is_def(k);
+#define YH_T(KK, L) (def ? launch_rk<KK, L, true>(k, a, st) : launch_rk<KK, L, false>(k, a, st))
+  if (k.timeIntOrder == 4) return lap4 ? YH_T(4, true) : YH_T(4, false);
+  return lap4 ? YH_T(2, true) : YH_T(2, false);
+#undef YH_T
+}
+
+int yh_launch_rd_tile_euler(const YhK &k, int tb, const double *u_in, const double *v_in, double *u_out,
+                            double *v_out, int nsims, long long sim_stride, const int *period_d,
+                            int duration_it, int count0, cudaStream_t st) {
+  if (!yh_rd_fast_supported(k, tb)) return YH_ERR_UNSUPPORTED;
+  if (k.row1 <= k.row0) return YH_OK;
+  TileArgs a{u_in, v_in, u_out, v_out, nullptr, nullptr, sim_stride, period_d, duration_it, count0};
+  const bool def = is_def(k) && k.tc == 1.0;
+#define YH_E(TT) (def ? launch_euler<TT, true>(k, a, nsims, st) : launch_euler<TT, false>(k, a, nsims, st))
+  switch (tb) {
+    case 1: return YH_E(1);
+    case 2: return YH_E(2);
+    default: return YH_E(4);
+  }
+#undef YH_E
+}

@@ -208,7 +208,11 @@ static int sim_run_impl(yh_sim *s, int nsteps, int tb_steps, double *trace_h, bo
       YH_LAUNCH_CHECK();
     }
     int rc;
-    if (fast1) {
+    const bool tile = yh_rd_prefer_tile((long long)s->n * s->n_sims) != 0;
+    if (fast1 && tile) {
+      rc = yh_launch_rd_tile_euler(k, T, s->u[c], s->v[c], s->u[o], s->v[o], s->n_sims, stride,
+                                   s->period_d, s->duration_it, s->count, s->st);
+    } else if (fast1) {
       rc = yh_launch_rd_fast_paced(k, T, s->u[c], s->v[c], s->u[o], s->v[o], s->n_sims, stride,
                                    s->period_d, s->duration_it, s->count, s->raw_input, s->st);
     } else {
@@ -219,7 +223,10 @@ static int sim_run_impl(yh_sim *s, int nsteps, int tb_steps, double *trace_h, bo
           const int per = s->period_h[z];
           kz.stim = per > 0 && (s->count % per) <= s->duration_it;
         }
-        if (yh_rd_rk_supported(kz))
+        if (tile && yh_rd_tile_rk_supported(kz))
+          rc = yh_launch_rd_tile_rk(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
+                                    s->v[o] + s->n * z, nullptr, nullptr, s->st);
+        else if (yh_rd_rk_supported(kz))
           rc = yh_launch_rd_rk(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
                                s->v[o] + s->n * z, nullptr, nullptr, s->solid, s->st);
         else

@@ -123,3 +123,12 @@ int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const doub
 int yh_rd_rk_supported(const YhK &k);
 int yh_launch_rd_rk(const YhK &k, const double *u_in, const double *v_in, double *u_out,
                     double *v_out, double *vtu, double *vtv, const uint8_t *solid, cudaStream_t st);
+
+// Shared-memory tile kernels for small sheets (rd_tile.cu).
+int yh_rd_prefer_tile(long long cells);
+int yh_rd_tile_rk_supported(const YhK &k);
+int yh_launch_rd_tile_rk(const YhK &k, const double *u_in, const double *v_in, double *u_out,
+                         double *v_out, double *vtu, double *vtv, cudaStream_t st);
+int yh_launch_rd_tile_euler(const YhK &k, int tb, const double *u_in, const double *v_in, double *u_out,
+                            double *v_out, int nsims, long long sim_stride, const int *period_d,
+                            int duration_it, int count0, cudaStream_t st);
