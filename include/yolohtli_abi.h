@@ -28,6 +28,8 @@
  *   yh_solve_matrix            solve_matrix (host)            symmetryReduction.cu:329-420
  *   yh_sapd                    sAPD_wrapper                   spaceAPD.cu:376-384
  *   yh_probe                   singleCell_wrapper             singleCell.cu:22-30
+ *   yh_contour                 countour_wrapper               spaceAPD.cu:256-276
+ *   yh_rgba                    get_rgba_wrapper               main.cu:1633-1641
  *   yh_sim_*                   the display() step loop, headless   main.cu:862-1043
  */
 #ifndef YOLOHTLI_ABI_H
@@ -197,6 +199,27 @@ int yh_sapd(const yh_params *p, int count, const double *uold, const double *une
 /* pt_d[0..1] = (u,v) at (x,y); no host sync.  pt_h non-NULL adds the reference's blocking copy. */
 int yh_probe(const yh_params *p, const double *u, const double *v, double *pt_d,
              int x, int y, double *pt_h, void *stream);
+
+/* ---- contour extraction and frame colouring --------------------------
+ * One contour point: layout of the float3 the reference appends (spaceAPD.cu:66). */
+#ifndef YH_CONTOUR_PT_DEFINED
+#define YH_CONTOUR_PT_DEFINED
+typedef struct yh_contour_pt { float x, y, t; } yh_contour_pt;
+#endif
+/* countour_kernel modes 1-3.  mode 1: field2 = sAPD (field1 unused, may be NULL); modes 2, 3:
+ * field1 = u, field2 = v with the thresholds conTh1..3 (saveFiles.cu:215-217: 0.8, 0.85, 0.7).
+ * Resets *contour_count (device int) and contour_plot (may be NULL), then appends every point
+ * in canonical order (ascending linear cell index).  stimArea NULL = every cell counts.
+ * *contour_count is the number found; at most `capacity` are stored. */
+int yh_contour(const yh_params *p, const double *field1, const double *field2,
+               uint8_t *contour_plot, const uint8_t *stimArea, int *contour_count,
+               yh_contour_pt *contour_vector, int capacity, double physical_time, int mode,
+               double thresh1, double thresh2, double thresh3, void *stream);
+/* plot_rgba[c] = (!lines[c]) * cmap[(int)((float)frac*(float)ncol)], frac = (field-min)/(max-min);
+ * the colour index is clamped to the map.  lines may be NULL. */
+int yh_rgba(const yh_params *p, const double *field, uint32_t *plot_rgba,
+            const uint32_t *cmap_rgba, int ncol, double min_var, double max_var,
+            const uint8_t *lines, void *stream);
 
 /* ---- headless driver: the display() loop without GL (main.cu:862-1043) ------------
  * An opaque simulation owning device state for n_sims independent nx x ny sheets

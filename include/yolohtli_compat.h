@@ -40,10 +40,18 @@ void singleCell_wrapper(size_t pitch, dim3 grid0D, dim3 block0D, stateVar gOut_d
 void sAPD_wrapper(size_t pitch, dim3 grid1D, dim3 block1D, int count, REAL *uold, REAL *unew,
                   REAL *APD1, REAL *APD2, REAL *sAPD, REAL *dAPD, REAL *back, REAL *front,
                   bool *first, bool *stimArea, bool stimulate);
+void countour_wrapper(size_t pitch, dim3 grid2D, dim3 block2D, REAL *field1, REAL *field2,
+                      bool *contour_plot, bool *stimArea, int *contour_count,
+                      float3 *contour_vector, float physicalTime, int mode);
+void get_rgba_wrapper(size_t pitch, dim3 grid2D, dim3 block2D, int ncol, REAL *field,
+                      unsigned int *plot_rba_data, unsigned int *cmap_rgba_data, bool *lines);
 void swapSoA(stateVar *A, stateVar *B);
 
 /* New: replaces the ~45 cudaMemcpyToSymbol calls of main.cu:309-402. */
 struct yh_params;
 extern "C" int yh_shim_configure(const struct yh_params *p);
 extern "C" int yh_shim_last_status(void);
+/* conTh1_d..3 (main.cu:378-383) and minVarColor_d / maxVarColor_d (main.cu:366-369). */
+extern "C" int yh_shim_set_contour_thresholds(double th1, double th2, double th3);
+extern "C" int yh_shim_set_color_range(double min_var, double max_var);
 #endif

@@ -414,4 +414,32 @@ float yref_apd_run(double *u_h, double *v_h, int nsteps, int period_it, int dura
   return g_err ? -1.f : ms;
 }
 
+// countour_wrapper (spaceAPD.cu:256-276).  field2 is allocated with nx+1 zero cells of padding
+// because the kernel reads I2D(i+1,j) / I2D(i,j+1) past the end of the array on the last row
+// (:52-53); fixtures keep the last row free of hits, where the reference's result is undefined.
+// Returns the point count (list in atomicAdd order) or <0.
+int yref_contour(const double *field1_h, const double *field2_h, const uint8_t *stimArea_h,
+                 float t, int mode, yh_contour_pt *pts_h, int capacity, uint8_t *plot_h) {
+  g_err = 0;
+  const size_t n = (size_t)param.nx * param.ny;
+  REAL *f1 = dalloc(n + param.nx + 1, nullptr), *f2 = dalloc(n + param.nx + 1, nullptr);
+  if (field1_h) CK(cudaMemcpy(f1, field1_h, n * sizeof(REAL), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(f2, field2_h, n * sizeof(REAL), cudaMemcpyHostToDevice));
+  bool *plot_d = balloc(n, nullptr), *area_d = balloc(n, stimArea_h);
+  int *cnt_d = nullptr; float3 *vec_d = nullptr;
+  CK(cudaMalloc(&cnt_d, sizeof(int)));
+  CK(cudaMalloc(&vec_d, sizeof(float3) * 2 * n));
+  CK(cudaMemset(vec_d, 0, sizeof(float3) * 2 * n));
+  countour_wrapper(pitch, grid2D, block2D, f1, f2, plot_d, area_d, cnt_d, vec_d, t, mode);
+  CK(cudaDeviceSynchronize());
+  cudaGetLastError();   // cudaMemset of an uninitialised size (spaceAPD.cu:262-265, defect B4)
+  int cnt = 0;
+  CK(cudaMemcpy(&cnt, cnt_d, sizeof(int), cudaMemcpyDeviceToHost));
+  int m = cnt < capacity ? cnt : capacity;
+  if (m > 0) CK(cudaMemcpy(pts_h, vec_d, sizeof(float3) * (size_t)m, cudaMemcpyDeviceToHost));
+  if (plot_h) CK(cudaMemcpy(plot_h, plot_d, n, cudaMemcpyDeviceToHost));
+  cudaFree(f1); cudaFree(f2); cudaFree(plot_d); cudaFree(area_d); cudaFree(cnt_d); cudaFree(vec_d);
+  return g_err ? -1 : cnt;
+}
+
 }  // extern "C"

@@ -1046,3 +1046,92 @@ int yho_sapd(const yh_params *p, int count, const double *uold, const double *un
   }
   return YH_OK;
 }
+
+/* ------------------------------------------------------------------------------------
+ * Contours: countour_kernel modes 1-3, spaceAPD.cu:18-153 (+ countour_wrapper :256-276),
+ * list in canonical order (ascending i + j*nx; mode 3: -conTh2 crossing first).
+ * Reads past the end of the array (last row / last cell, :52-53) return the cell's own value.
+ * ------------------------------------------------------------------------------------ */
+static void contour_push(const yh_params *p, double ppx, double ppy, double pTime,
+                         uint8_t *plot, int *count, yh_contour_pt *vec, int capacity) {
+  yh_contour_pt d;
+  d.x = (float)ppx; d.y = (float)ppy; d.t = (float)pTime;   /* make_float3, :66 */
+  if (*count < capacity) vec[*count] = d;
+  (*count)++;
+  if (plot) {   /* plot_field, helper_functions.cu:45-51 */
+    float fx = floorf(d.x), fy = floorf(d.y);
+    if (fabsf(fx) < 1e9f && fabsf(fy) < 1e9f) {
+      long long idx = (long long)fx + (long long)p->nx * (long long)fy;
+      if (idx >= 0 && idx < (long long)p->nx * p->ny) plot[idx] = 1;
+    }
+  }
+}
+
+int yho_contour(const yh_params *p, const double *field1, const double *field2,
+                uint8_t *contour_plot, const uint8_t *stimArea, int *contour_count,
+                yh_contour_pt *contour_vector, int capacity, double pTime, int mode,
+                double th1, double th2, double th3) {
+  if (!p || !field2 || !contour_count || !contour_vector || mode < 1 || mode > 3) return YH_ERR_INVALID_ARG;
+  if (mode != 1 && !field1) return YH_ERR_INVALID_ARG;
+  const int nx = p->nx, ny = p->ny;
+  const long long ncell = (long long)nx * ny;
+  *contour_count = 0;                                            /* :258 */
+  if (contour_plot) memset(contour_plot, 0, (size_t)ncell);      /* :268 */
+  for (int j = 0; j < ny; j++) {
+    for (int i = 0; i < nx; i++) {
+      const long long c = I2D(nx, i, j);
+      const int sc = stimArea ? stimArea[c] != 0 : 1;            /* :43 */
+      const double f0 = field2[c];
+      const double fx = (c + 1 < ncell) ? field2[c + 1] : f0;    /* I2D(nx_d,i+1,j), unclamped */
+      const double fy = (c + nx < ncell) ? field2[c + nx] : f0;  /* I2D(nx_d,i,j+1) */
+      if (mode == 1) {                                           /* :50-71 */
+        double v0 = f0, v1x = fx, v1y = fy;
+        double zpmx = i < (nx - 1) ? v0 * v1x : v0 * v0;
+        double zpmy = j < (ny - 1) ? v0 * v1y : v0 * v0;
+        if ((zpmx < 0.0) || ((zpmy < 0.0) && sc)) {              /* `a || b && sc` as written, :62 */
+          double ppx = fabs(v0 - v1x) > 2.220446049250313e-16 ? i + v0 / (v0 - v1x) : i;
+          double ppy = fabs(v0 - v1y) > 2.220446049250313e-16 ? j + v0 / (v0 - v1y) : j;
+          contour_push(p, ppx, ppy, pTime, contour_plot, contour_count, contour_vector, capacity);
+        }
+      } else if (mode == 2) {                                    /* :74-95 */
+        if ((field1[c] < th1) && sc) {
+          double v0 = f0 - th2, v1x = fx - th2, v1y = fy - th2;
+          double zpmx = i < (nx - 1) ? v0 * v1x : v0 * v0;
+          double zpmy = j < (ny - 1) ? v0 * v1y : v0 * v0;
+          if ((zpmx < 0.0) || (zpmy < 0.0))
+            contour_push(p, i, j, pTime, contour_plot, contour_count, contour_vector, capacity);
+        }
+      } else {                                                   /* :97-141 */
+        double V0 = f0 - th2, V1x = fx - th2, V1y = fy - th2;
+        if ((field1[c] < th1) && (fabs(V0) < (th3 + 0.1)) && (fabs(V1x) < (th3 + 0.1)) &&
+            (fabs(V1y) < (th3 + 0.1)) && sc) {
+          double v0 = V0 - th2, v1x = V1x - th2, v1y = V1y - th2;
+          double zpmx = i < (nx - 1) ? v0 * v1x : v0 * v0;
+          double zpmy = j < (ny - 1) ? v0 * v1y : v0 * v0;
+          if ((zpmx < 0.0) || (zpmy < 0.0))
+            contour_push(p, i, j, pTime, contour_plot, contour_count, contour_vector, capacity);
+          v0 = V0 + th3; v1x = V1x + th3; v1y = V1y + th3;
+          zpmx = i < (nx - 1) ? v0 * v1x : v0 * v0;
+          zpmy = j < (ny - 1) ? v0 * v1y : v0 * v0;
+          if ((zpmx < 0.0) || (zpmy < 0.0))
+            contour_push(p, i, j, pTime, contour_plot, contour_count, contour_vector, capacity);
+        }
+      }
+    }
+  }
+  return YH_OK;
+}
+
+/* get_rgba_kernel, main.cu:1604-1631 (colour index clamped to the map) */
+int yho_rgba(const yh_params *p, const double *field, uint32_t *plot_rgba, const uint32_t *cmap,
+             int ncol, double vmin, double vmax, const uint8_t *lines) {
+  if (!p || !field || !plot_rgba || !cmap || ncol <= 0) return YH_ERR_INVALID_ARG;
+  const long long n = (long long)p->nx * p->ny;
+  for (long long c = 0; c < n; c++) {
+    double frac = (field[c] - vmin) / (vmax - vmin);
+    int icol = (int)((float)frac * (float)ncol);
+    icol = icol < 0 ? 0 : (icol >= ncol ? ncol - 1 : icol);
+    plot_rgba[c] = (uint32_t)(lines ? !lines[c] : 1) * cmap[icol];
+  }
+  return YH_OK;
+}

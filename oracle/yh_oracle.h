@@ -79,6 +79,15 @@ int yho_sapd(const yh_params *p, int count, const double *uold, const double *un
              double *back, double *front, uint8_t *first, const uint8_t *stimArea,
              int stimulate);
 
+/* countour_kernel modes 1-3 + countour_wrapper, spaceAPD.cu:18-153, 256-276 */
+int yho_contour(const yh_params *p, const double *field1, const double *field2,
+                uint8_t *contour_plot, const uint8_t *stimArea, int *contour_count,
+                yh_contour_pt *contour_vector, int capacity, double physical_time, int mode,
+                double thresh1, double thresh2, double thresh3);
+/* get_rgba_kernel, main.cu:1604-1631 */
+int yho_rgba(const yh_params *p, const double *field, uint32_t *plot_rgba, const uint32_t *cmap,
+             int ncol, double vmin, double vmax, const uint8_t *lines);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,11 +83,41 @@ def check_oracle(oracle, g):
         uo, vo = oracle.advect_bfecc(p, g["u"], g["v"], g["ax"], g["ay"])
         # reference kernel called 3x on the same buffers = its synchronous fixed point (see ref_harness.cu)
         assert np.array_equal(uo, g["uo"]) and np.array_equal(vo, g["vo"])
+    elif kind == "contour":
+        from tests import oracle_lib
+        ny, nx = g["f2"].shape
+        p = oracle.params_default(nx, ny)
+        mode = int(g["mode"])
+        pts, n, plot = oracle.contour(p, g["f1"] if mode != 1 else None, g["f2"], mode, t=float(g["t"]),
+                                      stimArea=g["area"], plot=True)
+        ref = g["pts"].view(oracle_lib.CONTOUR_DTYPE).reshape(-1)
+        key = ("y", "x", "t")   # the reference appends by atomicAdd: compare as sorted multisets
+        assert n == len(ref) and np.array_equal(np.sort(pts, order=key), np.sort(ref, order=key))
+        assert np.array_equal(plot, g["plot"].reshape(-1))
     else:
         raise AssertionError(kind)
 
 
+def contour_fixtures():
+    """python -m tests.golden.make_golden contour  (on the B200 box)."""
+    from tests import oracle_lib
+    from tests.test_gpu_aux import contour_fields
+    oracle = oracle_lib.load()
+    ref = oracle_lib.Reference(nofma=True)
+    ref.init(oracle.params_default(NX, NY))
+    for mode in (1, 2, 3):
+        f1, f2, area = contour_fields(NX, NY, mode, seed=40 + mode)
+        pts, plot = ref.contour(f1, f2, mode, t=7.25, stimArea=area)
+        name = os.path.join(HERE, f"contour_{mode}.npz")
+        np.savez_compressed(name, kind="contour", mode=mode, t=7.25, f1=f1 if f1 is not None else np.zeros(1),
+                            f2=f2, area=area, pts=pts.view(np.uint8), plot=plot)
+        check_oracle(oracle, np.load(name))
+        print("  oracle == reference:", os.path.basename(name), len(pts), "points")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "contour":
+        return contour_fixtures()
     from tests import oracle_lib
     from yolohtli_b200 import synth
     oracle = oracle_lib.load()

@@ -16,6 +16,8 @@ REF_NOFMA_SO = os.path.join(ORACLE_DIR, "_ref", "libyhref_nofma.so")
 from yolohtli_b200._lib import YhParams, YhTip  # noqa: E402  (struct layouts only)
 
 TIP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("vx", "<f4"), ("vy", "<f4"), ("t", "<f4")])
+CONTOUR_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("t", "<f4")])
+CONTOUR_THRESH = (0.8, 0.85, 0.7)   # saveFiles.cu:215-217
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
 _P = C.POINTER(YhParams)
 
@@ -163,6 +165,32 @@ class Oracle:
         return st
 
 
+    def contour(self, p, field1, field2, mode, t=0.0, stimArea=None, thresh=CONTOUR_THRESH, plot=False,
+                capacity=None):
+        """countour_wrapper (spaceAPD.cu:256-276): points in canonical order (+ raster)."""
+        f2 = _np(field2)
+        f1 = _np(field1) if field1 is not None else None
+        sa = _np(stimArea, np.uint8) if stimArea is not None else None
+        cap = capacity if capacity is not None else 2 * f2.size
+        vec = np.zeros(cap, dtype=CONTOUR_DTYPE)
+        n = C.c_int(0)
+        pl = np.full(f2.size, 7, dtype=np.uint8) if plot else None
+        rc = self.l.yho_contour(C.byref(p), _p(f1), _p(f2), _p(pl), _p(sa), C.byref(n), _p(vec), cap,
+                                _d(t), mode, _d(thresh[0]), _d(thresh[1]), _d(thresh[2]))
+        assert rc == 0, rc
+        out = vec[: min(n.value, cap)].copy()
+        return (out, n.value, pl) if plot else (out, n.value)
+
+    def rgba(self, p, field, cmap, vmin, vmax, lines=None):
+        f = _np(field)
+        cm = np.ascontiguousarray(cmap, dtype=np.uint32)
+        ln = _np(lines, np.uint8) if lines is not None else None
+        out = np.zeros(f.size, dtype=np.uint32)
+        rc = self.l.yho_rgba(C.byref(p), _p(f), _p(out), _p(cm), len(cm), _d(vmin), _d(vmax), _p(ln))
+        assert rc == 0, rc
+        return out
+
+
 class Reference:
     """The reference's own CUDA kernels (oracle/_ref), driven through ref_harness.cu."""
 
@@ -215,6 +243,18 @@ class Reference:
         n = self.l.yref_tip(_p(a), _p(b), _d(t), algorithm, _p(vec), capacity, None)
         assert n >= 0
         return vec[: min(n, capacity)].copy()
+
+    def contour(self, field1, field2, mode, t=0.0, stimArea=None):
+        """countour_wrapper with the reference's default thresholds; list in atomicAdd order."""
+        f2 = _np(field2)
+        f1 = _np(field1) if field1 is not None else None
+        sa = _np(stimArea, np.uint8) if stimArea is not None else np.ones(f2.size, dtype=np.uint8)
+        cap = 2 * f2.size
+        vec = np.zeros(cap, dtype=CONTOUR_DTYPE)
+        pl = np.zeros(f2.size, dtype=np.uint8)
+        n = self.l.yref_contour(_p(f1), _p(f2), _p(sa), C.c_float(t), mode, _p(vec), cap, _p(pl))
+        assert n >= 0
+        return vec[:n].copy(), pl
 
     def slice_trapz(self, u, v, adv_x, adv_y, vtu, vtv, tipx, tipy, count, want_slices=False):
         u, v, ax, ay, vtu, vtv = map(_np, (u, v, adv_x, adv_y, vtu, vtv))

@@ -34,7 +34,8 @@ def test_shim_exports_reference_signatures():
     # mangled names of hostPrototypes.h:22-57 (plain C++ linkage, structs by value)
     for frag in ("reactionDiffusion_wrapper", "tip_wrapper", "slice_wrapper", "Cxy_field_wrapper",
                  "advFDBFECC_wrapper", "solve_matrix", "trapz_wrapper", "singleCell_wrapper",
-                 "sAPD_wrapper", "swapSoA", "yh_shim_configure"):
+                 "sAPD_wrapper", "countour_wrapper", "get_rgba_wrapper", "swapSoA", "yh_shim_configure",
+                 "yh_shim_set_contour_thresholds", "yh_shim_set_color_range"):
         assert frag in out, frag
     assert "_Z25reactionDiffusion_wrapperm4dim3S_8stateVarS0_S0_S0_bPbbPdb4int2" in out
 

@@ -363,3 +363,101 @@ def test_apd_loop_batched_matches_oracle_and_reference(oracle, yh):
             ru, rv, r1, r2, _ = ref.apd_run(np.zeros((ny, nx)), np.zeros((ny, nx)), nsteps, int(per), dur, area)
             assert np.array_equal(ru, u) and np.array_equal(r1, st["APD1"]) and np.array_equal(r2, st["APD2"]), z
     assert np.abs(a1).max() > 0, "an action potential should have completed so APD1 is exercised"
+
+
+# ---- contours and frame colouring ----------------------------------------
+def contour_fields(nx, ny, mode, seed=3):
+    """Inputs with plenty of crossings; the LAST ROW holds none (there the reference reads past
+    the end of the array, spaceAPD.cu:52-53)."""
+    X, Y = np.meshgrid(np.arange(nx, dtype=float), np.arange(ny, dtype=float))
+    rng = np.random.default_rng(seed)
+    area = (rng.uniform(size=(ny, nx)) > 0.2).astype(np.uint8)
+    if mode == 1:   # sAPD: sign field with a few exact zeros (spaceAPD.cu:343)
+        s = np.sign(np.sin(0.23 * X + 0.4) * np.cos(0.19 * Y) + 0.3 * np.sin(0.05 * X * Y / nx))
+        s[rng.uniform(size=(ny, nx)) < 0.01] = 0.0
+        s[-1, :] = 1.0
+        return None, s, area
+    u = 0.55 + 0.5 * np.sin(0.13 * X) * np.cos(0.17 * Y + 0.3)
+    v = 0.9 + 0.85 * np.sin(0.21 * X + 0.1 * Y) + 0.02 * rng.normal(size=(ny, nx))
+    u[-1, :] = 1.0
+    return u, v, area
+
+
+def gpu_contour(p, f1, f2, mode, t=0.0, area=None, capacity=None):
+    n = p.nx * p.ny
+    cap = capacity if capacity is not None else 2 * n
+    cnt = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    vec = torch.zeros(cap * 12, dtype=torch.uint8, device="cuda")
+    pl = torch.full((n,), 7, dtype=torch.uint8, device="cuda")   # must be reset by the call
+    host.contour(p, dev(f1) if f1 is not None else None, dev(f2), cnt, vec, mode, contour_plot=pl,
+                 stimArea=dev(area, torch.uint8) if area is not None else None, t=t, capacity=cap)
+    torch.cuda.synchronize()
+    pts, count = host.contour_to_numpy(cnt, vec)
+    return pts, count, pl.cpu().numpy()
+
+
+@pytest.mark.parametrize("nx,ny", [(48, 40), (333, 257), (1024, 1024)])
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_contour_vs_oracle_bitwise(oracle, nx, ny, mode):
+    p = oracle.params_default(nx, ny)
+    f1, f2, area = contour_fields(nx, ny, mode)
+    for a in (area, None):
+        want, wn, wplot = oracle.contour(p, f1, f2, mode, t=12.5, stimArea=a, plot=True)
+        got, gn, gplot = gpu_contour(p, f1, f2, mode, t=12.5, area=a)
+        assert wn > nx // 4 and gn == wn
+        assert got.tobytes() == want.tobytes()            # same points, same (canonical) order
+        assert np.array_equal(gplot, wplot)
+    # a second call on the same buffers (ticket re-armed, epoch bumped), and a clipped list
+    got2, gn2, _ = gpu_contour(p, f1, f2, mode, t=12.5, area=None, capacity=5)
+    assert gn2 == wn and got2.tobytes() == want[:5].tobytes()
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_contour_vs_reference_kernels(oracle, mode):
+    """The reference appends by atomicAdd (order = scheduling): compare as sorted multisets; the
+    raster must be identical."""
+    if not oracle_lib.have_reference():
+        pytest.skip("oracle/_ref not built")
+    nx, ny = 333, 257
+    p = oracle.params_default(nx, ny)
+    ref = oracle_lib.Reference(nofma=True)
+    ref.init(p)
+    f1, f2, area = contour_fields(nx, ny, mode)
+    rpts, rplot = ref.contour(f1, f2, mode, t=3.5, stimArea=area)
+    got, gn, gplot = gpu_contour(p, f1, f2, mode, t=3.5, area=area)
+    assert gn == len(rpts) > 50
+    assert np.array_equal(np.sort(got, order=("y", "x", "t")), np.sort(rpts, order=("y", "x", "t")))
+    assert np.array_equal(gplot, rplot)
+
+
+def test_contour_golden_fixtures(oracle):
+    import glob
+    import os
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "contour_*.npz")))
+    if not files:
+        pytest.skip("no contour fixtures yet")
+    for f in files:
+        g = np.load(f)
+        ny, nx = g["f2"].shape
+        p = oracle.params_default(nx, ny)
+        f1 = g["f1"] if int(g["mode"]) != 1 else None
+        got, gn, gplot = gpu_contour(p, f1, g["f2"], int(g["mode"]), t=float(g["t"]), area=g["area"])
+        ref = g["pts"].view(oracle_lib.CONTOUR_DTYPE).reshape(-1)
+        assert np.array_equal(np.sort(got, order=("y", "x", "t")), np.sort(ref, order=("y", "x", "t")))
+        assert np.array_equal(gplot, g["plot"].reshape(-1))
+
+
+def test_rgba_vs_oracle(oracle, yh):
+    nx, ny = 300, 200
+    p = oracle.params_default(nx, ny)
+    rng = np.random.default_rng(9)
+    field = rng.uniform(-0.4, 1.4, (ny, nx))                 # leaves the colour range on both sides
+    lines = (rng.uniform(size=(ny, nx)) < 0.05).astype(np.uint8)
+    cmap = yh.io.cmap_read(None, capacity=500)
+    want = oracle.rgba(p, field, cmap, -0.1, 1.1, lines=lines)
+    out = torch.zeros(nx * ny, dtype=torch.int32, device="cuda")
+    host.rgba(p, dev(field), out, dev(cmap.view(np.int32), torch.int32), -0.1, 1.1, lines=dev(lines, torch.uint8))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want)
+    host.rgba(p, dev(field), out, dev(cmap.view(np.int32), torch.int32), -0.1, 1.1)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), oracle.rgba(p, field, cmap, -0.1, 1.1))

@@ -91,6 +91,37 @@ def test_temporal_blocking_is_bitwise_invariant(oracle, nx, ny, tb):
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
 
 
+@pytest.mark.parametrize("nx,ny", [(64, 48), (300, 200), (1024, 1024)])
+@pytest.mark.parametrize("tb", [1, 2, 4])
+def test_masked_temporal_blocking_is_bitwise_invariant(oracle, yh, nx, ny, tb):
+    """Obstacle masks on the temporally blocked Euler kernel (C2: 1024^2 + holes): T steps per HBM
+    pass == the oracle's single steps, bit for bit; non-tissue cells are exactly +0.0; lap4 is
+    ignored in the mask branch (reactionDiffusion.cu:154-184).  Same through the headless driver."""
+    u, v = rand_fields(nx, ny, 23)
+    masks = [(np.random.default_rng(8).uniform(size=(ny, nx)) > 0.25).astype(np.uint8)]
+    if nx == ny:
+        masks.append(synth.hole_mask(nx, seed=4))
+    n = 9
+    for mask, gd in itertools.product(masks, (1, 0)):
+        p = oracle.params_default(nx, ny, timeIntOrder=1, solidSwitch=1, gateDiff=gd)   # lap4 = 4 (default)
+        want = oracle.rd_advance(p, n, u, v, solid=mask, stim_mouse=True, point=(nx // 2, ny // 3))
+        got = gpu_advance(p, n, u, v, tb=tb, solid=mask, stim_mouse=True, point=(nx // 2, ny // 3))
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (gd, mask.mean())
+        assert (got[0][mask == 0] == 0.0).all() and not np.signbit(got[0][mask == 0]).any()
+    if nx <= 300:
+        p = oracle.params_default(nx, ny, timeIntOrder=1, lap4=0, solidSwitch=1)
+        sim = yh.Sim(p, n_sims=2)
+        sim.set_solid(masks[0])
+        sim.set_state(np.stack([u, v]), np.stack([v, u]))
+        sim.run(n, tb_steps=tb)
+        su, sv = sim.get_state()
+        sim.close()
+        w0 = oracle.rd_advance(p, n, u, v, solid=masks[0])
+        w1 = oracle.rd_advance(p, n, v, u, solid=masks[0])
+        assert np.array_equal(su[0], w0[0]) and np.array_equal(sv[0], w0[1])
+        assert np.array_equal(su[1], w1[0]) and np.array_equal(sv[1], w1[1])
+
+
 def test_fast_path_gate_diff_off_and_negative_zero(oracle):
     p = oracle.params_default(96, 80, timeIntOrder=1, lap4=0, gateDiff=0)
     u, v = rand_fields(96, 80, 3)

@@ -208,6 +208,50 @@ def test_sapd_state_machine(oracle):
     assert st["sAPD"][0] in (1.0, -1.0)
 
 
+def test_contour_known_answers(oracle):
+    """countour_kernel (spaceAPD.cu:18-153) by hand on a 5 x 4 sheet."""
+    nx, ny = 5, 4
+    p = oracle.params_default(nx, ny)
+    # mode 1 (space-APD sign field): one sign change between columns 1|2 on every row
+    s = np.ones((ny, nx)); s[:, 2:] = -1.0
+    pts, n, plot = oracle.contour(p, None, s, 1, t=2.5, plot=True)
+    # v0 = +1, v1x = -1 -> ppx = i + 1/(1+1) = 1.5; ppy = j (v0 == v1y); one hit per row, row order.
+    # i = nx-1 reads the next row's first cell (+1) but zpmx uses v0*v0 there: no hit.
+    assert n == ny and [tuple(q) for q in pts] == [(1.5, float(j), 2.5) for j in range(ny)]
+    assert plot.reshape(ny, nx)[:, 1].all() and plot.sum() == ny
+    # `zpmx<0 || zpmy<0 && sc`: the mask gates only the y-crossing (precedence as written, :62)
+    s = np.ones((ny, nx)); s[2:, :] = -1.0; s[:, 3:] *= -1.0
+    area = np.zeros((ny, nx), dtype=np.uint8)
+    pts, n = oracle.contour(p, None, s, 1, stimArea=area)
+    assert n == ny and all(q["x"] == 2.5 for q in pts)            # x-crossings survive the mask
+    area[:] = 1
+    pts, n = oracle.contour(p, None, s, 1, stimArea=area)
+    assert n == ny + nx - 1    # + the y-crossing of row 1 in every column; (2,1) has both, one point
+    both = [q for q in pts if q["x"] == 2.5 and q["y"] == 1.5]
+    assert len(both) == 1
+    # mode 2: u < th1 and v crosses th2 (0.85) -> the cell's integer coordinates
+    u = np.full((ny, nx), 0.5); v = np.full((ny, nx), 0.9); v[:, 3:] = 0.8
+    u[0, 2] = 0.95                                                 # not below th1 = 0.8: no point
+    pts, n = oracle.contour(p, u, v, 2, t=1.0)
+    assert [tuple(q) for q in pts] == [(2.0, float(j), 1.0) for j in range(1, ny)]
+    # mode 3: both crossings of one cell, `-th2` first; |V| < th3 + 0.1 gates everything
+    u = np.full((ny, nx), 0.5); v = np.full((ny, nx), 0.85 + 0.85 + 0.05); v[:, 3:] = 0.85 + 0.85 - 0.05
+    pts, n = oracle.contour(p, u, v, 3)
+    assert n == 0                                                  # |V0| = 0.9 > th3 + 0.1 = 0.8
+    v = np.full((ny, nx), 0.85 - 0.7 + 0.02); v[:, 3:] = 0.85 - 0.7 - 0.02   # V + th3 changes sign
+    pts, n = oracle.contour(p, u, v, 3, t=0.5)
+    assert [tuple(q) for q in pts] == [(2.0, float(j), 0.5) for j in range(ny)]
+    # capacity clips the stored list, not the count
+    pts, n = oracle.contour(p, u, v, 3, capacity=2)
+    assert n == ny and len(pts) == 2
+    # colouring: get_rgba_kernel index = (int)((float)frac*(float)ncol), clamped; lines blank a pixel
+    cm = np.arange(10, dtype=np.uint32) + 100
+    f = np.array([[-0.1, 0.5, 1.0999, 1.1, 5.0], [-3.0, 0.02, 0.14, 0.26, 0.38]] * 2)
+    ln = np.zeros((ny, nx), dtype=np.uint8); ln[0, 1] = 1
+    out = oracle.rgba(p, f, cm, -0.1, 1.1, lines=ln).reshape(ny, nx)
+    assert out[0].tolist() == [100, 0, 109, 109, 109] and out[1].tolist() == [100, 101, 102, 103, 104]
+
+
 def test_hole_mask_generator_and_dat_roundtrip(tmp_path):
     m = synth.hole_mask(128, seed=7)
     frac = 1.0 - m.mean()

@@ -9,7 +9,7 @@ headless driver (``host``), synthetic inputs (``synth``) and the row-slab multi-
 calling a compute entry point without a CUDA device, raises.
 """
 from .host import Params, Sim, default_params, check  # noqa: F401
-from . import host, slab, synth  # noqa: F401
+from . import host, io, slab, synth  # noqa: F401
 from ._lib import lib, load_library, LIB_PATH, YolohtliError  # noqa: F401
 
 __all__ = ["Params", "Sim", "default_params", "check", "lib", "load_library", "LIB_PATH",

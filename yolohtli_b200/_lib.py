@@ -43,7 +43,43 @@ class YhTip(C.Structure):
                 ("t", C.c_float)]
 
 
+class YhContourPt(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("t", C.c_float)]
+
+
+class YhRunParams(C.Structure):
+    """struct yh_run_params of include/yolohtli_io.h (same order, same types)."""
+    _fields_ = [
+        ("k", YhParams),
+        ("read_path", C.c_char * 200), ("results_path", C.c_char * 200),
+        ("saveEveryIt", C.c_int32), ("plotTip", C.c_int32), ("recordTip", C.c_int32),
+        ("plotContour", C.c_int32), ("recordContour", C.c_int32), ("stimulate", C.c_int32),
+        ("plotTimeSeries", C.c_int32), ("recordTimeSeries", C.c_int32), ("reduceSym", C.c_int32),
+        ("contourMode", C.c_int32), ("clock", C.c_int32), ("counterclock", C.c_int32),
+        ("diff_par", C.c_double), ("diff_per", C.c_double), ("degrad", C.c_double),
+        ("Dxx", C.c_double), ("Dyy", C.c_double), ("Dxy", C.c_double),
+        ("physicalTimeLim", C.c_double), ("startRecTime", C.c_double),
+        ("eSize", C.c_int32), ("point_x", C.c_int32), ("point_y", C.c_int32),
+        ("stimPeriod", C.c_double), ("stimMag", C.c_double), ("stimDuration", C.c_double),
+        ("fibThreshold", C.c_double),
+        ("fibTerminated", C.c_int32), ("leapShocks", C.c_int32), ("nc", C.c_int32),
+        ("stcx", C.c_double), ("stcy", C.c_double), ("rdomStim", C.c_double),
+        ("rdomAPD", C.c_double), ("rdomTrapz", C.c_double),
+        ("itPerFrame", C.c_int32),
+        ("sample", C.c_double),
+        ("minVarColor", C.c_double), ("maxVarColor", C.c_double),
+        ("wnx", C.c_int32), ("wny", C.c_int32),
+        ("uMin", C.c_double), ("uMax", C.c_double), ("vMin", C.c_double), ("vMax", C.c_double),
+        ("tipx", C.c_double), ("tipy", C.c_double),
+        ("contourThresh1", C.c_double), ("contourThresh2", C.c_double),
+        ("contourThresh3", C.c_double),
+    ]
+
+
 _P = C.POINTER(YhParams)
+_RP = C.POINTER(YhRunParams)
+_s = C.c_char_p
+_ll = C.c_longlong
 _vp = C.c_void_p
 _i = C.c_int
 _d = C.c_double
@@ -72,6 +108,8 @@ SIGNATURES = {
                                   _vp, _vp]),
     "yh_sapd": (_i, [_P, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "yh_probe": (_i, [_P, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "yh_contour": (_i, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _i, _d, _d, _d, _vp]),
+    "yh_rgba": (_i, [_P, _vp, _vp, _vp, _i, _d, _d, _vp, _vp]),
     "yh_sim_create": (_i, [C.POINTER(_vp), _P, _i, _i]),
     "yh_sim_destroy": (_i, [_vp]),
     "yh_sim_set_state": (_i, [_vp, _vp, _vp]),
@@ -95,6 +133,30 @@ SIGNATURES = {
     "yh_sim_device_u": (_vp, [_vp]),
     "yh_sim_device_v": (_vp, [_vp]),
 }
+
+# include/yolohtli_io.h -- host-side data formats (no GPU needed)
+SIGNATURES.update({
+    "yh_io_run_params_default": (_i, [_RP, _i, _i]),
+    "yh_io_params_write_csv": (_i, [_s, _RP]),
+    "yh_io_params_read_csv": (_i, [_s, _RP]),
+    "yh_io_state_write_text": (_i, [_s, _vp, _vp, _i, _i]),
+    "yh_io_state_read_text": (_i, [_s, _vp, _vp, _i, _i]),
+    "yh_io_state_write_window": (_i, [_s, _vp, _vp, _i, _i, _d, _d, _i, _i, C.POINTER(_ll)]),
+    "yh_io_snapshot_write": (_i, [_s, _vp, _vp, _i, _i, _i, _ll, _d]),
+    "yh_io_snapshot_info": (_i, [_s, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_ll),
+                                 C.POINTER(_d)]),
+    "yh_io_snapshot_read": (_i, [_s, _vp, _vp, _ll]),
+    "yh_io_mask_read": (_i, [_s, _vp, _ll]),
+    "yh_io_mask_write": (_i, [_s, _vp, _ll]),
+    "yh_io_tips_append": (_i, [_s, _s, _vp, _i, _i]),
+    "yh_io_contour_append": (_i, [_s, _s, _vp, _i, _i]),
+    "yh_io_sym_write": (_i, [_s, _vp, _i]),
+    "yh_io_series_write": (_i, [_s, _vp, _vp, _i, _d, _i]),
+    "yh_io_contour_length_write": (_i, [_s, _vp, _i, _d, _i]),
+    "yh_io_reconstruct_tip": (_i, [_vp, _vp, _vp, _i, _d, _d, _vp, _vp]),
+    "yh_io_cmap_read": (_i, [_s, _vp, _i, C.POINTER(_i)]),
+    "yh_io_frame_write_ppm": (_i, [_s, _vp, _i, _i]),
+})
 
 _lib = None
 

@@ -155,7 +155,7 @@ int yh_rd_step(const yh_params *p, const double *u_in, const double *v_in, doubl
   // single steps that need no velTan take the Euler kernels (T = 1)
   if (!(velTan_u && k.gateDiff) && yh_rd_fast_supported(k, 1)) {
     if (tile) return yh_launch_rd_tile_euler(k, 1, u_in, v_in, u_out, v_out, 1, 0, nullptr, 0, 0, st);
-    return yh_launch_rd_fast(k, 1, u_in, v_in, u_out, v_out, solid, 1, st);
+    return yh_launch_rd_fast(k, 1, u_in, v_in, u_out, v_out, nullptr, 1, st);
   }
   if (tile && yh_rd_tile_rk_supported(k))
     return yh_launch_rd_tile_rk(k, u_in, v_in, u_out, v_out, velTan_u, velTan_v, st);
@@ -183,9 +183,18 @@ int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, int flags, doubl
   int left = nsteps;
   int tb = tb_steps ? tb_steps : 4;
   int canon = (flags & YH_RD_INPUT_CANONICAL) ? 0 : 1;   // only the first pass can see user data
+  // obstacle masks + Euler: the temporally blocked kernel reads per-cell mask patterns, made
+  // once per call (mask contents belong to the caller and may change between calls)
+  uint8_t *pat = nullptr;
+  if (yh_rd_fast_solid_supported(k, 1) && nsteps > 1) {
+    rc = yh_workspace((size_t)p->nx * p->ny, (void **)&pat, 4);
+    if (rc != YH_OK) return rc;
+    rc = yh_rd_solid_patterns(k, solid, pat, st);
+    if (rc != YH_OK) return rc;
+  }
   while (left > 0) {
     int T = 1;
-    if (yh_rd_fast_supported(k, 1)) { T = tb; while (T > left) T >>= 1; }
+    if (pat || yh_rd_fast_supported(k, 1)) { T = tb; while (T > left) T >>= 1; }
     // rows that must be valid after this pass so that the remaining steps stay exact
     const int ext = (left - T) * K;
     k.row0 = row0 - ext > dom_lo ? row0 - ext : dom_lo;
@@ -193,9 +202,12 @@ int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, int flags, doubl
     if (k.row0 < 0) k.row0 = 0;
     if (k.row1 > p->ny) k.row1 = p->ny;
     const bool tile = yh_rd_prefer_tile((long long)k.nx * (k.row1 - k.row0)) != 0;
-    if (yh_rd_fast_supported(k, T)) {
+    if (pat) {
+      rc = yh_launch_rd_fast(k, T, cu, cv, nu, nv, pat, canon, st);
+      canon = 0;
+    } else if (yh_rd_fast_supported(k, T)) {
       if (tile) rc = yh_launch_rd_tile_euler(k, T, cu, cv, nu, nv, 1, 0, nullptr, 0, 0, st);
-      else rc = yh_launch_rd_fast(k, T, cu, cv, nu, nv, solid, canon, st);
+      else rc = yh_launch_rd_fast(k, T, cu, cv, nu, nv, nullptr, canon, st);
       canon = 0;
     } else if (tile && yh_rd_tile_rk_supported(k)) rc = yh_launch_rd_tile_rk(k, cu, cv, nu, nv, nullptr, nullptr, st);
     else if (yh_rd_rk_supported(k)) rc = yh_launch_rd_rk(k, cu, cv, nu, nv, nullptr, nullptr, solid, st);

@@ -31,6 +31,7 @@ struct FastArgs {
   const int *period;      // per-sheet pacing period in steps (NULL: k.stim decides)
   int duration, count0;   // stimulus on while (step % period) <= duration; step of level 1
   YhApd apd;              // fused APD bookkeeping (STIM variants only); apd.APD1 == NULL: off
+  const uint8_t *pat;     // SOLID variants: 5-bit mask pattern per cell (solid_pattern_kernel)
 };
 
 // The APD state machine of one cell (spaceAPD.cu:296-342), entered only when the step crossed
@@ -79,19 +80,15 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // DEF (the reference's default constants tc = mu = delta = 1, gamma = theta = 0,
 // saveFiles.cu:220-227) drops the operations that are exact identities in IEEE arithmetic:
 // 1.0*x == x, x - 0.0 == x.  2.0*u is exact, so fma(-2.0, u, w) == w - 2.0*u bit for bit.
+// Everything after the Laplacian: ionic terms and the update (du, dv hold the diffusion part).
 template <bool DEF>
-__device__ __forceinline__ void euler_cell(const YhK &k, double u, double v, double uW, double uE,
-                                           double uN, double uS, double vW, double vE, double vN,
-                                           double vS, bool scs, double &un, double &vn) {
+__device__ __forceinline__ void euler_finish(const YhK &k, double u, double v, double du, double dv,
+                                             bool scs, double &un, double &vn) {
   const double mu_u = DEF ? u : k.mu * u;
   const double X = mu_u * (1.0 - u) * (u - k.alpha) - u * v;
   const double ug = DEF ? u : k.delta * (u - k.gamma);
   const double yv = ug * (k.beta - u) - v;
   const double Y = k.eps * (DEF ? yv : yv - k.theta);
-  double du = ((fma(-2.0, u, uW) + uE) * k.rx + (fma(-2.0, u, uN) + uS) * k.ry);
-  double dv = 0.0;
-  if (k.gateDiff)
-    dv = ((fma(-2.0, v, vW) + vE) * k.rx * k.rscale + (fma(-2.0, v, vN) + vS) * k.ry * k.rscale);
   if (!scs) {
     du = du + k.dt * X;
   } else {   // inside the stimulus disc: the literal expression
@@ -103,10 +100,49 @@ __device__ __forceinline__ void euler_cell(const YhK &k, double u, double v, dou
   vn = v + (DEF ? dv : k.tc * dv);
 }
 
+template <bool DEF>
+__device__ __forceinline__ void euler_cell(const YhK &k, double u, double v, double uW, double uE,
+                                           double uN, double uS, double vW, double vE, double vN,
+                                           double vS, bool scs, double &un, double &vn) {
+  const double du = ((fma(-2.0, u, uW) + uE) * k.rx + (fma(-2.0, u, uN) + uS) * k.ry);
+  double dv = 0.0;
+  if (k.gateDiff)
+    dv = ((fma(-2.0, v, vW) + vE) * k.rx * k.rscale + (fma(-2.0, v, vN) + vS) * k.ry * k.rscale);
+  euler_finish<DEF>(k, u, v, du, dv, scs, un, vn);
+}
+
+// Obstacle masks (reactionDiffusion.cu:154-184, 515-537).  pat = sc | sw<<1 | se<<2 | sn<<3 | ss<<4
+// (mask of the cell and of its mirrored W / E / N = j+1 / S = j-1 neighbours).  The six
+// coefficients are exact 0 / 1 / 2 and the products are formed literally; non-tissue cells come
+// out as exactly 0.0.  For the all-tissue pattern (31) this is bit-identical to euler_cell
+// (1.0*x == x, 2.0*u exact), which is what lets a warp whose cells are all standard skip it.
+__device__ __forceinline__ double c012(unsigned c2) {   // 0 / 1 / 2 as a double, no conversion
+  return __hiloint2double(c2 ? (int)(0x3FE00000u + (c2 << 20)) : 0, 0);
+}
+template <bool DEF>
+__device__ __forceinline__ void euler_cell_solid(const YhK &k, unsigned pat, double u, double v,
+                                                 double uW, double uE, double uN, double uS,
+                                                 double vW, double vE, double vN, double vS, bool scs,
+                                                 double &un, double &vn) {
+  const bool sc = pat & 1u, sw = pat & 2u, se = pat & 4u, sn = pat & 8u, ss = pat & 16u;
+  const double cxx = c012((sw && se) && (sw && sc) ? 1u : ((sw && sc) ? 2u : 0u));   // :162-169
+  const double cxy = c012(sc ? ((sw || se) ? 2u : 0u) : 0u);
+  const double cxz = c012((sw && se) && (sc && se) ? 1u : ((sc && se) ? 2u : 0u));
+  const double cyx = c012((sn && ss) && (sn && sc) ? 1u : ((sn && sc) ? 2u : 0u));
+  const double cyy = c012(sc ? ((sn || ss) ? 2u : 0u) : 0u);
+  const double cyz = c012((sn && ss) && (sc && ss) ? 1u : ((sc && ss) ? 2u : 0u));
+  const double du = ((cxx * uW - cxy * u + cxz * uE) * k.rx + (cyx * uN - cyy * u + cyz * uS) * k.ry);
+  double dv = 0.0;
+  if (k.gateDiff)
+    dv = ((cxx * vW - cxy * v + cxz * vE) * k.rx * k.rscale + (cyx * vN - cyy * v + cyz * vS) * k.ry * k.rscale);
+  euler_finish<DEF>(k, u, v, du, dv, scs, un, vn);
+  if (!sc) { un = 0.0; vn = 0.0; }   // :521-522
+}
+
 // T time levels, strip of W columns, one extra warp that only feeds level 0.
 // The compute loop is unrolled by three so that the S / C / N row registers rotate by renaming
 // instead of by moves; every sub-iteration ends in the CTA-wide barrier.
-template <int T, int W, bool CANON, bool TC1, bool STIM>
+template <int T, int W, bool CANON, bool TC1, bool STIM, bool SOLID>
 __global__ void __launch_bounds__(T *(W / 2) + 32)
 rd_euler_stream(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a) {
   constexpr int H = (T + 1) & ~1;        // halo columns each side (even: 16-byte alignment)
@@ -204,10 +240,22 @@ rd_euler_stream(const __grid_constant__ YhK k, const __grid_constant__ FastArgs 
     if (canon) { pu.x += 0.0; pu.y += 0.0; pv.x += 0.0; pv.y += 0.0; }
   };
 
+  // mask patterns of the pair, fetched one row ahead of use (global / L2; 1 B per cell)
+  unsigned pat_next = 0x1F1Fu;
+  auto ld_pat = [&](int row) -> unsigned {
+    return *reinterpret_cast<const unsigned short *>(a.pat + (size_t)row * nx + gx);
+  };
+
   // one row: S / C / N are the register-resident source rows m-1, m, m+1
   auto row_step = [&](int m, double2 &uS, double2 &vS, double2 &uC, double2 &vC, double2 &uN,
                       double2 &vN) {
     if (m >= lo_l && m < hi_l) {
+      unsigned pat = 0x1F1Fu;
+      if (SOLID) {
+        if (m == lo_l) pat_next = ld_pat(m);
+        pat = pat_next;
+        if (m + 1 < hi_l) pat_next = ld_pat(m + 1);
+      }
       if (m == lo_l) {                   // first row of this level: nothing in registers yet
         ld_pair(m, uC, vC);
         ld_pair((m - 1 < dom_lo) ? m + 1 : m - 1, uS, vS);   // no-flux mirror at the first row
@@ -221,8 +269,13 @@ rd_euler_stream(const __grid_constant__ YhK k, const __grid_constant__ FastArgs 
       bool s0 = false, s1 = false;
       if (STIM && stim_on) { s0 = yh_scs_on(k, gx, m + k.jg0); s1 = yh_scs_on(k, gx + 1, m + k.jg0); }
       double2 uo, vo;
-      euler_cell<TC1>(k, uC.x, vC.x, uw, uC.y, uN.x, uS.x, vw, vC.y, vN.x, vS.x, s0, uo.x, vo.x);
-      euler_cell<TC1>(k, uC.y, vC.y, uC.x, ue, uN.y, uS.y, vC.x, ve, vN.y, vS.y, s1, uo.y, vo.y);
+      if (!SOLID || __all_sync(__activemask(), pat == 0x1F1Fu)) {   // all tissue around: plain stencil
+        euler_cell<TC1>(k, uC.x, vC.x, uw, uC.y, uN.x, uS.x, vw, vC.y, vN.x, vS.x, s0, uo.x, vo.x);
+        euler_cell<TC1>(k, uC.y, vC.y, uC.x, ue, uN.y, uS.y, vC.x, ve, vN.y, vS.y, s1, uo.y, vo.y);
+      } else {
+        euler_cell_solid<TC1>(k, pat & 0xFFu, uC.x, vC.x, uw, uC.y, uN.x, uS.x, vw, vC.y, vN.x, vS.x, s0, uo.x, vo.x);
+        euler_cell_solid<TC1>(k, pat >> 8, uC.y, vC.y, uC.x, ue, uN.y, uS.y, vC.x, ve, vN.y, vS.y, s1, uo.y, vo.y);
+      }
       if (STIM && a.apd.APD1 && out_col && m >= y0 && m < y0 + RYe) {   // fused sAPD epilogue (owner cells)
         const double th = 0.15;
         const bool e0 = ((uC.x > th) && (uo.x < th)) || ((uC.x < th) && (uo.x > th));
@@ -277,7 +330,7 @@ static int pick_ry(int rows, int strips, int nsims, int T, int slots) {
   return best_ry;
 }
 
-template <int T, int W, bool CANON, bool TC1, bool STIM>
+template <int T, int W, bool CANON, bool TC1, bool STIM, bool SOLID>
 int launch3(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   constexpr int H = (T + 1) & ~1, BX = W - 2 * H, PITCH = W + 4, ROW = 2 * PITCH;
   constexpr int NT = T * (W / 2) + 32;
@@ -286,14 +339,14 @@ int launch3(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    YH_CUDA(cudaFuncSetAttribute(rd_euler_stream<T, W, CANON, TC1, STIM>,
+    YH_CUDA(cudaFuncSetAttribute(rd_euler_stream<T, W, CANON, TC1, STIM, SOLID>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[dev & 63] = true;
   }
   static int slots[64] = {0};
   if (!slots[dev & 63]) {
     int per_sm = 1, sms = 148;
-    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_euler_stream<T, W, CANON, TC1, STIM>,
+    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_euler_stream<T, W, CANON, TC1, STIM, SOLID>,
                                                           NT, smem));
     YH_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     slots[dev & 63] = (per_sm > 0 ? per_sm : 1) * sms;
@@ -303,7 +356,7 @@ int launch3(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   const int strips = (k.nx + BX - 1) / BX;
   b.RY = a.RY > 0 ? a.RY : pick_ry(rows, strips, nsims, T, slots[dev & 63]);
   dim3 grd(strips, (rows + b.RY - 1) / b.RY, nsims);
-  rd_euler_stream<T, W, CANON, TC1, STIM><<<grd, NT, smem, st>>>(k, b);
+  rd_euler_stream<T, W, CANON, TC1, STIM, SOLID><<<grd, NT, smem, st>>>(k, b);
   YH_LAUNCH_CHECK();
   return YH_OK;
 }
@@ -311,8 +364,10 @@ int launch3(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
 template <int T, int W, bool CANON, bool TC1>
 int launch2(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   const bool stim = k.stim != 0 || a.period != nullptr || a.apd.APD1 != nullptr;
-  return stim ? launch3<T, W, CANON, TC1, true>(k, a, nsims, st)
-              : launch3<T, W, CANON, TC1, false>(k, a, nsims, st);
+  if (a.pat)   // obstacle masks: one variant (STIM on) keeps the instantiation count down
+    return launch3<T, W, CANON, TC1, true, true>(k, a, nsims, st);
+  return stim ? launch3<T, W, CANON, TC1, true, false>(k, a, nsims, st)
+              : launch3<T, W, CANON, TC1, false, false>(k, a, nsims, st);
 }
 
 template <int T, int W>
@@ -323,23 +378,60 @@ int launch(const YhK &k, const FastArgs &a, int nsims, bool canon, cudaStream_t 
   return tc1 ? launch2<T, W, false, true>(k, a, nsims, st) : launch2<T, W, false, false>(k, a, nsims, st);
 }
 
+// pat[c] = sc | sw<<1 | se<<2 | sn<<3 | ss<<4 with the neighbour indices of
+// reactionDiffusion.cu:149-152 (mirrored at the GLOBAL edges); rows whose vertical neighbour is
+// not stored locally (outermost ghost rows of a slab) are never computed, they get a clamped index.
+__global__ void solid_pattern_kernel(const __grid_constant__ YhK k, const uint8_t *__restrict__ solid,
+                                     uint8_t *__restrict__ pat) {
+  const long long n = (long long)k.nx * k.ny;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n;
+       c += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(c % k.nx), j = (int)(c / k.nx), gj = j + k.jg0;
+    int jS = yh_mir(gj - 1, k.nyg) - k.jg0, jN = yh_mir(gj + 1, k.nyg) - k.jg0;
+    jS = min(max(jS, 0), k.ny - 1); jN = min(max(jN, 0), k.ny - 1);
+    const unsigned sc = solid[c] != 0;
+    const unsigned sw = solid[(size_t)j * k.nx + yh_mir(i - 1, k.nx)] != 0;
+    const unsigned se = solid[(size_t)j * k.nx + yh_mir(i + 1, k.nx)] != 0;
+    const unsigned sn = solid[(size_t)jN * k.nx + i] != 0;
+    const unsigned ss = solid[(size_t)jS * k.nx + i] != 0;
+    pat[c] = (uint8_t)(sc | (sw << 1) | (se << 2) | (sn << 3) | (ss << 4));
+  }
+}
+
 }  // namespace
 
-int yh_rd_fast_supported(const YhK &k, int tb) {
-  if (k.timeIntOrder != 1 || k.lap4 || !k.neumannBC || k.solidSwitch || k.anisotropy)
-    return 0;
+// Euler / 5-point / no-flux; the obstacle-mask mode is covered too when the caller supplies the
+// pattern array (yh_rd_solid_patterns), see yh_rd_fast_solid_supported.
+static int fast_mode_ok(const YhK &k, int tb) {
+  if (k.timeIntOrder != 1 || !k.neumannBC) return 0;
   if (!(k.tc > 0.0)) return 0;            // zero-sign argument needs tc > 0
   if ((k.nx & 1) || k.nx < 8) return 0;   // two cells per thread, 16-byte rows
   if (tb != 1 && tb != 2 && tb != 4) return 0;
   return 1;
 }
+int yh_rd_fast_supported(const YhK &k, int tb) {
+  if (k.lap4 || k.solidSwitch || k.anisotropy) return 0;
+  return fast_mode_ok(k, tb);
+}
+// lap4 and anisotropy are ignored in the mask branch (reactionDiffusion.cu:154-184)
+int yh_rd_fast_solid_supported(const YhK &k, int tb) {
+  return k.solidSwitch ? fast_mode_ok(k, tb) : 0;
+}
+
+int yh_rd_solid_patterns(const YhK &k, const uint8_t *solid, uint8_t *pat, cudaStream_t st) {
+  const long long n = (long long)k.nx * k.ny;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  solid_pattern_kernel<<<blocks, 256, 0, st>>>(k, solid, pat);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
 
 int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const double *v_in,
                             double *u_out, double *v_out, int nsims, long long sim_stride,
                             const int *period_d, int duration_it, int count0, int canon_in,
-                            cudaStream_t st, const YhApd *apd) {
-  if (!yh_rd_fast_supported(k, tb)) return YH_ERR_UNSUPPORTED;
-  FastArgs a{u_in, v_in, u_out, v_out, 0, sim_stride, period_d, duration_it, count0, {}};
+                            cudaStream_t st, const YhApd *apd, const uint8_t *pat) {
+  if (!(pat ? yh_rd_fast_solid_supported(k, tb) : yh_rd_fast_supported(k, tb))) return YH_ERR_UNSUPPORTED;
+  FastArgs a{u_in, v_in, u_out, v_out, 0, sim_stride, period_d, duration_it, count0, {}, pat};
   if (apd) a.apd = *apd; else memset(&a.apd, 0, sizeof(a.apd));
   const int rows = k.row1 - k.row0;
   if (rows <= 0) return YH_OK;
@@ -365,8 +457,8 @@ int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const doub
 }
 
 int yh_launch_rd_fast(const YhK &k, int tb, const double *u_in, const double *v_in,
-                      double *u_out, double *v_out, const uint8_t *solid, int canon_in,
+                      double *u_out, double *v_out, const uint8_t *pat, int canon_in,
                       cudaStream_t st) {
-  (void)solid;
-  return yh_launch_rd_fast_paced(k, tb, u_in, v_in, u_out, v_out, 1, 0, nullptr, 0, 0, canon_in, st);
+  return yh_launch_rd_fast_paced(k, tb, u_in, v_in, u_out, v_out, 1, 0, nullptr, 0, 0, canon_in, st,
+                                 nullptr, pat);
 }

@@ -119,6 +119,40 @@ void sAPD_wrapper(size_t, dim3, dim3, int count, REAL *uold, REAL *unew, REAL *A
        "sAPD_wrapper");
 }
 
+// conTh1_d..conTh3_d and minVarColor_d / maxVarColor_d are __constant__ symbols in the reference
+// (main.cu:378-383, 366-369); defaults of parameterSetup (saveFiles.cu:196-217).
+static double g_con_th[3] = {0.8, 0.85, 0.7};
+static double g_color[2] = {-0.1f, 1.1f};
+extern "C" int yh_shim_set_contour_thresholds(double th1, double th2, double th3) {
+  g_con_th[0] = th1; g_con_th[1] = th2; g_con_th[2] = th3;
+  return YH_OK;
+}
+extern "C" int yh_shim_set_color_range(double min_var, double max_var) {
+  if (min_var == max_var) return YH_ERR_INVALID_ARG;
+  g_color[0] = min_var; g_color[1] = max_var;
+  return YH_OK;
+}
+
+void countour_wrapper(size_t, dim3, dim3, REAL *field1, REAL *field2, bool *contour_plot,
+                      bool *stimArea, int *contour_count, float3 *contour_vector, float physicalTime,
+                      int mode) {
+  if (!ready("countour_wrapper")) return;
+  // capacity: the reference allocates nx*ny float3 (main.cu:300)
+  note(yh_contour(&g_p, field1, field2, reinterpret_cast<uint8_t *>(contour_plot),
+                  reinterpret_cast<const uint8_t *>(stimArea), contour_count,
+                  reinterpret_cast<yh_contour_pt *>(contour_vector), g_p.nx * g_p.ny, physicalTime,
+                  mode, g_con_th[0], g_con_th[1], g_con_th[2], nullptr),
+       "countour_wrapper");
+}
+
+void get_rgba_wrapper(size_t, dim3, dim3, int ncol, REAL *field, unsigned int *plot_rba_data,
+                      unsigned int *cmap_rgba_data, bool *lines) {
+  if (!ready("get_rgba_wrapper")) return;
+  note(yh_rgba(&g_p, field, plot_rba_data, cmap_rgba_data, ncol, g_color[0], g_color[1],
+               reinterpret_cast<const uint8_t *>(lines), nullptr),
+       "get_rgba_wrapper");
+}
+
 void swapSoA(stateVar *A, stateVar *B) {
   stateVar t = *A;
   *A = *B;

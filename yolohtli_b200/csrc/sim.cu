@@ -29,6 +29,7 @@ struct yh_sim {
   double c[3], phi[3];   // drift velocities and frame phase (main.cu:60-61)
   double *apd[6];        // APD1 APD2 sAPD dAPD back front, n_sims sheets each (lazily allocated)
   uint8_t *apd_first, *stim_area;
+  uint8_t *pat;          // mask patterns of the temporally blocked Euler kernel (yh_rd_solid_patterns)
   int apd_init;          // sAPD / dAPD hold values for every cell (one full pass done)
   cudaStream_t st;
 };
@@ -65,7 +66,7 @@ int yh_sim_create(yh_sim **out, const yh_params *p, int n_sims, int device) {
   s->p = *p;
   s->n_sims = n_sims; s->device = device;
   s->n = (size_t)p->nx * p->ny;
-  s->cur = 0; s->solid = nullptr; s->trace_d = nullptr; s->trace_cap = 0;
+  s->cur = 0; s->solid = nullptr; s->pat = nullptr; s->trace_d = nullptr; s->trace_cap = 0;
   s->period_d = nullptr; s->duration_it = 0; s->count = 0; s->have_prev = 0; s->raw_input = 1;
   s->px = p->nx / 2; s->py = p->ny / 2;   // param.point, saveFiles.cu:180
   s->vt[0] = s->vt[1] = s->adv[0] = s->adv[1] = nullptr;
@@ -93,7 +94,7 @@ int yh_sim_destroy(yh_sim *s) {
   DevGuard g(s->device);
   cudaStreamSynchronize(s->st);
   for (int b = 0; b < 2; b++) { cudaFree(s->u[b]); cudaFree(s->v[b]); }
-  cudaFree(s->solid); cudaFree(s->trace_d); cudaFree(s->tip_count_d); cudaFree(s->tip_vec_d);
+  cudaFree(s->solid); cudaFree(s->pat); cudaFree(s->trace_d); cudaFree(s->tip_count_d); cudaFree(s->tip_vec_d);
   cudaFree(s->period_d);
   cudaFree(s->vt[0]); cudaFree(s->vt[1]); cudaFree(s->adv[0]); cudaFree(s->adv[1]);
   for (int q = 0; q < 6; q++) cudaFree(s->apd[q]);
@@ -129,7 +130,11 @@ int yh_sim_set_solid(yh_sim *s, const uint8_t *solid_h) {
   YH_REQUIRE(s && solid_h, "null pointer");
   DevGuard g(s->device);
   if (!s->solid) YH_CUDA(cudaMalloc(&s->solid, s->n));
+  if (!s->pat) YH_CUDA(cudaMalloc(&s->pat, s->n));
   YH_CUDA(cudaMemcpy(s->solid, solid_h, s->n, cudaMemcpyHostToDevice));
+  int rc = yh_rd_solid_patterns(yh_make_k(&s->p), s->solid, s->pat, s->st);
+  if (rc != YH_OK) return rc;
+  YH_CUDA(cudaStreamSynchronize(s->st));
   return YH_OK;
 }
 
@@ -195,7 +200,8 @@ static int sim_run_impl(yh_sim *s, int nsteps, int tb_steps, double *trace_h, bo
       s->trace_cap = need;
     }
   }
-  const bool fast1 = yh_rd_fast_supported(k, 1) != 0;
+  const uint8_t *pat = (s->pat && yh_rd_fast_solid_supported(k, 1)) ? s->pat : nullptr;
+  const bool fast1 = pat != nullptr || yh_rd_fast_supported(k, 1) != 0;
   int left = nsteps, step = 0;
   while (left > 0) {
     int T = 1;
@@ -208,13 +214,13 @@ static int sim_run_impl(yh_sim *s, int nsteps, int tb_steps, double *trace_h, bo
       YH_LAUNCH_CHECK();
     }
     int rc;
-    const bool tile = yh_rd_prefer_tile((long long)s->n * s->n_sims) != 0;
+    const bool tile = !pat && yh_rd_prefer_tile((long long)s->n * s->n_sims) != 0;
     if (fast1 && tile) {
       rc = yh_launch_rd_tile_euler(k, T, s->u[c], s->v[c], s->u[o], s->v[o], s->n_sims, stride,
                                    s->period_d, s->duration_it, s->count, s->st);
     } else if (fast1) {
       rc = yh_launch_rd_fast_paced(k, T, s->u[c], s->v[c], s->u[o], s->v[o], s->n_sims, stride,
-                                   s->period_d, s->duration_it, s->count, s->raw_input, s->st);
+                                   s->period_d, s->duration_it, s->count, s->raw_input, s->st, nullptr, pat);
     } else {
       rc = YH_OK;
       for (int z = 0; z < s->n_sims && rc == YH_OK; z++) {

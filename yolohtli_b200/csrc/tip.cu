@@ -8,6 +8,7 @@
 // comes out in ascending linear cell index, '+' root before '-' root, in one launch, with no
 // sort and no host round trip.  Cost: 16 B per cell of reads -- HBM-bound.
 #include "yh_common.cuh"
+#include "yh_ordered.cuh"
 
 namespace {
 
@@ -23,9 +24,7 @@ struct TipArgs {
   int capacity;
   int algorithm;
   float t;
-  unsigned long long *state;   // [0] ticket, [1 + b] look-back word of chunk b
-  unsigned epoch;              // distinguishes this launch's words from stale ones
-  int nchunks;
+  YhOrdered ord;               // ticket + look-back words (yh_ordered.cuh)
 };
 
 __device__ __forceinline__ bool equals_tol(double a, double b, double tol) {   // helper_functions.cu:58
@@ -133,18 +132,13 @@ __device__ int tip_cell(const YhK &k, const TipArgs &a, int i, int j, float2 *ro
   return n;
 }
 
-// look-back word: [63:40] epoch, [33:32] flag (1 = aggregate, 2 = inclusive prefix), [31:0] value
-__device__ __forceinline__ unsigned long long lb_pack(unsigned epoch, unsigned flag, unsigned v) {
-  return ((unsigned long long)(epoch & 0xFFFFFFu) << 40) | ((unsigned long long)flag << 32) | v;
-}
-
 __global__ void __launch_bounds__(TIP_THREADS)
 tip_kernel(const __grid_constant__ YhK k, const __grid_constant__ TipArgs a) {
   __shared__ int s_chunk;
   __shared__ int s_warp[TIP_THREADS / 32];
   __shared__ int s_base;
   const int tid = threadIdx.x;
-  if (tid == 0) s_chunk = (int)atomicAdd(&a.state[0], 1ull);   // ticket = chunk, in launch order
+  if (tid == 0) s_chunk = (int)atomicAdd(&a.ord.state[0], 1ull);   // ticket = chunk, in launch order
   __syncthreads();
   const int chunk = s_chunk;
   const long long ncell = (long long)k.nx * k.ny;
@@ -177,45 +171,10 @@ tip_kernel(const __grid_constant__ YhK k, const __grid_constant__ TipArgs a) {
     mine += nr[r];
   }
 
-  // block-wide exclusive scan of `mine` in thread order (= cell order)
-  const int lane = tid & 31, wid = tid >> 5;
-  int incl = mine;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += t;
-  }
-  if (lane == 31) s_warp[wid] = incl;
-  __syncthreads();
-  int woff = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < TIP_THREADS / 32; w++) {
-    if (w < wid) woff += s_warp[w];
-    total += s_warp[w];
-  }
-  const int excl = woff + incl - mine;
-
-  if (tid == 0) {
-    volatile unsigned long long *st = a.state + 1;
-    unsigned prefix = 0;
-    if (chunk > 0) {
-      st[chunk] = lb_pack(a.epoch, 1u, (unsigned)total);
-      __threadfence();
-      for (int b = chunk - 1; b >= 0; b--) {
-        unsigned long long w;
-        do { w = st[b]; } while ((unsigned)(w >> 40) != (a.epoch & 0xFFFFFFu) || ((w >> 32) & 3u) == 0u);
-        prefix += (unsigned)w;
-        if (((w >> 32) & 3u) == 2u) break;
-      }
-    }
-    st[chunk] = lb_pack(a.epoch, 2u, prefix + (unsigned)total);
-    __threadfence();
-    s_base = (int)prefix;
-    if (chunk == a.nchunks - 1) {
-      *a.count = (int)(prefix + (unsigned)total);   // replaces cudaMemset(tip_count) + atomicAdd
-      a.state[0] = 0ull;                            // every ticket has been taken: re-arm
-    }
-  }
+  // block-wide exclusive scan of `mine` in thread order (= cell order), then the chunk prefix
+  int total;
+  const int excl = yh_block_excl_scan<TIP_THREADS>(mine, s_warp, total);
+  if (tid == 0) s_base = (int)yh_ordered_prefix(a.ord, chunk, (unsigned)total, a.count);
   __syncthreads();
   if (mine == 0) return;
 
@@ -261,7 +220,7 @@ extern "C" int yh_tip_track(const yh_params *p, const double *u_past, const doub
   epoch = (epoch + 1) & 0xFFFFFFu;
   if (epoch == 0) epoch = 1;   // zero-initialised workspace must never look current
   TipArgs a{u_past, u_present, tip_plot, tip_count, tip_vector, capacity, algorithm,
-            (float)physical_time, state, epoch, nchunks};
+            (float)physical_time, {state, epoch, nchunks}};
   tip_kernel<<<nchunks, TIP_THREADS, 0, (cudaStream_t)stream>>>(k, a);
   YH_LAUNCH_CHECK();
   return YH_OK;

@@ -111,13 +111,17 @@ int yh_launch_rd_generic(const YhK &k, const double *u_in, const double *v_in, d
 int yh_rd_fast_supported(const YhK &k, int tb);
 // canon_in: the input may hold -0.0 (user data) and must go through "u0 + 0.0" literally;
 // outputs of these kernels never hold -0.0, so later passes skip it (zero signs).
+// Obstacle masks on the same path: pat = per-cell 5-bit neighbourhood pattern produced once from
+// the mask by yh_rd_solid_patterns (nx*ny bytes, local rows); NULL = no mask.
+int yh_rd_fast_solid_supported(const YhK &k, int tb);
+int yh_rd_solid_patterns(const YhK &k, const uint8_t *solid, uint8_t *pat, cudaStream_t st);
 int yh_launch_rd_fast(const YhK &k, int tb, const double *u_in, const double *v_in,
-                      double *u_out, double *v_out, const uint8_t *solid, int canon_in,
+                      double *u_out, double *v_out, const uint8_t *pat, int canon_in,
                       cudaStream_t st);
 int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const double *v_in,
                             double *u_out, double *v_out, int nsims, long long sim_stride,
                             const int *period_d, int duration_it, int count0, int canon_in,
-                            cudaStream_t st, const YhApd *apd = nullptr);
+                            cudaStream_t st, const YhApd *apd = nullptr, const uint8_t *pat = nullptr);
 
 // Fused Runge-Kutta (RK2/RK4, optional 4th-order Laplacian) step, one launch per time step.
 int yh_rd_rk_supported(const YhK &k);

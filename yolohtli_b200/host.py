@@ -160,6 +160,34 @@ def sapd(p, count, uold, unew, APD1, APD2, sAPD, dAPD, back, front, first, stimA
                         int(stimulate), _stream()))
 
 
+CONTOUR_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("t", "<f4")])
+CONTOUR_THRESH = (0.8, 0.85, 0.7)   # contourThresh1..3, saveFiles.cu:215-217
+
+
+def contour(p, field1, field2, contour_count, contour_vector, mode, contour_plot=None, stimArea=None,
+            t=0.0, thresh=CONTOUR_THRESH, capacity=None):
+    """countour_wrapper (spaceAPD.cu:256-276).  contour_vector: CUDA uint8 tensor of capacity*12
+    bytes; contour_count: CUDA int32 tensor of one element."""
+    cap = capacity if capacity is not None else contour_vector.numel() // 12
+    check(lib().yh_contour(C.byref(p), _ptr(field1), _ptr(field2), _ptr(contour_plot), _ptr(stimArea),
+                           _ptr(contour_count), _ptr(contour_vector), cap, float(t), mode,
+                           float(thresh[0]), float(thresh[1]), float(thresh[2]), _stream()))
+
+
+def contour_to_numpy(contour_count, contour_vector):
+    n = int(contour_count.item())
+    m = min(n, contour_vector.numel() // 12)
+    raw = contour_vector[: m * 12].cpu().numpy().tobytes()
+    return np.frombuffer(raw, dtype=CONTOUR_DTYPE).copy(), n
+
+
+def rgba(p, field, plot_rgba, cmap_rgba, min_var=-0.1, max_var=1.1, lines=None):
+    """get_rgba_wrapper (main.cu:1633-1641); plot_rgba / cmap_rgba: CUDA int32 tensors holding the
+    packed 0xAABBGGRR words."""
+    check(lib().yh_rgba(C.byref(p), _ptr(field), _ptr(plot_rgba), _ptr(cmap_rgba), cmap_rgba.numel(),
+                        float(min_var), float(max_var), _ptr(lines), _stream()))
+
+
 def probe(p, u, v, pt_d, x, y):
     """singleCell_wrapper (singleCell.cu:22-30) without the blocking copy."""
     check(lib().yh_probe(C.byref(p), _ptr(u), _ptr(v), _ptr(pt_d), x, y, None, _stream()))
