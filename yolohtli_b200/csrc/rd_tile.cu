@@ -19,7 +19,7 @@
 namespace {
 
 constexpr int TB = 32;          // output tile edge
-constexpr int NTHR = 256;
+constexpr int NTHR = 416;        // RK kernel: 13 warps, 2 pairs per thread (832 slots for 800 pairs), 2 CTAs/SM
 
 template <bool DEF>
 __device__ __forceinline__ double t_Isum(const YhK &k, double u, double v, bool scs) {
@@ -53,7 +53,7 @@ struct TileArgs {
 // Runge-Kutta tile kernel
 // ------------------------------------------------------------------------------------------
 template <int K, bool LAP4, bool DEF>
-__global__ void __launch_bounds__(NTHR)
+__global__ void __launch_bounds__(NTHR, 2)
 rd_tile_rk(const __grid_constant__ YhK k, const __grid_constant__ TileArgs a) {
   constexpr int H = K;                       // halo (K = 2 or 4: even, keeps pairs 16-byte aligned)
   constexpr int TW = TB + 2 * H;             // tile width / height in cells
@@ -219,40 +219,54 @@ rd_tile_rk(const __grid_constant__ YhK k, const __grid_constant__ TileArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Euler tile kernel: T steps per launch, ping-pong planes in shared memory
+// Euler tile kernel: T steps per launch.  ONE pair per thread for the whole launch: the pair's own
+// values stay in registers from step to step, only its neighbours come from the ping-pong planes
+// in shared memory; index arithmetic and boundary selections are done once.  ~800 threads per
+// CTA, two CTAs per SM: the small sheet becomes enough warps to hide the FP64 latency.
 // ------------------------------------------------------------------------------------------
+template <int T>
+struct EulerTile {
+  static constexpr int H = (T + 1) & ~1;
+  static constexpr int TW = TB + 2 * H;
+  static constexpr int NP = TW / 2;
+  static constexpr int NPAIR = NP * TW;
+  static constexpr int NT = (NPAIR + 31) & ~31;
+  static constexpr int PL = TW * TW;
+};
+
 template <int T, bool DEF>
-__global__ void __launch_bounds__(NTHR)
+__global__ void __launch_bounds__(EulerTile<T>::NT, 2)
 rd_tile_euler(const __grid_constant__ YhK k, const __grid_constant__ TileArgs a) {
-  constexpr int H = (T + 1) & ~1;
-  constexpr int TW = TB + 2 * H;
-  constexpr int NP = TW / 2;
-  constexpr int NPAIR = NP * TW;
-  constexpr int PL = TW * TW;
+  using E = EulerTile<T>;
+  constexpr int H = E::H, TW = E::TW, NP = E::NP, NPAIR = E::NPAIR, PL = E::PL;
   extern __shared__ __align__(16) double sm[];
 
   const int tid = threadIdx.x;
   const int nx = k.nx;
-  const int gx0 = blockIdx.x * TB - H;
-  const int ly0 = k.row0 + blockIdx.y * TB - H;
-  const int dom_lo = -k.jg0, dom_hi = k.nyg - k.jg0;
+  const int ty = tid / NP, tx = 2 * (tid % NP);
+  const int gx = blockIdx.x * TB - H + tx;
+  const int ly = k.row0 + blockIdx.y * TB - H + ty;        // LOCAL row
+  const int dom_lo = -k.jg0, dom_hi = k.nyg - k.jg0;       // local rows that exist globally
   const int out_hi = min(k.row1, k.row0 + (int)(blockIdx.y + 1) * TB);
-  const size_t zoff = (size_t)blockIdx.z * (size_t)a.sim_stride;
-  const double *u_in = a.u_in + zoff, *v_in = a.v_in + zoff;
-  double *u_out = a.u_out + zoff, *v_out = a.v_out + zoff;
+  const bool in_dom = tid < NPAIR && gx >= 0 && gx < nx && ly >= dom_lo && ly < dom_hi;
+  const size_t o = (size_t)blockIdx.z * (size_t)a.sim_stride + (size_t)(in_dom ? ly : 0) * nx + (in_dom ? gx : 0);
 
-  for (int t = tid; t < NPAIR; t += NTHR) {
-    const int ty = t / NP, tx = 2 * (t % NP);
-    const int gx = gx0 + tx, ly = ly0 + ty;
-    double2 u = make_double2(0, 0), v = u;
-    if (gx >= 0 && gx < nx && ly >= dom_lo && ly < dom_hi) {
-      const size_t o = (size_t)ly * nx + gx;
-      u = *reinterpret_cast<const double2 *>(u_in + o);
-      v = *reinterpret_cast<const double2 *>(v_in + o);
-      u.x += 0.0; u.y += 0.0; v.x += 0.0; v.y += 0.0;   // the reference's u0 + (0.0*0.0)
-    }
-    *reinterpret_cast<double2 *>(sm + ty * TW + tx) = u;
-    *reinterpret_cast<double2 *>(sm + PL + ty * TW + tx) = v;
+  // no-flux mirror = index selection inside the tile (helper_functions.cu:69-79); tile-edge pairs
+  // hold one cell outside every ring: it only must not read outside the tile
+  const int c = ty * TW + tx;
+  const int cs = (ly - 1 < dom_lo) ? c + TW : c - TW;
+  const int cn = (ly + 1 >= dom_hi) ? c - TW : c + TW;
+  const bool le = (gx == 0) || (tx == 0), re = (gx + 2 == nx) || (tx == TW - 2);
+
+  double2 uC = make_double2(0.0, 0.0), vC = uC;
+  if (in_dom) {
+    uC = *reinterpret_cast<const double2 *>(a.u_in + o);
+    vC = *reinterpret_cast<const double2 *>(a.v_in + o);
+    uC.x += 0.0; uC.y += 0.0; vC.x += 0.0; vC.y += 0.0;   // the reference's u0 + (0.0*0.0)
+  }
+  if (tid < NPAIR) {
+    *reinterpret_cast<double2 *>(sm + c) = uC;
+    *reinterpret_cast<double2 *>(sm + PL + c) = vC;
   }
   __syncthreads();
 
@@ -266,26 +280,23 @@ rd_tile_euler(const __grid_constant__ YhK k, const __grid_constant__ TileArgs a)
       const int per = a.period[blockIdx.z];
       stim_on = per > 0 && ((a.count0 + s - 1) % per) <= a.duration;
     }
-    for (int t = tid; t < NPAIR; t += NTHR) {
-      const int ty = t / NP, tx = 2 * (t % NP);
-      const int gx = gx0 + tx, ly = ly0 + ty;
-      if (!(gx >= 0 && gx < nx && ly >= dom_lo && ly < dom_hi)) continue;
-      if (!pair_in_ring(tx, ty, ring, TW)) continue;
-      const int c = ty * TW + tx;
-      const int cs = (ly - 1 < dom_lo) ? c + TW : c - TW;
-      const int cn = (ly + 1 >= dom_hi) ? c - TW : c + TW;
-      const bool le = (gx == 0) || (tx == 0), re = (gx + 2 == nx) || (tx == TW - 2);
-      const double2 uC = *reinterpret_cast<const double2 *>(iu + c), vC = *reinterpret_cast<const double2 *>(iv + c);
-      const double2 uS = *reinterpret_cast<const double2 *>(iu + cs), vS = *reinterpret_cast<const double2 *>(iv + cs);
-      const double2 uN = *reinterpret_cast<const double2 *>(iu + cn), vN = *reinterpret_cast<const double2 *>(iv + cn);
+    if (in_dom && pair_in_ring(tx, ty, ring, TW)) {
+      const double2 uS = *reinterpret_cast<const double2 *>(iu + cs), uN = *reinterpret_cast<const double2 *>(iu + cn);
       const double uw = le ? uC.y : iu[c - 1], ue = re ? uC.x : iu[c + 2];
-      const double vw = le ? vC.y : iv[c - 1], ve = re ? vC.x : iv[c + 2];
-      double2 uo, vo;
+      double2 un, vn;
+      double du0 = ((fma(-2.0, uC.x, uw) + uC.y) * k.rx + (fma(-2.0, uC.x, uN.x) + uS.x) * k.ry);
+      double du1 = ((fma(-2.0, uC.y, uC.x) + ue) * k.rx + (fma(-2.0, uC.y, uN.y) + uS.y) * k.ry);
+      double dv0 = 0.0, dv1 = 0.0;
+      if (k.gateDiff) {
+        const double2 vS = *reinterpret_cast<const double2 *>(iv + cs), vN = *reinterpret_cast<const double2 *>(iv + cn);
+        const double vw = le ? vC.y : iv[c - 1], ve = re ? vC.x : iv[c + 2];
+        dv0 = ((fma(-2.0, vC.x, vw) + vC.y) * k.rx * k.rscale + (fma(-2.0, vC.x, vN.x) + vS.x) * k.ry * k.rscale);
+        dv1 = ((fma(-2.0, vC.y, vC.x) + ve) * k.rx * k.rscale + (fma(-2.0, vC.y, vN.y) + vS.y) * k.ry * k.rscale);
+      }
 #pragma unroll
       for (int q = 0; q < 2; q++) {
         const double u = q ? uC.y : uC.x, v = q ? vC.y : vC.x;
-        const double W = q ? uC.x : uw, E = q ? ue : uC.y, N = q ? uN.y : uN.x, S = q ? uS.y : uS.x;
-        const double Wv = q ? vC.x : vw, Ev = q ? ve : vC.y, Nv = q ? vN.y : vN.x, Sv = q ? vS.y : vS.x;
+        double du = q ? du1 : du0, dv = q ? dv1 : dv0;
         const bool scs = stim_on && yh_scs_on(k, gx + q, ly + k.jg0);
         // same rewrites as rd_fast.cu::euler_cell (bit-exact identities, see there)
         const double mu_u = DEF ? u : k.mu * u;
@@ -293,23 +304,19 @@ rd_tile_euler(const __grid_constant__ YhK k, const __grid_constant__ TileArgs a)
         const double ug = DEF ? u : k.delta * (u - k.gamma);
         const double yv = ug * (k.beta - u) - v;
         const double Y = k.eps * (DEF ? yv : yv - k.theta);
-        double du = ((fma(-2.0, u, W) + E) * k.rx + (fma(-2.0, u, N) + S) * k.ry);
-        double dv = 0.0;
-        if (k.gateDiff)
-          dv = ((fma(-2.0, v, Wv) + Ev) * k.rx * k.rscale + (fma(-2.0, v, Nv) + Sv) * k.ry * k.rscale);
         if (!scs) du = du + k.dt * X;
         else { const double I_sum = -X - 24.7; du = du - k.dt * I_sum; }
         dv = dv + k.dt * Y;
-        const double un = u + (DEF ? du : k.tc * du), vn = v + (DEF ? dv : k.tc * dv);
-        if (q) { uo.y = un; vo.y = vn; } else { uo.x = un; vo.x = vn; }
+        const double u1 = u + (DEF ? du : k.tc * du), v1 = v + (DEF ? dv : k.tc * dv);
+        if (q) { un.y = u1; vn.y = v1; } else { un.x = u1; vn.x = v1; }
       }
+      uC = un; vC = vn;
       if (s < T) {
-        *reinterpret_cast<double2 *>(ou + c) = uo;
-        *reinterpret_cast<double2 *>(ov + c) = vo;
-      } else if (ly >= k.row0 && ly < out_hi) {
-        const size_t o = (size_t)ly * nx + gx;
-        *reinterpret_cast<double2 *>(u_out + o) = uo;
-        *reinterpret_cast<double2 *>(v_out + o) = vo;
+        *reinterpret_cast<double2 *>(ou + c) = uC;
+        *reinterpret_cast<double2 *>(ov + c) = vC;
+      } else if (ly >= k.row0 && ly < out_hi) {   // ring == H here: exactly the output tile
+        *reinterpret_cast<double2 *>(a.u_out + o) = uC;
+        *reinterpret_cast<double2 *>(a.v_out + o) = vC;
       }
     }
     if (s < T) __syncthreads();
@@ -338,14 +345,14 @@ int launch_rk(const YhK &k, const TileArgs &a, cudaStream_t st) {
 
 template <int T, bool DEF>
 int launch_euler(const YhK &k, const TileArgs &a, int nsims, cudaStream_t st) {
-  constexpr int H = (T + 1) & ~1, TW = TB + 2 * H;
+  constexpr int TW = EulerTile<T>::TW;
   const size_t smem = (size_t)4 * TW * TW * sizeof(double);
   static bool done[64] = {false};
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
   if (!done[dev & 63]) { int rc = set_smem(rd_tile_euler<T, DEF>, smem); if (rc) return rc; done[dev & 63] = true; }
   dim3 grd((k.nx + TB - 1) / TB, (k.row1 - k.row0 + TB - 1) / TB, nsims);
-  rd_tile_euler<T, DEF><<<grd, NTHR, smem, st>>>(k, a);
+  rd_tile_euler<T, DEF><<<grd, EulerTile<T>::NT, smem, st>>>(k, a);
   YH_LAUNCH_CHECK();
   return YH_OK;
 }
