@@ -122,6 +122,52 @@ def test_masked_temporal_blocking_is_bitwise_invariant(oracle, yh, nx, ny, tb):
         assert np.array_equal(su[1], w1[0]) and np.array_equal(sv[1], w1[1])
 
 
+@pytest.mark.parametrize("mode", ["euler", "euler_holes", "rk4lap4", "rk2"])
+def test_graph_replay_of_the_step_loop_is_bitwise_invariant(oracle, yh, mode, monkeypatch):
+    """Small sheets replay the step loop from a CUDA graph (64 time steps per graph, abi.cu): same
+    bits as plain launches and as the oracle, on a cache miss, on a cache hit, with the result
+    landing in either buffer pair, and through the headless driver (tips need the final
+    single-step pass to stay last)."""
+    nx, ny = 96, 80
+    kw = dict(euler=dict(timeIntOrder=1, lap4=0), euler_holes=dict(timeIntOrder=1, lap4=0, solidSwitch=1),
+              rk4lap4=dict(), rk2=dict(timeIntOrder=2, lap4=0))[mode]
+    p = oracle.params_default(nx, ny, **kw)
+    u, v = synth.cross_field_ic(nx, ny)
+    u = u + 0.0
+    u[40:50, 30:40] = -0.0                       # raw input: the first chunk must run un-graphed
+    mask = (np.random.default_rng(2).uniform(size=(ny, nx)) > 0.1).astype(np.uint8) if "holes" in mode else None
+    for n in (331, 256):                         # odd tail (T = 2, 1 at the end) and whole chunks
+        want = oracle.rd_advance(p, n, u, v, solid=mask)
+        monkeypatch.setenv("YH_GRAPHS", "0")
+        plain = gpu_advance(p, n, u, v, tb=4, solid=mask)
+        monkeypatch.setenv("YH_GRAPHS", "1")
+        for rep in range(2):                     # miss, then hit (fresh tensors may or may not reuse addresses)
+            got = gpu_advance(p, n, u, v, tb=4, solid=mask)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (n, rep)
+            assert np.array_equal(got[0], plain[0]) and np.array_equal(got[1], plain[1])
+    # same device buffers twice: the second call is a guaranteed cache hit; state continues
+    uA, vA = dev(u), dev(v)
+    uB, vB = torch.zeros_like(uA), torch.zeros_like(vA)
+    ds = dev(mask, torch.uint8) if mask is not None else None
+    ru, rv = host.rd_advance(p, 256, uA, vA, uB, vB, tb_steps=4, solid=ds)
+    assert ru is uA
+    ru, rv = host.rd_advance(p, 257, uA, vA, uB, vB, tb_steps=4, solid=ds, flags=host.RD_INPUT_CANONICAL)
+    torch.cuda.synchronize()
+    want = oracle.rd_advance(p, 513, u, v, solid=mask)
+    assert ru is uB and np.array_equal(ru.cpu().numpy().reshape(ny, nx), want[0])
+    assert np.array_equal(rv.cpu().numpy().reshape(ny, nx), want[1])
+    if mask is None:
+        sim = yh.Sim(p)
+        sim.set_state(u, v)
+        sim.run(321, tb_steps=4)
+        su, sv = sim.get_state()
+        w = oracle.rd_advance(p, 321, u, v)
+        assert np.array_equal(su[0], w[0]) and np.array_equal(sv[0], w[1])
+        prev = oracle.rd_advance(p, 320, u, v)
+        assert sim.tips().tobytes() == oracle.tip_track(p, prev[0], w[0], t=p.dt * 321).tobytes()
+        sim.close()
+
+
 def test_fast_path_gate_diff_off_and_negative_zero(oracle):
     p = oracle.params_default(96, 80, timeIntOrder=1, lap4=0, gateDiff=0)
     u, v = rand_fields(96, 80, 3)

@@ -38,6 +38,8 @@ int yh_check_device(void) {
 static void *g_ws[YH_MAX_DEV][YH_WS_SLOTS];
 static size_t g_ws_sz[YH_MAX_DEV][YH_WS_SLOTS];
 
+void yh_graphs_release(void);
+
 int yh_workspace(size_t bytes, void **ptr, int slot) {
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
@@ -73,6 +75,7 @@ int yh_release_workspace(void) {
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
   YH_CUDA(cudaDeviceSynchronize());
+  yh_graphs_release();   // captured graphs hold workspace addresses
   for (int s = 0; s < YH_WS_SLOTS; s++) {
     if (g_ws[dev][s]) YH_CUDA(cudaFree(g_ws[dev][s]));
     g_ws[dev][s] = nullptr; g_ws_sz[dev][s] = 0;
@@ -163,6 +166,207 @@ int yh_rd_step(const yh_params *p, const double *u_in, const double *v_in, doubl
   return yh_launch_rd_generic(k, u_in, v_in, u_out, v_out, velTan_u, velTan_v, solid, st);
 }
 
+}  // extern "C"
+
+// nsteps x {step; swapSoA} as plain launches on `st`; (cu,cv) holds the state on entry and on exit.
+struct AdvanceCtx {
+  const yh_params *p;
+  YhK k;
+  int tb, row0, row1;
+  const uint8_t *solid, *pat;
+};
+
+static int advance_plain(const AdvanceCtx &x, int nsteps, int &canon, double *&cu, double *&cv,
+                         double *&nu, double *&nv, int &inB, cudaStream_t st) {
+  const yh_params *p = x.p;
+  YhK k = x.k;
+  const int K = p->timeIntOrder;
+  const int dom_lo = -p->jg0, dom_hi = p->ny_global - p->jg0;
+  int left = nsteps;
+  while (left > 0) {
+    int T = 1;
+    if (x.pat || yh_rd_fast_supported(k, 1)) { T = x.tb; while (T > left) T >>= 1; }
+    // rows that must be valid after this pass so that the remaining steps stay exact
+    const int ext = (left - T) * K;
+    k.row0 = x.row0 - ext > dom_lo ? x.row0 - ext : dom_lo;
+    k.row1 = x.row1 + ext < dom_hi ? x.row1 + ext : dom_hi;
+    if (k.row0 < 0) k.row0 = 0;
+    if (k.row1 > p->ny) k.row1 = p->ny;
+    const bool tile = yh_rd_prefer_tile((long long)k.nx * (k.row1 - k.row0)) != 0;
+    int rc;
+    if (x.pat) {
+      rc = yh_launch_rd_fast(k, T, cu, cv, nu, nv, x.pat, canon, st);
+      canon = 0;
+    } else if (yh_rd_fast_supported(k, T)) {
+      if (tile) rc = yh_launch_rd_tile_euler(k, T, cu, cv, nu, nv, 1, 0, nullptr, 0, 0, st);
+      else rc = yh_launch_rd_fast(k, T, cu, cv, nu, nv, nullptr, canon, st);
+      canon = 0;
+    } else if (tile && yh_rd_tile_rk_supported(k)) rc = yh_launch_rd_tile_rk(k, cu, cv, nu, nv, nullptr, nullptr, st);
+    else if (yh_rd_rk_supported(k)) rc = yh_launch_rd_rk(k, cu, cv, nu, nv, nullptr, nullptr, x.solid, st);
+    else rc = yh_launch_rd_generic(k, cu, cv, nu, nv, nullptr, nullptr, x.solid, st);
+    if (rc != YH_OK) return rc;
+    double *t = cu; cu = nu; nu = t;   // swapSoA (helper_functions.cu:140)
+    t = cv; cv = nv; nv = t;
+    inB ^= 1;
+    left -= T;
+  }
+  return YH_OK;
+}
+
+// ---- CUDA-graph replay of the step loop for small sheets ------------------------------------
+// A 512^2 step is a few microseconds of kernel time; dependent launches in a stream complete on a
+// ~2 us cadence (measured: wall time per launch is a multiple of 2.05 us, profiles/), which a
+// captured graph does not pay.  A chunk of YH_GRAPH_CHUNK time steps (an even number of launches,
+// so the ping-pong returns to the same buffers) is captured once per {parameters, buffers} and
+// replayed; the head of the run (raw input, remainder) goes through plain launches.
+// Capture needs a non-legacy stream: graphs run on an internal stream fenced with events against
+// the caller's stream, so the call stays stream-ordered for the caller.
+#define YH_GRAPH_CHUNK 64
+#define YH_GRAPH_CACHE 8
+
+struct GraphKey {
+  yh_params p;
+  int stim, px, py, tb, row0, row1;
+  const void *cu, *cv, *nu, *nv, *solid, *pat;
+};
+struct GraphEntry {
+  GraphKey key;
+  cudaGraphExec_t exec;
+  unsigned long long stamp;
+  int dev;
+};
+static thread_local GraphEntry g_graphs[YH_GRAPH_CACHE];
+static thread_local unsigned long long g_graph_clock = 0;
+static cudaStream_t g_graph_stream[YH_MAX_DEV];
+static cudaEvent_t g_graph_ev[YH_MAX_DEV][2];
+
+static int graph_stream(int dev, cudaStream_t *gs) {
+  if (!g_graph_stream[dev]) {
+    YH_CUDA(cudaStreamCreateWithFlags(&g_graph_stream[dev], cudaStreamNonBlocking));
+    YH_CUDA(cudaEventCreateWithFlags(&g_graph_ev[dev][0], cudaEventDisableTiming));
+    YH_CUDA(cudaEventCreateWithFlags(&g_graph_ev[dev][1], cudaEventDisableTiming));
+  }
+  *gs = g_graph_stream[dev];
+  return YH_OK;
+}
+
+int yh_graphs_enabled(long long cells) {
+  const char *f = getenv("YH_GRAPHS");   // 0: never, 1: whenever the shape allows
+  if (f && f[0] == '0') return 0;
+  if (f && f[0] == '1') return 1;
+  return cells <= (3ll << 20);           // the launch-cadence regime: small sheets only
+}
+
+static GraphKey graph_key(const AdvanceCtx &x, const double *cu, const double *cv, const double *nu,
+                          const double *nv) {
+  GraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.p = *x.p; key.stim = x.k.stim; key.px = x.k.px; key.py = x.k.py; key.tb = x.tb;
+  key.row0 = x.row0; key.row1 = x.row1;
+  key.cu = cu; key.cv = cv; key.nu = nu; key.nv = nv; key.solid = x.solid; key.pat = x.pat;
+  return key;
+}
+
+static GraphEntry *graph_find(const GraphKey &key, int dev) {
+  for (int q = 0; q < YH_GRAPH_CACHE; q++) {
+    GraphEntry &g = g_graphs[q];
+    if (g.exec && g.dev == dev && memcmp(&g.key, &key, sizeof(key)) == 0) return &g;
+  }
+  return nullptr;
+}
+
+// Capture one chunk (state in (cu,cv) before and after) into the least recently used cache slot.
+static int graph_capture(const AdvanceCtx &x, const GraphKey &key, int dev, double *cu, double *cv,
+                         double *nu, double *nv, cudaStream_t gs, GraphEntry **out) {
+  GraphEntry *victim = &g_graphs[0];
+  for (int q = 0; q < YH_GRAPH_CACHE; q++) {
+    if (!g_graphs[q].exec) { victim = &g_graphs[q]; break; }
+    if (g_graphs[q].stamp < victim->stamp) victim = &g_graphs[q];
+  }
+  if (victim->exec) { cudaGraphExecDestroy(victim->exec); victim->exec = nullptr; }
+  cudaGraph_t graph = nullptr;
+  YH_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+  int canon = 0, inB = 0;
+  int rc = advance_plain(x, YH_GRAPH_CHUNK, canon, cu, cv, nu, nv, inB, gs);
+  cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+  if (rc != YH_OK || ce != cudaSuccess || inB != 0) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc == YH_OK) { yh_set_error("graph capture of the step loop failed"); rc = YH_ERR_CUDA; }
+    return rc;
+  }
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) { cudaGetLastError(); yh_set_error("cudaGraphInstantiate failed"); return YH_ERR_CUDA; }
+  victim->key = key; victim->exec = exec; victim->dev = dev;
+  *out = victim;
+  return YH_OK;
+}
+
+void yh_graphs_release(void) {
+  for (int q = 0; q < YH_GRAPH_CACHE; q++)
+    if (g_graphs[q].exec) { cudaGraphExecDestroy(g_graphs[q].exec); g_graphs[q].exec = nullptr; }
+}
+
+// The whole-sheet step loop used by yh_rd_advance and the headless driver.  Order of passes:
+// [one plain chunk when the input is raw or the graph is new] [graph replays] [plain remainder],
+// so the LAST pass is the shortest one, as in the plain loop (yh_sim_tips relies on a final
+// single-step pass).
+int yh_advance_whole(const yh_params *p, const YhK &k, int nsteps, int tb, int canon_in, double *uA,
+                     double *vA, double *uB, double *vB, const uint8_t *solid, const uint8_t *pat,
+                     int row0, int row1, int *result_in_B, int *last_T, cudaStream_t st) {
+  AdvanceCtx x{p, k, tb, row0, row1, solid, pat};
+  double *cu = uA, *cv = vA, *nu = uB, *nv = vB;
+  int inB = 0, canon = canon_in, rc, dev = 0;
+  if (last_T) {   // length of the final pass
+    const bool fast = pat || yh_rd_fast_supported(k, 1);
+    int T = fast ? tb : 1, left = nsteps;
+    while (fast && left > 0 && left % T) T >>= 1;   // tb is a power of two: the tail runs T/2, T/4, ...
+    *last_T = nsteps > 0 ? T : 0;
+  }
+  const bool whole = p->jg0 == 0 && p->ny_global == p->ny && row0 == 0 && row1 == p->ny;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cudaGetLastError();
+  int nch = nsteps / YH_GRAPH_CHUNK;
+  YH_CUDA(cudaGetDevice(&dev));
+  if (whole && cap == cudaStreamCaptureStatusNone && nch >= 3 && dev < YH_MAX_DEV &&
+      yh_graphs_enabled((long long)p->nx * p->ny)) {
+    cudaStream_t gs;
+    rc = graph_stream(dev, &gs);
+    if (rc != YH_OK) return rc;
+    GraphKey key = graph_key(x, cu, cv, nu, nv);
+    GraphEntry *e = graph_find(key, dev);
+    if (canon || !e) {   // raw input, or first use of these kernel variants: one chunk of plain launches
+      rc = advance_plain(x, YH_GRAPH_CHUNK, canon, cu, cv, nu, nv, inB, st);
+      if (rc != YH_OK) return rc;
+      nch--;
+    }
+    if (!e) rc = graph_capture(x, key, dev, cu, cv, nu, nv, gs, &e);
+    if (rc == YH_OK) {
+      e->stamp = ++g_graph_clock;
+      YH_CUDA(cudaEventRecord(g_graph_ev[dev][0], st));
+      YH_CUDA(cudaStreamWaitEvent(gs, g_graph_ev[dev][0], 0));
+      for (int q = 0; q < nch; q++) YH_CUDA(cudaGraphLaunch(e->exec, gs));
+      YH_CUDA(cudaEventRecord(g_graph_ev[dev][1], gs));
+      YH_CUDA(cudaStreamWaitEvent(st, g_graph_ev[dev][1], 0));
+      nch = 0;
+    } else if (rc != YH_ERR_CUDA) {
+      return rc;
+    }   // capture refused: the rest of the run goes through plain launches
+    rc = advance_plain(x, nch * YH_GRAPH_CHUNK + nsteps % YH_GRAPH_CHUNK, canon, cu, cv, nu, nv, inB, st);
+    if (rc != YH_OK) return rc;
+    *result_in_B = inB;
+    return YH_OK;
+  }
+  rc = advance_plain(x, nsteps, canon, cu, cv, nu, nv, inB, st);
+  if (rc != YH_OK) return rc;
+  *result_in_B = inB;
+  return YH_OK;
+}
+
+extern "C" {
+
 int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, int flags, double *uA, double *vA,
                   double *uB, double *vB, const uint8_t *solid, int stim_mouse, int point_x,
                   int point_y, int row0, int row1, int *result_in_B, void *stream) {
@@ -176,13 +380,8 @@ int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, int flags, doubl
   YhK k = yh_make_k(p);
   k.stim = stim_mouse != 0; k.px = point_x; k.py = point_y;
   cudaStream_t st = (cudaStream_t)stream;
-  double *cu = uA, *cv = vA, *nu = uB, *nv = vB;
-  int inB = 0;
-  const int K = p->timeIntOrder;
-  const int dom_lo = -p->jg0, dom_hi = p->ny_global - p->jg0;
-  int left = nsteps;
-  int tb = tb_steps ? tb_steps : 4;
-  int canon = (flags & YH_RD_INPUT_CANONICAL) ? 0 : 1;   // only the first pass can see user data
+  const int tb = tb_steps ? tb_steps : 4;
+  const int canon = (flags & YH_RD_INPUT_CANONICAL) ? 0 : 1;   // only the first pass can see user data
   // obstacle masks + Euler: the temporally blocked kernel reads per-cell mask patterns, made
   // once per call (mask contents belong to the caller and may change between calls)
   uint8_t *pat = nullptr;
@@ -192,34 +391,7 @@ int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, int flags, doubl
     rc = yh_rd_solid_patterns(k, solid, pat, st);
     if (rc != YH_OK) return rc;
   }
-  while (left > 0) {
-    int T = 1;
-    if (pat || yh_rd_fast_supported(k, 1)) { T = tb; while (T > left) T >>= 1; }
-    // rows that must be valid after this pass so that the remaining steps stay exact
-    const int ext = (left - T) * K;
-    k.row0 = row0 - ext > dom_lo ? row0 - ext : dom_lo;
-    k.row1 = row1 + ext < dom_hi ? row1 + ext : dom_hi;
-    if (k.row0 < 0) k.row0 = 0;
-    if (k.row1 > p->ny) k.row1 = p->ny;
-    const bool tile = yh_rd_prefer_tile((long long)k.nx * (k.row1 - k.row0)) != 0;
-    if (pat) {
-      rc = yh_launch_rd_fast(k, T, cu, cv, nu, nv, pat, canon, st);
-      canon = 0;
-    } else if (yh_rd_fast_supported(k, T)) {
-      if (tile) rc = yh_launch_rd_tile_euler(k, T, cu, cv, nu, nv, 1, 0, nullptr, 0, 0, st);
-      else rc = yh_launch_rd_fast(k, T, cu, cv, nu, nv, nullptr, canon, st);
-      canon = 0;
-    } else if (tile && yh_rd_tile_rk_supported(k)) rc = yh_launch_rd_tile_rk(k, cu, cv, nu, nv, nullptr, nullptr, st);
-    else if (yh_rd_rk_supported(k)) rc = yh_launch_rd_rk(k, cu, cv, nu, nv, nullptr, nullptr, solid, st);
-    else rc = yh_launch_rd_generic(k, cu, cv, nu, nv, nullptr, nullptr, solid, st);
-    if (rc != YH_OK) return rc;
-    double *t = cu; cu = nu; nu = t;   // swapSoA (helper_functions.cu:140)
-    t = cv; cv = nv; nv = t;
-    inB ^= 1;
-    left -= T;
-  }
-  *result_in_B = inB;
-  return YH_OK;
+  return yh_advance_whole(p, k, nsteps, tb, canon, uA, vA, uB, vB, solid, pat, row0, row1, result_in_B, nullptr, st);
 }
 
 // solve_matrix, symmetryReduction.cu:386-416 (host; same operation order; no leak)
@@ -227,25 +399,8 @@ int yh_solve_matrix(const double c_in[3], const double phi[3], const double Int[
                     double c_out[3]) {
   (void)c_in;
   if (!phi || !Int || !c_out) { yh_set_error("yh_solve_matrix: null pointer"); return YH_ERR_INVALID_ARG; }
-  double a1, a2, a3, b1, b2, b3, C1, C2, C3, d1, d2, d3;
-  double b2p, b3p, c2p, c3p, c3pp, d2p, d3p, d3pp, x1, x2, x3;
   const double pt = phi[2];
-  a1 = Int[0] * cos(pt) + Int[1] * sin(pt); a2 = Int[1] * cos(pt) - Int[0] * sin(pt); a3 = Int[2];
-  b1 = Int[3] * cos(pt) + Int[4] * sin(pt); b2 = Int[4] * cos(pt) - Int[3] * sin(pt); b3 = Int[5];
-  C1 = Int[6] * cos(pt) + Int[7] * sin(pt); C2 = Int[7] * cos(pt) - Int[6] * sin(pt); C3 = Int[8];
-  d1 = Int[9]; d2 = Int[10]; d3 = Int[11];
-  b2p = a1 / b1 * b2 - a2;
-  b3p = a1 / b1 * b3 - a3;
-  d2p = a1 / b1 * d2 - d1;
-  c2p = a1 / C1 * C2 - a2;
-  c3p = a1 / C1 * C3 - a3;
-  d3p = a1 / C1 * d3 - d1;
-  c3pp = b2p / c2p * c3p - b3p;
-  d3pp = b2p / c2p * d3p - d2p;
-  x3 = d3pp / c3pp;
-  x2 = (d2p - b3p * x3) / b2p;
-  x1 = (d1 - a2 * x2 - a3 * x3) / a1;
-  c_out[0] = x1; c_out[1] = x2; c_out[2] = x3;
+  yh_solve3(Int, cos(pt), sin(pt), c_out);
   return YH_OK;
 }
 

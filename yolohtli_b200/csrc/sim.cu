@@ -202,6 +202,20 @@ static int sim_run_impl(yh_sim *s, int nsteps, int tb_steps, double *trace_h, bo
   }
   const uint8_t *pat = (s->pat && yh_rd_fast_solid_supported(k, 1)) ? s->pat : nullptr;
   const bool fast1 = pat != nullptr || yh_rd_fast_supported(k, 1) != 0;
+  if (!trace_h && !pacing && s->n_sims == 1 && nsteps > 0) {
+    // a single unpaced sheet: the library's step loop (CUDA-graph replay when the sheet is small)
+    int inB = 0, last_T = 0;
+    const int c = s->cur, o = c ^ 1;
+    int rc = yh_advance_whole(&s->p, k, nsteps, tb, s->raw_input, s->u[c], s->v[c], s->u[o], s->v[o],
+                              s->solid, pat, 0, s->p.ny, &inB, &last_T, s->st);
+    if (rc != YH_OK) return rc;
+    if (inB) s->cur = o;
+    s->raw_input = 0;
+    s->have_prev = (last_T == 1);
+    s->count += nsteps;
+    if (sync) YH_CUDA(cudaStreamSynchronize(s->st));
+    return YH_OK;
+  }
   int left = nsteps, step = 0;
   while (left > 0) {
     int T = 1;

@@ -192,6 +192,37 @@ __global__ void integrals_final_kernel(const __grid_constant__ YhK k, const __gr
   a.out[q] = 0.25 * k.hx * k.hy * tot;   // integralTrapz.cu:79
 }
 
+// Device-resident closing of the SR step (yh_sim_run_sr_device): the 12 integrals, the deferred
+// frame update phi += c*dt of the PREVIOUS step (main.cu:936-938), the (c, phi) record of this step
+// (main.cu:902-903), the 3x3 solve (symmetryReduction.cu:386-416) and cos/sin(phi.t) for the
+// advection that follows -- no host round trip.  cos/sin are libdevice's here and libm's in the
+// host path: results agree to rounding, not bit for bit.
+__global__ void integrals_solve_kernel(const __grid_constant__ YhK k, const __grid_constant__ IntArgs a,
+                                       double *sr, double *log_row, double dt_phi) {
+  __shared__ double I[12];
+  const int q = threadIdx.x;
+  if (q < 12) {
+    double tot = 0.0;
+    for (int w = 0; w < 2 * a.R + 1; w++) tot += a.rows[(size_t)w * 12 + q];   // ascending j
+    I[q] = 0.25 * k.hx * k.hy * tot;
+    a.out[q] = I[q];
+  }
+  __syncthreads();
+  if (q == 0) {
+    double c[3], phi[3];
+    for (int m = 0; m < 3; m++) { c[m] = sr[YH_SR_C + m]; phi[m] = sr[YH_SR_PHI + m] + c[m] * dt_phi; }
+    if (log_row) for (int m = 0; m < 3; m++) { log_row[m] = c[m]; log_row[3 + m] = phi[m]; }
+    const double cs = cos(phi[2]), sn = sin(phi[2]);
+    yh_solve3(I, cs, sn, c);
+    for (int m = 0; m < 3; m++) { sr[YH_SR_C + m] = c[m]; sr[YH_SR_PHI + m] = phi[m]; }
+    sr[YH_SR_CS] = cs; sr[YH_SR_SN] = sn;
+  }
+}
+
+__global__ void sr_flush_phi_kernel(double *sr, double dt_phi) {
+  if (threadIdx.x < 3) sr[YH_SR_PHI + threadIdx.x] = sr[YH_SR_PHI + threadIdx.x] + sr[YH_SR_C + threadIdx.x] * dt_phi;
+}
+
 int run_integrals(const yh_params *p, IntArgs &a, bool fused, double *integrals_host, cudaStream_t st) {
   YhK k = yh_make_k(p);
   const long long r2 = (long long)p->tipOffsetX * p->tipOffsetY;
@@ -207,6 +238,7 @@ int run_integrals(const yh_params *p, IntArgs &a, bool fused, double *integrals_
   if (fused) integrals_rows_kernel<true><<<blocks, 128, 0, st>>>(k, a);
   else integrals_rows_kernel<false><<<blocks, 128, 0, st>>>(k, a);
   YH_LAUNCH_CHECK();
+  if (!integrals_host) return YH_OK;   // device-resident closing follows (integrals_solve_kernel)
   integrals_final_kernel<<<1, 32, 0, st>>>(k, a);
   YH_LAUNCH_CHECK();
   static thread_local double *pinned = nullptr;
@@ -256,6 +288,7 @@ struct BfArgs {
   const uint8_t *solid;
   CxyArgs cxy;
   int from_c;
+  const double *sr_state;   // from_c with (c, cos, sin) read from device memory (yh_sim_run_sr_device)
 };
 
 __device__ __forceinline__ int sgn(double x) { int t = x < 0.0 ? -1 : 0; return x > 0.0 ? 1 : t; }
@@ -337,6 +370,11 @@ bfecc_kernel(const __grid_constant__ YhK k, const __grid_constant__ BfArgs a) {
   const int tid = threadIdx.x;
   const bool neu = k.neumannBC != 0;
   const double tc = k.tc, bv = k.boundaryVal;
+  CxyArgs cxy = a.cxy;
+  if (a.sr_state) {
+    cxy.cx = a.sr_state[YH_SR_C]; cxy.cy = a.sr_state[YH_SR_C + 1]; cxy.ct = a.sr_state[YH_SR_C + 2];
+    cxy.cs = a.sr_state[YH_SR_CS]; cxy.sn = a.sr_state[YH_SR_SN];
+  }
 
   // per-cell Courant numbers, once for the three sweeps and both fields (advFDBFECC.cu:30-34)
   for (int t = tid; t < BP * BP; t += BTHREADS) {
@@ -347,7 +385,7 @@ bfecc_kernel(const __grid_constant__ YhK k, const __grid_constant__ BfArgs a) {
       const int c = gi + k.nx * gj;
       double ax, ay;
       if (a.from_c) {
-        cxy_cell(k, a.cxy, gi, gj, ax, ay);
+        cxy_cell(k, cxy, gi, gj, ax, ay);
         const bool own = (t % BP >= BH) && (t % BP < BH + BT) && (t / BP >= BH) && (t / BP < BH + BT);
         if (own && a.ax_out) { a.ax_out[c] = ax; a.ay_out[c] = ay; }
       } else { ax = a.ax[c]; ay = a.ay[c]; }
@@ -529,6 +567,31 @@ int yh_sr_integrals(const yh_params *p, const double *u, const double *v, const 
   return run_integrals(p, a, true, integrals_host, (cudaStream_t)stream);
 }
 
+}  // extern "C"
+
+int yh_sr_integrals_solve_device(const yh_params *p, const double *u, const double *v,
+                                 const double *vtu, const double *vtv, const double *ax,
+                                 const double *ay, const int *tip_count, const yh_tip *tv, int count,
+                                 double *sr_state, double *log_row, double dt_phi, cudaStream_t st) {
+  IntArgs a;
+  memset(&a, 0, sizeof(a));
+  a.u = u; a.v = v; a.ax = ax; a.ay = ay; a.vtu = vtu; a.vtv = vtv;
+  a.count = count; a.tip_count = tip_count; a.tv = tv; a.tipx0 = p->tipx0; a.tipy0 = p->tipy0;
+  int rc = run_integrals(p, a, true, nullptr, st);
+  if (rc != YH_OK) return rc;
+  integrals_solve_kernel<<<1, 32, 0, st>>>(yh_make_k(p), a, sr_state, log_row, dt_phi);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
+
+int yh_sr_flush_phi_device(double *sr_state, double dt_phi, cudaStream_t st) {
+  sr_flush_phi_kernel<<<1, 32, 0, st>>>(sr_state, dt_phi);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
+
+extern "C" {
+
 static CxyArgs make_cxy(double *ax, double *ay, const uint8_t *solid, const double c[3], const double phi[3]) {
   CxyArgs a;
   a.ax = ax; a.ay = ay; a.solid = solid;
@@ -603,3 +666,14 @@ int yh_advect_bfecc_cphi(const yh_params *p, const double *u_in, const double *v
 }
 
 }  // extern "C"
+
+int yh_advect_bfecc_device_c(const yh_params *p, const double *u_in, const double *v_in, double *u_out,
+                             double *v_out, const double *sr_state, double *adv_x, double *adv_y,
+                             const uint8_t *solid, cudaStream_t st) {
+  BfArgs a;
+  memset(&a, 0, sizeof(a));
+  a.u_in = u_in; a.v_in = v_in; a.u_out = u_out; a.v_out = v_out;
+  a.ax_out = adv_x; a.ay_out = adv_y; a.solid = solid; a.from_c = 1; a.sr_state = sr_state;
+  a.cxy.solid = solid;
+  return bfecc_common(p, a, (void *)st);
+}

@@ -65,6 +65,51 @@ int yh_check_device(void);   // YH_OK or YH_ERR_NO_DEVICE
 // internal workspace (per device, grown on demand, abi.cu)
 int yh_workspace(size_t bytes, void **ptr, int slot);
 
+// nsteps x {RD step; swapSoA} on (uA,vA) <-> (uB,vB), CUDA-graph replay for small whole sheets
+// (abi.cu).  *last_T (optional) = time steps of the final pass.
+int yh_advance_whole(const yh_params *p, const YhK &k, int nsteps, int tb, int canon_in, double *uA,
+                     double *vA, double *uB, double *vB, const uint8_t *solid, const uint8_t *pat,
+                     int row0, int row1, int *result_in_B, int *last_T, cudaStream_t st);
+
+// solve_matrix, symmetryReduction.cu:386-416: rotate the first two columns by phi.t, then the 3x3
+// elimination without pivoting, operation for operation.  Host (libm cos/sin, as the reference)
+// and device (libdevice cos/sin; yh_sim_run_sr_device) share the text.
+__host__ __device__ inline void yh_solve3(const double *Int, double cs, double sn, double *c_out) {
+  double a1, a2, a3, b1, b2, b3, C1, C2, C3, d1, d2, d3;
+  double b2p, b3p, c2p, c3p, c3pp, d2p, d3p, d3pp, x1, x2, x3;
+  a1 = Int[0] * cs + Int[1] * sn; a2 = Int[1] * cs - Int[0] * sn; a3 = Int[2];
+  b1 = Int[3] * cs + Int[4] * sn; b2 = Int[4] * cs - Int[3] * sn; b3 = Int[5];
+  C1 = Int[6] * cs + Int[7] * sn; C2 = Int[7] * cs - Int[6] * sn; C3 = Int[8];
+  d1 = Int[9]; d2 = Int[10]; d3 = Int[11];
+  b2p = a1 / b1 * b2 - a2;
+  b3p = a1 / b1 * b3 - a3;
+  d2p = a1 / b1 * d2 - d1;
+  c2p = a1 / C1 * C2 - a2;
+  c3p = a1 / C1 * C3 - a3;
+  d3p = a1 / C1 * d3 - d1;
+  c3pp = b2p / c2p * c3p - b3p;
+  d3pp = b2p / c2p * d3p - d2p;
+  x3 = d3pp / c3pp;
+  x2 = (d2p - b3p * x3) / b2p;
+  x1 = (d1 - a2 * x2 - a3 * x3) / a1;
+  c_out[0] = x1; c_out[1] = x2; c_out[2] = x3;
+}
+
+// Device-resident symmetry-reduction state (yh_sim_run_sr_device): c[3], phi[3], cos/sin(phi.t)
+#define YH_SR_C 0
+#define YH_SR_PHI 3
+#define YH_SR_CS 6
+#define YH_SR_SN 7
+#define YH_SR_WORDS 8
+int yh_sr_integrals_solve_device(const yh_params *p, const double *u, const double *v,
+                                 const double *vtu, const double *vtv, const double *ax,
+                                 const double *ay, const int *tip_count, const yh_tip *tv, int count,
+                                 double *sr_state, double *log_row, double dt_phi, cudaStream_t st);
+int yh_sr_flush_phi_device(double *sr_state, double dt_phi, cudaStream_t st);
+int yh_advect_bfecc_device_c(const yh_params *p, const double *u_in, const double *v_in, double *u_out,
+                             double *v_out, const double *sr_state, double *adv_x, double *adv_y,
+                             const uint8_t *solid, cudaStream_t st);
+
 // ---- device helpers --------------------------------------------------------------------
 // Neumann mirror index (the rule of coord_i/coord_j, helper_functions.cu:69-79).
 __device__ __forceinline__ int yh_mir(int i, int n) {
