@@ -249,6 +249,10 @@ int yh_sim_tips(yh_sim *s, yh_tip *tips_h, int capacity, int *count_out);
  * clist/philist (main.cu:902-903).  Sheet 0 only; (tipx0,tipy0) of the params centre the disc
  * while count == 0.  yh_sim_sr_state reads / sets (c, phi). */
 int yh_sim_run_sr(yh_sim *s, int nsteps, double *c_phi_h);
+/* Same steps with the integrals, the 3x3 solve and the frame update resident on the device: no
+ * host round trip inside a step.  cos/sin(phi.t) are the device library's, so (c, phi) and the
+ * fields agree with yh_sim_run_sr to rounding (1e-12 over hundreds of steps), not bit for bit. */
+int yh_sim_run_sr_device(yh_sim *s, int nsteps, double *c_phi_h);
 /* contourMode == 1 loop (main.cu:879-885, 1035): every step RD, swap, then sAPD_wrapper with the
  * reference's argument order (uold := gateIn = NEW state, unew := gateOut = OLD state) and
  * stimulate = 1 masked by stim_area_h (nx*ny bytes; NULL: every cell, stimulate = 0).  All sheets

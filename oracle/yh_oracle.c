@@ -665,21 +665,27 @@ int yho_slice(const yh_params *p, const double *u, const double *v,
 /*
  * Canonical summation order of the 12 integrals (the reference's is nondeterministic:
  * 256 blocks atomicAdd(double), integralTrapz.cu:78-80):
- *   row sum   : 32 lane accumulators, lane l takes i = l, l+32, ... ascending, each term
- *               4.0*(f*g + h*w) inside the disc (:55-57; the scb / 2.0 branches multiply 0);
- *               lanes combined by the xor-butterfly 16,8,4,2,1 (x = x + partner);
+ *   row sum   : 256 accumulators (8 warps x 32 lanes), accumulator a takes i = a, a+256, ...
+ *               ascending, each term 4.0*(f*g + h*w) inside the disc (:55-57; the scb / 2.0
+ *               branches multiply 0); the 32 lanes of a warp combined by the xor-butterfly
+ *               16,8,4,2,1 (x = x + partner); the 8 warp sums added in ascending warp index;
  *   total     : rows added in ascending j;  result = (0.25*hx*hy) * total   (:79).
  */
+#define YHO_ROW_WARPS 8
 typedef struct { double a[12]; } acc12;
 
-static void integrals_rowsum(double lane[32][12], double out[12]) {
-  for (int m = 16; m >= 1; m >>= 1) {
-    double t[32][12];
-    for (int l = 0; l < 32; l++)
-      for (int k = 0; k < 12; k++) t[l][k] = lane[l][k] + lane[l ^ m][k];
-    memcpy(lane, t, sizeof(t));
+static void integrals_rowsum(double acc[YHO_ROW_WARPS * 32][12], double out[12]) {
+  for (int k = 0; k < 12; k++) out[k] = 0.0;
+  for (int w = 0; w < YHO_ROW_WARPS; w++) {
+    double (*lane)[12] = acc + 32 * w;
+    for (int m = 16; m >= 1; m >>= 1) {
+      double t[32][12];
+      for (int l = 0; l < 32; l++)
+        for (int k = 0; k < 12; k++) t[l][k] = lane[l][k] + lane[l ^ m][k];
+      memcpy(lane, t, sizeof(t));
+    }
+    for (int k = 0; k < 12; k++) out[k] = (w == 0) ? lane[0][k] : out[k] + lane[0][k];
   }
-  for (int k = 0; k < 12; k++) out[k] = lane[0][k];
 }
 
 /* pairs: Int[3a+b] = <slice0.a , slice.b>, Int[9+a] = <slice0.a , velTan>, a,b in {x,y,t} */
@@ -701,7 +707,7 @@ static int integrals_generic(const yh_params *p, cell12_fn fn, void *ctx,
   if (!rows) return YH_ERR_INVALID_ARG;
 #pragma omp parallel for schedule(static)
   for (int j = 0; j < ny; j++) {
-    double lane[32][12];
+    double lane[YHO_ROW_WARPS * 32][12];
     memset(lane, 0, sizeof(lane));
     for (int i = 0; i < nx; i++) {
       double s[6], s0[6], t12[12];
@@ -711,7 +717,7 @@ static int integrals_generic(const yh_params *p, cell12_fn fn, void *ctx,
                               because every accumulator starts at +0.0 and x + 0.0 == x */
       size_t c = (size_t)i + (size_t)nx * j;
       integrand12(s, s0, vtu[c], vtv[c], t12);
-      for (int k = 0; k < 12; k++) lane[i & 31][k] += t12[k];
+      for (int k = 0; k < 12; k++) lane[i % (YHO_ROW_WARPS * 32)][k] += t12[k];
     }
     integrals_rowsum(lane, rows + (size_t)j * 12);
   }

@@ -122,6 +122,7 @@ SIGNATURES = {
     "yh_sim_run_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
     "yh_sim_tips": (_i, [_vp, _vp, _i, C.POINTER(_i)]),
     "yh_sim_run_sr": (_i, [_vp, _i, _vp]),
+    "yh_sim_run_sr_device": (_i, [_vp, _i, _vp]),
     "yh_sim_run_apd": (_i, [_vp, _i, _vp]),
     "yh_sim_get_apd": (_i, [_vp, _vp, _vp]),
     "yh_sim_sr_state": (_i, [_vp, C.POINTER(_d), C.POINTER(_d), _i]),

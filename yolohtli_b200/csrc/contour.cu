@@ -102,7 +102,10 @@ contour_kernel(const __grid_constant__ YhK k, const __grid_constant__ ContourArg
   }
   int total;
   const int excl = yh_block_excl_scan<CT_THREADS>(mine, s_warp, total);
-  if (tid == 0) s_base = (int)yh_ordered_prefix(a.ord, chunk, (unsigned)total, a.count);
+  if (tid < 32) {   // warp 0 chains this chunk to its predecessors
+    const unsigned prefix = yh_ordered_prefix(a.ord, chunk, (unsigned)total, a.count);
+    if (tid == 0) s_base = (int)prefix;
+  }
   __syncthreads();
   if (mine == 0) return;
   int pos = s_base + excl;

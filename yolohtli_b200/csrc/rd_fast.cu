@@ -112,29 +112,34 @@ __device__ __forceinline__ void euler_cell(const YhK &k, double u, double v, dou
 }
 
 // Obstacle masks (reactionDiffusion.cu:154-184, 515-537).  pat = sc | sw<<1 | se<<2 | sn<<3 | ss<<4
-// (mask of the cell and of its mirrored W / E / N = j+1 / S = j-1 neighbours).  The six
-// coefficients are exact 0 / 1 / 2 and the products are formed literally; non-tissue cells come
-// out as exactly 0.0.  For the all-tissue pattern (31) this is bit-identical to euler_cell
-// (1.0*x == x, 2.0*u exact), which is what lets a warp whose cells are all standard skip it.
-__device__ __forceinline__ double c012(unsigned c2) {   // 0 / 1 / 2 as a double, no conversion
-  return __hiloint2double(c2 ? (int)(0x3FE00000u + (c2 << 20)) : 0, 0);
-}
+// (mask of the cell and of its mirrored W / E / N = j+1 / S = j-1 neighbours).  The reference
+// multiplies by coefficient triples that are exact 0 / 1 / 2 (:162-169); per axis, for a tissue
+// cell, only four triples occur and each reduces -- bit for bit, for finite fields -- to the plain
+// stencil on substituted neighbours, r = fma(-2, u, A) + B:
+//     both neighbours tissue  (1,2,1):  1*W - 2*u + 1*E            A = W,    B = E
+//     only W                  (2,2,0):  2*W - 2*u + 0*E            A = W+W,  B = 0   (2*W exact;
+//     only E                  (0,2,2):  0*W - 2*u + 2*E            A = E+E,  B = 0    one rounding)
+//     neither                 (0,0,0):  zero                       r = 0
+// (x + (+-0) == x for x != 0, and the sign of a zero du cannot reach the output: rhs = 0.0 + 1.0*du,
+// DESIGN.md "zero signs").  Non-tissue cells come out as exactly 0.0.  No multiplies, one DADD per
+// axis and field, the rest are selects -- the FP64 pipe is what this kernel is short of.
 template <bool DEF>
 __device__ __forceinline__ void euler_cell_solid(const YhK &k, unsigned pat, double u, double v,
                                                  double uW, double uE, double uN, double uS,
                                                  double vW, double vE, double vN, double vS, bool scs,
                                                  double &un, double &vn) {
   const bool sc = pat & 1u, sw = pat & 2u, se = pat & 4u, sn = pat & 8u, ss = pat & 16u;
-  const double cxx = c012((sw && se) && (sw && sc) ? 1u : ((sw && sc) ? 2u : 0u));   // :162-169
-  const double cxy = c012(sc ? ((sw || se) ? 2u : 0u) : 0u);
-  const double cxz = c012((sw && se) && (sc && se) ? 1u : ((sc && se) ? 2u : 0u));
-  const double cyx = c012((sn && ss) && (sn && sc) ? 1u : ((sn && sc) ? 2u : 0u));
-  const double cyy = c012(sc ? ((sn || ss) ? 2u : 0u) : 0u);
-  const double cyz = c012((sn && ss) && (sc && ss) ? 1u : ((sc && ss) ? 2u : 0u));
-  const double du = ((cxx * uW - cxy * u + cxz * uE) * k.rx + (cyx * uN - cyy * u + cyz * uS) * k.ry);
+  const bool xb = sw && se, yb = sn && ss, xany = sw || se, yany = sn || ss;
+  double t, rx_, ry_;
+  t = sw ? uW : uE; rx_ = fma(-2.0, u, xb ? uW : t + t) + (xb ? uE : 0.0);
+  t = sn ? uN : uS; ry_ = fma(-2.0, u, yb ? uN : t + t) + (yb ? uS : 0.0);
+  const double du = (xany ? rx_ : 0.0) * k.rx + (yany ? ry_ : 0.0) * k.ry;
   double dv = 0.0;
-  if (k.gateDiff)
-    dv = ((cxx * vW - cxy * v + cxz * vE) * k.rx * k.rscale + (cyx * vN - cyy * v + cyz * vS) * k.ry * k.rscale);
+  if (k.gateDiff) {
+    t = sw ? vW : vE; rx_ = fma(-2.0, v, xb ? vW : t + t) + (xb ? vE : 0.0);
+    t = sn ? vN : vS; ry_ = fma(-2.0, v, yb ? vN : t + t) + (yb ? vS : 0.0);
+    dv = (xany ? rx_ : 0.0) * k.rx * k.rscale + (yany ? ry_ : 0.0) * k.ry * k.rscale;
+  }
   euler_finish<DEF>(k, u, v, du, dv, scs, un, vn);
   if (!sc) { un = 0.0; vn = 0.0; }   // :521-522
 }
@@ -240,8 +245,8 @@ rd_euler_stream(const __grid_constant__ YhK k, const __grid_constant__ FastArgs 
     if (canon) { pu.x += 0.0; pu.y += 0.0; pv.x += 0.0; pv.y += 0.0; }
   };
 
-  // mask patterns of the pair, fetched one row ahead of use (global / L2; 1 B per cell)
-  unsigned pat_next = 0x1F1Fu;
+  // mask patterns of the pair, fetched two rows ahead of use (global / L2; 1 B per cell)
+  unsigned pat_q0 = 0x1F1Fu, pat_q1 = 0x1F1Fu;
   auto ld_pat = [&](int row) -> unsigned {
     return *reinterpret_cast<const unsigned short *>(a.pat + (size_t)row * nx + gx);
   };
@@ -252,9 +257,10 @@ rd_euler_stream(const __grid_constant__ YhK k, const __grid_constant__ FastArgs 
     if (m >= lo_l && m < hi_l) {
       unsigned pat = 0x1F1Fu;
       if (SOLID) {
-        if (m == lo_l) pat_next = ld_pat(m);
-        pat = pat_next;
-        if (m + 1 < hi_l) pat_next = ld_pat(m + 1);
+        if (m == lo_l) { pat_q0 = ld_pat(m); if (m + 1 < hi_l) pat_q1 = ld_pat(m + 1); }
+        pat = pat_q0;
+        pat_q0 = pat_q1;
+        if (m + 2 < hi_l) pat_q1 = ld_pat(m + 2);
       }
       if (m == lo_l) {                   // first row of this level: nothing in registers yet
         ld_pair(m, uC, vC);

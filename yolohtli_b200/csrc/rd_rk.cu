@@ -144,13 +144,14 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
   const bool left_edge = (gx == 0), right_edge = (gx + 2 == nx);
   const int cc = c + 2;                  // column offset inside a padded ring row
 
-  // Runge-Kutta tables (reactionDiffusion.cu:71-86)
+  // Runge-Kutta tables (reactionDiffusion.cu:71-86): ki = {0, .5, .5, 1}, w = {1/6, 1/3, 1/3, 1/6}
+  // as literals; selected arithmetically -- an indexed local array lands in local memory and was
+  // re-read every row (ncu: 5.9 M local loads per launch, long-scoreboard stalls).
   double a_next = 0.0, w_k = 0.0;
   const int st = g - 1;                  // stage index of this group
   if (K == 4) {
-    const double ki[5] = {0.0, 0.5, 0.5, 1.0, 0.0};
-    const double ws[4] = {0.166666666666667, 0.333333333333333, 0.333333333333333, 0.166666666666667};
-    if (st >= 0) { a_next = ki[st + 1]; w_k = ws[st]; }
+    a_next = (st == 2) ? 1.0 : ((st == 0 || st == 1) ? 0.5 : 0.0);
+    w_k = (st == 0 || st == 3) ? 0.166666666666667 : ((st == 1 || st == 2) ? 0.333333333333333 : 0.0);
   } else if (K == 2) {
     if (st == 0) { a_next = 0.5; w_k = 0.0; }
     if (st == 1) { a_next = 0.0; w_k = 1.0; }

@@ -29,6 +29,8 @@ struct yh_sim {
   double c[3], phi[3];   // drift velocities and frame phase (main.cu:60-61)
   double *apd[6];        // APD1 APD2 sAPD dAPD back front, n_sims sheets each (lazily allocated)
   uint8_t *apd_first, *stim_area;
+  double *sr_d, *sr_log_d;   // device-resident (c, phi, cos, sin) and its per-step record (yh_sim_run_sr_device)
+  size_t sr_log_cap;
   uint8_t *pat;          // mask patterns of the temporally blocked Euler kernel (yh_rd_solid_patterns)
   int apd_init;          // sAPD / dAPD hold values for every cell (one full pass done)
   cudaStream_t st;
@@ -66,7 +68,7 @@ int yh_sim_create(yh_sim **out, const yh_params *p, int n_sims, int device) {
   s->p = *p;
   s->n_sims = n_sims; s->device = device;
   s->n = (size_t)p->nx * p->ny;
-  s->cur = 0; s->solid = nullptr; s->pat = nullptr; s->trace_d = nullptr; s->trace_cap = 0;
+  s->cur = 0; s->solid = nullptr; s->pat = nullptr; s->sr_d = nullptr; s->sr_log_d = nullptr; s->sr_log_cap = 0; s->trace_d = nullptr; s->trace_cap = 0;
   s->period_d = nullptr; s->duration_it = 0; s->count = 0; s->have_prev = 0; s->raw_input = 1;
   s->px = p->nx / 2; s->py = p->ny / 2;   // param.point, saveFiles.cu:180
   s->vt[0] = s->vt[1] = s->adv[0] = s->adv[1] = nullptr;
@@ -94,7 +96,7 @@ int yh_sim_destroy(yh_sim *s) {
   DevGuard g(s->device);
   cudaStreamSynchronize(s->st);
   for (int b = 0; b < 2; b++) { cudaFree(s->u[b]); cudaFree(s->v[b]); }
-  cudaFree(s->solid); cudaFree(s->pat); cudaFree(s->trace_d); cudaFree(s->tip_count_d); cudaFree(s->tip_vec_d);
+  cudaFree(s->solid); cudaFree(s->pat); cudaFree(s->sr_d); cudaFree(s->sr_log_d); cudaFree(s->trace_d); cudaFree(s->tip_count_d); cudaFree(s->tip_vec_d);
   cudaFree(s->period_d);
   cudaFree(s->vt[0]); cudaFree(s->vt[1]); cudaFree(s->adv[0]); cudaFree(s->adv[1]);
   for (int q = 0; q < 6; q++) cudaFree(s->apd[q]);
@@ -309,21 +311,26 @@ int yh_sim_tips(yh_sim *s, yh_tip *tips_h, int capacity, int *count_out) {
   return YH_OK;
 }
 
+static int sr_alloc(yh_sim *s) {   // velTan and the advection field, zeroed (main.cu:431-434)
+  const size_t bytes = s->n * sizeof(double);
+  if (s->vt[0]) return YH_OK;
+  for (int q = 0; q < 2; q++) {
+    YH_CUDA(cudaMalloc(&s->vt[q], bytes));
+    YH_CUDA(cudaMalloc(&s->adv[q], bytes));
+    YH_CUDA(cudaMemsetAsync(s->vt[q], 0, bytes, s->st));
+    YH_CUDA(cudaMemsetAsync(s->adv[q], 0, bytes, s->st));
+  }
+  return YH_OK;
+}
+
 // One symmetry-reduction step per iteration, as display() does when param.reduceSym
 // (main.cu:894-954), with slice+trapz fused and Cxy fused into the advection.
 int yh_sim_run_sr(yh_sim *s, int nsteps, double *c_phi_h) {
   YH_REQUIRE(s && nsteps >= 0, "bad arguments");
   YH_REQUIRE(s->n_sims == 1, "symmetry reduction drives a single sheet");
   DevGuard g(s->device);
-  const size_t bytes = s->n * sizeof(double);
-  if (!s->vt[0]) {
-    for (int q = 0; q < 2; q++) {
-      YH_CUDA(cudaMalloc(&s->vt[q], bytes));
-      YH_CUDA(cudaMalloc(&s->adv[q], bytes));
-      YH_CUDA(cudaMemsetAsync(s->vt[q], 0, bytes, s->st));    // main.cu:431-434
-      YH_CUDA(cudaMemsetAsync(s->adv[q], 0, bytes, s->st));
-    }
-  }
+  int rc0 = sr_alloc(s);
+  if (rc0 != YH_OK) return rc0;
   const yh_params *p = &s->p;
   double I[12];
   for (int it = 0; it < nsteps; it++) {
@@ -363,6 +370,69 @@ int yh_sim_run_sr(yh_sim *s, int nsteps, double *c_phi_h) {
     s->raw_input = 0;
   }
   YH_CUDA(cudaStreamSynchronize(s->st));
+  return YH_OK;
+}
+
+// The same symmetry-reduction steps with the drift solve RESIDENT ON THE DEVICE: the 12 integrals,
+// the 3x3 solve, the frame update and the (c, phi) record never leave the GPU, so a step is five
+// back-to-back launches {RD, tips, integral rows, integrals+solve, BFECC} with no host round trip
+// (the reference blocks the host 12 times per step, integralTrapz.cu:97-179).  cos/sin(phi.t) come
+// from libdevice instead of libm: (c, phi) agree with yh_sim_run_sr to rounding, not bit for bit.
+// The very first step of a run (count == 0: two solves, main.cu:910-921) goes through the host path.
+int yh_sim_run_sr_device(yh_sim *s, int nsteps, double *c_phi_h) {
+  YH_REQUIRE(s && nsteps >= 0, "bad arguments");
+  YH_REQUIRE(s->n_sims == 1, "symmetry reduction drives a single sheet");
+  int done = 0;
+  if (s->count == 0 && nsteps > 0) {
+    int rc = yh_sim_run_sr(s, 1, c_phi_h);
+    if (rc != YH_OK) return rc;
+    done = 1;
+  }
+  if (done == nsteps) return YH_OK;
+  DevGuard g(s->device);
+  int rc0 = sr_alloc(s);
+  if (rc0 != YH_OK) return rc0;
+  const yh_params *p = &s->p;
+  const int n = nsteps - done;
+  if (!s->sr_d) YH_CUDA(cudaMalloc(&s->sr_d, YH_SR_WORDS * sizeof(double)));
+  if (s->sr_log_cap < (size_t)n) {
+    cudaFree(s->sr_log_d); s->sr_log_d = nullptr; s->sr_log_cap = 0;
+    YH_CUDA(cudaMalloc(&s->sr_log_d, (size_t)6 * n * sizeof(double)));
+    s->sr_log_cap = (size_t)n;
+  }
+  // upload (c, phi - c*dt): the closing kernel of every step first applies the deferred
+  // phi += c*dt of the step before it; the host path has already applied it
+  double h[YH_SR_WORDS] = {0};
+  for (int q = 0; q < 3; q++) { h[YH_SR_C + q] = s->c[q]; h[YH_SR_PHI + q] = s->phi[q]; }
+  YH_CUDA(cudaMemcpyAsync(s->sr_d, h, sizeof(h), cudaMemcpyHostToDevice, s->st));
+  YH_CUDA(cudaStreamSynchronize(s->st));   // h lives on this stack frame
+  for (int it = 0; it < n; it++) {
+    const int c = s->cur, o = c ^ 1;
+    int rc = yh_rd_step(p, s->u[c], s->v[c], s->u[o], s->v[o], s->vt[0], s->vt[1], s->solid, 0, s->px,
+                        s->py, 0, p->ny, s->st);
+    if (rc != YH_OK) return rc;
+    rc = yh_tip_track(p, s->u[o], s->u[c], nullptr, s->tip_count_d, s->tip_vec_d, YH_TIPVECSIZE,
+                      p->dt * (double)s->count, p->tipAlgorithm, s->st);
+    if (rc != YH_OK) return rc;
+    rc = yh_sr_integrals_solve_device(p, s->u[c], s->v[c], s->vt[0], s->vt[1], s->adv[0], s->adv[1],
+                                      s->tip_count_d, s->tip_vec_d, s->count, s->sr_d,
+                                      s->sr_log_d + (size_t)6 * it, it == 0 ? 0.0 : p->dt, s->st);
+    if (rc != YH_OK) return rc;
+    rc = yh_advect_bfecc_device_c(p, s->u[o], s->v[o], s->u[c], s->v[c], s->sr_d, s->adv[0], s->adv[1],
+                                  s->solid, s->st);
+    if (rc != YH_OK) return rc;
+    s->count++;
+  }
+  int rc = yh_sr_flush_phi_device(s->sr_d, p->dt, s->st);   // the last step's phi += c*dt
+  if (rc != YH_OK) return rc;
+  YH_CUDA(cudaMemcpyAsync(h, s->sr_d, sizeof(h), cudaMemcpyDeviceToHost, s->st));
+  if (c_phi_h)
+    YH_CUDA(cudaMemcpyAsync(c_phi_h + (size_t)6 * done, s->sr_log_d, (size_t)6 * n * sizeof(double),
+                            cudaMemcpyDeviceToHost, s->st));
+  YH_CUDA(cudaStreamSynchronize(s->st));
+  for (int q = 0; q < 3; q++) { s->c[q] = h[YH_SR_C + q]; s->phi[q] = h[YH_SR_PHI + q]; }
+  s->have_prev = 0;
+  s->raw_input = 0;
   return YH_OK;
 }
 

@@ -134,21 +134,27 @@ struct IntArgs {
   int R;               // ceil(sqrt(tipOffX*tipOffY)): rows cy-R .. cy+R can intersect the disc
 };
 
+// Summation order (shared with the oracle, yh_oracle.c): per grid row 256 accumulators -- warp w,
+// lane l takes i = 32w + l, +256, ... -- lanes combined by the xor-butterfly 16..1, the 8 warp
+// sums added in ascending w; rows added in ascending j.  One CTA per row slot: a 512-cell row is
+// two cells per thread instead of sixteen per lane of a lone warp (the pass is pure latency).
+constexpr int ROW_WARPS = 8;
+
 template <bool FUSED>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(ROW_WARPS * 32)
 integrals_rows_kernel(const __grid_constant__ YhK k, const __grid_constant__ IntArgs a) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // row slot
-  const int lane = threadIdx.x & 31;
-  if (warp >= 2 * a.R + 1) return;
+  __shared__ double s_w[ROW_WARPS][12];
+  const int slot = blockIdx.x;   // row slot
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int cx, cy;
   disc_centre(k, a.tipx0, a.tipy0, a.tip_count, a.tv, a.count, cx, cy);
-  const int j = cy + k.ny / 2 - a.R + warp;   // grid row of this slot
+  const int j = cy + k.ny / 2 - a.R + slot;   // grid row of this slot
   double acc[12];
 #pragma unroll
   for (int q = 0; q < 12; q++) acc[q] = 0.0;
   if (j >= 0 && j < k.ny) {
     const int jc = j - k.ny / 2;
-    for (int i = lane; i < k.nx; i += 32) {
+    for (int i = threadIdx.x; i < k.nx; i += ROW_WARPS * 32) {
       const int ic = i - k.nx / 2;
       const bool sc = ((ic - cx) * (ic - cx) + (jc - cy) * (jc - cy)) < k.tipOffX * k.tipOffY;
       if (!sc) continue;   // the reference adds exactly +0.0 here (integralTrapz.cu:55-57)
@@ -174,22 +180,39 @@ integrals_rows_kernel(const __grid_constant__ YhK k, const __grid_constant__ Int
     double x = acc[q];
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, m);
-    acc[q] = x;
+    if (lane == 0) s_w[wid][q] = x;
   }
-  if (lane < 12) {
-    double r = 0.0;
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    double r = s_w[0][threadIdx.x];
 #pragma unroll
-    for (int q = 0; q < 12; q++) if (lane == q) r = acc[q];
-    a.rows[(size_t)warp * 12 + lane] = r;
+    for (int w = 1; w < ROW_WARPS; w++) r = r + s_w[w][threadIdx.x];
+    a.rows[(size_t)slot * 12 + threadIdx.x] = r;
   }
 }
 
-__global__ void integrals_final_kernel(const __grid_constant__ YhK k, const __grid_constant__ IntArgs a) {
-  const int q = threadIdx.x;
-  if (q >= 12) return;
+// Sum of the row sums in ascending j, by thread q < 12 -- the rows are first staged in shared
+// memory by the whole CTA so the serial chain is 2R+1 additions, not 2R+1 global-load latencies.
+constexpr int FIN_THREADS = 256, FIN_ROWS = 256;
+__device__ __forceinline__ double rows_total(const IntArgs &a, double (*stage)[12]) {
+  const int nrows = 2 * a.R + 1;
   double tot = 0.0;
-  for (int w = 0; w < 2 * a.R + 1; w++) tot += a.rows[(size_t)w * 12 + q];   // ascending j
-  a.out[q] = 0.25 * k.hx * k.hy * tot;   // integralTrapz.cu:79
+  for (int r0 = 0; r0 < nrows; r0 += FIN_ROWS) {
+    const int nr = min(FIN_ROWS, nrows - r0);
+    for (int t = threadIdx.x; t < nr * 12; t += FIN_THREADS) stage[0][t] = a.rows[(size_t)r0 * 12 + t];
+    __syncthreads();
+    if (threadIdx.x < 12)
+      for (int w = 0; w < nr; w++) tot += stage[w][threadIdx.x];
+    __syncthreads();
+  }
+  return tot;
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+integrals_final_kernel(const __grid_constant__ YhK k, const __grid_constant__ IntArgs a) {
+  __shared__ double stage[FIN_ROWS][12];
+  const double tot = rows_total(a, stage);
+  if (threadIdx.x < 12) a.out[threadIdx.x] = 0.25 * k.hx * k.hy * tot;   // integralTrapz.cu:79
 }
 
 // Device-resident closing of the SR step (yh_sim_run_sr_device): the 12 integrals, the deferred
@@ -197,13 +220,14 @@ __global__ void integrals_final_kernel(const __grid_constant__ YhK k, const __gr
 // (main.cu:902-903), the 3x3 solve (symmetryReduction.cu:386-416) and cos/sin(phi.t) for the
 // advection that follows -- no host round trip.  cos/sin are libdevice's here and libm's in the
 // host path: results agree to rounding, not bit for bit.
-__global__ void integrals_solve_kernel(const __grid_constant__ YhK k, const __grid_constant__ IntArgs a,
-                                       double *sr, double *log_row, double dt_phi) {
+__global__ void __launch_bounds__(FIN_THREADS)
+integrals_solve_kernel(const __grid_constant__ YhK k, const __grid_constant__ IntArgs a,
+                       double *sr, double *log_row, double dt_phi) {
+  __shared__ double stage[FIN_ROWS][12];
   __shared__ double I[12];
   const int q = threadIdx.x;
+  const double tot = rows_total(a, stage);
   if (q < 12) {
-    double tot = 0.0;
-    for (int w = 0; w < 2 * a.R + 1; w++) tot += a.rows[(size_t)w * 12 + q];   // ascending j
     I[q] = 0.25 * k.hx * k.hy * tot;
     a.out[q] = I[q];
   }
@@ -234,12 +258,11 @@ int run_integrals(const yh_params *p, IntArgs &a, bool fused, double *integrals_
   int rc = yh_workspace(((size_t)nrows * 12 + 12) * sizeof(double), (void **)&ws, 2);
   if (rc != YH_OK) return rc;
   a.rows = ws; a.out = ws + (size_t)nrows * 12;
-  const int blocks = (nrows * 32 + 127) / 128;
-  if (fused) integrals_rows_kernel<true><<<blocks, 128, 0, st>>>(k, a);
-  else integrals_rows_kernel<false><<<blocks, 128, 0, st>>>(k, a);
+  if (fused) integrals_rows_kernel<true><<<nrows, ROW_WARPS * 32, 0, st>>>(k, a);
+  else integrals_rows_kernel<false><<<nrows, ROW_WARPS * 32, 0, st>>>(k, a);
   YH_LAUNCH_CHECK();
   if (!integrals_host) return YH_OK;   // device-resident closing follows (integrals_solve_kernel)
-  integrals_final_kernel<<<1, 32, 0, st>>>(k, a);
+  integrals_final_kernel<<<1, FIN_THREADS, 0, st>>>(k, a);
   YH_LAUNCH_CHECK();
   static thread_local double *pinned = nullptr;
   if (!pinned) YH_CUDA(cudaMallocHost(&pinned, 12 * sizeof(double)));
@@ -278,7 +301,8 @@ cxy_kernel(const __grid_constant__ YhK k, const __grid_constant__ CxyArgs a) {
 constexpr int BT = 32;            // output tile edge
 constexpr int BH = 3;             // halo
 constexpr int BP = BT + 2 * BH;   // 38
-constexpr int BTHREADS = 256;
+constexpr int BTHREADS = 512;
+constexpr int FO = 3 * BP * BP;   // plane offset between the two fields: [g uf ue](u) [g uf ue](v) Rx Ry mask
 
 struct BfArgs {
   const double *u_in, *v_in;
@@ -364,8 +388,8 @@ __global__ void __launch_bounds__(BTHREADS)
 bfecc_kernel(const __grid_constant__ YhK k, const __grid_constant__ BfArgs a) {
   extern __shared__ __align__(16) double bsm[];
   double *g = bsm, *uf = bsm + BP * BP, *ue = bsm + 2 * BP * BP;
-  double *sRx = bsm + 3 * BP * BP, *sRy = bsm + 4 * BP * BP;   // |c| dt / h, upwind direction in the sign bit
-  uint8_t *msk = reinterpret_cast<uint8_t *>(bsm + 5 * BP * BP);
+  double *sRx = bsm + 6 * BP * BP, *sRy = bsm + 7 * BP * BP;   // |c| dt / h, upwind direction in the sign bit
+  uint8_t *msk = reinterpret_cast<uint8_t *>(bsm + 8 * BP * BP);
   const int ti0 = blockIdx.x * BT - BH, tj0 = blockIdx.y * BT - BH;
   const int tid = threadIdx.x;
   const bool neu = k.neumannBC != 0;
@@ -398,95 +422,122 @@ bfecc_kernel(const __grid_constant__ YhK k, const __grid_constant__ BfArgs a) {
     sRx[t] = rx; sRy[t] = ry; msk[t] = m;
   }
 
-  for (int f = 0; f < 2; f++) {
-    const double *gin = f ? a.v_in : a.u_in;
-    double *gout = f ? a.v_out : a.u_out;
-    __syncthreads();
-    for (int t = tid; t < BP * BP; t += BTHREADS) {
-      const int gi = ti0 + t % BP, gj = tj0 + t / BP;
-      g[t] = (gi >= 0 && gi < k.nx && gj >= 0 && gj < k.ny) ? gin[gi + k.nx * gj] : 0.0;
-    }
-    __syncthreads();
-    // sweep 1 (forward) on the tile minus one ring
-    for (int t = tid; t < BP * BP; t += BTHREADS) {
-      const int li = t % BP, lj = t / BP, gi = ti0 + li, gj = tj0 + lj;
-      if (li < 1 || li >= BP - 1 || lj < 1 || lj >= BP - 1) continue;
-      if (gi < 0 || gi >= k.nx || gj < 0 || gj >= k.ny) continue;
-      const bool px = !signbit(sRx[t]), py = !signbit(sRy[t]);
-      const double Rx = fabs(sRx[t]), Ry = fabs(sRy[t]);
-      if (neu) {
-        const NbrIdx x = neumann_idx(k, msk, gi, gj, ti0, tj0);
-        const double FDx = px ? g[t] - g[x.W] : g[t] - g[x.E];
-        const double FDy = py ? g[t] - g[x.S] : g[t] - g[x.N];
-        uf[t] = g[t] - tc * (Rx * FDx + Ry * FDy);
-      } else {
-        const DirMask d = dir_mask(k, msk, gi, gj, t);
-        const double u = d.sc ? g[t] : 0.0;
-        const double W = d.sc && d.sw ? g[t - 1] : (d.sc ? bv : 0.0);
-        const double E = d.sc && d.se ? g[t + 1] : (d.sc ? bv : 0.0);
-        const double S = d.sc && d.sS ? g[TL(k, gi, gj - 1, ti0, tj0)] : (d.sc ? bv : 0.0);
-        const double N = d.sc && d.sN ? g[TL(k, gi, gj + 1, ti0, tj0)] : (d.sc ? bv : 0.0);
+  // Both fields go through every sweep together: the index selections, the upwind directions and
+  // the Courant numbers of a cell are shared by u and v, and the pass has 4 barriers instead of 8.
+  // Plane f of g / uf / ue is at offset f * FO.
+  const double *gin[2] = {a.u_in, a.v_in};
+  double *gout[2] = {a.u_out, a.v_out};
+  __syncthreads();
+  for (int t = tid; t < BP * BP; t += BTHREADS) {
+    const int gi = ti0 + t % BP, gj = tj0 + t / BP;
+    const bool in = gi >= 0 && gi < k.nx && gj >= 0 && gj < k.ny;
+    g[t] = in ? gin[0][gi + k.nx * gj] : 0.0;
+    g[FO + t] = in ? gin[1][gi + k.nx * gj] : 0.0;
+  }
+  __syncthreads();
+  // sweep 1 (forward) on the tile minus one ring
+  for (int t = tid; t < BP * BP; t += BTHREADS) {
+    const int li = t % BP, lj = t / BP, gi = ti0 + li, gj = tj0 + lj;
+    if (li < 1 || li >= BP - 1 || lj < 1 || lj >= BP - 1) continue;
+    if (gi < 0 || gi >= k.nx || gj < 0 || gj >= k.ny) continue;
+    const bool px = !signbit(sRx[t]), py = !signbit(sRy[t]);
+    const double Rx = fabs(sRx[t]), Ry = fabs(sRy[t]);
+    if (neu) {
+      const NbrIdx x = neumann_idx(k, msk, gi, gj, ti0, tj0);
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        const double *gf = g + f * FO;
+        const double FDx = px ? gf[t] - gf[x.W] : gf[t] - gf[x.E];
+        const double FDy = py ? gf[t] - gf[x.S] : gf[t] - gf[x.N];
+        uf[f * FO + t] = gf[t] - tc * (Rx * FDx + Ry * FDy);
+      }
+    } else {
+      const DirMask d = dir_mask(k, msk, gi, gj, t);
+      const int iS = TL(k, gi, gj - 1, ti0, tj0), iN = TL(k, gi, gj + 1, ti0, tj0);
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        const double *gf = g + f * FO;
+        const double u = d.sc ? gf[t] : 0.0;
+        const double W = d.sc && d.sw ? gf[t - 1] : (d.sc ? bv : 0.0);
+        const double E = d.sc && d.se ? gf[t + 1] : (d.sc ? bv : 0.0);
+        const double S = d.sc && d.sS ? gf[iS] : (d.sc ? bv : 0.0);
+        const double N = d.sc && d.sN ? gf[iN] : (d.sc ? bv : 0.0);
         const double FDx = px ? u - W : u - E, FDy = py ? u - S : u - N;
-        uf[t] = u - tc * (Rx * FDx + Ry * FDy);
+        uf[f * FO + t] = u - tc * (Rx * FDx + Ry * FDy);
       }
     }
-    __syncthreads();
-    // sweep 2 (backward + error compensation) on the tile minus two rings
-    for (int t = tid; t < BP * BP; t += BTHREADS) {
-      const int li = t % BP, lj = t / BP, gi = ti0 + li, gj = tj0 + lj;
-      if (li < 2 || li >= BP - 2 || lj < 2 || lj >= BP - 2) continue;
-      if (gi < 0 || gi >= k.nx || gj < 0 || gj >= k.ny) continue;
-      const bool px = !signbit(sRx[t]), py = !signbit(sRy[t]);
-      const double Rx = fabs(sRx[t]), Ry = fabs(sRy[t]);
-      if (neu) {
-        const NbrIdx x = neumann_idx(k, msk, gi, gj, ti0, tj0);
-        const double FDx = px ? uf[x.i2dE] - uf[x.E2] : uf[x.i2dW] - uf[x.W2];
-        const double FDy = py ? uf[x.i2dN] - uf[x.N2] : uf[x.i2dS] - uf[x.S2];
-        const double ub = uf[t] - tc * (Rx * FDx + Ry * FDy);
-        ue[t] = g[t] - 0.5 * (ub - g[t]);
-      } else {
-        const DirMask d = dir_mask(k, msk, gi, gj, t);
-        const double u = d.sc ? g[t] : 0.0;
-        const double uuf = d.sc ? uf[t] : 0.0;
-        const double W = d.sc && d.sw ? uf[t - 1] : (d.sc ? uf[t] : 0.0);
-        const double E = d.sc && d.se ? uf[t + 1] : (d.sc ? uf[t] : 0.0);
-        const double S = d.sc && d.sS ? uf[TL(k, gi, gj - 1, ti0, tj0)] : (d.sc ? uf[t] : 0.0);
-        const double N = d.sc && d.sN ? uf[TL(k, gi, gj + 1, ti0, tj0)] : (d.sc ? uf[t] : 0.0);
+  }
+  __syncthreads();
+  // sweep 2 (backward + error compensation) on the tile minus two rings
+  for (int t = tid; t < BP * BP; t += BTHREADS) {
+    const int li = t % BP, lj = t / BP, gi = ti0 + li, gj = tj0 + lj;
+    if (li < 2 || li >= BP - 2 || lj < 2 || lj >= BP - 2) continue;
+    if (gi < 0 || gi >= k.nx || gj < 0 || gj >= k.ny) continue;
+    const bool px = !signbit(sRx[t]), py = !signbit(sRy[t]);
+    const double Rx = fabs(sRx[t]), Ry = fabs(sRy[t]);
+    if (neu) {
+      const NbrIdx x = neumann_idx(k, msk, gi, gj, ti0, tj0);
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        const double *gf = g + f * FO, *uff = uf + f * FO;
+        const double FDx = px ? uff[x.i2dE] - uff[x.E2] : uff[x.i2dW] - uff[x.W2];
+        const double FDy = py ? uff[x.i2dN] - uff[x.N2] : uff[x.i2dS] - uff[x.S2];
+        const double ub = uff[t] - tc * (Rx * FDx + Ry * FDy);
+        ue[f * FO + t] = gf[t] - 0.5 * (ub - gf[t]);
+      }
+    } else {
+      const DirMask d = dir_mask(k, msk, gi, gj, t);
+      const int iS = TL(k, gi, gj - 1, ti0, tj0), iN = TL(k, gi, gj + 1, ti0, tj0);
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        const double *gf = g + f * FO, *uff = uf + f * FO;
+        const double u = d.sc ? gf[t] : 0.0;
+        const double uuf = d.sc ? uff[t] : 0.0;
+        const double W = d.sc && d.sw ? uff[t - 1] : (d.sc ? uff[t] : 0.0);
+        const double E = d.sc && d.se ? uff[t + 1] : (d.sc ? uff[t] : 0.0);
+        const double S = d.sc && d.sS ? uff[iS] : (d.sc ? uff[t] : 0.0);
+        const double N = d.sc && d.sN ? uff[iN] : (d.sc ? uff[t] : 0.0);
         const double FDx = px ? uuf - E : uuf - W, FDy = py ? uuf - N : uuf - S;
         // advFDBFECC.cu:287 ships "Rx*FDx - Ry*FDy" for u in the Dirichlet-square branch (B8)
         const double ub = (!k.solidSwitch && f == 0) ? uuf - tc * (Rx * FDx - Ry * FDy)
                                                      : uuf - tc * (Rx * FDx + Ry * FDy);
-        ue[t] = u - 0.5 * (ub - u);
+        ue[f * FO + t] = u - 0.5 * (ub - u);
       }
     }
-    __syncthreads();
-    // sweep 3 (forward) on the 32 x 32 interior -> HBM
-    for (int t = tid; t < BT * BT; t += BTHREADS) {
-      const int li = BH + t % BT, lj = BH + t / BT, gi = ti0 + li, gj = tj0 + lj;
-      if (gi >= k.nx || gj >= k.ny) continue;
-      const int q = li + BP * lj;
-      const bool px = !signbit(sRx[q]), py = !signbit(sRy[q]);
-      const double Rx = fabs(sRx[q]), Ry = fabs(sRy[q]);
-      double r;
-      bool sc;
-      if (neu) {
-        const NbrIdx x = neumann_idx(k, msk, gi, gj, ti0, tj0);
-        const double FDx = px ? ue[q] - ue[x.W] : ue[q] - ue[x.E];
-        const double FDy = py ? ue[q] - ue[x.S] : ue[q] - ue[x.N];
-        r = ue[q] - tc * (Rx * FDx + Ry * FDy);
-        sc = x.sc;
-      } else {
-        const DirMask d = dir_mask(k, msk, gi, gj, q);
-        const double uue = d.sc ? ue[q] : 0.0;
-        const double W = d.sc && d.sw ? ue[q - 1] : (d.sc ? bv : 0.0);
-        const double E = d.sc && d.se ? ue[q + 1] : (d.sc ? bv : 0.0);
-        const double S = d.sc && d.sS ? ue[TL(k, gi, gj - 1, ti0, tj0)] : (d.sc ? bv : 0.0);
-        const double N = d.sc && d.sN ? ue[TL(k, gi, gj + 1, ti0, tj0)] : (d.sc ? bv : 0.0);
-        const double FDx = px ? uue - W : uue - E, FDy = py ? uue - S : uue - N;
-        r = uue - tc * (Rx * FDx + Ry * FDy);
-        sc = d.sc;
+  }
+  __syncthreads();
+  // sweep 3 (forward) on the 32 x 32 interior -> HBM
+  for (int t = tid; t < BT * BT; t += BTHREADS) {
+    const int li = BH + t % BT, lj = BH + t / BT, gi = ti0 + li, gj = tj0 + lj;
+    if (gi >= k.nx || gj >= k.ny) continue;
+    const int q = li + BP * lj;
+    const bool px = !signbit(sRx[q]), py = !signbit(sRy[q]);
+    const double Rx = fabs(sRx[q]), Ry = fabs(sRy[q]);
+    if (neu) {
+      const NbrIdx x = neumann_idx(k, msk, gi, gj, ti0, tj0);
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        const double *uef = ue + f * FO;
+        const double FDx = px ? uef[q] - uef[x.W] : uef[q] - uef[x.E];
+        const double FDy = py ? uef[q] - uef[x.S] : uef[q] - uef[x.N];
+        const double r = uef[q] - tc * (Rx * FDx + Ry * FDy);
+        gout[f][gi + k.nx * gj] = x.sc ? r : 0.0;
       }
-      gout[gi + k.nx * gj] = sc ? r : 0.0;
+    } else {
+      const DirMask d = dir_mask(k, msk, gi, gj, q);
+      const int iS = TL(k, gi, gj - 1, ti0, tj0), iN = TL(k, gi, gj + 1, ti0, tj0);
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        const double *uef = ue + f * FO;
+        const double uue = d.sc ? uef[q] : 0.0;
+        const double W = d.sc && d.sw ? uef[q - 1] : (d.sc ? bv : 0.0);
+        const double E = d.sc && d.se ? uef[q + 1] : (d.sc ? bv : 0.0);
+        const double S = d.sc && d.sS ? uef[iS] : (d.sc ? bv : 0.0);
+        const double N = d.sc && d.sN ? uef[iN] : (d.sc ? bv : 0.0);
+        const double FDx = px ? uue - W : uue - E, FDy = py ? uue - S : uue - N;
+        const double r = uue - tc * (Rx * FDx + Ry * FDy);
+        gout[f][gi + k.nx * gj] = d.sc ? r : 0.0;
+      }
     }
   }
 }
@@ -579,7 +630,7 @@ int yh_sr_integrals_solve_device(const yh_params *p, const double *u, const doub
   a.count = count; a.tip_count = tip_count; a.tv = tv; a.tipx0 = p->tipx0; a.tipy0 = p->tipy0;
   int rc = run_integrals(p, a, true, nullptr, st);
   if (rc != YH_OK) return rc;
-  integrals_solve_kernel<<<1, 32, 0, st>>>(yh_make_k(p), a, sr_state, log_row, dt_phi);
+  integrals_solve_kernel<<<1, FIN_THREADS, 0, st>>>(yh_make_k(p), a, sr_state, log_row, dt_phi);
   YH_LAUNCH_CHECK();
   return YH_OK;
 }
@@ -618,7 +669,7 @@ int yh_cxy_field(const yh_params *p, double *adv_x, double *adv_y, const double 
 static int bfecc_common(const yh_params *p, BfArgs &a, void *stream) {
   YhK k = yh_make_k(p);
   dim3 grd((p->nx + BT - 1) / BT, (p->ny + BT - 1) / BT);
-  const size_t smem = (size_t)5 * BP * BP * sizeof(double) + BP * BP;
+  const size_t smem = (size_t)8 * BP * BP * sizeof(double) + BP * BP;
   static bool attr_set[64] = {false};
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));

@@ -84,6 +84,18 @@ __device__ int tip_cell(const YhK &k, const TipArgs &a, int i, int j, float2 *ro
   const double x1 = a.present[s0], x2 = a.present[sx], x4 = a.present[sy], x3 = a.present[sxy];
   const double y1 = a.past[s0], y2 = a.past[sx], y4 = a.past[sy], y3 = a.past[sxy];
   const double Uth = k.Uth;
+  // A root must lie strictly inside the cell (0 < s,t < 1, :215), where each bilinear interpolant
+  // is a convex combination of its four corners: if either field keeps all four corners strictly on
+  // one side of Uth it has no Uth-point in the closed cell and the system no solution there.  Such
+  // cells (almost all of them) skip the closed form -- 2 divisions + a square root per root in
+  // FP64, which made this pass as expensive as an RK4 step.  Corners equal to Uth are not skipped.
+  {
+    // Newton accepts |u - Uth| <= 1e-15 (:335): its cells are skipped only beyond that margin
+    const double hi = Uth + ((a.algorithm == 2) ? 2e-15 : 0.0), lo = Uth - ((a.algorithm == 2) ? 2e-15 : 0.0);
+    const bool xa = x1 > hi && x2 > hi && x3 > hi && x4 > hi, xb = x1 < lo && x2 < lo && x3 < lo && x4 < lo;
+    const bool ya = y1 > hi && y2 > hi && y3 > hi && y4 > hi, yb = y1 < lo && y2 < lo && y3 < lo && y4 < lo;
+    if (xa || xb || ya || yb) return 0;
+  }
   int n = 0;
   if (a.algorithm == 1) {   // :150-200
     const double x3y1 = x3 * y1, x4y1 = x4 * y1, x3y2 = x3 * y2, x4y2 = x4 * y2;
@@ -174,7 +186,10 @@ tip_kernel(const __grid_constant__ YhK k, const __grid_constant__ TipArgs a) {
   // block-wide exclusive scan of `mine` in thread order (= cell order), then the chunk prefix
   int total;
   const int excl = yh_block_excl_scan<TIP_THREADS>(mine, s_warp, total);
-  if (tid == 0) s_base = (int)yh_ordered_prefix(a.ord, chunk, (unsigned)total, a.count);
+  if (tid < 32) {   // warp 0 chains this chunk to its predecessors
+    const unsigned prefix = yh_ordered_prefix(a.ord, chunk, (unsigned)total, a.count);
+    if (tid == 0) s_base = (int)prefix;
+  }
   __syncthreads();
   if (mine == 0) return;
 

@@ -22,28 +22,48 @@ __device__ __forceinline__ unsigned long long yh_lb_pack(unsigned epoch, unsigne
   return ((unsigned long long)(epoch & 0xFFFFFFu) << 40) | ((unsigned long long)flag << 32) | v;
 }
 
-// Called by ONE thread of the CTA that holds `chunk` with the CTA's hit total; returns the
-// number of hits in all earlier chunks.  The CTA of the last chunk publishes the grand total to
-// *count (replaces cudaMemset(count) + atomicAdd) and re-arms the ticket counter.
+// Called by ONE WARP (all 32 lanes, converged) of the CTA that holds `chunk` with the CTA's hit
+// total; returns (in every lane) the number of hits in all earlier chunks.  Look-back is
+// warp-parallel: lane l examines predecessor chunk-1-l (32 at a time), the nearest one that already
+// holds an inclusive prefix ends the walk -- a single-thread walk made the 256-chunk pass of a
+// 512^2 sheet a 20 us kernel.  The CTA of the last chunk publishes the grand total to *count
+// (replaces cudaMemset(count) + atomicAdd) and re-arms the ticket counter.
 __device__ __forceinline__ unsigned yh_ordered_prefix(const YhOrdered &o, int chunk, unsigned total,
                                                       int *count) {
   volatile unsigned long long *st = o.state + 1;
+  const int lane = threadIdx.x & 31;
+  const unsigned ep = o.epoch & 0xFFFFFFu;
   unsigned prefix = 0;
   if (chunk > 0) {
-    st[chunk] = yh_lb_pack(o.epoch, 1u, total);
-    __threadfence();
-    for (int b = chunk - 1; b >= 0; b--) {
-      unsigned long long w;
-      do { w = st[b]; } while ((unsigned)(w >> 40) != (o.epoch & 0xFFFFFFu) || ((w >> 32) & 3u) == 0u);
-      prefix += (unsigned)w;
-      if (((w >> 32) & 3u) == 2u) break;
+    if (lane == 0) {
+      st[chunk] = yh_lb_pack(o.epoch, 1u, total);
+      __threadfence();
+    }
+    for (int base = chunk - 1;; base -= 32) {
+      const int b = base - lane;
+      unsigned flag = 2u, val = 0u;   // before the first chunk: an inclusive prefix of zero
+      if (b >= 0) {
+        unsigned long long w;
+        do { w = st[b]; } while ((unsigned)(w >> 40) != ep || ((w >> 32) & 3u) == 0u);
+        flag = (unsigned)(w >> 32) & 3u;
+        val = (unsigned)w;
+      }
+      const unsigned incl = __ballot_sync(0xffffffffu, flag == 2u);
+      const int first = __ffs(incl) - 1;            // nearest predecessor with an inclusive prefix
+      unsigned x = (incl == 0u || lane <= first) ? val : 0u;
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
+      prefix += x;
+      if (incl != 0u) break;
     }
   }
-  st[chunk] = yh_lb_pack(o.epoch, 2u, prefix + total);
-  __threadfence();
-  if (chunk == o.nchunks - 1) {
-    *count = (int)(prefix + total);
-    o.state[0] = 0ull;   // every ticket has been taken
+  if (lane == 0) {
+    st[chunk] = yh_lb_pack(o.epoch, 2u, prefix + total);
+    __threadfence();
+    if (chunk == o.nchunks - 1) {
+      *count = (int)(prefix + total);
+      o.state[0] = 0ull;   // every ticket has been taken
+    }
   }
   return prefix;
 }

@@ -266,6 +266,12 @@ class Sim:
         check(lib().yh_sim_run_sr(self._h, nsteps, out.ctypes.data_as(C.c_void_p) if record else None))
         return out
 
+    def run_sr_device(self, nsteps, record=True):
+        """Same steps with the drift solve resident on the device (no host round trip per step)."""
+        out = np.zeros((nsteps, 6), dtype=np.float64) if record else None
+        check(lib().yh_sim_run_sr_device(self._h, nsteps, out.ctypes.data_as(C.c_void_p) if record else None))
+        return out
+
     def run_apd(self, nsteps, stim_area=None):
         """contourMode == 1 loop: RD + sAPD every step (main.cu:1035) for every sheet."""
         ptr = None
