@@ -84,18 +84,6 @@ __device__ int tip_cell(const YhK &k, const TipArgs &a, int i, int j, float2 *ro
   const double x1 = a.present[s0], x2 = a.present[sx], x4 = a.present[sy], x3 = a.present[sxy];
   const double y1 = a.past[s0], y2 = a.past[sx], y4 = a.past[sy], y3 = a.past[sxy];
   const double Uth = k.Uth;
-  // A root must lie strictly inside the cell (0 < s,t < 1, :215), where each bilinear interpolant
-  // is a convex combination of its four corners: if either field keeps all four corners strictly on
-  // one side of Uth it has no Uth-point in the closed cell and the system no solution there.  Such
-  // cells (almost all of them) skip the closed form -- 2 divisions + a square root per root in
-  // FP64, which made this pass as expensive as an RK4 step.  Corners equal to Uth are not skipped.
-  {
-    // Newton accepts |u - Uth| <= 1e-15 (:335): its cells are skipped only beyond that margin
-    const double hi = Uth + ((a.algorithm == 2) ? 2e-15 : 0.0), lo = Uth - ((a.algorithm == 2) ? 2e-15 : 0.0);
-    const bool xa = x1 > hi && x2 > hi && x3 > hi && x4 > hi, xb = x1 < lo && x2 < lo && x3 < lo && x4 < lo;
-    const bool ya = y1 > hi && y2 > hi && y3 > hi && y4 > hi, yb = y1 < lo && y2 < lo && y3 < lo && y4 < lo;
-    if (xa || xb || ya || yb) return 0;
-  }
   int n = 0;
   if (a.algorithm == 1) {   // :150-200
     const double x3y1 = x3 * y1, x4y1 = x4 * y1, x3y2 = x3 * y2, x4y2 = x4 * y2;
@@ -111,11 +99,21 @@ __device__ int tip_cell(const YhK &k, const TipArgs &a, int i, int j, float2 *ro
     const double px = ctn2 - Uth * ctn1;
     const double py = Uth * ctn1 - x3y1 + x4y2 + x1y3 - x2y4 + 2.0 * (x2y1 - x1y2);
     const bool ok = k.solidSwitch ? true : (disc >= 0.0);
-    float2 r;
-    r.x = (float)((px + disc) / den1); r.y = (float)((py + disc) / den2);
-    if (ok && ((r.x > 0.0) && (r.x < 1.0)) && ((r.y > 0.0) && (r.y < 1.0))) roots[n++] = r;
-    r.x = (float)((px - disc) / den1); r.y = (float)((py - disc) / den2);
-    if (ok && ((r.x > 0.0) && (r.x < 1.0)) && ((r.y > 0.0) && (r.y < 1.0))) roots[n++] = r;
+    // The root is (N/D) cast to float and must land in (0, 1) (:182-185, :215).  N == 0, opposite
+    // signs, or |N| >= |D| put the exact quotient outside (0, 1) and rounding is monotone, so those
+    // candidates are rejected WITHOUT the FP64 division (4 per cell, most of this kernel's
+    // arithmetic); NaNs fail every comparison here and fall through to the literal path.
+    auto outside = [](double N, double D) {
+      return (N == 0.0) || (N > 0.0 && D < 0.0) || (N < 0.0 && D > 0.0) || (fabs(N) >= fabs(D));
+    };
+#pragma unroll
+    for (int sg = 0; sg < 2; sg++) {   // '+' root first (:182-183), then '-'
+      const double Nx = sg ? px - disc : px + disc, Ny = sg ? py - disc : py + disc;
+      if (!ok || outside(Nx, den1) || outside(Ny, den2)) continue;
+      float2 r;
+      r.x = (float)(Nx / den1); r.y = (float)(Ny / den2);
+      if (((r.x > 0.0) && (r.x < 1.0)) && ((r.y > 0.0) && (r.y < 1.0))) roots[n++] = r;
+    }
   } else {   // Newton, :384-424
     double s = 0.5, t = 0.5;
     for (int it = 0; it < 4; it++) {
