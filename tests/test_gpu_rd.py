@@ -303,14 +303,22 @@ def test_racy_reference_modes_within_tolerance(oracle):
 
 
 @pytest.mark.skipif(not oracle_lib.have_reference(), reason="oracle/_ref not built")
-def test_default_mode_trace_and_tip_trajectory_vs_reference(oracle, yh):
-    """North-star acceptance for the reference's DEFAULT mode (RK4 + 4th-order Laplacian, racy in
-    the reference): on a rotating spiral, over 3000 steps (60 ms), our synchronous-stage path and
-    the reference's own kernels agree on the electrode voltage trace (rms <= 5e-3, max 2e-2 at a
-    passing front) and on the tip trajectory sampled every sampleIt = 100 steps (<= 0.5 cell), both
-    tip lists holding the same number of tips.  Tolerances: the front is ~10 cells wide with
-    u in [0, 1], so 0.5 cell of front displacement is ~5e-2 in u; we ask for better."""
+def test_default_mode_trace_and_tip_trajectory_vs_reference(oracle, yh, rd_path):
+    """North-star acceptance for the reference's DEFAULT mode (RK4 + 4th-order Laplacian).  The
+    reference kernel races in this mode (reactionDiffusion.cu:117,219) and is not reproducible run
+    to run, so the bound is calibrated on the reference itself (tier T2): over 2000 steps
+    (40 ms) of a rotating spiral, sampled every sampleIt = 100 steps, our synchronous-stage path must
+    stay within max(0.5 cell, 3x the spread of FIVE reference runs) in tip position (median <= 0.25
+    cell) and within max(1e-3, 3x spread) in the voltage of a 5 x 5 grid of electrodes.
+    The tip LIST is checked separately and exactly: the reference's own tip kernel (--fmad=false
+    build) applied to OUR fields returns our list bit for bit -- including the spurious roots the
+    shipped closed form (no residual check) reports wherever the sheet still has the x-only
+    symmetry of the initial condition exactly, which our arithmetic preserves and the reference's
+    races break at 1e-19."""
+    if rd_path == "tile":
+        pytest.skip("one path is enough for this statistical tier")
     nx = ny = 256
+    nseg = 20   # beyond ~2000 steps the reference's tip starts splitting into 2-3 noisy crossings
     pe = oracle.params_default(nx, ny, timeIntOrder=1, lap4=0)
     sim = yh.Sim(pe)
     sim.cross_field_ic()
@@ -320,47 +328,57 @@ def test_default_mode_trace_and_tip_trajectory_vs_reference(oracle, yh):
     p = oracle.params_default(nx, ny)   # default: RK4 + lap4
     ref = oracle_lib.Reference(nofma=False)
     ref.init(p)
+    probe = np.ix_(np.arange(24, ny, 52), np.arange(24, nx, 52))   # 5 x 5 electrodes
+    r_path, r_trace = [], []
+    for run in range(5):
+        ru, rv = u0, v0
+        path, trace = [], []
+        for seg in range(nseg):
+            ru, rv, _ = ref.rd_run(ru, rv, 99)
+            pu_r = ru
+            ru, rv, _ = ref.rd_run(ru, rv, 1)
+            t_r = ref.tip(ru, pu_r, t=0.0, algorithm=1)      # (present, past), main.cu:963
+            assert 1 <= len(t_r) <= 5, (run, seg, t_r)       # one spiral; the racy fields can split its tip
+            assert np.ptp(t_r["x"]) < 4 and np.ptp(t_r["y"]) < 4, (run, seg, t_r)
+            path.append((float(t_r["x"].mean()), float(t_r["y"].mean())))
+            trace.append(ru[probe])
+        r_path.append(path); r_trace.append(trace)
+    r_path, r_trace = np.array(r_path), np.array(r_trace).reshape(5, nseg, -1)    # [run, seg, 2], [run, seg, electrode]
+    refn = oracle_lib.Reference(nofma=True)
+    refn.init(p)
     ours = yh.Sim(p)
     ours.set_state(u0, v0)
-    ru, rv = u0, v0
-    tr_o, tr_r, dtip, seen = [], [], [], 0
-
-    def physical(t, u):
-        """The shipped closed form has no residual check: in cells whose two rows are bit-identical
-        (the quiescent part of the sheet keeps the x-only symmetry of the IC exactly in our
-        arithmetic; the reference's races break it at 1e-19) it returns spurious roots at u ~ 1e-15
-        -- the reference's own kernel reports them too when given our fields.  Keep the tips whose
-        cell really straddles Uth."""
-        keep = []
-        for q in t:
-            i, j = int(q["x"]), int(q["y"])
-            c = u[j:j + 2, i:i + 2]
-            keep.append(c.min() <= p.Uth <= c.max())
-        return t[np.array(keep, dtype=bool)] if len(t) else t
-
-    for seg in range(30):
+    o_path, o_trace = [], []
+    for seg in range(nseg):
         ours.run(99, tb_steps=1)
-        ru, rv, _ = ref.rd_run(ru, rv, 99)
-        pu_r = ru
+        pu_o = ours.get_state()[0][0].copy()
         ours.run(1, tb_steps=1)
-        ru, rv, _ = ref.rd_run(ru, rv, 1)
-        ou, ov = (a[0] for a in ours.get_state())
-        tr_o.append(ou[ny // 2, nx // 2]); tr_r.append(ru[ny // 2, nx // 2])
-        t_o = physical(ours.tips(), ou)
-        t_r = physical(ref.tip(ru, pu_r, t=0.0, algorithm=1), ru)      # (present, past), main.cu:963
-        assert len(t_o) == len(t_r), (seg, len(t_o), len(t_r))
-        if len(t_o):
-            seen += 1
-            a = np.sort(np.stack([t_o["x"], t_o["y"]], 1), axis=0)
-            b = np.sort(np.stack([t_r["x"], t_r["y"]], 1), axis=0)
-            dtip.append(float(np.abs(a - b).max()))
+        ou = ours.get_state()[0][0]
+        t_o = ours.tips()
+        t_x = refn.tip(ou, pu_o, t=p.dt * ours.count, algorithm=1)
+        key = ("y", "x")
+        assert np.array_equal(np.sort(t_o, order=key), np.sort(t_x, order=key)), seg
+        centre = r_path[:, seg].mean(axis=0)
+        d = np.hypot(t_o["x"] - centre[0], t_o["y"] - centre[1])
+        o_path.append((float(t_o["x"][d.argmin()]), float(t_o["y"][d.argmin()])))
+        o_trace.append(ou[probe])
     ours.close()
-    tr_o, tr_r = np.array(tr_o), np.array(tr_r)
-    assert seen >= 20 and max(dtip) <= 0.5, (seen, dtip)
-    assert np.sqrt(((tr_o - tr_r) ** 2).mean()) <= 5e-3 and np.abs(tr_o - tr_r).max() <= 2e-2
-    assert tr_r.max() - tr_r.min() > 0.5, "the electrode must see the wave pass"
-    print("default-mode parity vs reference: tip max dev %.3g cells, trace rms %.3g" %
-          (max(dtip), np.sqrt(((tr_o - tr_r) ** 2).mean())))
+    o_path, o_trace = np.array(o_path), np.array(o_trace).reshape(nseg, -1)
+    spread_tip = np.array([max(np.hypot(*(r_path[a, k] - r_path[b, k])) for a in range(5) for b in range(5))
+                           for k in range(nseg)])
+    spread_u = r_trace.max(axis=0) - r_trace.min(axis=0)
+    dev_tip = np.array([min(np.hypot(*(o_path[k] - r_path[a, k])) for a in range(5)) for k in range(nseg)])
+    dev_u = np.abs(o_trace[None] - r_trace).min(axis=0)
+    print("reference run-to-run tip spread (cells):", np.round(spread_tip, 3))
+    print("ours - nearest reference run      (cells):", np.round(dev_tip, 3))
+    print("reference trace spread (max over electrodes):", np.round(spread_u.max(axis=1), 6))
+    print("ours - nearest reference trace (max over electrodes):", np.round(dev_u.max(axis=1), 6))
+    # measured on B200: ours sits a steady 0.10-0.17 cell from the reference path (the racy stage
+    # reads are a slightly different scheme, not noise: its own spread is 0.01 cell there) and
+    # follows it to within the reference's spread once its tip starts splitting (0.5-1.4 cells)
+    assert (dev_tip <= np.maximum(0.5, 3.0 * spread_tip)).all() and np.median(dev_tip) <= 0.25
+    assert (dev_u <= np.maximum(1e-3, 3.0 * spread_u)).all()   # measured: <= 2.7e-4 (reference spread 5e-5)
+    assert (np.ptp(r_trace[0], axis=0) > 0.02).sum() >= 4, "several electrodes must see the voltage move"
 
 
 def test_full_size_16384_sheet(oracle, rd_path):
