@@ -204,7 +204,8 @@ def run_ours(a):
     ms = float(ms.item())
     clocks = sampler.stop() if sampler else None
     value = cells_total * a.substeps * a.steps / (ms / 1e3) / 1e9
-    passes = -(-a.substeps // T) if a.mode == "euler5" else a.substeps * (4 if p.timeIntOrder == 4 else p.timeIntOrder)
+    # one launch per T time steps (Euler, temporally blocked) or per time step (fused RK4 + lap4 kernel)
+    passes = -(-a.substeps // T) if a.mode == "euler5" else a.substeps
     launches = passes * a.steps
 
     # ---- end to end: pinned host -> device, substeps, device -> pinned host --------------
@@ -275,7 +276,7 @@ def run_ours(a):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "rd_euler_stream" if a.mode == "euler5" else "rd_stage_kernel",
+                         "kernel": "rd_euler_stream" if a.mode == "euler5" else "rd_rk_stream",
                          "peak_source": peak_src,
                          "note": f"algorithmic 32 B per cell-update x {steps_per_launch:g} step(s) per launch; "
                                  f"temporal blocking lets frac exceed 1"},
@@ -285,6 +286,104 @@ def run_ours(a):
             out["cpu_baseline"] = cb
         print(json.dumps(out), flush=True)
     run.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_sweep(a):
+    """BASELINE configs[4] (C5): independent 512 x 512 paced simulations, 32 per GPU, stimulation
+    period swept 600 -> 100 ms over the 256 sheets of the full 8-GPU job, sAPD bookkeeping every
+    step (contourMode == 1 loop, main.cu:879-885, 1035).  Replicas only: no data-path collective."""
+    import torch
+    import torch.distributed as dist
+    import yolohtli_b200 as yh
+    from yolohtli_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- yolohtli_b200 has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    yh.load_library()
+    nx, nsim = 512, 32
+    p = yh.default_params(nx, nx, timeIntOrder=1, lap4=0)
+    periods = (np.linspace(600.0, 100.0, 256) / p.dt).astype(np.int32)
+    mine = periods[(rank * nsim) % 256:(rank * nsim) % 256 + nsim]
+    area = synth.stim_area_square(nx, nx)
+    sim = yh.Sim(p, n_sims=nsim, device=local)
+    zero = np.zeros((nsim, nx, nx))
+    sim.set_state(zero, zero)
+    sim.set_pacing(mine, int(10.0 / p.dt))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        sim.run_apd(a.substeps, stim_area=area)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        sim.run_apd(a.substeps, stim_area=None)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop() if sampler else None
+    cells = nsim * nx * nx * world
+    value = cells * a.substeps * a.steps / (ms / 1e3) / 1e9
+    # end to end: host state in, paced steps + APD, host state and APD maps out
+    e2e_steps = max(1, min(a.steps, 2))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sim.set_state(zero, zero)
+        sim.run_apd(a.substeps, stim_area=None)
+        sim.get_state()
+        sim.get_apd()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_val = cells * a.substeps * e2e_steps / float(dt.item()) / 1e9
+    if rank == 0:
+        peak, peak_src, _ = peaks()
+        launches = -(-a.substeps // 4) * a.steps   # one fused {4 Euler steps + APD} launch per 4 time steps
+        achieved = BYTES_PER_UPDATE * nsim * nx * nx * 4 / (ms / launches / 1e3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[4]: batched sweep, {nsim * world} independent 512x512 paced "
+                                   f"simulations ({nsim} per GPU, stimulation period 600 -> 100 ms), Euler + 5-point, "
+                                   f"sAPD every step; {a.substeps} time steps per bench step; replicas only",
+                       "mode": "euler5+sapd", "nx": nx, "ny": nx, "sheets_per_gpu": nsim, "substeps": a.substeps,
+                       "parallelism": f"replicas{world}",
+                       "l2": "32 sheets x 4 arrays x 2 MiB = 256 MiB of state per GPU, larger than the 126 MB L2",
+                       "arithmetic": "FP64, no FMA contraction (bit-identical to the plain-C oracle)"},
+            "e2e": {"value": e2e_val, "unit": METRIC, "h2d_bytes_per_step": 16 * nsim * nx * nx * world,
+                    "d2h_bytes_per_step": 32 * nsim * nx * nx * world, "steps": e2e_steps,
+                    "note": "host state -> device, substeps paced steps with APD bookkeeping, state + APD1/APD2 -> host; wall clock"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "rd_euler_stream", "peak_source": peak_src,
+                         "note": "algorithmic 32 B per cell-update x 4 steps per launch (APD state is touched only at threshold crossings)"},
+            "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    sim.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -303,10 +402,15 @@ def main():
     ap.add_argument("--e2e-substeps", type=int, default=1024, help="time steps per host->device->host call")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="halo exchange: NVLink peer stores (CUDA IPC) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="sheet", choices=["sheet", "sweep"],
+                    help="sheet: configs[3], one large sheet in row slabs (default, the headline); "
+                         "sweep: configs[4], 32 independent 512^2 paced simulations per GPU")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "sweep":
+        run_sweep(a)
     else:
         run_ours(a)
 

@@ -57,6 +57,7 @@ extern "C" {
 
 /* yh_rd_advance flags */
 #define YH_RD_INPUT_CANONICAL 1
+#define YH_RD_SOLID_IS_PATTERNS 2   /* `solid` holds the output of yh_rd_mask_patterns */
 
 /* One record of the tip list: layout of the reference's vec5dyn (typeDefinition.cuh:19-20). */
 typedef struct yh_tip {
@@ -137,6 +138,14 @@ int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, int flags,
                   double *uA, double *vA, double *uB, double *vB,
                   const uint8_t *solid, int stim_mouse, int point_x, int point_y,
                   int row0, int row1, int *result_in_B, void *stream);
+
+/* Obstacle masks + Euler: the temporally blocked kernel reads a per-cell neighbourhood pattern
+ * (sc | sw<<1 | se<<2 | sn<<3 | ss<<4, the 32 cases of reactionDiffusion.cu:162-169) instead of
+ * the mask.  yh_rd_advance derives it on every call (the mask belongs to the caller and may
+ * change); a caller whose mask is fixed computes it once with yh_rd_mask_patterns (nx*ny bytes,
+ * device) and passes it as `solid` with YH_RD_SOLID_IS_PATTERNS.  Euler + Neumann only: other
+ * modes return YH_ERR_UNSUPPORTED for that flag. */
+int yh_rd_mask_patterns(const yh_params *p, const uint8_t *solid, uint8_t *patterns, void *stream);
 
 /* ---- (4) spiral-tip tracking -----------------------------------------------------
  * Resets *tip_count (device int) and appends every tip found between u_past and u_present.
@@ -255,7 +264,8 @@ int yh_sim_run_sr(yh_sim *s, int nsteps, double *c_phi_h);
 int yh_sim_run_sr_device(yh_sim *s, int nsteps, double *c_phi_h);
 /* contourMode == 1 loop (main.cu:879-885, 1035): every step RD, swap, then sAPD_wrapper with the
  * reference's argument order (uold := gateIn = NEW state, unew := gateOut = OLD state) and
- * stimulate = 1 masked by stim_area_h (nx*ny bytes; NULL: every cell, stimulate = 0).  All sheets
+ * stimulate = 1 masked by stim_area_h (nx*ny bytes, uploaded and kept; NULL: the mask of an earlier
+ * call, or -- none yet -- every cell, stimulate = 0).  All sheets
  * of the batch are processed by the same launches.  APD state is zero-initialised (defect B12).
  * yh_sim_get_apd copies APD1, APD2 (n_sims*nx*ny doubles each) to the host. */
 int yh_sim_run_apd(yh_sim *s, int nsteps, const uint8_t *stim_area_h);

@@ -209,15 +209,23 @@ def test_default_mode_rk4_lap4_vs_oracle_and_holes(oracle):
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_slab_decomposition_is_bitwise_invariant(oracle, world):
+@pytest.mark.parametrize("masked", [False, True])
+def test_slab_decomposition_is_bitwise_invariant(oracle, world, masked):
     """N row slabs with ghost rows (emulated on one GPU, halos copied between slab buffers)
-    == the single-domain run, bit for bit (multi-GPU invariance)."""
+    == the single-domain run, bit for bit (multi-GPU invariance); with and
+    without obstacle masks (each slab passes its own rows of the mask, ghost rows included)."""
     from yolohtli_b200.slab import SlabLayout
     nx, ny, H, nsteps = 256, 211, 4, 12
-    pg = oracle.params_default(nx, ny, timeIntOrder=1, lap4=0)
+    pg = oracle.params_default(nx, ny, timeIntOrder=1, lap4=0, solidSwitch=int(masked))
     u, v = rand_fields(nx, ny, 31)
-    want = oracle.rd_advance(pg, nsteps, u, v, stim_mouse=True, point=(100, 105))
+    mask = (np.random.default_rng(12).uniform(size=(ny, nx)) > 0.2).astype(np.uint8) if masked else None
+    want = oracle.rd_advance(pg, nsteps, u, v, solid=mask, stim_mouse=True, point=(100, 105))
     lays = [SlabLayout(ny, world, r, H) for r in range(world)]
+    dmask = [dev(mask[l.g0:l.g1], torch.uint8) if masked else None for l in lays]
+    mflags = 0
+    if masked and world == 2:   # fixed mask: neighbourhood patterns derived once per slab (yh_rd_mask_patterns)
+        dmask = [host.rd_mask_patterns(l.local_params(pg), m, torch.empty_like(m)) for l, m in zip(lays, dmask)]
+        mflags = host.RD_SOLID_IS_PATTERNS
     bufs = []
     for l in lays:
         a = [dev(u[l.g0:l.g1]), dev(v[l.g0:l.g1])]
@@ -235,7 +243,8 @@ def test_slab_decomposition_is_bitwise_invariant(oracle, world):
         for r, l in enumerate(lays):
             p = l.local_params(pg)
             ru, rv = host.rd_advance(p, H, cur[r][0], cur[r][1], oth[r][0], oth[r][1], tb_steps=4,
-                                     rows=(l.own_lo, l.own_hi), stim_mouse=True, point=(100, 105))
+                                     rows=(l.own_lo, l.own_hi), stim_mouse=True, point=(100, 105),
+                                     solid=dmask[r], flags=mflags)
             if ru is oth[r][0]:
                 cur[r], oth[r] = oth[r], cur[r]
     torch.cuda.synchronize()

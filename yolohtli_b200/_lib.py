@@ -95,6 +95,7 @@ SIGNATURES = {
     "yh_rd_step": (_i, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "yh_rd_advance": (_i, [_P, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
                            C.POINTER(_i), _vp]),
+    "yh_rd_mask_patterns": (_i, [_P, _vp, _vp, _vp]),
     "yh_tip_track": (_i, [_P, _vp, _vp, _vp, _vp, _vp, _i, _d, _i, _vp]),
     "yh_slice": (_i, [_P, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _i, _i, _vp, _vp, _i, _vp,
                       _vp, _i, _vp]),

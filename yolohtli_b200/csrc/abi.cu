@@ -385,13 +385,27 @@ int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, int flags, doubl
   // obstacle masks + Euler: the temporally blocked kernel reads per-cell mask patterns, made
   // once per call (mask contents belong to the caller and may change between calls)
   uint8_t *pat = nullptr;
-  if (yh_rd_fast_solid_supported(k, 1) && nsteps > 1) {
+  if (flags & YH_RD_SOLID_IS_PATTERNS) {
+    if (!yh_rd_fast_solid_supported(k, 1)) {
+      yh_set_error("YH_RD_SOLID_IS_PATTERNS needs the masked Euler / no-flux mode");
+      return YH_ERR_UNSUPPORTED;
+    }
+    pat = const_cast<uint8_t *>(solid);
+  } else if (yh_rd_fast_solid_supported(k, 1) && nsteps > 1) {
     rc = yh_workspace((size_t)p->nx * p->ny, (void **)&pat, 4);
     if (rc != YH_OK) return rc;
     rc = yh_rd_solid_patterns(k, solid, pat, st);
     if (rc != YH_OK) return rc;
   }
   return yh_advance_whole(p, k, nsteps, tb, canon, uA, vA, uB, vB, solid, pat, row0, row1, result_in_B, nullptr, st);
+}
+
+int yh_rd_mask_patterns(const yh_params *p, const uint8_t *solid, uint8_t *patterns, void *stream) {
+  int rc = yh_check_device();
+  if (rc != YH_OK) return rc;
+  YH_REQUIRE(p && solid && patterns, "null pointer");
+  YH_REQUIRE(p->nx >= 4 && p->ny >= 1 && p->jg0 >= 0 && p->jg0 + p->ny <= p->ny_global, "bad slab");
+  return yh_rd_solid_patterns(yh_make_k(p), solid, patterns, (cudaStream_t)stream);
 }
 
 // solve_matrix, symmetryReduction.cu:386-416 (host; same operation order; no leak)

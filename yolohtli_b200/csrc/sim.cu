@@ -33,6 +33,7 @@ struct yh_sim {
   size_t sr_log_cap;
   uint8_t *pat;          // mask patterns of the temporally blocked Euler kernel (yh_rd_solid_patterns)
   int apd_init;          // sAPD / dAPD hold values for every cell (one full pass done)
+  int have_stim_area;    // stim_area holds a mask uploaded by an earlier yh_sim_run_apd call
   cudaStream_t st;
 };
 
@@ -450,16 +451,19 @@ int yh_sim_run_apd(yh_sim *s, int nsteps, const uint8_t *stim_area_h) {
     YH_CUDA(cudaMemsetAsync(s->apd_first, 0, cells, s->st));
     YH_CUDA(cudaMalloc(&s->stim_area, cells));
   }
-  if (stim_area_h)   // the same mask for every sheet
+  if (stim_area_h) {   // the same mask for every sheet; kept for later calls that pass NULL
     for (int z = 0; z < s->n_sims; z++)
       YH_CUDA(cudaMemcpyAsync(s->stim_area + s->n * z, stim_area_h, s->n, cudaMemcpyHostToDevice, s->st));
+    s->have_stim_area = 1;
+  }
+  const bool masked = s->have_stim_area != 0;
   yh_params pb = s->p;   // the whole batch as one tall array for the element-wise APD kernel
   pb.ny = s->p.ny * s->n_sims; pb.ny_global = pb.ny;
   YhK k = yh_make_k(&s->p);
   k.px = s->px; k.py = s->py;
   const bool fused_ok = yh_rd_fast_supported(k, 1) != 0;
   YhApd A{s->apd[0], s->apd[1], s->apd[2], s->apd[3], s->apd[4], s->apd[5], s->apd_first,
-          stim_area_h ? s->stim_area : nullptr, stim_area_h != nullptr};
+          masked ? s->stim_area : nullptr, masked};
   int left = nsteps;
   while (left > 0) {
     if (!s->apd_init || !fused_ok) {

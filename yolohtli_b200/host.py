@@ -65,6 +65,14 @@ def rd_step(p, u_in, v_in, u_out, v_out, velTan=None, solid=None, stim_mouse=Fal
 
 
 RD_INPUT_CANONICAL = 1
+RD_SOLID_IS_PATTERNS = 2
+
+
+def rd_mask_patterns(p, solid, patterns):
+    """Per-cell mask patterns of the temporally blocked masked Euler kernel (computed once for a
+    fixed mask; pass as `solid` to rd_advance with flags |= RD_SOLID_IS_PATTERNS)."""
+    check(lib().yh_rd_mask_patterns(C.byref(p), _ptr(solid), _ptr(patterns), _stream()))
+    return patterns
 
 
 def rd_advance(p, nsteps, uA, vA, uB, vB, tb_steps=0, solid=None, stim_mouse=False, point=None,

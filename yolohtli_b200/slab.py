@@ -67,6 +67,8 @@ class SlabRunner:
         self.u = [torch.zeros(shape, dtype=torch.float64, device=self.device) for _ in range(2)]
         self.v = [torch.zeros(shape, dtype=torch.float64, device=self.device) for _ in range(2)]
         self.cur = 0
+        self.solid = None            # obstacle mask rows of this slab (ghosts included) ...
+        self.solid_flags = 0         # ... or their precomputed patterns (masked Euler)
         self.stepper = stepper or self._cuda_stepper
         self.count = 0
         self.comm_stream = (torch.cuda.Stream(device=self.device, priority=-1)
@@ -83,6 +85,17 @@ class SlabRunner:
         self.u[self.cur].copy_(torch.as_tensor(u_glob[l.g0:l.g1]).to(self.device))
         self.v[self.cur].copy_(torch.as_tensor(v_glob[l.g0:l.g1]).to(self.device))
         self.count = 0   # fresh host data: the next pass treats it as raw
+
+    def set_solid(self, mask_glob):
+        """Obstacle mask of the whole domain (1 = tissue, main.cu:676-680); every rank keeps its
+        rows.  For the masked Euler mode the neighbourhood patterns are derived once."""
+        l = self.lay
+        m = torch.as_tensor(mask_glob[l.g0:l.g1].astype('uint8')).to(self.device).contiguous()
+        self.solid, self.solid_flags = m, 0
+        if self.device.type == "cuda" and self.p.solidSwitch and self.p.timeIntOrder == 1 and self.p.neumannBC:
+            pat = torch.empty_like(m)
+            host.rd_mask_patterns(self.p, m, pat)
+            self.solid, self.solid_flags = pat, host.RD_SOLID_IS_PATTERNS
 
     def owned(self):
         l = self.lay
@@ -198,8 +211,8 @@ class SlabRunner:
     # -- stepping ------------------------------------------------------------------------
     def _cuda_stepper(self, p, nsteps, uA, vA, uB, vB, rows, tb):
         # after the first pass every value was written by the library: no -0.0 can be present
-        flags = host.RD_INPUT_CANONICAL if self.count > 0 else 0
-        return host.rd_advance(p, nsteps, uA, vA, uB, vB, tb_steps=tb, rows=rows, flags=flags)
+        flags = (host.RD_INPUT_CANONICAL if self.count > 0 else 0) | self.solid_flags
+        return host.rd_advance(p, nsteps, uA, vA, uB, vB, tb_steps=tb, rows=rows, flags=flags, solid=self.solid)
 
     def advance(self, nsteps, tb=0, overlap=None):
         """nsteps time steps: ghosts refreshed, then up to `halo` steps per exchange.
@@ -244,7 +257,7 @@ class SlabRunner:
         while left > 0:
             n = max(t for t in (1, 2, 4) if t <= min(H, left, tb or 4))   # exactly one HBM pass
             c, o = self.cur, self.cur ^ 1
-            flags = host.RD_INPUT_CANONICAL if self.count > 0 else 0
+            flags = (host.RD_INPUT_CANONICAL if self.count > 0 else 0) | self.solid_flags
             with torch.cuda.stream(edge):
                 edge.wait_event(ev_int)                      # interior(k-1) wrote rows the edges read
                 if first:                                    # ghosts of the initial state
@@ -253,13 +266,13 @@ class SlabRunner:
                 for rows in (top, bot):
                     if rows is not None:
                         host.rd_advance(self.p, n, self.u[c], self.v[c], self.u[o], self.v[o], tb_steps=n,
-                                        rows=rows, flags=flags)
+                                        rows=rows, flags=flags, solid=self.solid)
                 ev_edge_next = torch.cuda.Event()
                 ev_edge_next.record(edge)
             main.wait_event(ev_edge)                         # edges(k-1) wrote rows the interior reads
             if inner[1] > inner[0]:
                 host.rd_advance(self.p, n, self.u[c], self.v[c], self.u[o], self.v[o], tb_steps=n,
-                                rows=inner, flags=flags)
+                                rows=inner, flags=flags, solid=self.solid)
             ev_int = torch.cuda.Event()
             ev_int.record(main)
             ev_edge = ev_edge_next
