@@ -669,7 +669,10 @@ int yho_slice(const yh_params *p, const double *u, const double *v,
  *               ascending, each term 4.0*(f*g + h*w) inside the disc (:55-57; the scb / 2.0
  *               branches multiply 0); the 32 lanes of a warp combined by the xor-butterfly
  *               16,8,4,2,1 (x = x + partner); the 8 warp sums added in ascending warp index;
- *   total     : rows added in ascending j;  result = (0.25*hx*hy) * total   (:79).
+ *   total     : row slots w = 0 .. 2R (slot w = grid row cy + ny/2 - R + w, R = ceil(sqrt(tipOffsetX*
+ *               tipOffsetY)); rows outside the grid hold +0.0): 32 partial sums, partial l takes
+ *               w = l, l+32, ... ascending; partials combined by the xor-butterfly 16..1;
+ *               result = (0.25*hx*hy) * total   (:79).
  */
 #define YHO_ROW_WARPS 8
 typedef struct { double a[12]; } acc12;
@@ -700,7 +703,7 @@ static inline void integrand12(const double s[6], const double s0[6], double vtu
 
 typedef void (*cell12_fn)(void *ctx, int i, int j, int *sc, double s[6], double s0[6]);
 
-static int integrals_generic(const yh_params *p, cell12_fn fn, void *ctx,
+static int integrals_generic(const yh_params *p, cell12_fn fn, void *ctx, int cy,
                              const double *vtu, const double *vtv, double *integrals) {
   const int nx = p->nx, ny = p->ny;
   double *rows = (double *)calloc((size_t)ny * 12, sizeof(double));
@@ -721,10 +724,22 @@ static int integrals_generic(const yh_params *p, cell12_fn fn, void *ctx,
     }
     integrals_rowsum(lane, rows + (size_t)j * 12);
   }
-  double tot[12] = {0};
-  for (int j = 0; j < ny; j++)
-    for (int k = 0; k < 12; k++) tot[k] += rows[(size_t)j * 12 + k];
-  for (int k = 0; k < 12; k++) integrals[k] = 0.25 * p->hx * p->hy * tot[k];
+  int R = (int)ceil(sqrt((double)((long long)p->tipOffsetX * p->tipOffsetY)));
+  if (R > ny) R = ny;
+  double part[32][12];
+  memset(part, 0, sizeof(part));
+  for (int w = 0; w <= 2 * R; w++) {
+    const int j = cy + ny / 2 - R + w;
+    if (j < 0 || j >= ny) continue;   /* +0.0 */
+    for (int k = 0; k < 12; k++) part[w & 31][k] += rows[(size_t)j * 12 + k];
+  }
+  for (int m = 16; m >= 1; m >>= 1) {
+    double t[32][12];
+    for (int l = 0; l < 32; l++)
+      for (int k = 0; k < 12; k++) t[l][k] = part[l][k] + part[l ^ m][k];
+    memcpy(part, t, sizeof(t));
+  }
+  for (int k = 0; k < 12; k++) integrals[k] = 0.25 * p->hx * p->hy * part[0][k];
   free(rows);
   return YH_OK;
 }
@@ -747,7 +762,7 @@ int yho_trapz(const yh_params *p, const double *const slice[6], const double *co
   if (!p || !slice || !slice0 || !velTan_u || !velTan_v || !integrals) return YH_ERR_INVALID_ARG;
   trapz_ctx c = {p, slice, slice0, 0, 0};
   disc_centre(p, tip_count, tip_vector, count, &c.cx, &c.cy);
-  return integrals_generic(p, trapz_cell, &c, velTan_u, velTan_v, integrals);
+  return integrals_generic(p, trapz_cell, &c, c.cy, velTan_u, velTan_v, integrals);
 }
 
 typedef struct {
@@ -766,7 +781,7 @@ int yho_sr_integrals(const yh_params *p, const double *u, const double *v,
     return YH_ERR_INVALID_ARG;
   sri_ctx c = {p, u, v, adv_x, adv_y, 0, 0};
   disc_centre(p, tip_count, tip_vector, count, &c.cx, &c.cy);
-  return integrals_generic(p, sri_cell, &c, velTan_u, velTan_v, integrals);
+  return integrals_generic(p, sri_cell, &c, c.cy, velTan_u, velTan_v, integrals);
 }
 
 /* symmetryReduction.cu:386-416 */

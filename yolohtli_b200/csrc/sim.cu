@@ -401,29 +401,57 @@ int yh_sim_run_sr_device(yh_sim *s, int nsteps, double *c_phi_h) {
     YH_CUDA(cudaMalloc(&s->sr_log_d, (size_t)6 * n * sizeof(double)));
     s->sr_log_cap = (size_t)n;
   }
-  // upload (c, phi - c*dt): the closing kernel of every step first applies the deferred
-  // phi += c*dt of the step before it; the host path has already applied it
+  // upload (c, phi, step): the closing kernel of a step first applies the deferred phi += c*dt of
+  // the step before it -- except for the first step of this run, where the host has applied it
   double h[YH_SR_WORDS] = {0};
   for (int q = 0; q < 3; q++) { h[YH_SR_C + q] = s->c[q]; h[YH_SR_PHI + q] = s->phi[q]; }
+  h[YH_SR_STEP] = (double)s->count;
   YH_CUDA(cudaMemcpyAsync(s->sr_d, h, sizeof(h), cudaMemcpyHostToDevice, s->st));
   YH_CUDA(cudaStreamSynchronize(s->st));   // h lives on this stack frame
-  for (int it = 0; it < n; it++) {
-    const int c = s->cur, o = c ^ 1;
+  const double step0 = (double)s->count;
+  const int c = s->cur, o = c ^ 1;          // RD c -> o, BFECC o -> c: the same buffers every step
+  // One step = {RD, tips, integral rows + closing, BFECC}.  No argument changes from step to step
+  // (the step counter, the time tag of the tips and the record slot live on the device), so a
+  // chunk of steps is captured once and replayed as a CUDA graph; the tail runs as plain launches.
+  auto one_step = [&](cudaStream_t st) -> int {
     int rc = yh_rd_step(p, s->u[c], s->v[c], s->u[o], s->v[o], s->vt[0], s->vt[1], s->solid, 0, s->px,
-                        s->py, 0, p->ny, s->st);
+                        s->py, 0, p->ny, st);
     if (rc != YH_OK) return rc;
-    rc = yh_tip_track(p, s->u[o], s->u[c], nullptr, s->tip_count_d, s->tip_vec_d, YH_TIPVECSIZE,
-                      p->dt * (double)s->count, p->tipAlgorithm, s->st);
+    // tips between u^n (present) and u* (past); tagged t = dt*count (main.cu:900)
+    rc = yh_tip_track_device_step(p, s->u[o], s->u[c], s->tip_count_d, s->tip_vec_d, YH_TIPVECSIZE,
+                                  s->sr_d, 0, st);
     if (rc != YH_OK) return rc;
     rc = yh_sr_integrals_solve_device(p, s->u[c], s->v[c], s->vt[0], s->vt[1], s->adv[0], s->adv[1],
-                                      s->tip_count_d, s->tip_vec_d, s->count, s->sr_d,
-                                      s->sr_log_d + (size_t)6 * it, it == 0 ? 0.0 : p->dt, s->st);
+                                      s->tip_count_d, s->tip_vec_d, s->sr_d, s->sr_log_d, step0, st);
     if (rc != YH_OK) return rc;
-    rc = yh_advect_bfecc_device_c(p, s->u[o], s->v[o], s->u[c], s->v[c], s->sr_d, s->adv[0], s->adv[1],
-                                  s->solid, s->st);
+    return yh_advect_bfecc_device_c(p, s->u[o], s->v[o], s->u[c], s->v[c], s->sr_d, s->adv[0], s->adv[1],
+                                    s->solid, st);
+  };
+  constexpr int G = 8;
+  int left = n;
+  if (n >= 4 * G && yh_graphs_enabled((long long)s->n)) {
+    int rc = one_step(s->st);              // first use of every kernel variant outside the capture
     if (rc != YH_OK) return rc;
-    s->count++;
+    left--;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    YH_CUDA(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal));
+    for (int g = 0; g < G && rc == YH_OK; g++) rc = one_step(s->st);
+    cudaError_t ce = cudaStreamEndCapture(s->st, &graph);
+    if (rc == YH_OK && ce == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+      for (; left >= G; left -= G) YH_CUDA(cudaGraphLaunch(exec, s->st));
+    } else {
+      cudaGetLastError();                  // capture refused: plain launches do the whole run
+      if (rc != YH_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
   }
+  for (; left > 0; left--) {
+    int rc = one_step(s->st);
+    if (rc != YH_OK) return rc;
+  }
+  s->count += n;
   int rc = yh_sr_flush_phi_device(s->sr_d, p->dt, s->st);   // the last step's phi += c*dt
   if (rc != YH_OK) return rc;
   YH_CUDA(cudaMemcpyAsync(h, s->sr_d, sizeof(h), cudaMemcpyDeviceToHost, s->st));

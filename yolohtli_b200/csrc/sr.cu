@@ -127,6 +127,11 @@ struct IntArgs {
   const double *vtu, *vtv;
   double *rows;        // [nrows_max][12] row sums
   double *out;         // [12] device result
+  unsigned *done;      // CTAs finished (the last one closes the pass and re-arms it)
+  double *sr;          // device-resident (c, phi, cos, sin): solve on the device when non-NULL
+  double *log_base;    // (c, phi) records of the run (device solve), may be NULL
+  double step0;        // first step of the run: no deferred phi update before it
+  double dt;
   int count;
   const int *tip_count;
   const yh_tip *tv;
@@ -136,14 +141,22 @@ struct IntArgs {
 
 // Summation order (shared with the oracle, yh_oracle.c): per grid row 256 accumulators -- warp w,
 // lane l takes i = 32w + l, +256, ... -- lanes combined by the xor-butterfly 16..1, the 8 warp
-// sums added in ascending w; rows added in ascending j.  One CTA per row slot: a 512-cell row is
-// two cells per thread instead of sixteen per lane of a lone warp (the pass is pure latency).
+// sums added in ascending w; then over the row slots: 32 partial sums (partial l takes slots
+// l, l+32, ...), combined by the same butterfly.  One CTA per row slot: a 512-cell row is two cells
+// per thread instead of sixteen per lane of a lone warp (the pass is pure latency).
+// The LAST CTA to finish closes the pass in the same launch: the 12 totals and, for the
+// device-resident SR step (yh_sim_run_sr_device), the deferred frame update phi += c*dt of the
+// PREVIOUS step (main.cu:936-938), the (c, phi) record (main.cu:902-903), the 3x3 solve
+// (symmetryReduction.cu:386-416) and cos/sin(phi.t) for the advection that follows.  cos/sin are
+// libdevice's there and libm's in the host path: results agree to rounding, not bit for bit.
 constexpr int ROW_WARPS = 8;
 
 template <bool FUSED>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 integrals_rows_kernel(const __grid_constant__ YhK k, const __grid_constant__ IntArgs a) {
   __shared__ double s_w[ROW_WARPS][12];
+  __shared__ double s_I[12];
+  __shared__ bool s_last;
   const int slot = blockIdx.x;   // row slot
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int cx, cy;
@@ -187,59 +200,45 @@ integrals_rows_kernel(const __grid_constant__ YhK k, const __grid_constant__ Int
     double r = s_w[0][threadIdx.x];
 #pragma unroll
     for (int w = 1; w < ROW_WARPS; w++) r = r + s_w[w][threadIdx.x];
-    a.rows[(size_t)slot * 12 + threadIdx.x] = r;
-  }
-}
-
-// Sum of the row sums in ascending j, by thread q < 12 -- the rows are first staged in shared
-// memory by the whole CTA so the serial chain is 2R+1 additions, not 2R+1 global-load latencies.
-constexpr int FIN_THREADS = 256, FIN_ROWS = 256;
-__device__ __forceinline__ double rows_total(const IntArgs &a, double (*stage)[12]) {
-  const int nrows = 2 * a.R + 1;
-  double tot = 0.0;
-  for (int r0 = 0; r0 < nrows; r0 += FIN_ROWS) {
-    const int nr = min(FIN_ROWS, nrows - r0);
-    for (int t = threadIdx.x; t < nr * 12; t += FIN_THREADS) stage[0][t] = a.rows[(size_t)r0 * 12 + t];
-    __syncthreads();
-    if (threadIdx.x < 12)
-      for (int w = 0; w < nr; w++) tot += stage[w][threadIdx.x];
-    __syncthreads();
-  }
-  return tot;
-}
-
-__global__ void __launch_bounds__(FIN_THREADS)
-integrals_final_kernel(const __grid_constant__ YhK k, const __grid_constant__ IntArgs a) {
-  __shared__ double stage[FIN_ROWS][12];
-  const double tot = rows_total(a, stage);
-  if (threadIdx.x < 12) a.out[threadIdx.x] = 0.25 * k.hx * k.hy * tot;   // integralTrapz.cu:79
-}
-
-// Device-resident closing of the SR step (yh_sim_run_sr_device): the 12 integrals, the deferred
-// frame update phi += c*dt of the PREVIOUS step (main.cu:936-938), the (c, phi) record of this step
-// (main.cu:902-903), the 3x3 solve (symmetryReduction.cu:386-416) and cos/sin(phi.t) for the
-// advection that follows -- no host round trip.  cos/sin are libdevice's here and libm's in the
-// host path: results agree to rounding, not bit for bit.
-__global__ void __launch_bounds__(FIN_THREADS)
-integrals_solve_kernel(const __grid_constant__ YhK k, const __grid_constant__ IntArgs a,
-                       double *sr, double *log_row, double dt_phi) {
-  __shared__ double stage[FIN_ROWS][12];
-  __shared__ double I[12];
-  const int q = threadIdx.x;
-  const double tot = rows_total(a, stage);
-  if (q < 12) {
-    I[q] = 0.25 * k.hx * k.hy * tot;
-    a.out[q] = I[q];
+    __stcg(a.rows + (size_t)slot * 12 + threadIdx.x, r);
+    __threadfence();
   }
   __syncthreads();
-  if (q == 0) {
-    double c[3], phi[3];
-    for (int m = 0; m < 3; m++) { c[m] = sr[YH_SR_C + m]; phi[m] = sr[YH_SR_PHI + m] + c[m] * dt_phi; }
-    if (log_row) for (int m = 0; m < 3; m++) { log_row[m] = c[m]; log_row[3 + m] = phi[m]; }
-    const double cs = cos(phi[2]), sn = sin(phi[2]);
-    yh_solve3(I, cs, sn, c);
-    for (int m = 0; m < 3; m++) { sr[YH_SR_C + m] = c[m]; sr[YH_SR_PHI + m] = phi[m]; }
-    sr[YH_SR_CS] = cs; sr[YH_SR_SN] = sn;
+  if (threadIdx.x == 0) s_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+
+  // ---- the last CTA: totals over the row slots (every row sum is visible: fence + atomic) ----
+  __threadfence();
+  const int nrows = gridDim.x;
+  for (int q = wid; q < 12; q += ROW_WARPS) {   // one warp per integral
+    double x = 0.0;
+    for (int w = lane; w < nrows; w += 32) x += __ldcg(a.rows + (size_t)w * 12 + q);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, m);
+    if (lane == 0) {
+      s_I[q] = 0.25 * k.hx * k.hy * x;   // integralTrapz.cu:79
+      a.out[q] = s_I[q];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *a.done = 0u;   // re-arm
+    if (a.sr) {
+      double c[3], phi[3];
+      const double step = a.sr[YH_SR_STEP];
+      const double dt_phi = (step > a.step0) ? a.dt : 0.0;
+      for (int m = 0; m < 3; m++) { c[m] = a.sr[YH_SR_C + m]; phi[m] = a.sr[YH_SR_PHI + m] + c[m] * dt_phi; }
+      if (a.log_base) {
+        double *log_row = a.log_base + 6 * (size_t)(step - a.step0);
+        for (int m = 0; m < 3; m++) { log_row[m] = c[m]; log_row[3 + m] = phi[m]; }
+      }
+      a.sr[YH_SR_STEP] = step + 1.0;
+      const double cs = cos(phi[2]), sn = sin(phi[2]);
+      yh_solve3(s_I, cs, sn, c);
+      for (int m = 0; m < 3; m++) { a.sr[YH_SR_C + m] = c[m]; a.sr[YH_SR_PHI + m] = phi[m]; }
+      a.sr[YH_SR_CS] = cs; a.sr[YH_SR_SN] = sn;
+    }
   }
 }
 
@@ -255,15 +254,15 @@ int run_integrals(const yh_params *p, IntArgs &a, bool fused, double *integrals_
   a.R = R;
   const int nrows = 2 * R + 1;
   double *ws = nullptr;
-  int rc = yh_workspace(((size_t)nrows * 12 + 12) * sizeof(double), (void **)&ws, 2);
+  int rc = yh_workspace(((size_t)nrows * 12 + 12 + 1) * sizeof(double), (void **)&ws, 2);   // zero-filled when (re)allocated
   if (rc != YH_OK) return rc;
-  a.rows = ws; a.out = ws + (size_t)nrows * 12;
+  // fixed places for the counter and the result: the row count changes with the disc radius, and a
+  // counter that moved onto old row sums would not start at zero
+  a.done = reinterpret_cast<unsigned *>(ws); a.out = ws + 1; a.rows = ws + 13;
   if (fused) integrals_rows_kernel<true><<<nrows, ROW_WARPS * 32, 0, st>>>(k, a);
   else integrals_rows_kernel<false><<<nrows, ROW_WARPS * 32, 0, st>>>(k, a);
   YH_LAUNCH_CHECK();
-  if (!integrals_host) return YH_OK;   // device-resident closing follows (integrals_solve_kernel)
-  integrals_final_kernel<<<1, FIN_THREADS, 0, st>>>(k, a);
-  YH_LAUNCH_CHECK();
+  if (!integrals_host) return YH_OK;   // device-resident closing was done by the last CTA
   static thread_local double *pinned = nullptr;
   if (!pinned) YH_CUDA(cudaMallocHost(&pinned, 12 * sizeof(double)));
   YH_CUDA(cudaMemcpyAsync(pinned, a.out, 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -622,17 +621,15 @@ int yh_sr_integrals(const yh_params *p, const double *u, const double *v, const 
 
 int yh_sr_integrals_solve_device(const yh_params *p, const double *u, const double *v,
                                  const double *vtu, const double *vtv, const double *ax,
-                                 const double *ay, const int *tip_count, const yh_tip *tv, int count,
-                                 double *sr_state, double *log_row, double dt_phi, cudaStream_t st) {
+                                 const double *ay, const int *tip_count, const yh_tip *tv,
+                                 double *sr_state, double *log_base, double step0, cudaStream_t st) {
   IntArgs a;
   memset(&a, 0, sizeof(a));
   a.u = u; a.v = v; a.ax = ax; a.ay = ay; a.vtu = vtu; a.vtv = vtv;
-  a.count = count; a.tip_count = tip_count; a.tv = tv; a.tipx0 = p->tipx0; a.tipy0 = p->tipy0;
-  int rc = run_integrals(p, a, true, nullptr, st);
-  if (rc != YH_OK) return rc;
-  integrals_solve_kernel<<<1, FIN_THREADS, 0, st>>>(yh_make_k(p), a, sr_state, log_row, dt_phi);
-  YH_LAUNCH_CHECK();
-  return YH_OK;
+  a.count = 1;   // never the first step of a run: the disc follows the last tip
+  a.tip_count = tip_count; a.tv = tv; a.tipx0 = p->tipx0; a.tipy0 = p->tipy0;
+  a.sr = sr_state; a.log_base = log_base; a.step0 = step0; a.dt = p->dt;
+  return run_integrals(p, a, true, nullptr, st);
 }
 
 int yh_sr_flush_phi_device(double *sr_state, double dt_phi, cudaStream_t st) {

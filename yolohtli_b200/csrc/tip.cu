@@ -25,6 +25,9 @@ struct TipArgs {
   int algorithm;
   float t;
   YhOrdered ord;               // ticket + look-back words (yh_ordered.cuh)
+  const double *step;          // device-resident step counter (graph-replayable launches) or NULL
+  double dt;
+  int steps_ahead;
 };
 
 __device__ __forceinline__ bool equals_tol(double a, double b, double tol) {   // helper_functions.cu:58
@@ -148,7 +151,11 @@ tip_kernel(const __grid_constant__ YhK k, const __grid_constant__ TipArgs a) {
   __shared__ int s_warp[TIP_THREADS / 32];
   __shared__ int s_base;
   const int tid = threadIdx.x;
-  if (tid == 0) s_chunk = (int)atomicAdd(&a.ord.state[0], 1ull);   // ticket = chunk, in launch order
+  // graph-replayable launches take the time tag from the device-resident step counter
+  const YhOrdered &ord = a.ord;
+  float t_tag = a.t;
+  if (a.step) t_tag = (float)(a.dt * (*a.step + (double)a.steps_ahead));
+  if (tid == 0) s_chunk = (int)atomicAdd(&ord.state[0], 1ull);   // ticket = chunk, in launch order
   __syncthreads();
   const int chunk = s_chunk;
   const long long ncell = (long long)k.nx * k.ny;
@@ -185,7 +192,7 @@ tip_kernel(const __grid_constant__ YhK k, const __grid_constant__ TipArgs a) {
   int total;
   const int excl = yh_block_excl_scan<TIP_THREADS>(mine, s_warp, total);
   if (tid < 32) {   // warp 0 chains this chunk to its predecessors
-    const unsigned prefix = yh_ordered_prefix(a.ord, chunk, (unsigned)total, a.count);
+    const unsigned prefix = yh_ordered_prefix(ord, chunk, (unsigned)total, a.count);
     if (tid == 0) s_base = (int)prefix;
   }
   __syncthreads();
@@ -202,7 +209,7 @@ tip_kernel(const __grid_constant__ YhK k, const __grid_constant__ TipArgs a) {
       float gx = 0.f, gy = 0.f;
       if (k.tipGrad) tip_gradient(k, i, j, tip.x, tip.y, a.present, gx, gy);
       yh_tip d;
-      d.x = (float)(i + tip.x); d.y = (float)(j + tip.y); d.vx = gx; d.vy = gy; d.t = a.t;
+      d.x = (float)(i + tip.x); d.y = (float)(j + tip.y); d.vx = gx; d.vy = gy; d.t = t_tag;
       if (pos < a.capacity) a.vec[pos] = d;
       if (a.plot) {   // plot_field, helper_functions.cu:45-51
         const int xi = (int)floorf(d.x), yi = (int)floorf(d.y);
@@ -233,8 +240,28 @@ extern "C" int yh_tip_track(const yh_params *p, const double *u_past, const doub
   epoch = (epoch + 1) & 0xFFFFFFu;
   if (epoch == 0) epoch = 1;   // zero-initialised workspace must never look current
   TipArgs a{u_past, u_present, tip_plot, tip_count, tip_vector, capacity, algorithm,
-            (float)physical_time, {state, epoch, nchunks}};
+            (float)physical_time, {state, epoch, nchunks}, nullptr, 0.0, 0};
   tip_kernel<<<nchunks, TIP_THREADS, 0, (cudaStream_t)stream>>>(k, a);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
+
+// Same pass for the device-resident SR loop, replayable from a CUDA graph: the time tag is
+// dt*(sr_state[YH_SR_STEP] + steps_ahead), read on the device, and the look-back words are cleared by
+// a memset in front of the launch instead of being told apart by a per-launch epoch.
+int yh_tip_track_device_step(const yh_params *p, const double *u_past, const double *u_present,
+                             int *tip_count, yh_tip *tip_vector, int capacity, const double *sr_state,
+                             int steps_ahead, cudaStream_t st) {
+  YhK k = yh_make_k(p);
+  const long long ncell = (long long)p->nx * p->ny;
+  const int nchunks = (int)((ncell + TIP_CHUNK - 1) / TIP_CHUNK);
+  unsigned long long *state = nullptr;
+  int rc = yh_workspace(((size_t)nchunks + 1) * sizeof(unsigned long long), (void **)&state, 1);
+  if (rc != YH_OK) return rc;
+  YH_CUDA(cudaMemsetAsync(state + 1, 0, (size_t)nchunks * sizeof(unsigned long long), st));
+  TipArgs a{u_past, u_present, nullptr, tip_count, tip_vector, capacity, p->tipAlgorithm, 0.f,
+            {state, 0xABCDEFu, nchunks}, sr_state + YH_SR_STEP, p->dt, steps_ahead};
+  tip_kernel<<<nchunks, TIP_THREADS, 0, st>>>(k, a);
   YH_LAUNCH_CHECK();
   return YH_OK;
 }

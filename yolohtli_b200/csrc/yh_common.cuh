@@ -100,15 +100,25 @@ __host__ __device__ inline void yh_solve3(const double *Int, double cs, double s
 #define YH_SR_PHI 3
 #define YH_SR_CS 6
 #define YH_SR_SN 7
-#define YH_SR_WORDS 8
+#define YH_SR_STEP 8     /* param.count as a double: advanced by the closing kernel of every step */
+#define YH_SR_WORDS 10
+// log_base / step0: the (c, phi) record of step n goes to log_base + 6*(n - step0); the deferred
+// phi += c*dt is applied for n > step0.  Every argument is the same for every step of a run, so
+// the step can be replayed from a CUDA graph.
 int yh_sr_integrals_solve_device(const yh_params *p, const double *u, const double *v,
                                  const double *vtu, const double *vtv, const double *ax,
-                                 const double *ay, const int *tip_count, const yh_tip *tv, int count,
-                                 double *sr_state, double *log_row, double dt_phi, cudaStream_t st);
+                                 const double *ay, const int *tip_count, const yh_tip *tv,
+                                 double *sr_state, double *log_base, double step0, cudaStream_t st);
+// tip_wrapper with the time tag and the look-back epoch taken from the device-resident step counter
+int yh_tip_track_device_step(const yh_params *p, const double *u_past, const double *u_present,
+                             int *tip_count, yh_tip *tip_vector, int capacity, const double *sr_state,
+                             int steps_ahead, cudaStream_t st);
 int yh_sr_flush_phi_device(double *sr_state, double dt_phi, cudaStream_t st);
 int yh_advect_bfecc_device_c(const yh_params *p, const double *u_in, const double *v_in, double *u_out,
                              double *v_out, const double *sr_state, double *adv_x, double *adv_y,
                              const uint8_t *solid, cudaStream_t st);
+
+int yh_graphs_enabled(long long cells);   // abi.cu: YH_GRAPHS = 0 | 1 override, else small sheets only
 
 // ---- device helpers --------------------------------------------------------------------
 // Neumann mirror index (the rule of coord_i/coord_j, helper_functions.cu:69-79).
