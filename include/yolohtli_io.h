@@ -13,6 +13,7 @@
  *   yh_io_state_write_window   print2DSubWindow              printFunctions.cu:81-104
  *   yh_io_state_read_text      loadData                      saveFiles.cu:508-538
  *   yh_io_mask_read/_write     domainObjects mask parse      main.cu:676-680 (common/Hole_generator.m:27-40)
+ *   yh_io_domain_objects       domainObjects (intglArea, stimArea, stimulus)   main.cu:686-848
  *   yh_io_tips_append          printTip                      printFunctions.cu:149-197
  *   yh_io_contour_append       printContour                  printFunctions.cu:199-247
  *   yh_io_sym_write            printSym                      printFunctions.cu:249-264
@@ -93,6 +94,12 @@ int yh_io_snapshot_read(const char *path, double *u, double *v, long long capaci
  * in file order = i + j*nx.  Bit-exact rule of main.cu:676-680. */
 int yh_io_mask_read(const char *path, uint8_t *solid, long long n);
 int yh_io_mask_write(const char *path, const uint8_t *solid, long long n);
+
+/* The host-built masks of domainObjects (main.cu:686-848); any output may be NULL.  intglArea: disc of
+ * radius rdomTrapz about the centre; stimArea: 1 where APD is measured (solid domains: outside the
+ * disc rdomAPD about (stcx, stcy); square domains: rows j >= 35); stimulus: stimMag inside the
+ * disc rdomStim about (stcx, stcy).  nx*ny entries each, i fastest. */
+int yh_io_domain_objects(const yh_run_params *rp, uint8_t *intglArea, uint8_t *stimArea, double *stimulus);
 
 /* dataTip.dat ("%f %f %f %f %f\n" = x y vx vy t) + dataTipSize.dat (count per sample; nothing is
  * written for an empty sample, as shipped).  first != 0 truncates both files. */

@@ -130,6 +130,25 @@ def test_mask_parse_rule(yh, tmp_path):
         yh.io.mask_read(g, 96, 96)
 
 
+def test_domain_objects(yh):
+    """intglArea / stimArea / stimulus of domainObjects (main.cu:686-848), float-narrowed coordinates."""
+    from yolohtli_b200 import synth
+    rp = yh.io.run_params_default(512, 512)
+    ia, sa, st = yh.io.domain_objects(rp)
+    assert np.array_equal(sa, synth.stim_area_square(512, 512))          # square domain: rows j >= 35
+    f32 = np.float32
+    i = np.arange(512)
+    x0 = (i.astype(f32).astype(np.float64) * rp.k.hx - 0.5 * rp.k.Lx).astype(f32).astype(np.float64)
+    X, Y = np.meshgrid(x0, x0)
+    rt = 0.5 * ((rp.k.tipOffsetX + rp.k.tipOffsetY) * rp.k.hx)
+    assert np.array_equal(ia, ((X.astype(f32) * X.astype(f32) + Y.astype(f32) * Y.astype(f32)).astype(np.float64) < rt * rt).astype(np.uint8))
+    inside = ((X - rp.stcx) ** 2 + (Y - rp.stcy) ** 2) < rp.rdomStim ** 2
+    assert np.array_equal(st, np.where(inside, rp.stimMag, 0.0)) and 300 < inside.sum() < 900
+    rp.k.solidSwitch = 1
+    _, sa, _ = yh.io.domain_objects(rp)
+    assert np.array_equal(sa, (~(((X - rp.stcx) ** 2 + (Y - rp.stcy) ** 2) < rp.rdomAPD ** 2)).astype(np.uint8))
+
+
 def test_series_writers(yh, tmp_path):
     from yolohtli_b200.host import CONTOUR_DTYPE, TIP_DTYPE
     tips = np.array([(10.25, 20.5, 0.0, 0.0, 1.5), (300.125, 7.0, -1.0, 2.0, 1.5)], dtype=TIP_DTYPE)

@@ -150,6 +150,7 @@ SIGNATURES.update({
     "yh_io_snapshot_read": (_i, [_s, _vp, _vp, _ll]),
     "yh_io_mask_read": (_i, [_s, _vp, _ll]),
     "yh_io_mask_write": (_i, [_s, _vp, _ll]),
+    "yh_io_domain_objects": (_i, [_RP, _vp, _vp, _vp]),
     "yh_io_tips_append": (_i, [_s, _s, _vp, _i, _i]),
     "yh_io_contour_append": (_i, [_s, _s, _vp, _i, _i]),
     "yh_io_sym_write": (_i, [_s, _vp, _i]),

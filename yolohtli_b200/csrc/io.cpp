@@ -380,6 +380,35 @@ int yh_io_mask_write(const char *path, const uint8_t *solid, long long n) {
   return ferror(f) ? fail("write error", path) : YH_OK;
 }
 
+// ---- domainObjects, main.cu:686-848: the host-built masks the kernels take ------------------
+// intglArea (the disc of radius rdomTrapz about the domain centre, :696-703), stimArea (:816-848:
+// solid domains exclude the disc of radius rdomAPD about the stimulus point, square domains the
+// rows j < 35) and the stimulus field (:770-801).  x0 / y0 are `float` in the reference: the
+// double expression is narrowed before the comparisons.  coeffTrapz is not built: no kernel reads
+// it (integralTrapz.cu:30-32) and the reference's loop indexes intglArea[-1].
+int yh_io_domain_objects(const yh_run_params *rp, uint8_t *intglArea, uint8_t *stimArea, double *stimulus) {
+  if (!rp || rp->k.nx <= 0 || rp->k.ny <= 0) return fail("yh_io_domain_objects: bad arguments", nullptr);
+  const yh_params &k = rp->k;
+  const double rdomTrapz = 0.5 * ((k.tipOffsetX + k.tipOffsetY) * k.hx);   // recomputed at :691
+  for (int j = 0; j < k.ny; j++) {
+    for (int i = 0; i < k.nx; i++) {
+      const size_t idx = (size_t)i + (size_t)k.nx * j;
+      const float x0 = (float)((float)i * k.hx - 0.5 * k.Lx);
+      const float y0 = (float)((float)j * k.hy - 0.5 * k.Ly);
+      if (intglArea) intglArea[idx] = ((x0 * x0 + y0 * y0) < rdomTrapz * rdomTrapz) ? 1 : 0;
+      const bool in_stim = ((x0 - rp->stcx) * (x0 - rp->stcx) + (y0 - rp->stcy) * (y0 - rp->stcy)) < rp->rdomStim * rp->rdomStim;
+      if (stimulus) stimulus[idx] = in_stim ? rp->stimMag : 0.0;
+      if (stimArea) {
+        if (k.solidSwitch)
+          stimArea[idx] = (((x0 - rp->stcx) * (x0 - rp->stcx) + (y0 - rp->stcy) * (y0 - rp->stcy)) < rp->rdomAPD * rp->rdomAPD) ? 0 : 1;
+        else
+          stimArea[idx] = (j < 35) ? 0 : 1;
+      }
+    }
+  }
+  return YH_OK;
+}
+
 // ---- series writers ---------------------------------------------------------------------------
 // printTip, printFunctions.cu:149-197
 int yh_io_tips_append(const char *path_points, const char *path_counts, const yh_tip *tips, int n,

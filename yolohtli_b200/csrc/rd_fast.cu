@@ -445,10 +445,12 @@ int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const doub
   const char *force_ry = getenv("YH_FAST_RY");  // tuning hook
   a.RY = force_ry ? atoi(force_ry) : 0;                // 0: chosen per kernel variant
   const bool canon = canon_in != 0;
-  // strip width: wide strips (less halo redundancy) for big sheets, narrow ones when the sheet
-  // is too small to fill 148 SMs otherwise (latency-bound regime)
+  // strip width: narrow strips when the sheet is too small to fill 148 SMs otherwise (latency-bound
+  // regime).  For big sheets W = 128 beats W = 256 (16384^2, T = 4: 331 vs 316 Gcell/s) although it
+  // doubles the halo redundancy (6 % vs 3 %): four resident CTAs of 9 warps are four independent
+  // per-row barrier domains instead of two of 17 warps.
   const long long cells = (long long)k.nx * rows * nsims;
-  int W = cells >= (1ll << 24) ? 256 : (cells >= (1ll << 21) ? 128 : 64);
+  int W = cells >= (1ll << 21) ? 128 : 64;
   if (force_w) W = atoi(force_w);
 #define YH_FAST_DISPATCH(WW)                                     \
   switch (tb) {                                                  \

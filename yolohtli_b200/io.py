@@ -97,6 +97,15 @@ def mask_write(path, mask):
     check(lib().yh_io_mask_write(_b(path), _p(m), m.size))
 
 
+def domain_objects(rp):
+    """domainObjects (main.cu:686-848): returns (intglArea, stimArea, stimulus), shaped (ny, nx)."""
+    ny, nx = rp.k.ny, rp.k.nx
+    ia, sa = np.zeros((ny, nx), dtype=np.uint8), np.zeros((ny, nx), dtype=np.uint8)
+    st = np.zeros((ny, nx))
+    check(lib().yh_io_domain_objects(C.byref(rp), _p(ia), _p(sa), _p(st)))
+    return ia, sa, st
+
+
 def tips_append(path_points, path_counts, tips, first=False):
     """printTip (printFunctions.cu:149-197)."""
     t = np.ascontiguousarray(tips, dtype=TIP_DTYPE)
