@@ -325,6 +325,7 @@ static int pick_ry(int rows, int strips, int nsims, int T, int slots) {
   const int cmax = rows / min_ry > 0 ? rows / min_ry : 1;
   for (int C = 1; C <= cmax; C++) {
     const int ry = (rows + C - 1) / C;
+    if (ry > 512 && ry > min_ry) continue;   // measured (16384^2): chunks of 256-512 rows beat ~1000-row ones by 1.7 %
     const int chunks = (rows + ry - 1) / ry;
     const long long ctas = (long long)strips * chunks * nsims;
     const long long waves = (ctas + slots - 1) / slots;
