@@ -350,14 +350,14 @@ def run_sweep(a):
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         sim.set_state(zero, zero)
-        sim.run_apd(a.substeps, stim_area=None)
+        sim.run_apd(a.e2e_substeps, stim_area=None)
         sim.get_state()
         sim.get_apd()
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_val = cells * a.substeps * e2e_steps / float(dt.item()) / 1e9
+    e2e_val = cells * a.e2e_substeps * e2e_steps / float(dt.item()) / 1e9
     if rank == 0:
         peak, peak_src, _ = peaks()
         launches = -(-a.substeps // 4) * a.steps   # one fused {4 Euler steps + APD} launch per 4 time steps
@@ -375,7 +375,8 @@ def run_sweep(a):
                        "arithmetic": "FP64, no FMA contraction (bit-identical to the plain-C oracle)"},
             "e2e": {"value": e2e_val, "unit": METRIC, "h2d_bytes_per_step": 16 * nsim * nx * nx * world,
                     "d2h_bytes_per_step": 32 * nsim * nx * nx * world, "steps": e2e_steps,
-                    "note": "host state -> device, substeps paced steps with APD bookkeeping, state + APD1/APD2 -> host; wall clock"},
+                    "time_steps_per_call": a.e2e_substeps,
+                    "note": "host state -> device, e2e-substeps paced steps with APD bookkeeping, state + APD1/APD2 -> host; wall clock"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "rd_euler_stream", "peak_source": peak_src,

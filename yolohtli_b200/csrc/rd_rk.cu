@@ -39,12 +39,6 @@ __device__ __forceinline__ unsigned solid_code(bool sc, bool sw, bool se, bool s
   const unsigned cyz = (sn && ss) && (sc && ss) ? 1u : ((sc && ss) ? 2u : 0u);
   return cxx | (cxy << 2) | (cxz << 4) | (cyx << 6) | (cyy << 8) | (cyz << 10) | ((sc ? 1u : 0u) << 12);
 }
-// 0 / 1 / 2 as an exact double without a conversion instruction
-__device__ __forceinline__ double coef(unsigned code, int shift) {
-  const unsigned c2 = (code >> shift) & 3u;
-  return __hiloint2double(c2 ? (int)(0x3FE00000u + (c2 << 20)) : 0, 0);
-}
-
 __device__ __forceinline__ void cp_async16(unsigned smem, const void *gmem, bool valid) {
   int sz = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem), "l"(gmem), "r"(sz)
@@ -238,17 +232,25 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
       const double Wv = f ? C.vw : C.uw, Ev = f ? C.ve : C.ue;
       double d0, d1;
       if (SOLID) {   // reactionDiffusion.cu:171-180
+        // The coefficient triples are exact 0 / 1 / 2 and only four occur per axis for a tissue cell:
+        // (1,2,1), (2,2,0), (0,2,2), (0,0,0).  Each equals -- bit for bit, for finite fields -- the
+        // plain stencil fma(-2, c, A) + B on substituted neighbours (table in rd_fast.cu), which
+        // trades three DMULs per axis for one DADD.  cL = coefficient of the first neighbour.
         const unsigned k0 = codes & 0xFFFFu, k1 = codes >> 16;
+        auto axis = [](unsigned cL, unsigned cC, double c, double L, double R) {
+          const bool both = cL == 1u;
+          const double t = (cL == 2u) ? L : R;
+          const double r = fma(-2.0, c, both ? L : t + t) + (both ? R : 0.0);
+          return cC ? r : 0.0;
+        };
+        const double x0 = axis(k0 & 3u, (k0 >> 2) & 3u, Cc.x, Wv, Cc.y), y0 = axis((k0 >> 6) & 3u, (k0 >> 8) & 3u, Cc.x, Nn.x, Ss.x);
+        const double x1 = axis(k1 & 3u, (k1 >> 2) & 3u, Cc.y, Cc.x, Ev), y1 = axis((k1 >> 6) & 3u, (k1 >> 8) & 3u, Cc.y, Nn.y, Ss.y);
         if (f == 0) {
-          d0 = ((coef(k0, 0) * Wv - coef(k0, 2) * Cc.x + coef(k0, 4) * Cc.y) * k.rx +
-                (coef(k0, 6) * Nn.x - coef(k0, 8) * Cc.x + coef(k0, 10) * Ss.x) * k.ry);
-          d1 = ((coef(k1, 0) * Cc.x - coef(k1, 2) * Cc.y + coef(k1, 4) * Ev) * k.rx +
-                (coef(k1, 6) * Nn.y - coef(k1, 8) * Cc.y + coef(k1, 10) * Ss.y) * k.ry);
+          d0 = (x0 * k.rx + y0 * k.ry);
+          d1 = (x1 * k.rx + y1 * k.ry);
         } else if (k.gateDiff) {
-          d0 = ((coef(k0, 0) * Wv - coef(k0, 2) * Cc.x + coef(k0, 4) * Cc.y) * k.rx * k.rscale +
-                (coef(k0, 6) * Nn.x - coef(k0, 8) * Cc.x + coef(k0, 10) * Ss.x) * k.ry * k.rscale);
-          d1 = ((coef(k1, 0) * Cc.x - coef(k1, 2) * Cc.y + coef(k1, 4) * Ev) * k.rx * k.rscale +
-                (coef(k1, 6) * Nn.y - coef(k1, 8) * Cc.y + coef(k1, 10) * Ss.y) * k.ry * k.rscale);
+          d0 = (x0 * k.rx * k.rscale + y0 * k.ry * k.rscale);
+          d1 = (x1 * k.rx * k.rscale + y1 * k.ry * k.rscale);
         } else {
           d0 = 0.0; d1 = 0.0;
         }

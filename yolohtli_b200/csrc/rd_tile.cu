@@ -363,13 +363,15 @@ bool is_def(const YhK &k) {
 
 }  // namespace
 
-// Policy: tiles win while the sheet cannot fill the streaming pipelines (measured crossover
-// between 1024^2 and 2048^2 cells per launch); YH_RD_PATH = tile | stream overrides (tests).
+// Policy: tiles win while the sheet cannot fill the streaming pipelines.  Measured (B200, Gcell/s,
+// tiles vs strips): 512^2 Euler T=4 102 vs 85, RK4+lap4 14.2 vs 12.8; 1024^2 Euler 158 vs 181,
+// RK4+lap4 18.9 vs 20.6 -- the crossover sits between them.  YH_RD_PATH = tile | stream overrides
+// (tests run every case through both).
 int yh_rd_prefer_tile(long long cells) {
   const char *f = getenv("YH_RD_PATH");
   if (f && f[0] == 't') return 1;
   if (f && f[0] == 's') return 0;
-  return cells <= (3ll << 20);
+  return cells <= (640ll << 10);
 }
 
 int yh_rd_tile_rk_supported(const YhK &k) {
