@@ -315,7 +315,8 @@ def run_sweep(a):
     mine = periods[(rank * nsim) % 256:(rank * nsim) % 256 + nsim]
     area = synth.stim_area_square(nx, nx)
     sim = yh.Sim(p, n_sims=nsim, device=local)
-    zero = np.zeros((nsim, nx, nx))
+    pin = [torch.zeros((nsim, nx, nx), dtype=torch.float64).pin_memory().numpy() for _ in range(5)]
+    zero = pin[0]                       # quiescent initial state; pinned host buffers for the e2e leg
     sim.set_state(zero, zero)
     sim.set_pacing(mine, int(10.0 / p.dt))
 
@@ -351,8 +352,8 @@ def run_sweep(a):
     for _ in range(e2e_steps):
         sim.set_state(zero, zero)
         sim.run_apd(a.e2e_substeps, stim_area=None)
-        sim.get_state()
-        sim.get_apd()
+        sim.get_state(out=(pin[1], pin[2]))
+        sim.get_apd(out=(pin[3], pin[4]))
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -376,7 +377,7 @@ def run_sweep(a):
             "e2e": {"value": e2e_val, "unit": METRIC, "h2d_bytes_per_step": 16 * nsim * nx * nx * world,
                     "d2h_bytes_per_step": 32 * nsim * nx * nx * world, "steps": e2e_steps,
                     "time_steps_per_call": a.e2e_substeps,
-                    "note": "host state -> device, e2e-substeps paced steps with APD bookkeeping, state + APD1/APD2 -> host; wall clock"},
+                    "note": "pinned host state -> device, e2e-substeps paced steps with APD bookkeeping, state + APD1/APD2 -> pinned host; wall clock"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "rd_euler_stream", "peak_source": peak_src,

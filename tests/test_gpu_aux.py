@@ -257,6 +257,36 @@ def test_sim_driver_trace_batch_and_pacing(oracle, yh):
     sim.close()
 
 
+@pytest.mark.parametrize("kw", [dict(timeIntOrder=1, lap4=0), dict()])
+def test_traced_loop_graph_replay(oracle, yh, kw, monkeypatch):
+    """The reference's own loop {step; swap; probe every step} (main.cu:879-885, 1040): on small
+    sheets the driver replays 64 {probe, step} pairs from a CUDA graph with the sample slot kept on
+    the device.  Trace and state are identical to plain launches and to the oracle."""
+    nx = ny = 96
+    p = oracle.params_default(nx, ny, **kw)
+    u0, v0 = synth.cross_field_ic(nx, ny)
+    n = 64 * 4 + 37
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("YH_GRAPHS", mode)
+        sim = yh.Sim(p, n_sims=2)
+        sim.set_state(np.stack([u0, v0]), np.stack([v0, u0]))
+        sim.set_point(nx // 8, ny // 2)
+        tr = sim.run(n, trace=True)
+        out[mode] = (tr, sim.get_state(), sim.count)
+        sim.close()
+    assert np.array_equal(out["0"][0], out["1"][0]) and out["0"][2] == out["1"][2] == n
+    assert np.array_equal(out["0"][1][0], out["1"][1][0]) and np.array_equal(out["0"][1][1], out["1"][1][1])
+    uu, vv = u0, v0
+    for k in range(3):   # sample k = state k at the electrode (one-step lag of main.cu:1040)
+        assert out["1"][0][k, 0, 0] == uu[ny // 2, nx // 8] and out["1"][0][k, 0, 1] == vv[ny // 2, nx // 8]
+        uu, vv = oracle.rd_step(p, uu, vv)
+    wu, wv = oracle.rd_advance(p, n, u0, v0)
+    assert np.array_equal(out["1"][1][0][0], wu) and np.array_equal(out["1"][1][1][0], wv)
+    prev = oracle.rd_advance(p, n - 1, u0, v0)
+    assert out["1"][0][n - 1, 0, 0] == prev[0][ny // 2, nx // 8]
+
+
 def test_reference_launch_api_through_the_shim(oracle):
     """The display()-style loop of tests/shim_driver.cu calls reactionDiffusion_wrapper / swapSoA /
     singleCell_wrapper / tip_wrapper with the reference's signatures (hostPrototypes.h:22-57),

@@ -46,6 +46,14 @@ def main():
             u0, v0 = u0 * solid, v0 * solid
         gu, gv, ms = ours(p, u0, v0, nsteps, solid=solid)
         rec = {"config": name, "steps": nsteps, "ours_Gcell_s": nx * nx * nsteps / ms / 1e6, "ours_ms": ms}
+        if solid is None:   # the as-shipped loop: electrode probe after every step (main.cu:1040)
+            sim = yh.Sim(p)
+            sim.set_state(u0, v0)
+            sim.run(256, trace=True)
+            t0 = time.perf_counter()
+            sim.run(nsteps, trace=True)
+            rec["ours_traced_Gcell_s"] = nx * nx * nsteps / (time.perf_counter() - t0) / 1e9
+            sim.close()
         if oracle_lib.have_reference():
             ref = oracle_lib.Reference(nofma=False)
             ref.init(p)

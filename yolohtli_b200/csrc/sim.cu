@@ -31,6 +31,7 @@ struct yh_sim {
   uint8_t *apd_first, *stim_area;
   double *sr_d, *sr_log_d;   // device-resident (c, phi, cos, sin) and its per-step record (yh_sim_run_sr_device)
   size_t sr_log_cap;
+  unsigned long long *probe_slot_d;   // sample slot of the graph-replayed probe (yh_sim_run with a trace)
   uint8_t *pat;          // mask patterns of the temporally blocked Euler kernel (yh_rd_solid_patterns)
   int apd_init;          // sAPD / dAPD hold values for every cell (one full pass done)
   int have_stim_area;    // stim_area holds a mask uploaded by an earlier yh_sim_run_apd call
@@ -45,6 +46,21 @@ __global__ void probe_batch_kernel(const double *u, const double *v, double *out
   if (s >= nsims) return;
   out[2 * s] = u[idx + stride * s];
   out[2 * s + 1] = v[idx + stride * s];
+}
+
+// Same probe for graph-replayed loops: the sample slot comes from a device-resident counter, so the
+// launch arguments do not change from step to step (one block: nsims <= blockDim.x).
+__global__ void probe_counted_kernel(const double *u, const double *v, double *out, long long idx,
+                                     long long stride, int nsims, unsigned long long *slot) {
+  __shared__ unsigned long long s_slot;
+  if (threadIdx.x == 0) s_slot = *slot;
+  __syncthreads();
+  const int z = threadIdx.x;
+  if (z < nsims) {
+    out[2 * (s_slot * nsims + z)] = u[idx + stride * z];
+    out[2 * (s_slot * nsims + z) + 1] = v[idx + stride * z];
+  }
+  if (threadIdx.x == 0) *slot = s_slot + 1;
 }
 
 struct DevGuard {
@@ -69,7 +85,7 @@ int yh_sim_create(yh_sim **out, const yh_params *p, int n_sims, int device) {
   s->p = *p;
   s->n_sims = n_sims; s->device = device;
   s->n = (size_t)p->nx * p->ny;
-  s->cur = 0; s->solid = nullptr; s->pat = nullptr; s->sr_d = nullptr; s->sr_log_d = nullptr; s->sr_log_cap = 0; s->trace_d = nullptr; s->trace_cap = 0;
+  s->cur = 0; s->solid = nullptr; s->pat = nullptr; s->sr_d = nullptr; s->sr_log_d = nullptr; s->sr_log_cap = 0; s->probe_slot_d = nullptr; s->trace_d = nullptr; s->trace_cap = 0;
   s->period_d = nullptr; s->duration_it = 0; s->count = 0; s->have_prev = 0; s->raw_input = 1;
   s->px = p->nx / 2; s->py = p->ny / 2;   // param.point, saveFiles.cu:180
   s->vt[0] = s->vt[1] = s->adv[0] = s->adv[1] = nullptr;
@@ -97,7 +113,7 @@ int yh_sim_destroy(yh_sim *s) {
   DevGuard g(s->device);
   cudaStreamSynchronize(s->st);
   for (int b = 0; b < 2; b++) { cudaFree(s->u[b]); cudaFree(s->v[b]); }
-  cudaFree(s->solid); cudaFree(s->pat); cudaFree(s->sr_d); cudaFree(s->sr_log_d); cudaFree(s->trace_d); cudaFree(s->tip_count_d); cudaFree(s->tip_vec_d);
+  cudaFree(s->solid); cudaFree(s->pat); cudaFree(s->sr_d); cudaFree(s->sr_log_d); cudaFree(s->probe_slot_d); cudaFree(s->trace_d); cudaFree(s->tip_count_d); cudaFree(s->tip_vec_d);
   cudaFree(s->period_d);
   cudaFree(s->vt[0]); cudaFree(s->vt[1]); cudaFree(s->adv[0]); cudaFree(s->adv[1]);
   for (int q = 0; q < 6; q++) cudaFree(s->apd[q]);
@@ -219,7 +235,79 @@ static int sim_run_impl(yh_sim *s, int nsteps, int tb_steps, double *trace_h, bo
     if (sync) YH_CUDA(cudaStreamSynchronize(s->st));
     return YH_OK;
   }
+  const bool tile = !pat && yh_rd_prefer_tile((long long)s->n * s->n_sims) != 0;
+  // one RD launch (all sheets) of T time steps from buffers c to o
+  auto rd_launch = [&](int c, int o, int T) -> int {
+    if (fast1 && tile)
+      return yh_launch_rd_tile_euler(k, T, s->u[c], s->v[c], s->u[o], s->v[o], s->n_sims, stride,
+                                     s->period_d, s->duration_it, s->count, s->st);
+    if (fast1)
+      return yh_launch_rd_fast_paced(k, T, s->u[c], s->v[c], s->u[o], s->v[o], s->n_sims, stride,
+                                     s->period_d, s->duration_it, s->count, s->raw_input, s->st, nullptr, pat);
+    int rc = YH_OK;
+    for (int z = 0; z < s->n_sims && rc == YH_OK; z++) {
+      YhK kz = k;
+      if (pacing) {
+        const int per = s->period_h[z];
+        kz.stim = per > 0 && (s->count % per) <= s->duration_it;
+      }
+      if (tile && yh_rd_tile_rk_supported(kz))
+        rc = yh_launch_rd_tile_rk(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
+                                  s->v[o] + s->n * z, nullptr, nullptr, s->st);
+      else if (yh_rd_rk_supported(kz))
+        rc = yh_launch_rd_rk(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
+                             s->v[o] + s->n * z, nullptr, nullptr, s->solid, s->st);
+      else
+        rc = yh_launch_rd_generic(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
+                                  s->v[o] + s->n * z, nullptr, nullptr, s->solid, s->st);
+    }
+    return rc;
+  };
   int left = nsteps, step = 0;
+  // The reference's own loop {step; swap; probe} (main.cu:879-885, 1040) on a small sheet: chunks of
+  // 64 {probe, step} pairs replayed from a CUDA graph (the probe's sample slot is a device-resident
+  // counter, so no launch argument changes); head (raw input) and tail run as plain launches.
+  constexpr int CH = 64;
+  if (trace_h && !pacing && s->n_sims <= 128 && nsteps >= 3 * CH &&
+      yh_graphs_enabled((long long)s->n * s->n_sims)) {
+    if (!s->probe_slot_d) YH_CUDA(cudaMalloc(&s->probe_slot_d, sizeof(unsigned long long)));
+    YH_CUDA(cudaMemsetAsync(s->probe_slot_d, 0, sizeof(unsigned long long), s->st));
+    const long long pidx = (long long)s->px + (long long)s->p.nx * s->py;
+    auto chunk = [&](int n) -> int {
+      for (int q = 0; q < n; q++) {
+        const int c = s->cur, o = c ^ 1;
+        probe_counted_kernel<<<1, 128, 0, s->st>>>(s->u[c], s->v[c], s->trace_d, pidx, stride, s->n_sims,
+                                                   s->probe_slot_d);
+        YH_LAUNCH_CHECK();
+        int rc = rd_launch(c, o, 1);
+        if (rc != YH_OK) return rc;
+        s->cur = o; s->raw_input = 0; s->count += 1;
+      }
+      return YH_OK;
+    };
+    int rc = chunk(CH);   // raw input and first use of the kernel variants: plain launches
+    if (rc != YH_OK) return rc;
+    left -= CH;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const int count_before = s->count;
+    YH_CUDA(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal));
+    rc = chunk(CH);
+    cudaError_t ce = cudaStreamEndCapture(s->st, &graph);
+    s->count = count_before;   // the capture launched nothing
+    if (rc == YH_OK && ce == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+      for (; left >= CH; left -= CH) { YH_CUDA(cudaGraphLaunch(exec, s->st)); s->count += CH; }
+    } else {
+      cudaGetLastError();
+      if (rc != YH_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    rc = chunk(left);
+    if (rc != YH_OK) return rc;
+    left = 0;
+    s->have_prev = 1;
+  }
   while (left > 0) {
     int T = 1;
     if (fast1) { T = tb; while (T > left) T >>= 1; }
@@ -230,33 +318,7 @@ static int sim_run_impl(yh_sim *s, int nsteps, int tb_steps, double *trace_h, bo
           (long long)s->px + (long long)s->p.nx * s->py, stride, s->n_sims);
       YH_LAUNCH_CHECK();
     }
-    int rc;
-    const bool tile = !pat && yh_rd_prefer_tile((long long)s->n * s->n_sims) != 0;
-    if (fast1 && tile) {
-      rc = yh_launch_rd_tile_euler(k, T, s->u[c], s->v[c], s->u[o], s->v[o], s->n_sims, stride,
-                                   s->period_d, s->duration_it, s->count, s->st);
-    } else if (fast1) {
-      rc = yh_launch_rd_fast_paced(k, T, s->u[c], s->v[c], s->u[o], s->v[o], s->n_sims, stride,
-                                   s->period_d, s->duration_it, s->count, s->raw_input, s->st, nullptr, pat);
-    } else {
-      rc = YH_OK;
-      for (int z = 0; z < s->n_sims && rc == YH_OK; z++) {
-        YhK kz = k;
-        if (pacing) {
-          const int per = s->period_h[z];
-          kz.stim = per > 0 && (s->count % per) <= s->duration_it;
-        }
-        if (tile && yh_rd_tile_rk_supported(kz))
-          rc = yh_launch_rd_tile_rk(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
-                                    s->v[o] + s->n * z, nullptr, nullptr, s->st);
-        else if (yh_rd_rk_supported(kz))
-          rc = yh_launch_rd_rk(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
-                               s->v[o] + s->n * z, nullptr, nullptr, s->solid, s->st);
-        else
-          rc = yh_launch_rd_generic(kz, s->u[c] + s->n * z, s->v[c] + s->n * z, s->u[o] + s->n * z,
-                                    s->v[o] + s->n * z, nullptr, nullptr, s->solid, s->st);
-      }
-    }
+    int rc = rd_launch(c, o, T);
     if (rc != YH_OK) return rc;
     s->cur = o;
     s->raw_input = 0;

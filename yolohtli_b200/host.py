@@ -231,9 +231,10 @@ class Sim:
         assert u.size == v.size == int(np.prod(self.shape))
         check(lib().yh_sim_set_state(self._h, u.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p)))
 
-    def get_state(self):
-        u = np.empty(self.shape, dtype=np.float64)
-        v = np.empty(self.shape, dtype=np.float64)
+    def get_state(self, out=None):
+        """State of every sheet; out = (u, v) host arrays to fill (e.g. pinned), else fresh ones."""
+        u, v = out if out is not None else (np.empty(self.shape, dtype=np.float64), np.empty(self.shape, dtype=np.float64))
+        assert u.size == v.size == int(np.prod(self.shape)) and u.dtype == v.dtype == np.float64
         check(lib().yh_sim_get_state(self._h, u.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p)))
         return u, v
 
@@ -289,9 +290,9 @@ class Sim:
             ptr = sa.ctypes.data_as(C.c_void_p)
         check(lib().yh_sim_run_apd(self._h, nsteps, ptr))
 
-    def get_apd(self):
-        a = np.empty(self.shape, dtype=np.float64)
-        b = np.empty(self.shape, dtype=np.float64)
+    def get_apd(self, out=None):
+        a, b = out if out is not None else (np.empty(self.shape, dtype=np.float64), np.empty(self.shape, dtype=np.float64))
+        assert a.size == b.size == int(np.prod(self.shape)) and a.dtype == b.dtype == np.float64
         check(lib().yh_sim_get_apd(self._h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))
         return a, b
 
