@@ -47,6 +47,10 @@ struct TileArgs {
   long long sim_stride;
   const int *period;
   int duration, count0;
+  // electrode trace fused into the Euler kernel (yh_sim_run with a trace): sample slot0 + s of sheet
+  // z = (u, v) at (k.px, k.py) after s of this launch's steps, s = 0 .. T-1; slot0 = *slot
+  double *trace;
+  const unsigned long long *slot;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -269,9 +273,19 @@ rd_tile_euler(const __grid_constant__ YhK k, const __grid_constant__ TileArgs a)
     *reinterpret_cast<double2 *>(sm + PL + c) = vC;
   }
   __syncthreads();
+  // the thread that OWNS the electrode cell (inside this CTA's output tile) records it at every level
+  const bool probe = a.trace != nullptr && in_dom && tx >= H && tx < H + TB && ty >= H && ty < H + TB &&
+                     (ly + k.jg0) == k.py && (k.px == gx || k.px == gx + 1);
+  double *probe_out = nullptr;
+  if (probe) probe_out = a.trace + 2 * ((size_t)(*a.slot) * gridDim.z + blockIdx.z);
 
 #pragma unroll
   for (int s = 1; s <= T; s++) {
+    if (probe) {   // state after s-1 steps = the sample taken BEFORE step s (one-step lag of main.cu:1040)
+      double *o2 = probe_out + 2 * (size_t)(s - 1) * gridDim.z;
+      o2[0] = (k.px == gx) ? uC.x : uC.y;
+      o2[1] = (k.px == gx) ? vC.x : vC.y;
+    }
     const double *iu = sm + ((s - 1) & 1) * 2 * PL, *iv = iu + PL;
     double *ou = sm + (s & 1) * 2 * PL, *ov = ou + PL;
     const int ring = (H - T) + s;   // valid region shrinks by one ring per step
@@ -385,7 +399,7 @@ int yh_launch_rd_tile_rk(const YhK &k, const double *u_in, const double *v_in, d
                          double *v_out, double *vtu, double *vtv, cudaStream_t st) {
   if (!yh_rd_tile_rk_supported(k)) return YH_ERR_UNSUPPORTED;
   if (k.row1 <= k.row0) return YH_OK;
-  TileArgs a{u_in, v_in, u_out, v_out, vtu, vtv, 0, nullptr, 0, 0};
+  TileArgs a{u_in, v_in, u_out, v_out, vtu, vtv, 0, nullptr, 0, 0, nullptr, nullptr};
   const bool lap4 = k.lap4 != 0, def = is_def(k);
 #define YH_T(KK, L) (def ? launch_rk<KK, L, true>(k, a, st) : launch_rk<KK, L, false>(k, a, st))
   if (k.timeIntOrder == 4) return lap4 ? YH_T(4, true) : YH_T(4, false);
@@ -393,12 +407,21 @@ int yh_launch_rd_tile_rk(const YhK &k, const double *u_in, const double *v_in, d
 #undef YH_T
 }
 
+__global__ void slot_bump_kernel(unsigned long long *slot, int n) { *slot += (unsigned long long)n; }
+
+int yh_slot_bump(unsigned long long *slot, int n, cudaStream_t st) {
+  slot_bump_kernel<<<1, 1, 0, st>>>(slot, n);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
+
 int yh_launch_rd_tile_euler(const YhK &k, int tb, const double *u_in, const double *v_in, double *u_out,
                             double *v_out, int nsims, long long sim_stride, const int *period_d,
-                            int duration_it, int count0, cudaStream_t st) {
+                            int duration_it, int count0, cudaStream_t st, double *trace,
+                            const unsigned long long *slot) {
   if (!yh_rd_fast_supported(k, tb)) return YH_ERR_UNSUPPORTED;
   if (k.row1 <= k.row0) return YH_OK;
-  TileArgs a{u_in, v_in, u_out, v_out, nullptr, nullptr, sim_stride, period_d, duration_it, count0};
+  TileArgs a{u_in, v_in, u_out, v_out, nullptr, nullptr, sim_stride, period_d, duration_it, count0, trace, slot};
   const bool def = is_def(k) && k.tc == 1.0;
 #define YH_E(TT) (def ? launch_euler<TT, true>(k, a, nsims, st) : launch_euler<TT, false>(k, a, nsims, st))
   switch (tb) {

@@ -273,15 +273,30 @@ static int sim_run_impl(yh_sim *s, int nsteps, int tb_steps, double *trace_h, bo
     if (!s->probe_slot_d) YH_CUDA(cudaMalloc(&s->probe_slot_d, sizeof(unsigned long long)));
     YH_CUDA(cudaMemsetAsync(s->probe_slot_d, 0, sizeof(unsigned long long), s->st));
     const long long pidx = (long long)s->px + (long long)s->p.nx * s->py;
+    // Euler on tiles: the probe is fused into the step kernel (the owner thread of the electrode
+    // cell records it at every time level), four steps per launch; otherwise {probe, step} pairs
+    const bool fused = fast1 && tile;
     auto chunk = [&](int n) -> int {
-      for (int q = 0; q < n; q++) {
+      for (int q = 0; q < n;) {
         const int c = s->cur, o = c ^ 1;
-        probe_counted_kernel<<<1, 128, 0, s->st>>>(s->u[c], s->v[c], s->trace_d, pidx, stride, s->n_sims,
-                                                   s->probe_slot_d);
-        YH_LAUNCH_CHECK();
-        int rc = rd_launch(c, o, 1);
-        if (rc != YH_OK) return rc;
-        s->cur = o; s->raw_input = 0; s->count += 1;
+        int T = 1;
+        if (fused) {
+          T = 4;
+          while (T > n - q) T >>= 1;
+          int rc = yh_launch_rd_tile_euler(k, T, s->u[c], s->v[c], s->u[o], s->v[o], s->n_sims, stride,
+                                           nullptr, 0, s->count, s->st, s->trace_d, s->probe_slot_d);
+          if (rc != YH_OK) return rc;
+          rc = yh_slot_bump(s->probe_slot_d, T, s->st);
+          if (rc != YH_OK) return rc;
+        } else {
+          probe_counted_kernel<<<1, 128, 0, s->st>>>(s->u[c], s->v[c], s->trace_d, pidx, stride, s->n_sims,
+                                                     s->probe_slot_d);
+          YH_LAUNCH_CHECK();
+          int rc = rd_launch(c, o, 1);
+          if (rc != YH_OK) return rc;
+        }
+        s->cur = o; s->raw_input = 0; s->count += T; s->have_prev = (T == 1);
+        q += T;
       }
       return YH_OK;
     };
@@ -306,7 +321,6 @@ static int sim_run_impl(yh_sim *s, int nsteps, int tb_steps, double *trace_h, bo
     rc = chunk(left);
     if (rc != YH_OK) return rc;
     left = 0;
-    s->have_prev = 1;
   }
   while (left > 0) {
     int T = 1;

@@ -188,6 +188,10 @@ int yh_rd_prefer_tile(long long cells);
 int yh_rd_tile_rk_supported(const YhK &k);
 int yh_launch_rd_tile_rk(const YhK &k, const double *u_in, const double *v_in, double *u_out,
                          double *v_out, double *vtu, double *vtv, cudaStream_t st);
+// trace / slot (optional): the electrode (k.px, k.py) of every sheet is recorded at each of the tb
+// levels into trace[2*((*slot + s)*nsims + z)]; yh_slot_bump advances the device-resident slot.
 int yh_launch_rd_tile_euler(const YhK &k, int tb, const double *u_in, const double *v_in, double *u_out,
                             double *v_out, int nsims, long long sim_stride, const int *period_d,
-                            int duration_it, int count0, cudaStream_t st);
+                            int duration_it, int count0, cudaStream_t st, double *trace = nullptr,
+                            const unsigned long long *slot = nullptr);
+int yh_slot_bump(unsigned long long *slot, int n, cudaStream_t st);
