@@ -275,6 +275,37 @@ int yh_sim_count(const yh_sim *s);             /* param.count */
 void *yh_sim_device_u(yh_sim *s);              /* current device pointers (for tests)     */
 void *yh_sim_device_v(yh_sim *s);
 
+/* ---- multi-GPU: row-slab forms of the symmetry-reduction pieces (new; SURVEY 8e, "SR mode") ---
+ * A process holds rows [jg0, jg0+ny) of the nx x ny_global sheet (ghost rows included) and OWNS a
+ * sub-range of them.  yh_slice, yh_cxy_field and yh_rd_step accept such a yh_params directly (all
+ * coordinates are global, mirror rules apply at the global edges); the three passes whose whole-sheet
+ * form ends in a global result have a slab form:
+ *   tips       yh_tip_track_rows: the cells of local rows [row0,row1), GLOBAL coordinates in the list;
+ *              lists of successive slabs concatenate to the whole-sheet list (ascending cell index).
+ *   integrals  yh_sr_integral_rows: row sums of the 12 inner products for the owned disc rows ->
+ *              rows_d[yh_sr_disc_slots(p)*12] (device; slots of rows owned elsewhere = +0.0).  The
+ *              element-wise SUM over processes (ncclAllReduce; one non-zero contributor per slot, so
+ *              exact) is closed by yh_sr_integrals_close into the 12 integrals on the host, bit for
+ *              bit those of yh_sr_integrals on the whole sheet.  (centre_x, centre_y) = the last tip
+ *              of the gathered list, or (tipx0, tipy0) when count == 0 / no tip.
+ *   advection  yh_advect_bfecc_cphi_rows: local rows [row0,row1) written; needs 3 valid rows beyond.
+ * Ghost depth of one SR step: timeIntOrder (RD) + 3 (BFECC); one exchange per step. */
+int yh_tip_track_rows(const yh_params *p, const double *u_past, const double *u_present,
+                      uint8_t *tip_plot, int *tip_count, yh_tip *tip_vector, int capacity,
+                      double physical_time, int algorithm, int row0, int row1, void *stream);
+int yh_sr_disc_slots(const yh_params *p);
+int yh_sr_integral_rows(const yh_params *p, const double *u, const double *v,
+                        const double *velTan_u, const double *velTan_v,
+                        const double *adv_x, const double *adv_y,
+                        float centre_x, float centre_y, int row0, int row1, double *rows_d,
+                        void *stream);
+int yh_sr_integrals_close(const yh_params *p, const double *rows_d, double *integrals_host,
+                          void *stream);
+int yh_advect_bfecc_cphi_rows(const yh_params *p, const double *u_in, const double *v_in,
+                              double *u_out, double *v_out, const double c[3], const double phi[3],
+                              double *adv_x, double *adv_y, const uint8_t *solid,
+                              int row0, int row1, void *stream);
+
 /* ---- multi-GPU: flags for the NVLink peer-to-peer halo exchange (new) -----------
  * yh_flag_set releases `value` into a flag word that may live in a PEER's memory (CUDA-IPC
  * mapping), stream-ordered after the ghost-row copies; yh_flag_wait blocks the stream until the

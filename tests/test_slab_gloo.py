@@ -74,6 +74,55 @@ def test_slab_exchange_matches_single_domain(oracle, tmp_path, world, halo, nste
     assert rows == ny
 
 
+def _sr_comm_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests import oracle_lib
+    from yolohtli_b200.slab import SlabRunner
+    oracle = oracle_lib.load()
+    nx, ny, H = 16, 30, 7
+    pg = oracle.params_default(nx, ny)
+    run = SlabRunner(pg, rank=rank, world=world, halo=H, device=torch.device("cpu"), stepper=lambda *a: None)
+    l = run.lay
+    glob = np.arange(ny * nx, dtype=np.float64).reshape(ny, nx)
+    run.u[run.cur][l.own_lo:l.own_hi] = torch.from_numpy(glob[l.j0:l.j1])       # owned rows only: ghosts stale
+    run.v[run.cur][l.own_lo:l.own_hi] = torch.from_numpy(-glob[l.j0:l.j1])
+    seen = {}
+
+    def fake_steps(nsteps, record):     # the three communication points of SlabRunner._sr_steps
+        yield ("exchange", None)
+        seen["u"] = run.u[run.cur].clone()
+        infos = yield ("gather", torch.tensor([float(rank + 1), 10.0 * rank, 0.5], dtype=torch.float64))
+        seen["infos"] = torch.stack(infos)
+        rows = torch.zeros(24, dtype=torch.float64)
+        rows[rank::world] = 1.0 + rank                                           # one contributor per slot
+        yield ("sum", rows)
+        seen["rows"] = rows.clone()
+
+    run._sr_steps = fake_steps
+    run.advance_sr(1)
+    assert torch.equal(seen["u"], torch.from_numpy(glob[l.g0:l.g1])), "ghost rows not refreshed"
+    assert seen["infos"].shape == (world, 3)
+    assert seen["infos"][:, 0].tolist() == [float(r + 1) for r in range(world)]   # rank order
+    want = torch.zeros(24, dtype=torch.float64)
+    for r in range(world):
+        want[r::world] = 1.0 + r
+    assert torch.equal(seen["rows"], want)
+    open(os.path.join(out_dir, f"ok{rank}"), "w").close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sr_step_collectives_over_gloo(tmp_path):
+    """The communication points of the symmetry-reduction slab step (ghost exchange, tip-info
+    gather in rank order, row-sum reduction) served by torch.distributed, world_size 2 on CPU."""
+    world = 2
+    mp.spawn(_sr_comm_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"ok{r}")) for r in range(world))
+
+
 def test_partition_covers_domain():
     from yolohtli_b200.slab import SlabLayout, partition
     for ny, world in [(16384, 8), (67, 3), (1000, 7)]:

@@ -127,6 +127,12 @@ SIGNATURES = {
     "yh_sim_run_apd": (_i, [_vp, _i, _vp]),
     "yh_sim_get_apd": (_i, [_vp, _vp, _vp]),
     "yh_sim_sr_state": (_i, [_vp, C.POINTER(_d), C.POINTER(_d), _i]),
+    "yh_tip_track_rows": (_i, [_P, _vp, _vp, _vp, _vp, _vp, _i, _d, _i, _i, _i, _vp]),
+    "yh_sr_disc_slots": (_i, [_P]),
+    "yh_sr_integral_rows": (_i, [_P, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _i, _i, _vp, _vp]),
+    "yh_sr_integrals_close": (_i, [_P, _vp, C.POINTER(_d), _vp]),
+    "yh_advect_bfecc_cphi_rows": (_i, [_P, _vp, _vp, _vp, _vp, C.POINTER(_d), C.POINTER(_d), _vp, _vp,
+                                       _vp, _i, _i, _vp]),
     "yh_flag_set": (_i, [_vp, _i, _vp]),
     "yh_flag_wait": (_i, [_vp, _i, _vp, _vp]),
     "yh_memcpy_async": (_i, [_vp, _vp, C.c_size_t, _vp]),

@@ -25,17 +25,19 @@ __device__ __forceinline__ void disc_centre(const YhK &k, float tipx0, float tip
     if (n > 0) { fx = tv[n - 1].x; fy = tv[n - 1].y; }
   }
   cx = __float2int_rn(fx - (float)(k.nx / 2));
-  cy = __float2int_rn(fy - (float)(k.ny / 2));
+  cy = __float2int_rn(fy - (float)(k.nyg / 2));
 }
 
-__device__ __forceinline__ int IDX(const YhK &k, int i, int j) { return i + k.nx * j; }
+// (i, j) with j a GLOBAL row: a process may hold only rows [jg0, jg0 + ny) of the sheet (row slabs,
+// ghost rows included); mirror rules apply at the global edges.  Whole sheet: jg0 = 0, nyg = ny.
+__device__ __forceinline__ int IDX(const YhK &k, int i, int j) { return i + k.nx * (j - k.jg0); }
 
 __device__ __forceinline__ double fb2x(const YhK &k, const double *f, int i, int j, int C, int E, int W, double ax) {
   const int WW = IDX(k, yh_mir(i - 2, k.nx), j), EE = IDX(k, yh_mir(i + 2, k.nx), j);
   return (ax > 0.0) ? (-3.0 * f[C] + 4.0 * f[E] - f[EE]) * k.invdx : (3.0 * f[C] - 4.0 * f[W] + f[WW]) * k.invdx;
 }
 __device__ __forceinline__ double fb2y(const YhK &k, const double *f, int i, int j, int C, int N, int S, double ay) {
-  const int SS = IDX(k, i, yh_mir(j - 2, k.ny)), NN = IDX(k, i, yh_mir(j + 2, k.ny));
+  const int SS = IDX(k, i, yh_mir(j - 2, k.nyg)), NN = IDX(k, i, yh_mir(j + 2, k.nyg));
   return (ay > 0.0) ? (-3.0 * f[C] + 4.0 * f[N] - f[NN]) * k.invdy : (3.0 * f[C] - 4.0 * f[S] + f[SS]) * k.invdy;
 }
 __device__ __forceinline__ double cen2x(const YhK &k, const double *f, int i, int j, int E, int W) {
@@ -43,7 +45,7 @@ __device__ __forceinline__ double cen2x(const YhK &k, const double *f, int i, in
   return (f[EE] - 8.0 * f[E] + 8.0 * f[W] - f[WW]) * k.invdx * (1.0 / 6.0);
 }
 __device__ __forceinline__ double cen2y(const YhK &k, const double *f, int i, int j, int N, int S) {
-  const int SS = IDX(k, i, yh_mir(j - 2, k.ny)), NN = IDX(k, i, yh_mir(j + 2, k.ny));
+  const int SS = IDX(k, i, yh_mir(j - 2, k.nyg)), NN = IDX(k, i, yh_mir(j + 2, k.nyg));
   return (f[NN] - 8.0 * f[N] + 8.0 * f[S] - f[SS]) * k.invdy * (1.0 / 6.0);
 }
 
@@ -52,9 +54,9 @@ __device__ __forceinline__ void slice_cell(const YhK &k, const double *gu, const
                                            const double *ay, int scheme, bool sc, int i, int j, bool want0,
                                            double s[6], double s0[6]) {
   const int c = IDX(k, i, j);
-  const double x = (double)(c % k.nx);
-  const double y = (double)floorf((float)((c / k.nx) % k.nx));   // as shipped (:109-110)
-  const int S = IDX(k, i, yh_mir(j - 1, k.ny)), N = IDX(k, i, yh_mir(j + 1, k.ny));
+  const double x = (double)i;                                    // (i + nx*j) % nx
+  const double y = (double)floorf((float)(j % k.nx));            // (idx / nx) % nx as shipped (:109-110)
+  const int S = IDX(k, i, yh_mir(j - 1, k.nyg)), N = IDX(k, i, yh_mir(j + 1, k.nyg));
   const int W = IDX(k, yh_mir(i - 1, k.nx), j), E = IDX(k, yh_mir(i + 1, k.nx), j);
   const bool on = (scheme == 1) ? true : sc;
   if (on) {
@@ -102,11 +104,12 @@ struct SliceArgs {
 __global__ void __launch_bounds__(256)
 slice_kernel(const __grid_constant__ YhK k, const __grid_constant__ SliceArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  if (i >= k.nx || j >= k.ny) return;
+  const int jl = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= k.nx || jl >= k.ny) return;
+  const int j = jl + k.jg0;
   int cx, cy;
   disc_centre(k, a.tipx0, a.tipy0, a.tip_count, a.tv, a.count, cx, cy);
-  const int ic = i - k.nx / 2, jc = j - k.ny / 2;
+  const int ic = i - k.nx / 2, jc = j - k.nyg / 2;
   const bool sc = ((ic - cx) * (ic - cx) + (jc - cy) * (jc - cy)) < k.tipOffX * k.tipOffY;
   double s[6], s0[6];
   slice_cell(k, a.u, a.v, a.ax, a.ay, a.scheme, sc, i, j, a.start != 0, s, s0);
@@ -137,6 +140,7 @@ struct IntArgs {
   const yh_tip *tv;
   float tipx0, tipy0;
   int R;               // ceil(sqrt(tipOffX*tipOffY)): rows cy-R .. cy+R can intersect the disc
+  int own0, own1;      // GLOBAL rows this process sums (row slabs; whole sheet: 0, ny); other slots get +0.0
 };
 
 // Summation order (shared with the oracle, yh_oracle.c): per grid row 256 accumulators -- warp w,
@@ -161,12 +165,12 @@ integrals_rows_kernel(const __grid_constant__ YhK k, const __grid_constant__ Int
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int cx, cy;
   disc_centre(k, a.tipx0, a.tipy0, a.tip_count, a.tv, a.count, cx, cy);
-  const int j = cy + k.ny / 2 - a.R + slot;   // grid row of this slot
+  const int j = cy + k.nyg / 2 - a.R + slot;   // (global) grid row of this slot
   double acc[12];
 #pragma unroll
   for (int q = 0; q < 12; q++) acc[q] = 0.0;
-  if (j >= 0 && j < k.ny) {
-    const int jc = j - k.ny / 2;
+  if (j >= a.own0 && j < a.own1) {
+    const int jc = j - k.nyg / 2;
     for (int i = threadIdx.x; i < k.nx; i += ROW_WARPS * 32) {
       const int ic = i - k.nx / 2;
       const bool sc = ((ic - cx) * (ic - cx) + (jc - cy) * (jc - cy)) < k.tipOffX * k.tipOffY;
@@ -203,6 +207,7 @@ integrals_rows_kernel(const __grid_constant__ YhK k, const __grid_constant__ Int
     __stcg(a.rows + (size_t)slot * 12 + threadIdx.x, r);
     __threadfence();
   }
+  if (!a.done) return;   // slab form: the row sums are combined across processes before the closing
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
   __syncthreads();
@@ -242,16 +247,43 @@ integrals_rows_kernel(const __grid_constant__ YhK k, const __grid_constant__ Int
   }
 }
 
+// Closing of the slab form: the totals over the row slots in the canonical order of the last-CTA
+// code above (32 interleaved partial sums, xor-butterfly), one warp per integral.
+__global__ void __launch_bounds__(12 * 32)
+integrals_close_kernel(const double *rows, int nrows, double hx, double hy, double *out) {
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+  double x = 0.0;
+  for (int w = lane; w < nrows; w += 32) x += rows[(size_t)w * 12 + q];
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, m);
+  if (lane == 0) out[q] = 0.25 * hx * hy * x;   // integralTrapz.cu:79, same operation order as above
+}
+
 __global__ void sr_flush_phi_kernel(double *sr, double dt_phi) {
   if (threadIdx.x < 3) sr[YH_SR_PHI + threadIdx.x] = sr[YH_SR_PHI + threadIdx.x] + sr[YH_SR_C + threadIdx.x] * dt_phi;
 }
 
-int run_integrals(const yh_params *p, IntArgs &a, bool fused, double *integrals_host, cudaStream_t st) {
-  YhK k = yh_make_k(p);
+int disc_radius_rows(const yh_params *p) {
   const long long r2 = (long long)p->tipOffsetX * p->tipOffsetY;
   int R = (int)ceil(sqrt((double)r2));
-  if (R > p->ny) R = p->ny;
+  if (R > p->ny_global) R = p->ny_global;
+  return R;
+}
+
+int fetch12(const double *out_d, double *integrals_host, cudaStream_t st) {
+  static thread_local double *pinned = nullptr;
+  if (!pinned) YH_CUDA(cudaMallocHost(&pinned, 12 * sizeof(double)));
+  YH_CUDA(cudaMemcpyAsync(pinned, out_d, 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  YH_CUDA(cudaStreamSynchronize(st));   // the ONE host sync of the SR step (reference: 12 + malloc/free)
+  for (int q = 0; q < 12; q++) integrals_host[q] = pinned[q];
+  return YH_OK;
+}
+
+int run_integrals(const yh_params *p, IntArgs &a, bool fused, double *integrals_host, cudaStream_t st) {
+  YhK k = yh_make_k(p);
+  const int R = disc_radius_rows(p);
   a.R = R;
+  a.own0 = p->jg0; a.own1 = p->jg0 + p->ny;
   const int nrows = 2 * R + 1;
   double *ws = nullptr;
   int rc = yh_workspace(((size_t)nrows * 12 + 12 + 1) * sizeof(double), (void **)&ws, 2);   // zero-filled when (re)allocated
@@ -263,12 +295,7 @@ int run_integrals(const yh_params *p, IntArgs &a, bool fused, double *integrals_
   else integrals_rows_kernel<false><<<nrows, ROW_WARPS * 32, 0, st>>>(k, a);
   YH_LAUNCH_CHECK();
   if (!integrals_host) return YH_OK;   // device-resident closing was done by the last CTA
-  static thread_local double *pinned = nullptr;
-  if (!pinned) YH_CUDA(cudaMallocHost(&pinned, 12 * sizeof(double)));
-  YH_CUDA(cudaMemcpyAsync(pinned, a.out, 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  YH_CUDA(cudaStreamSynchronize(st));   // the ONE host sync of the SR step (reference: 12 + malloc/free)
-  for (int q = 0; q < 12; q++) integrals_host[q] = pinned[q];
-  return YH_OK;
+  return fetch12(a.out, integrals_host, st);
 }
 
 // ---- Cxy ----------------------------------------------------------------------------------
@@ -276,13 +303,13 @@ struct CxyArgs { double *ax, *ay; const uint8_t *solid; double cx, cy, ct, cs, s
 
 // adv of one cell (symmetryReduction.cu:45-56); cos/sin(phi.t) are computed on the HOST so the
 // field is reproducible by the plain-C oracle bit for bit.
+// j is the GLOBAL row (row slabs: arrays hold rows [jg0, jg0 + ny)).
 __device__ __forceinline__ void cxy_cell(const YhK &k, const CxyArgs &a, int i, int j, double &ax, double &ay) {
-  const int c = i + k.nx * j;
-  const double x = (double)(c % k.nx);
-  const double y = (double)floorf((float)((c / k.nx) % k.nx));
+  const double x = (double)i;                               // (i + nx*j) % nx
+  const double y = (double)floorf((float)(j % k.nx));       // (idx / nx) % nx as shipped
   ax = k.hy * y * a.ct - a.cx * a.cs + a.cy * a.sn;
   ay = -k.hx * x * a.ct - a.cx * a.sn - a.cy * a.cs;
-  if (k.solidSwitch && !a.solid[c]) { ax = 0.0; ay = 0.0; }
+  if (k.solidSwitch && !a.solid[IDX(k, i, j)]) { ax = 0.0; ay = 0.0; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -291,7 +318,7 @@ cxy_kernel(const __grid_constant__ YhK k, const __grid_constant__ CxyArgs a) {
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= k.nx || j >= k.ny) return;
   double ax, ay;
-  cxy_cell(k, a, i, j, ax, ay);
+  cxy_cell(k, a, i, j + k.jg0, ax, ay);
   a.ax[i + k.nx * j] = ax;
   a.ay[i + k.nx * j] = ay;
 }
@@ -318,7 +345,7 @@ __device__ __forceinline__ int sgn(double x) { int t = x < 0.0 ? -1 : 0; return 
 
 // tile-local index of GLOBAL cell (gi, gj), mirrored into the domain first (defect B5)
 __device__ __forceinline__ int TL(const YhK &k, int gi, int gj, int ti0, int tj0) {
-  gi = yh_mir(gi, k.nx); gj = yh_mir(gj, k.ny);
+  gi = yh_mir(gi, k.nx); gj = yh_mir(gj, k.nyg);
   return (gi - ti0) + BP * (gj - tj0);
 }
 
@@ -334,12 +361,12 @@ __device__ __forceinline__ NbrIdx neumann_idx(const YhK &k, const uint8_t *msk, 
     sw = (gi > 0) && msk[C - 1];
     se = (gi < k.nx - 1) && msk[C + 1];
     sn = (gj > 0) && msk[C - BP];            // "sn" is the mask at j-1 (:47)
-    ss = (gj < k.ny - 1) && msk[C + BP];     // "ss" is the mask at j+1 (:48)
+    ss = (gj < k.nyg - 1) && msk[C + BP];    // "ss" is the mask at j+1 (:48)
   } else {
     x.sc = true;
     sw = gi > 0; se = gi < (k.nx - 1);
     ss = gj > 0;            // square branch tests the index itself: S uses (j>0), N uses (j<ny-1)
-    sn = gj < (k.ny - 1);
+    sn = gj < (k.nyg - 1);
   }
   if (k.solidSwitch) {
     const int Wm = TL(k, gi - 1, gj, ti0, tj0), Em = TL(k, gi + 1, gj, ti0, tj0);
@@ -374,11 +401,11 @@ __device__ __forceinline__ DirMask dir_mask(const YhK &k, const uint8_t *msk, in
     d.sw = (gi > 0) && msk[C - 1];
     d.se = (gi < k.nx - 1) && msk[C + 1];
     const bool sn = (gj > 0) && msk[C - BP];           // mask at j-1
-    const bool ss = (gj < k.ny - 1) && msk[C + BP];    // mask at j+1
+    const bool ss = (gj < k.nyg - 1) && msk[C + BP];   // mask at j+1
     d.sS = ss;   // the shipped code gates the (j-1) read by ss and the (j+1) read by sn (:182-183)
     d.sN = sn;
   } else {
-    d.sc = true; d.sw = gi > 0; d.se = gi < (k.nx - 1); d.sS = gj > 0; d.sN = gj < (k.ny - 1);
+    d.sc = true; d.sw = gi > 0; d.se = gi < (k.nx - 1); d.sS = gj > 0; d.sN = gj < (k.nyg - 1);
   }
   return d;
 }
@@ -389,7 +416,10 @@ bfecc_kernel(const __grid_constant__ YhK k, const __grid_constant__ BfArgs a) {
   double *g = bsm, *uf = bsm + BP * BP, *ue = bsm + 2 * BP * BP;
   double *sRx = bsm + 6 * BP * BP, *sRy = bsm + 7 * BP * BP;   // |c| dt / h, upwind direction in the sign bit
   uint8_t *msk = reinterpret_cast<uint8_t *>(bsm + 8 * BP * BP);
-  const int ti0 = blockIdx.x * BT - BH, tj0 = blockIdx.y * BT - BH;
+  // tile origin in GLOBAL rows: output rows are local rows [row0, row1) of a slab that holds global
+  // rows [jg0, jg0 + ny) (whole sheet: jg0 = 0, row0 = 0, row1 = ny = nyg)
+  const int ti0 = blockIdx.x * BT - BH, tj0 = k.jg0 + k.row0 + blockIdx.y * BT - BH;
+  const int lrow_hi = k.jg0 + k.ny;   // global rows [jg0, lrow_hi) are held; the others read as 0.0
   const int tid = threadIdx.x;
   const bool neu = k.neumannBC != 0;
   const double tc = k.tc, bv = k.boundaryVal;
@@ -404,12 +434,13 @@ bfecc_kernel(const __grid_constant__ YhK k, const __grid_constant__ BfArgs a) {
     const int gi = ti0 + t % BP, gj = tj0 + t / BP;
     double rx = 0.0, ry = 0.0;
     uint8_t m = 0;
-    if (gi >= 0 && gi < k.nx && gj >= 0 && gj < k.ny) {
-      const int c = gi + k.nx * gj;
+    if (gi >= 0 && gi < k.nx && gj >= k.jg0 && gj < lrow_hi) {
+      const int c = IDX(k, gi, gj);
       double ax, ay;
       if (a.from_c) {
         cxy_cell(k, cxy, gi, gj, ax, ay);
-        const bool own = (t % BP >= BH) && (t % BP < BH + BT) && (t / BP >= BH) && (t / BP < BH + BT);
+        const bool own = (t % BP >= BH) && (t % BP < BH + BT) && (t / BP >= BH) && (t / BP < BH + BT) &&
+                         (gj < k.jg0 + k.row1);
         if (own && a.ax_out) { a.ax_out[c] = ax; a.ay_out[c] = ay; }
       } else { ax = a.ax[c]; ay = a.ay[c]; }
       const double cx = -ax, cy = -ay;
@@ -429,16 +460,16 @@ bfecc_kernel(const __grid_constant__ YhK k, const __grid_constant__ BfArgs a) {
   __syncthreads();
   for (int t = tid; t < BP * BP; t += BTHREADS) {
     const int gi = ti0 + t % BP, gj = tj0 + t / BP;
-    const bool in = gi >= 0 && gi < k.nx && gj >= 0 && gj < k.ny;
-    g[t] = in ? gin[0][gi + k.nx * gj] : 0.0;
-    g[FO + t] = in ? gin[1][gi + k.nx * gj] : 0.0;
+    const bool in = gi >= 0 && gi < k.nx && gj >= k.jg0 && gj < lrow_hi;
+    g[t] = in ? gin[0][IDX(k, gi, gj)] : 0.0;
+    g[FO + t] = in ? gin[1][IDX(k, gi, gj)] : 0.0;
   }
   __syncthreads();
   // sweep 1 (forward) on the tile minus one ring
   for (int t = tid; t < BP * BP; t += BTHREADS) {
     const int li = t % BP, lj = t / BP, gi = ti0 + li, gj = tj0 + lj;
     if (li < 1 || li >= BP - 1 || lj < 1 || lj >= BP - 1) continue;
-    if (gi < 0 || gi >= k.nx || gj < 0 || gj >= k.ny) continue;
+    if (gi < 0 || gi >= k.nx || gj < 0 || gj >= k.nyg) continue;
     const bool px = !signbit(sRx[t]), py = !signbit(sRy[t]);
     const double Rx = fabs(sRx[t]), Ry = fabs(sRy[t]);
     if (neu) {
@@ -471,7 +502,7 @@ bfecc_kernel(const __grid_constant__ YhK k, const __grid_constant__ BfArgs a) {
   for (int t = tid; t < BP * BP; t += BTHREADS) {
     const int li = t % BP, lj = t / BP, gi = ti0 + li, gj = tj0 + lj;
     if (li < 2 || li >= BP - 2 || lj < 2 || lj >= BP - 2) continue;
-    if (gi < 0 || gi >= k.nx || gj < 0 || gj >= k.ny) continue;
+    if (gi < 0 || gi >= k.nx || gj < 0 || gj >= k.nyg) continue;
     const bool px = !signbit(sRx[t]), py = !signbit(sRy[t]);
     const double Rx = fabs(sRx[t]), Ry = fabs(sRy[t]);
     if (neu) {
@@ -508,7 +539,7 @@ bfecc_kernel(const __grid_constant__ YhK k, const __grid_constant__ BfArgs a) {
   // sweep 3 (forward) on the 32 x 32 interior -> HBM
   for (int t = tid; t < BT * BT; t += BTHREADS) {
     const int li = BH + t % BT, lj = BH + t / BT, gi = ti0 + li, gj = tj0 + lj;
-    if (gi >= k.nx || gj >= k.ny) continue;
+    if (gi >= k.nx || gj >= k.jg0 + k.row1) continue;
     const int q = li + BP * lj;
     const bool px = !signbit(sRx[q]), py = !signbit(sRy[q]);
     const double Rx = fabs(sRx[q]), Ry = fabs(sRy[q]);
@@ -520,7 +551,7 @@ bfecc_kernel(const __grid_constant__ YhK k, const __grid_constant__ BfArgs a) {
         const double FDx = px ? uef[q] - uef[x.W] : uef[q] - uef[x.E];
         const double FDy = py ? uef[q] - uef[x.S] : uef[q] - uef[x.N];
         const double r = uef[q] - tc * (Rx * FDx + Ry * FDy);
-        gout[f][gi + k.nx * gj] = x.sc ? r : 0.0;
+        gout[f][IDX(k, gi, gj)] = x.sc ? r : 0.0;
       }
     } else {
       const DirMask d = dir_mask(k, msk, gi, gj, q);
@@ -535,16 +566,25 @@ bfecc_kernel(const __grid_constant__ YhK k, const __grid_constant__ BfArgs a) {
         const double N = d.sc && d.sN ? uef[iN] : (d.sc ? bv : 0.0);
         const double FDx = px ? uue - W : uue - E, FDy = py ? uue - S : uue - N;
         const double r = uue - tc * (Rx * FDx + Ry * FDy);
-        gout[f][gi + k.nx * gj] = d.sc ? r : 0.0;
+        gout[f][IDX(k, gi, gj)] = d.sc ? r : 0.0;
       }
     }
   }
 }
 
-int check_sheet(const yh_params *p) {
+// a whole sheet or a row slab of one (rows [jg0, jg0 + ny) of nx x ny_global, ghost rows included)
+int check_slab(const yh_params *p) {
   YH_REQUIRE(p != nullptr, "null params");
-  YH_REQUIRE(p->nx >= 8 && p->ny >= 8, "grid too small");
-  YH_REQUIRE(p->jg0 == 0 && p->ny_global == p->ny, "symmetry-reduction kernels work on a whole sheet");
+  YH_REQUIRE(p->nx >= 8 && p->ny >= 1 && p->ny_global >= 8, "grid too small");
+  YH_REQUIRE(p->jg0 >= 0 && p->jg0 + p->ny <= p->ny_global, "slab outside the global domain");
+  return YH_OK;
+}
+// entry points whose result is a sum over the whole disc: a slab would silently drop rows
+int check_sheet(const yh_params *p) {
+  int rc = check_slab(p);
+  if (rc != YH_OK) return rc;
+  YH_REQUIRE(p->jg0 == 0 && p->ny_global == p->ny,
+             "needs the whole sheet (row slabs: yh_sr_integral_rows + yh_sr_integrals_close)");
   return YH_OK;
 }
 
@@ -558,7 +598,7 @@ int yh_slice(const yh_params *p, const double *u, const double *v, double *const
              int count, void *stream) {
   int rc = yh_check_device();
   if (rc != YH_OK) return rc;
-  if ((rc = check_sheet(p)) != YH_OK) return rc;
+  if ((rc = check_slab(p)) != YH_OK) return rc;
   YH_REQUIRE(u && v && slice && adv_x && adv_y, "null pointer");
   YH_REQUIRE(scheme == 1 || scheme == 2, "scheme must be 1 or 2");
   YH_REQUIRE(!reduce_sym_start || slice0, "slice0 == NULL with reduce_sym_start");
@@ -652,7 +692,7 @@ int yh_cxy_field(const yh_params *p, double *adv_x, double *adv_y, const double 
                  const double phi[3], const uint8_t *solid, void *stream) {
   int rc = yh_check_device();
   if (rc != YH_OK) return rc;
-  if ((rc = check_sheet(p)) != YH_OK) return rc;
+  if ((rc = check_slab(p)) != YH_OK) return rc;
   YH_REQUIRE(adv_x && adv_y && c && phi, "null pointer");
   YH_REQUIRE(!p->solidSwitch || solid, "solidSwitch set but solid == NULL");
   YhK k = yh_make_k(p);
@@ -663,9 +703,12 @@ int yh_cxy_field(const yh_params *p, double *adv_x, double *adv_y, const double 
   return YH_OK;
 }
 
-static int bfecc_common(const yh_params *p, BfArgs &a, void *stream) {
+static int bfecc_common(const yh_params *p, BfArgs &a, void *stream, int row0 = 0, int row1 = -1) {
   YhK k = yh_make_k(p);
-  dim3 grd((p->nx + BT - 1) / BT, (p->ny + BT - 1) / BT);
+  if (row1 < 0) row1 = p->ny;
+  YH_REQUIRE(row0 >= 0 && row0 < row1 && row1 <= p->ny, "bad row range");
+  k.row0 = row0; k.row1 = row1;
+  dim3 grd((p->nx + BT - 1) / BT, (row1 - row0 + BT - 1) / BT);
   const size_t smem = (size_t)8 * BP * BP * sizeof(double) + BP * BP;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -711,6 +754,80 @@ int yh_advect_bfecc_cphi(const yh_params *p, const double *u_in, const double *v
   a.ax_out = adv_x; a.ay_out = adv_y; a.solid = solid; a.from_c = 1;
   a.cxy = make_cxy(nullptr, nullptr, solid, c, phi);
   return bfecc_common(p, a, stream);
+}
+
+// Row-slab form (multi-GPU): rows [row0, row1) of the local arrays are written; they are
+// valid when rows [row0-3, row1+3) (clipped to the global sheet) of u_in / v_in are held and valid.
+int yh_advect_bfecc_cphi_rows(const yh_params *p, const double *u_in, const double *v_in,
+                              double *u_out, double *v_out, const double c[3], const double phi[3],
+                              double *adv_x, double *adv_y, const uint8_t *solid, int row0, int row1,
+                              void *stream) {
+  int rc = yh_check_device();
+  if (rc != YH_OK) return rc;
+  if ((rc = check_slab(p)) != YH_OK) return rc;
+  YH_REQUIRE(u_in && v_in && u_out && v_out && c && phi, "null pointer");
+  YH_REQUIRE(u_in != u_out && v_in != v_out, "in-place advection is not supported");
+  YH_REQUIRE((adv_x == nullptr) == (adv_y == nullptr), "adv_x / adv_y must both be set or NULL");
+  YH_REQUIRE(!p->solidSwitch || solid, "solidSwitch set but solid == NULL");
+  BfArgs a;
+  memset(&a, 0, sizeof(a));
+  a.u_in = u_in; a.v_in = v_in; a.u_out = u_out; a.v_out = v_out;
+  a.ax_out = adv_x; a.ay_out = adv_y; a.solid = solid; a.from_c = 1;
+  a.cxy = make_cxy(nullptr, nullptr, solid, c, phi);
+  return bfecc_common(p, a, stream, row0, row1);
+}
+
+int yh_sr_disc_slots(const yh_params *p) {
+  if (!p) return 0;
+  return 2 * disc_radius_rows(p) + 1;
+}
+
+// The fused slice + trapz pass of a row slab: row sums of the 12 inner products for the disc rows
+// this process owns (local rows [row0, row1)) -> rows_d[yh_sr_disc_slots(p) * 12] on the DEVICE;
+// slots whose row belongs to another process are written as +0.0, so an element-wise sum over the
+// processes (every slot has exactly one non-zero contributor: x + 0.0 == x) assembles the row sums of
+// the whole sheet bit for bit.  (centre_x, centre_y): the disc centre every process agreed on -- the
+// last tip of the gathered list, or (tipx0, tipy0).  No host sync.
+int yh_sr_integral_rows(const yh_params *p, const double *u, const double *v, const double *velTan_u,
+                        const double *velTan_v, const double *adv_x, const double *adv_y,
+                        float centre_x, float centre_y, int row0, int row1, double *rows_d,
+                        void *stream) {
+  int rc = yh_check_device();
+  if (rc != YH_OK) return rc;
+  if ((rc = check_slab(p)) != YH_OK) return rc;
+  YH_REQUIRE(u && v && velTan_u && velTan_v && adv_x && adv_y && rows_d, "null pointer");
+  YH_REQUIRE(row0 >= 0 && row0 <= row1 && row1 <= p->ny, "bad row range");
+  // the tangent stencils reach two rows beyond a summed row
+  const int lo = p->jg0 + row0 - 2, hi = p->jg0 + row1 + 2;
+  YH_REQUIRE((lo < 0 || lo >= p->jg0) && (hi > p->ny_global || hi <= p->jg0 + p->ny),
+             "summed rows need two ghost rows on each slab-internal side");
+  IntArgs a;
+  memset(&a, 0, sizeof(a));
+  a.u = u; a.v = v; a.ax = adv_x; a.ay = adv_y; a.vtu = velTan_u; a.vtv = velTan_v;
+  a.count = 0; a.tipx0 = centre_x; a.tipy0 = centre_y;   // disc_centre() returns exactly these
+  a.rows = rows_d;                                        // a.done == NULL: no closing in this launch
+  YhK k = yh_make_k(p);
+  a.R = disc_radius_rows(p);
+  a.own0 = p->jg0 + row0; a.own1 = p->jg0 + row1;
+  integrals_rows_kernel<true><<<2 * a.R + 1, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(k, a);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
+
+// Totals of assembled row sums in the canonical order of the single-sheet pass -> integrals_host[12]
+// (HOST, one sync), identical to yh_sr_integrals on the whole sheet.
+int yh_sr_integrals_close(const yh_params *p, const double *rows_d, double *integrals_host, void *stream) {
+  int rc = yh_check_device();
+  if (rc != YH_OK) return rc;
+  if ((rc = check_slab(p)) != YH_OK) return rc;
+  YH_REQUIRE(rows_d && integrals_host, "null pointer");
+  double *out = nullptr;
+  rc = yh_workspace(12 * sizeof(double), (void **)&out, 5);
+  if (rc != YH_OK) return rc;
+  integrals_close_kernel<<<1, 12 * 32, 0, (cudaStream_t)stream>>>(rows_d, 2 * disc_radius_rows(p) + 1, p->hx,
+                                                                  p->hy, out);
+  YH_LAUNCH_CHECK();
+  return fetch12(out, integrals_host, (cudaStream_t)stream);
 }
 
 }  // extern "C"

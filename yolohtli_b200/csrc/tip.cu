@@ -37,8 +37,8 @@ __device__ __forceinline__ bool equals_tol(double a, double b, double tol) {   /
 // gradient(), tipTracker.cu:519-566 (indices as shipped)
 __device__ void tip_gradient(const YhK &k, int i, int j, double s, double t, const double *g,
                              float &gx, float &gy) {
-  const int nx = k.nx, ny = k.ny;
-#define ID(a, b) ((a) + nx * (b))
+  const int nx = k.nx, ny = k.nyg;   // j is a GLOBAL row; the arrays hold rows [jg0, jg0 + k.ny)
+#define ID(a, b) ((a) + nx * ((b) - k.jg0))
   int S = (j > 0) ? ID(i, j - 1) : ID(i, j + 1);
   int Sx = ((j > 0) && (i < (nx - 1))) ? ID(i + 1, j - 1) : ID(i - 1, j + 1);
   int Sy = ID(i, j);
@@ -67,8 +67,9 @@ __device__ void tip_gradient(const YhK &k, int i, int j, double s, double t, con
 }
 
 // Up to two candidate roots of one cell; returns how many pass tipRecordPlane's test.
+// (i, j): j is the GLOBAL row (row slabs hold rows [jg0, jg0 + k.ny); whole sheet: jg0 = 0).
 __device__ int tip_cell(const YhK &k, const TipArgs &a, int i, int j, float2 *roots) {
-  const int nx = k.nx, ny = k.ny;
+  const int nx = k.nx, ny = k.nyg;
   bool inside;
   if (k.solidSwitch) {   // tipTracker.cu:49-51
     int ic = i - nx / 2, jc = j - ny / 2;
@@ -80,7 +81,7 @@ __device__ int tip_cell(const YhK &k, const TipArgs &a, int i, int j, float2 *ro
     inside = (i >= 1) && (i < (nx - 2)) && (j >= 1) && (j < (ny - 2));
   }
   if (!inside) return 0;
-  const int s0 = i + nx * j;
+  const int s0 = i + nx * (j - k.jg0);
   const int sx = (i < (nx - 1)) ? s0 + 1 : s0;
   const int sy = (j < (ny - 1)) ? s0 + nx : s0;
   const int sxy = ((j < (ny - 1)) && (i < (nx - 1))) ? s0 + nx + 1 : s0;
@@ -158,7 +159,7 @@ tip_kernel(const __grid_constant__ YhK k, const __grid_constant__ TipArgs a) {
   if (tid == 0) s_chunk = (int)atomicAdd(&ord.state[0], 1ull);   // ticket = chunk, in launch order
   __syncthreads();
   const int chunk = s_chunk;
-  const long long ncell = (long long)k.nx * k.ny;
+  const long long ncell = (long long)k.nx * (k.row1 - k.row0);   // local rows [row0, row1)
 
   float2 roots[TIP_CPT][2];
   int nr[TIP_CPT];
@@ -168,12 +169,12 @@ tip_kernel(const __grid_constant__ YhK k, const __grid_constant__ TipArgs a) {
     const long long cell = (long long)chunk * TIP_CHUNK + (long long)tid * TIP_CPT + r;
     nr[r] = 0;
     if (cell < ncell) {
-      const int i = (int)(cell % k.nx), j = (int)(cell / k.nx);
+      const int i = (int)(cell % k.nx), jl = k.row0 + (int)(cell / k.nx), j = jl + k.jg0;
       if (a.algorithm == 3) {   // abouzarTip_kernel, :434-517 -- raster only, no list
-        const int s0 = (int)cell;
+        const int s0 = i + k.nx * jl;
         const int sx = (i < (k.nx - 1)) ? s0 + 1 : s0;
-        const int sy = (j < (k.ny - 1)) ? s0 + k.nx : s0;
-        const int sxy = ((j < (k.ny - 1)) && (i < (k.nx - 1))) ? s0 + k.nx + 1 : s0;
+        const int sy = (j < (k.nyg - 1)) ? s0 + k.nx : s0;
+        const int sxy = ((j < (k.nyg - 1)) && (i < (k.nx - 1))) ? s0 + k.nx + 1 : s0;
         const double v0 = a.present[s0], vx = a.present[sx], vy = a.present[sy], vxy = a.present[sxy];
         int s = (0.0 >= v0 - k.Uth) + (0.0 >= vx - k.Uth) + (0.0 >= vy - k.Uth) + (0.0 >= vxy - k.Uth);
         const bool bv = (s > 0) && (s < 4);
@@ -203,7 +204,7 @@ tip_kernel(const __grid_constant__ YhK k, const __grid_constant__ TipArgs a) {
   for (int r = 0; r < TIP_CPT; r++) {
     if (nr[r] == 0) continue;
     const long long cell = (long long)chunk * TIP_CHUNK + (long long)tid * TIP_CPT + r;
-    const int i = (int)(cell % k.nx), j = (int)(cell / k.nx);
+    const int i = (int)(cell % k.nx), j = k.row0 + (int)(cell / k.nx) + k.jg0;
     for (int q = 0; q < nr[r]; q++, pos++) {   // tipRecordPlane, :210-241
       const float2 tip = roots[r][q];
       float gx = 0.f, gy = 0.f;
@@ -213,7 +214,7 @@ tip_kernel(const __grid_constant__ YhK k, const __grid_constant__ TipArgs a) {
       if (pos < a.capacity) a.vec[pos] = d;
       if (a.plot) {   // plot_field, helper_functions.cu:45-51
         const int xi = (int)floorf(d.x), yi = (int)floorf(d.y);
-        a.plot[xi + k.nx * yi] = 1;
+        a.plot[xi + k.nx * (yi - k.jg0)] = 1;
       }
     }
   }
@@ -221,18 +222,24 @@ tip_kernel(const __grid_constant__ YhK k, const __grid_constant__ TipArgs a) {
 
 }  // namespace
 
-extern "C" int yh_tip_track(const yh_params *p, const double *u_past, const double *u_present,
-                            uint8_t *tip_plot, int *tip_count, yh_tip *tip_vector, int capacity,
-                            double physical_time, int algorithm, void *stream) {
+// Cells of local rows [row0, row1); a cell reads the row above it, so the last row must be the
+// sheet's last row or have a (ghost) row after it.  Coordinates in the list are GLOBAL.
+extern "C" int yh_tip_track_rows(const yh_params *p, const double *u_past, const double *u_present,
+                                 uint8_t *tip_plot, int *tip_count, yh_tip *tip_vector, int capacity,
+                                 double physical_time, int algorithm, int row0, int row1, void *stream) {
   int rc = yh_check_device();
   if (rc != YH_OK) return rc;
   YH_REQUIRE(p && u_past && u_present && tip_count && tip_vector, "null pointer");
   YH_REQUIRE(algorithm >= 1 && algorithm <= 3, "tip algorithm must be 1, 2 or 3");
   YH_REQUIRE(capacity >= 0, "negative capacity");
-  YH_REQUIRE(p->jg0 == 0 && p->ny_global == p->ny, "tip tracking works on a whole sheet");
+  YH_REQUIRE(p->nx >= 4 && p->ny >= 1 && p->jg0 >= 0 && p->jg0 + p->ny <= p->ny_global, "bad slab");
+  YH_REQUIRE(row0 >= 0 && row0 < row1 && row1 <= p->ny, "bad row range");
+  YH_REQUIRE(row1 < p->ny || p->jg0 + p->ny == p->ny_global, "the last row needs the row after it");
+  YH_REQUIRE(!p->tipGrad || (p->jg0 == 0 && p->ny == p->ny_global), "tipGrad reads up to two rows away: whole sheets only");
   static thread_local unsigned epoch = 0;
   YhK k = yh_make_k(p);
-  const long long ncell = (long long)p->nx * p->ny;
+  k.row0 = row0; k.row1 = row1;
+  const long long ncell = (long long)p->nx * (row1 - row0);
   const int nchunks = (int)((ncell + TIP_CHUNK - 1) / TIP_CHUNK);
   unsigned long long *state = nullptr;
   rc = yh_workspace(((size_t)nchunks + 1) * sizeof(unsigned long long), (void **)&state, 1);
@@ -244,6 +251,15 @@ extern "C" int yh_tip_track(const yh_params *p, const double *u_past, const doub
   tip_kernel<<<nchunks, TIP_THREADS, 0, (cudaStream_t)stream>>>(k, a);
   YH_LAUNCH_CHECK();
   return YH_OK;
+}
+
+extern "C" int yh_tip_track(const yh_params *p, const double *u_past, const double *u_present,
+                            uint8_t *tip_plot, int *tip_count, yh_tip *tip_vector, int capacity,
+                            double physical_time, int algorithm, void *stream) {
+  YH_REQUIRE(p != nullptr, "null pointer");
+  YH_REQUIRE(p->jg0 == 0 && p->ny_global == p->ny, "whole sheets only (row slabs: yh_tip_track_rows)");
+  return yh_tip_track_rows(p, u_past, u_present, tip_plot, tip_count, tip_vector, capacity, physical_time,
+                           algorithm, 0, p->ny, stream);
 }
 
 // Same pass for the device-resident SR loop, replayable from a CUDA graph: the time tag is

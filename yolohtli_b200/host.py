@@ -95,6 +95,14 @@ def tip_track(p, u_past, u_present, tip_count, tip_vector, tip_plot=None, t=0.0,
                              _ptr(tip_count), _ptr(tip_vector), capacity, float(t), alg, _stream()))
 
 
+def tip_track_rows(p, u_past, u_present, tip_count, tip_vector, rows, t=0.0, algorithm=None,
+                   capacity=TIPVECSIZE):
+    """Row-slab form of tip_track: cells of local rows [rows[0], rows[1]), global coordinates."""
+    alg = algorithm if algorithm is not None else p.tipAlgorithm
+    check(lib().yh_tip_track_rows(C.byref(p), _ptr(u_past), _ptr(u_present), None, _ptr(tip_count),
+                                  _ptr(tip_vector), capacity, float(t), alg, rows[0], rows[1], _stream()))
+
+
 def tips_to_numpy(tip_count, tip_vector):
     n = int(tip_count.item())
     raw = tip_vector[: n * 20].cpu().numpy().tobytes()
@@ -132,6 +140,25 @@ def sr_integrals(p, u, v, velTan_u, velTan_v, adv_x, adv_y, tip_count=None, tip_
     return np.array(out[:], dtype=np.float64)
 
 
+def sr_disc_slots(p):
+    return lib().yh_sr_disc_slots(C.byref(p))
+
+
+def sr_integral_rows(p, u, v, velTan_u, velTan_v, adv_x, adv_y, centre, rows, rows_d):
+    """Row-slab form of sr_integrals, part 1: row sums of the owned disc rows -> rows_d (device)."""
+    assert rows_d.numel() >= 12 * sr_disc_slots(p)
+    check(lib().yh_sr_integral_rows(C.byref(p), _ptr(u), _ptr(v), _ptr(velTan_u), _ptr(velTan_v),
+                                    _ptr(adv_x), _ptr(adv_y), float(centre[0]), float(centre[1]),
+                                    rows[0], rows[1], _ptr(_f64(rows_d)), _stream()))
+
+
+def sr_integrals_close(p, rows_d):
+    """Part 2: the 12 integrals (host) from row sums assembled over all slabs."""
+    out = (C.c_double * 12)()
+    check(lib().yh_sr_integrals_close(C.byref(p), _ptr(_f64(rows_d)), out, _stream()))
+    return np.array(out[:], dtype=np.float64)
+
+
 def _d3(a):
     return (C.c_double * 3)(*[float(x) for x in a])
 
@@ -158,6 +185,12 @@ def advect_bfecc_cphi(p, u_in, v_in, u_out, v_out, c, phi, adv_x=None, adv_y=Non
     check(lib().yh_advect_bfecc_cphi(C.byref(p), _ptr(u_in), _ptr(v_in), _ptr(u_out), _ptr(v_out),
                                      _d3(c), _d3(phi), _ptr(adv_x), _ptr(adv_y), _ptr(solid),
                                      _stream()))
+
+
+def advect_bfecc_cphi_rows(p, u_in, v_in, u_out, v_out, c, phi, rows, adv_x=None, adv_y=None, solid=None):
+    check(lib().yh_advect_bfecc_cphi_rows(C.byref(p), _ptr(u_in), _ptr(v_in), _ptr(u_out), _ptr(v_out),
+                                          _d3(c), _d3(phi), _ptr(adv_x), _ptr(adv_y), _ptr(solid),
+                                          rows[0], rows[1], _stream()))
 
 
 def sapd(p, count, uold, unew, APD1, APD2, sAPD, dAPD, back, front, first, stimArea=None,

@@ -235,6 +235,107 @@ class SlabRunner:
             left -= n
             self.count += n
 
+    # -- symmetry-reduction (co-moving frame) steps on row slabs: SURVEY 8e, "SR mode" ------------
+    # One step (main.cu:894-954; yh_sim_run_sr on a whole sheet) needs timeIntOrder + 3 ghost rows:
+    #   exchange ghosts of (u, v)^n
+    #   RD            rows own-3 .. own+3 -> (u*, v*), velTan                       [yh_rd_step]
+    #   tips          owned rows, u^n vs u*; every rank learns the LAST tip of the    [yh_tip_track_rows]
+    #                 concatenated list (slabs are contiguous in j, so rank order = cell order)
+    #   integrals     row sums of the owned disc rows; element-wise sum over ranks    [yh_sr_integral_rows]
+    #                 (one non-zero contributor per row: exact), canonical closing    [yh_sr_integrals_close]
+    #   solve         3x3 on the host of EVERY rank (same 12 numbers -> same c)       [yh_solve_matrix]
+    #   BFECC         owned rows of u* -> (u, v)^{n+1} in the frame moving with c     [yh_advect_bfecc_cphi_rows]
+    # Written as a generator that yields at the three communication points so that the same text
+    # runs over torch.distributed (advance_sr) and, for tests, over N runners emulated in one
+    # process (advance_sr_emulated).  N slabs == the whole-sheet yh_sim_run_sr bit for bit.
+    def sr_setup(self, tip_capacity=65536):
+        need = self.K + 3
+        if self.world > 1 and self.halo < need:
+            raise ValueError(f"symmetry-reduction steps need {need} ghost rows (timeIntOrder + 3), have {self.halo}")
+        shape = (self.lay.ny_local, self.nx)
+        z = lambda: torch.zeros(shape, dtype=torch.float64, device=self.device)   # noqa: E731
+        self.vt = [z(), z()]            # velTan and the advection field start at zero (main.cu:431-434)
+        self.adv = [z(), z()]
+        self.tip_capacity = tip_capacity
+        self.tip_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.tip_vec = torch.zeros(tip_capacity * 20, dtype=torch.uint8, device=self.device)
+        self.sr_rows = torch.zeros(12 * host.sr_disc_slots(self.p), dtype=torch.float64, device=self.device)
+        self.c = [0.0, 0.0, 0.0]
+        self.phi = [0.0, 0.0, 0.0]
+        self.sr_count = 0
+        self.sr_tips = []               # this rank's tips of the last step (numpy records)
+
+    def _sr_local_tip_info(self):
+        """[n, x_last, y_last] of this rank's list (float32 values carried exactly in float64)."""
+        n = int(self.tip_count.item())
+        if n > self.tip_capacity:
+            raise RuntimeError("tip list overflow on a slab")
+        info = torch.zeros(3, dtype=torch.float64)
+        info[0] = n
+        self.sr_tips = host.tips_to_numpy(self.tip_count, self.tip_vec)
+        if n > 0:
+            info[1], info[2] = float(self.sr_tips[-1]["x"]), float(self.sr_tips[-1]["y"])
+        return info
+
+    def _sr_steps(self, nsteps, record):
+        l, p = self.lay, self.p
+        own = (l.own_lo, l.own_hi)
+        for it in range(nsteps):
+            if self.world > 1:
+                yield ("exchange", None)
+            c, o = self.cur, self.cur ^ 1
+            rows_rd = (max(0, l.own_lo - 3), min(l.ny_local, l.own_hi + 3))
+            host.rd_step(p, self.u[c], self.v[c], self.u[o], self.v[o], velTan=(self.vt[0], self.vt[1]),
+                         solid=self.solid, rows=rows_rd)
+            host.tip_track_rows(p, self.u[o], self.u[c], self.tip_count, self.tip_vec, own,
+                                t=p.dt * self.sr_count, capacity=self.tip_capacity)
+            infos = yield ("gather", self._sr_local_tip_info())
+            centre = (p.tipx0, p.tipy0)        # count == 0, or no tip anywhere (defect B3: keep the centre)
+            if self.sr_count != 0:
+                for info in infos:             # rank order = ascending j: the last non-empty list wins
+                    if info[0] > 0:
+                        centre = (float(info[1]), float(info[2]))
+            if record is not None:
+                record.append(list(self.c) + list(self.phi))          # main.cu:902-903
+            passes = 2 if self.sr_count == 0 else 1                    # first step: main.cu:910-921
+            for k in range(passes):
+                host.sr_integral_rows(p, self.u[c], self.v[c], self.vt[0], self.vt[1], self.adv[0], self.adv[1],
+                                      centre, own, self.sr_rows)
+                yield ("sum", self.sr_rows)
+                I = host.sr_integrals_close(p, self.sr_rows)
+                self.c = list(host.solve_matrix(self.c, self.phi, I))
+                if passes == 2 and k == 0:
+                    host.cxy_field(p, self.adv[0], self.adv[1], self.c, self.phi, solid=self.solid)
+            host.advect_bfecc_cphi_rows(p, self.u[o], self.v[o], self.u[c], self.v[c], self.c, self.phi, own,
+                                        adv_x=self.adv[0], adv_y=self.adv[1], solid=self.solid)
+            self.phi = [self.phi[q] + self.c[q] * p.dt for q in range(3)]   # main.cu:936-938
+            self.sr_count += 1
+            self.count += 1
+
+    def advance_sr(self, nsteps, record=None):
+        """nsteps symmetry-reduction steps over torch.distributed; record (a list) receives
+        [c, phi] per step as pushed to clist / philist."""
+        gen = self._sr_steps(nsteps, record)
+        reply = None
+        while True:
+            try:
+                what, arg = gen.send(reply)
+            except StopIteration:
+                return
+            reply = None
+            if what == "exchange":
+                self.exchange()
+            elif what == "gather":
+                t = arg.to(self.device) if self.device.type == "cuda" else arg
+                out = [torch.zeros_like(t) for _ in range(self.world)]
+                if self.world > 1:
+                    dist.all_gather(out, t)
+                else:
+                    out = [t]
+                reply = [x.cpu() for x in out]
+            elif what == "sum" and self.world > 1:
+                dist.all_reduce(arg, op=dist.ReduceOp.SUM)
+
     # -- overlapped schedule ----------------------------------------------------------------
     #   edge stream (high priority):  wait ghosts(k), interior(k-1) -> step edge rows -> NCCL
     #                                 send/recv of the fresh edge rows = ghosts(k+1)
@@ -284,3 +385,42 @@ class SlabRunner:
                     self.exchange()                          # fresh edge rows -> neighbours' ghosts
         main.wait_event(ev_edge)
         main.wait_stream(edge)
+
+
+def advance_sr_emulated(runners, nsteps, records=None):
+    """The symmetry-reduction steps of N SlabRunners (world = N, ranks 0..N-1, one process, one
+    device): the same per-rank text as SlabRunner.advance_sr with the three collectives served
+    locally -- ghost rows copied between the runners' buffers, tip infos gathered in rank order,
+    row sums added element-wise.  Test vehicle for the multi-GPU logic on a single GPU."""
+    n = len(runners)
+    gens = [r._sr_steps(nsteps, None if records is None else records[i]) for i, r in enumerate(runners)]
+    replies = [None] * n
+    while True:
+        reqs = []
+        for i, g in enumerate(gens):
+            try:
+                reqs.append(g.send(replies[i]))
+            except StopIteration:
+                reqs.append(None)
+        if all(q is None for q in reqs):
+            return
+        assert all(q is not None for q in reqs) and len({q[0] for q in reqs}) == 1, "ranks out of step"
+        what = reqs[0][0]
+        replies = [None] * n
+        if what == "exchange":
+            for i, r in enumerate(runners):
+                l, H = r.lay, r.halo
+                if l.down is not None:
+                    d = runners[l.down]
+                    for a, b in ((r.u[r.cur], d.u[d.cur]), (r.v[r.cur], d.v[d.cur])):
+                        b[d.lay.own_lo - H:d.lay.own_lo] = a[l.own_hi - H:l.own_hi]
+                        a[l.own_hi:l.own_hi + H] = b[d.lay.own_lo:d.lay.own_lo + H]
+        elif what == "gather":
+            infos = [q[1].clone() for q in reqs]
+            replies = [infos] * n
+        elif what == "sum":
+            total = reqs[0][1].clone()
+            for q in reqs[1:]:
+                total += q[1]
+            for q in reqs:
+                q[1].copy_(total)
