@@ -64,8 +64,19 @@ __device__ __forceinline__ double rk_Iv(const YhK &k, double u, double v) {
   return -(k.eps * (DEF ? yv : yv - k.theta));
 }
 
+// Runge-Kutta tables (reactionDiffusion.cu:71-86) as the reference's literals: a_{k+1} (weight of
+// du_k in the next stage state) and w_k, stage-indexed, for RK4 | RK2 | Euler.  In constant memory:
+// an indexed local array lands in local memory (ncu: 5.9 M local loads per launch), and selecting
+// the literals arithmetically from the stage index cost ~10 FSEL/ISETP per row (ncu source page).
+__constant__ double RK_A_NEXT[8] = {0.5, 0.5, 1.0, 0.0, /*RK2*/ 0.5, 0.0, /*Euler*/ 0.0, 0.0};
+__constant__ double RK_W[8] = {0.166666666666667, 0.333333333333333, 0.333333333333333, 0.166666666666667,
+                               /*RK2*/ 0.0, 1.0, /*Euler*/ 1.0, 0.0};
+
 // K stages, strip of W columns.  Arrays of one ring row: U V Ju Jv ru rv (6 x PITCH doubles).
-template <int K, int W, bool LAP4, bool SOLID, bool DEF>
+// GD: gateDiff known at compile time (1 / 0) or read from the parameters (-1); the default mode is
+// instantiated with GD = 1 so that the u and v halves of a stage form ONE basic block (ptxas does not
+// schedule across the branch: ncu showed the v half as a serial dependency chain).
+template <int K, int W, bool LAP4, bool SOLID, bool DEF, int GD>
 __global__ void __launch_bounds__((K + 1) * (W / 2) + 32)
 rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
   constexpr int H = (K + 1) & ~1;        // halo columns each side (even: 16-byte alignment)
@@ -138,20 +149,10 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
   const bool left_edge = (gx == 0), right_edge = (gx + 2 == nx);
   const int cc = c + 2;                  // column offset inside a padded ring row
 
-  // Runge-Kutta tables (reactionDiffusion.cu:71-86): ki = {0, .5, .5, 1}, w = {1/6, 1/3, 1/3, 1/6}
-  // as literals; selected arithmetically -- an indexed local array lands in local memory and was
-  // re-read every row (ncu: 5.9 M local loads per launch, long-scoreboard stalls).
-  double a_next = 0.0, w_k = 0.0;
-  const int st = g - 1;                  // stage index of this group
-  if (K == 4) {
-    a_next = (st == 2) ? 1.0 : ((st == 0 || st == 1) ? 0.5 : 0.0);
-    w_k = (st == 0 || st == 3) ? 0.166666666666667 : ((st == 1 || st == 2) ? 0.333333333333333 : 0.0);
-  } else if (K == 2) {
-    if (st == 0) { a_next = 0.5; w_k = 0.0; }
-    if (st == 1) { a_next = 0.0; w_k = 1.0; }
-  } else {   // Euler
-    w_k = 1.0;
-  }
+  const int st = g - 1;                  // stage index of this group (-1: group P)
+  const int rk_i = (K == 4 ? 0 : (K == 2 ? 4 : 6)) + (st > 0 ? st : 0);
+  const double a_next = RK_A_NEXT[rk_i], w_k = RK_W[rk_i];
+  const bool gd = GD < 0 ? (k.gateDiff != 0) : (GD != 0);
 
   // rows each group handles (empty for out-of-domain columns)
   int lo_g, hi_g;
@@ -175,13 +176,21 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
     const double *p = Ak + ((row - c0) & (NRA - 1)) * ROWA;
     R.u = *reinterpret_cast<const double2 *>(p);
     R.v = *reinterpret_cast<const double2 *>(p + PITCH);
+    // W of x=0 / E of x=nx-1: the producer of the row stored the mirror value (x=1 / x=nx-2) in the
+    // pad column (store_pads), so no select sits between this load and the stencil
     R.uw = p[-1]; R.ue = p[2]; R.vw = p[PITCH - 1]; R.ve = p[PITCH + 2];
-    if (left_edge) { R.uw = R.u.y; R.vw = R.v.y; }      // mirror: W of x=0 is x=1
-    if (right_edge) { R.ue = R.u.x; R.ve = R.v.x; }     // mirror: E of x=nx-1 is x=nx-2
     if (LAP4) {
       R.ju = *reinterpret_cast<const double2 *>(p + 2 * PITCH);
       R.jv = *reinterpret_cast<const double2 *>(p + 3 * PITCH);
     }
+  };
+
+  // No-flux mirror in x, once per produced row instead of once per read: the thread that owns x=0
+  // also writes its x=1 values into the column of x=-1 (owned by an out-of-domain, idle thread), the
+  // one that owns x=nx-1 its x=nx-2 values into the column of x=nx.
+  auto store_pads = [&](double *d, const double2 &u, const double2 &v, const double2 &ju, const double2 &jv) {
+    if (left_edge) { d[-1] = u.y; d[PITCH - 1] = v.y; d[2 * PITCH - 1] = ju.y; d[3 * PITCH - 1] = jv.y; }
+    if (right_edge) { d[2] = u.x; d[PITCH + 2] = v.x; d[2 * PITCH + 2] = ju.x; d[3 * PITCH + 2] = jv.x; }
   };
 
   auto p_step = [&](int m) {   // ---- P: stage-0 state u0 + (0.0*0.0) and its currents ----
@@ -200,6 +209,7 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
     *reinterpret_cast<double2 *>(d + PITCH) = v;
     *reinterpret_cast<double2 *>(d + 2 * PITCH) = ju;
     *reinterpret_cast<double2 *>(d + 3 * PITCH) = jv;
+    store_pads(d, u, v, ju, jv);
     if (SOLID) {
       const int ny = k.nyg;
       const uint8_t *mc = a.solid + (size_t)m * nx;
@@ -248,7 +258,7 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
         if (f == 0) {
           d0 = (x0 * k.rx + y0 * k.ry);
           d1 = (x1 * k.rx + y1 * k.ry);
-        } else if (k.gateDiff) {
+        } else if (gd) {
           d0 = (x0 * k.rx * k.rscale + y0 * k.ry * k.rscale);
           d1 = (x1 * k.rx * k.rscale + y1 * k.ry * k.rscale);
         } else {
@@ -258,7 +268,7 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
         // 2.0*C is exact, so fma(-2.0, C, w) == w - 2.0*C bit for bit
         d0 = ((fma(-2.0, Cc.x, Wv) + Cc.y) * k.rx + (fma(-2.0, Cc.x, Nn.x) + Ss.x) * k.ry);
         d1 = ((fma(-2.0, Cc.y, Cc.x) + Ev) * k.rx + (fma(-2.0, Cc.y, Nn.y) + Ss.y) * k.ry);
-      } else if (k.gateDiff) {
+      } else if (gd) {
         d0 = ((fma(-2.0, Cc.x, Wv) + Cc.y) * k.rx * k.rscale + (fma(-2.0, Cc.x, Nn.x) + Ss.x) * k.ry * k.rscale);
         d1 = ((fma(-2.0, Cc.y, Cc.x) + Ev) * k.rx * k.rscale + (fma(-2.0, Cc.y, Nn.y) + Ss.y) * k.ry * k.rscale);
       } else {
@@ -267,13 +277,11 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
       double2 Jc;
       if (LAP4) Jc = f ? C.jv : C.ju;
       else Jc = *reinterpret_cast<const double2 *>(pc + (2 + f) * PITCH);
-      if (LAP4 && (f == 0 || k.gateDiff)) {
+      if (LAP4 && (f == 0 || gd)) {
         const double SWv = f ? S.vw : S.uw, SEv = f ? S.ve : S.ue;
         const double NWv = f ? N.vw : N.uw, NEv = f ? N.ve : N.ue;
         const double2 Js = f ? S.jv : S.ju, Jn = f ? N.jv : N.ju;
-        double JW = pc[(2 + f) * PITCH - 1], JE = pc[(2 + f) * PITCH + 2];
-        if (left_edge) JW = Jc.y;
-        if (right_edge) JE = Jc.x;
+        const double JW = pc[(2 + f) * PITCH - 1], JE = pc[(2 + f) * PITCH + 2];   // mirrored by store_pads
         if (f == 0) {   // reactionDiffusion.cu:221-229
           d0 += m2q * (+(Wv - Cc.x + Cc.y) + (Nn.x - Cc.x + Ss.x));
           d1 += m2q * (+(Cc.x - Cc.y + Ev) + (Nn.y - Cc.y + Ss.y));
@@ -320,6 +328,7 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
       *reinterpret_cast<double2 *>(d + 3 * PITCH) = jv;
       *reinterpret_cast<double2 *>(d + 4 * PITCH) = ru;
       *reinterpret_cast<double2 *>(d + 5 * PITCH) = rv;
+      store_pads(d, un, vn, ju, jv);
     } else if (out_col) {
       double2 uo, vo;   // :512-513
       uo.x = u0.x + k.tc * ru.x; uo.y = u0.y + k.tc * ru.y;
@@ -332,7 +341,7 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
       const size_t o = (size_t)m * nx + gx;
       *reinterpret_cast<double2 *>(a.u_out + o) = uo;
       *reinterpret_cast<double2 *>(a.v_out + o) = vo;
-      if (a.vtu && k.gateDiff) {   // :551-552
+      if (a.vtu && gd) {   // :551-552
         double2 tu, tv;
         tu.x = sc0 ? ru.x / k.dt : 0.0; tu.y = sc1 ? ru.y / k.dt : 0.0;   // :529-530
         tv.x = sc0 ? rv.x / k.dt : 0.0; tv.y = sc1 ? rv.y / k.dt : 0.0;
@@ -379,7 +388,7 @@ static int pick_ry_rk(int rows, int strips, int K, int slots) {
   return best_ry;
 }
 
-template <int K, int W, bool LAP4, bool SOLID, bool DEF>
+template <int K, int W, bool LAP4, bool SOLID, bool DEF, int GD>
 int launch2(const YhK &k, RkArgs a, cudaStream_t st) {
   constexpr int PITCH = W + 4, BX = W - 2 * ((K + 1) & ~1);
   constexpr int NT = (K + 1) * (W / 2) + 32;
@@ -390,9 +399,9 @@ int launch2(const YhK &k, RkArgs a, cudaStream_t st) {
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    YH_CUDA(cudaFuncSetAttribute(rd_rk_stream<K, W, LAP4, SOLID, DEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    YH_CUDA(cudaFuncSetAttribute(rd_rk_stream<K, W, LAP4, SOLID, DEF, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1, sms = 148;
-    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_rk_stream<K, W, LAP4, SOLID, DEF>, NT, smem));
+    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_rk_stream<K, W, LAP4, SOLID, DEF, GD>, NT, smem));
     YH_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     slots[dev & 63] = (per_sm > 0 ? per_sm : 1) * sms;
     attr_set[dev & 63] = true;
@@ -402,7 +411,7 @@ int launch2(const YhK &k, RkArgs a, cudaStream_t st) {
   const char *force_ry = getenv("YH_RK_RY");
   a.RY = force_ry ? atoi(force_ry) : pick_ry_rk(rows, strips, K, slots[dev & 63]);
   dim3 grd(strips, (rows + a.RY - 1) / a.RY);
-  rd_rk_stream<K, W, LAP4, SOLID, DEF><<<grd, NT, smem, st>>>(k, a);
+  rd_rk_stream<K, W, LAP4, SOLID, DEF, GD><<<grd, NT, smem, st>>>(k, a);
   YH_LAUNCH_CHECK();
   return YH_OK;
 }
@@ -410,7 +419,11 @@ int launch2(const YhK &k, RkArgs a, cudaStream_t st) {
 template <int K, int W, bool LAP4, bool SOLID>
 int launch(const YhK &k, RkArgs a, cudaStream_t st) {
   const bool def = (k.mu == 1.0) && (k.delta == 1.0) && (k.gamma == 0.0) && (k.theta == 0.0);
-  return def ? launch2<K, W, LAP4, SOLID, true>(k, a, st) : launch2<K, W, LAP4, SOLID, false>(k, a, st);
+  if (K == 4 && LAP4 && !SOLID && k.gateDiff) {   // the reference's default mode: gateDiff compiled in
+    constexpr int GD1 = (K == 4 && LAP4 && !SOLID) ? 1 : -1;   // (other modes never instantiate GD = 1)
+    return def ? launch2<K, W, LAP4, SOLID, true, GD1>(k, a, st) : launch2<K, W, LAP4, SOLID, false, GD1>(k, a, st);
+  }
+  return def ? launch2<K, W, LAP4, SOLID, true, -1>(k, a, st) : launch2<K, W, LAP4, SOLID, false, -1>(k, a, st);
 }
 
 }  // namespace
