@@ -24,6 +24,12 @@ struct RkArgs {
   double *u_out, *v_out, *vtu, *vtv;
   const uint8_t *solid;   // SOLID variants: 1 = tissue (main.cu:676-680), local rows
   int RY;
+  // loop-invariant products of the 4th-order terms, formed on the host with the kernel's own
+  // operations (IEEE, no contraction): in registers they were rematerialised every row (ncu)
+  double q4;              // qx4 + qy4
+  double m2q;             // -2.0*( qx4+qy4 )                    (:221)
+  double mrs2q4;          // (-rscale*2.0)*( qx4+qy4 )           (:235)
+  double rsq;             // rscale*( qx4+qy4 )                  (:239)
 };
 
 // Obstacle masks (reactionDiffusion.cu:154-184): the six stencil coefficients of a cell depend
@@ -51,10 +57,15 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Ionic currents (reactionDiffusion.cu:131-141).  DEF = the reference's default constants
 // mu = delta = 1, gamma = theta = 0: 1.0*x == x and x - 0.0 == x exactly, so those operations
 // are dropped without changing a bit.
-template <bool DEF>
+// NOSTIM: the caller knows the stimulus is off; the negation is then the last operation before the
+// value goes to shared memory, and flipping the sign bit (ALU pipe) gives the bits of -(x) for every
+// non-NaN x without an instruction on the FP64 pipe (ptxas emits DADD -RZ, -x otherwise).
+template <bool DEF, bool NOSTIM>
 __device__ __forceinline__ double rk_Isum(const YhK &k, double u, double v, bool scs) {
   const double mu_u = DEF ? u : k.mu * u;
-  const double I = -(mu_u * (1.0 - u) * (u - k.alpha) - u * v);
+  const double t = mu_u * (1.0 - u) * (u - k.alpha) - u * v;
+  if (NOSTIM) return __hiloint2double(__double2hiint(t) ^ (int)0x80000000, __double2loint(t));
+  const double I = -t;
   return scs ? I - 24.7 : I;   // x - 0.0 == x
 }
 template <bool DEF>
@@ -73,10 +84,12 @@ __constant__ double RK_W[8] = {0.166666666666667, 0.333333333333333, 0.333333333
                                /*RK2*/ 0.0, 1.0, /*Euler*/ 1.0, 0.0};
 
 // K stages, strip of W columns.  Arrays of one ring row: U V Ju Jv ru rv (6 x PITCH doubles).
-// GD: gateDiff known at compile time (1 / 0) or read from the parameters (-1); the default mode is
-// instantiated with GD = 1 so that the u and v halves of a stage form ONE basic block (ptxas does not
-// schedule across the branch: ncu showed the v half as a serial dependency chain).
-template <int K, int W, bool LAP4, bool SOLID, bool DEF, int GD>
+// FAST: gateDiff on and the live stimulus off, known at compile time (the reference's default mode
+// is instantiated this way): the u and v halves of a stage and the next stage's currents then form
+// ONE basic block -- ptxas does not schedule across the (uniform) branches, and ncu showed the v
+// half and the current evaluation as serial dependency chains.  FAST = false reads both switches
+// from the parameters.
+template <int K, int W, bool LAP4, bool SOLID, bool DEF, bool FAST>
 __global__ void __launch_bounds__((K + 1) * (W / 2) + 32)
 rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
   constexpr int H = (K + 1) & ~1;        // halo columns each side (even: 16-byte alignment)
@@ -152,7 +165,7 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
   const int st = g - 1;                  // stage index of this group (-1: group P)
   const int rk_i = (K == 4 ? 0 : (K == 2 ? 4 : 6)) + (st > 0 ? st : 0);
   const double a_next = RK_A_NEXT[rk_i], w_k = RK_W[rk_i];
-  const bool gd = GD < 0 ? (k.gateDiff != 0) : (GD != 0);
+  const bool gd = FAST ? true : (k.gateDiff != 0);
 
   // rows each group handles (empty for out-of-domain columns)
   int lo_g, hi_g;
@@ -161,10 +174,7 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
   if (!col_ok) hi_g = lo_g;
   const int m_shift = (g == 0) ? 1 : 1 + 2 * g;   // row m = it + c0 - m_shift
 
-  const double q4 = k.qx4 + k.qy4;
-  const double m2q = -2.0 * q4;                    // -2.0*( qx4+qy4 )
-  const double mrs2 = -k.rscale * 2.0;             // -rscale*2.0  (then *q4, :235)
-  const double rsq = k.rscale * q4;                // rscale*( qx4+qy4 ) (:239)
+  const double q4 = a.q4, m2q = a.m2q, mrs2q4 = a.mrs2q4, rsq = a.rsq;
 
   // Source rows m-1, m, m+1 of this group's stage live in registers and rotate by renaming (loop
   // unrolled by three): per iteration only the new N row is read from shared memory -- the
@@ -200,8 +210,8 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
     double2 v = *reinterpret_cast<const double2 *>(r0 + PITCH);
     u.x += 0.0; u.y += 0.0; v.x += 0.0; v.y += 0.0;
     double2 ju, jv;
-    ju.x = rk_Isum<DEF>(k, u.x, v.x, yh_scs(k, gx, gj));
-    ju.y = rk_Isum<DEF>(k, u.y, v.y, yh_scs(k, gx + 1, gj));
+    ju.x = rk_Isum<DEF, FAST>(k, u.x, v.x, FAST ? false : yh_scs(k, gx, gj));
+    ju.y = rk_Isum<DEF, FAST>(k, u.y, v.y, FAST ? false : yh_scs(k, gx + 1, gj));
     jv.x = rk_Iv<DEF>(k, u.x, v.x);
     jv.y = rk_Iv<DEF>(k, u.y, v.y);
     double *d = A + ((m - c0) & (NRA - 1)) * ROWA + cc;
@@ -288,8 +298,8 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
           d0 += q4 * (SWv + Ss.y + NWv + Nn.y);
           d1 += q4 * (Ss.x + SEv + Nn.x + NEv);
         } else {        // :235-239
-          d0 += mrs2 * q4 * (+(Wv - Cc.x + Cc.y) + (Nn.x - Cc.x + Ss.x));
-          d1 += mrs2 * q4 * (+(Cc.x - Cc.y + Ev) + (Nn.y - Cc.y + Ss.y));
+          d0 += mrs2q4 * (+(Wv - Cc.x + Cc.y) + (Nn.x - Cc.x + Ss.x));
+          d1 += mrs2q4 * (+(Cc.x - Cc.y + Ev) + (Nn.y - Cc.y + Ss.y));
           d0 += rsq * (SWv + Ss.y + NWv + Nn.y);
           d1 += rsq * (Ss.x + SEv + Nn.x + NEv);
         }
@@ -317,8 +327,8 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
       double2 un, vn, ju, jv;
       un.x = u0.x + (a_next * du[0]); un.y = u0.y + (a_next * du[1]);
       vn.x = v0.x + (a_next * dv[0]); vn.y = v0.y + (a_next * dv[1]);
-      ju.x = rk_Isum<DEF>(k, un.x, vn.x, yh_scs(k, gx, gj));
-      ju.y = rk_Isum<DEF>(k, un.y, vn.y, yh_scs(k, gx + 1, gj));
+      ju.x = rk_Isum<DEF, FAST>(k, un.x, vn.x, FAST ? false : yh_scs(k, gx, gj));
+      ju.y = rk_Isum<DEF, FAST>(k, un.y, vn.y, FAST ? false : yh_scs(k, gx + 1, gj));
       jv.x = rk_Iv<DEF>(k, un.x, vn.x);
       jv.y = rk_Iv<DEF>(k, un.y, vn.y);
       double *d = A + (st + 1) * NRA * ROWA + slot * ROWA + cc;
@@ -388,7 +398,7 @@ static int pick_ry_rk(int rows, int strips, int K, int slots) {
   return best_ry;
 }
 
-template <int K, int W, bool LAP4, bool SOLID, bool DEF, int GD>
+template <int K, int W, bool LAP4, bool SOLID, bool DEF, bool FAST>
 int launch2(const YhK &k, RkArgs a, cudaStream_t st) {
   constexpr int PITCH = W + 4, BX = W - 2 * ((K + 1) & ~1);
   constexpr int NT = (K + 1) * (W / 2) + 32;
@@ -399,9 +409,9 @@ int launch2(const YhK &k, RkArgs a, cudaStream_t st) {
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    YH_CUDA(cudaFuncSetAttribute(rd_rk_stream<K, W, LAP4, SOLID, DEF, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    YH_CUDA(cudaFuncSetAttribute(rd_rk_stream<K, W, LAP4, SOLID, DEF, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1, sms = 148;
-    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_rk_stream<K, W, LAP4, SOLID, DEF, GD>, NT, smem));
+    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_rk_stream<K, W, LAP4, SOLID, DEF, FAST>, NT, smem));
     YH_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     slots[dev & 63] = (per_sm > 0 ? per_sm : 1) * sms;
     attr_set[dev & 63] = true;
@@ -411,7 +421,7 @@ int launch2(const YhK &k, RkArgs a, cudaStream_t st) {
   const char *force_ry = getenv("YH_RK_RY");
   a.RY = force_ry ? atoi(force_ry) : pick_ry_rk(rows, strips, K, slots[dev & 63]);
   dim3 grd(strips, (rows + a.RY - 1) / a.RY);
-  rd_rk_stream<K, W, LAP4, SOLID, DEF, GD><<<grd, NT, smem, st>>>(k, a);
+  rd_rk_stream<K, W, LAP4, SOLID, DEF, FAST><<<grd, NT, smem, st>>>(k, a);
   YH_LAUNCH_CHECK();
   return YH_OK;
 }
@@ -419,11 +429,11 @@ int launch2(const YhK &k, RkArgs a, cudaStream_t st) {
 template <int K, int W, bool LAP4, bool SOLID>
 int launch(const YhK &k, RkArgs a, cudaStream_t st) {
   const bool def = (k.mu == 1.0) && (k.delta == 1.0) && (k.gamma == 0.0) && (k.theta == 0.0);
-  if (K == 4 && LAP4 && !SOLID && k.gateDiff) {   // the reference's default mode: gateDiff compiled in
-    constexpr int GD1 = (K == 4 && LAP4 && !SOLID) ? 1 : -1;   // (other modes never instantiate GD = 1)
-    return def ? launch2<K, W, LAP4, SOLID, true, GD1>(k, a, st) : launch2<K, W, LAP4, SOLID, false, GD1>(k, a, st);
+  if (K == 4 && LAP4 && !SOLID && k.gateDiff && !k.stim) {   // the reference's default mode
+    constexpr bool F = (K == 4 && LAP4 && !SOLID);            // (other modes never instantiate FAST)
+    return def ? launch2<K, W, LAP4, SOLID, true, F>(k, a, st) : launch2<K, W, LAP4, SOLID, false, F>(k, a, st);
   }
-  return def ? launch2<K, W, LAP4, SOLID, true, -1>(k, a, st) : launch2<K, W, LAP4, SOLID, false, -1>(k, a, st);
+  return def ? launch2<K, W, LAP4, SOLID, true, false>(k, a, st) : launch2<K, W, LAP4, SOLID, false, false>(k, a, st);
 }
 
 }  // namespace
@@ -439,7 +449,15 @@ int yh_launch_rd_rk(const YhK &k, const double *u_in, const double *v_in, double
                     double *v_out, double *vtu, double *vtv, const uint8_t *solid, cudaStream_t st) {
   if (!yh_rd_rk_supported(k)) return YH_ERR_UNSUPPORTED;
   if (k.row1 <= k.row0) return YH_OK;
-  RkArgs a{u_in, v_in, u_out, v_out, vtu, vtv, solid, 0};
+  RkArgs a{u_in, v_in, u_out, v_out, vtu, vtv, solid, 0, 0.0, 0.0, 0.0, 0.0};
+  {
+    volatile double q4 = k.qx4 + k.qy4;          // volatile: every product is rounded to double here
+    volatile double m2q = -2.0 * q4;
+    volatile double mrs2 = -k.rscale * 2.0;
+    volatile double mrs2q4 = mrs2 * q4;
+    volatile double rsq = k.rscale * q4;
+    a.q4 = q4; a.m2q = m2q; a.mrs2q4 = mrs2q4; a.rsq = rsq;
+  }
   const char *force_w = getenv("YH_RK_W");
   const long long cells = (long long)k.nx * (k.row1 - k.row0);
   int W = cells >= (1ll << 23) ? 192 : (cells >= (1ll << 21) ? 128 : 64);
