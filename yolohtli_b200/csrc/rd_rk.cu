@@ -220,6 +220,10 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
     *reinterpret_cast<double2 *>(d + 2 * PITCH) = ju;
     *reinterpret_cast<double2 *>(d + 3 * PITCH) = jv;
     store_pads(d, u, v, ju, jv);
+    // the running rhs starts as 0.0 in the ring, so every stage group reads it the same way (no
+    // per-row select between "first stage" and the others in the heavy groups; P has cycles to spare)
+    *reinterpret_cast<double2 *>(d + 4 * PITCH) = make_double2(0.0, 0.0);
+    *reinterpret_cast<double2 *>(d + 5 * PITCH) = make_double2(0.0, 0.0);
     if (SOLID) {
       const int ny = k.nyg;
       const uint8_t *mc = a.solid + (size_t)m * nx;
@@ -312,11 +316,8 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
       else { dv[0] = d0; dv[1] = d1; }
     }
     // running rhs (:502-503)
-    double2 ru = make_double2(0.0, 0.0), rv = ru;
-    if (st > 0) {
-      ru = *reinterpret_cast<const double2 *>(pc + 4 * PITCH);
-      rv = *reinterpret_cast<const double2 *>(pc + 5 * PITCH);
-    }
+    double2 ru = *reinterpret_cast<const double2 *>(pc + 4 * PITCH);   // 0.0 from P for the first stage
+    double2 rv = *reinterpret_cast<const double2 *>(pc + 5 * PITCH);
     ru.x += (w_k * du[0]); ru.y += (w_k * du[1]);
     rv.x += (w_k * dv[0]); rv.y += (w_k * dv[1]);
     const double *r0 = R0 + ((m - c0) & (NR0 - 1)) * ROW0 + cc;
@@ -429,8 +430,8 @@ int launch2(const YhK &k, RkArgs a, cudaStream_t st) {
 template <int K, int W, bool LAP4, bool SOLID>
 int launch(const YhK &k, RkArgs a, cudaStream_t st) {
   const bool def = (k.mu == 1.0) && (k.delta == 1.0) && (k.gamma == 0.0) && (k.theta == 0.0);
-  if (K == 4 && LAP4 && !SOLID && k.gateDiff && !k.stim) {   // the reference's default mode
-    constexpr bool F = (K == 4 && LAP4 && !SOLID);            // (other modes never instantiate FAST)
+  if (K == 4 && k.gateDiff && !k.stim) {   // the reference's default switches (with or without masks / lap4)
+    constexpr bool F = (K == 4);           // (RK2 / Euler never instantiate FAST)
     return def ? launch2<K, W, LAP4, SOLID, true, F>(k, a, st) : launch2<K, W, LAP4, SOLID, false, F>(k, a, st);
   }
   return def ? launch2<K, W, LAP4, SOLID, true, false>(k, a, st) : launch2<K, W, LAP4, SOLID, false, false>(k, a, st);
