@@ -106,7 +106,10 @@ __device__ __forceinline__ void euler_cell(const YhK &k, double u, double v, dou
                                            double vS, bool scs, double &un, double &vn) {
   const double du = ((fma(-2.0, u, uW) + uE) * k.rx + (fma(-2.0, u, uN) + uS) * k.ry);
   double dv = 0.0;
-  if (k.gateDiff)
+  // DEF includes gateDiff == 1 (the reference's default, saveFiles.cu:126): a run-time branch here,
+  // uniform as it is, cuts the cell into basic blocks that ptxas schedules one by one -- the ncu
+  // source page showed each block as a serial DADD/DMUL chain waiting on its own latency
+  if (DEF || k.gateDiff)
     dv = ((fma(-2.0, v, vW) + vE) * k.rx * k.rscale + (fma(-2.0, v, vN) + vS) * k.ry * k.rscale);
   euler_finish<DEF>(k, u, v, du, dv, scs, un, vn);
 }
@@ -135,7 +138,7 @@ __device__ __forceinline__ void euler_cell_solid(const YhK &k, unsigned pat, dou
   t = sn ? uN : uS; ry_ = fma(-2.0, u, yb ? uN : t + t) + (yb ? uS : 0.0);
   const double du = (xany ? rx_ : 0.0) * k.rx + (yany ? ry_ : 0.0) * k.ry;
   double dv = 0.0;
-  if (k.gateDiff) {
+  if (DEF || k.gateDiff) {
     t = sw ? vW : vE; rx_ = fma(-2.0, v, xb ? vW : t + t) + (xb ? vE : 0.0);
     t = sn ? vN : vS; ry_ = fma(-2.0, v, yb ? vN : t + t) + (yb ? vS : 0.0);
     dv = (xany ? rx_ : 0.0) * k.rx * k.rscale + (yany ? ry_ : 0.0) * k.ry * k.rscale;
@@ -380,7 +383,8 @@ int launch2(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
 template <int T, int W>
 int launch(const YhK &k, const FastArgs &a, int nsims, bool canon, cudaStream_t st) {
   // DEF variant: every constant whose operation is an exact identity at the reference defaults
-  const bool tc1 = (k.tc == 1.0) && (k.mu == 1.0) && (k.delta == 1.0) && (k.gamma == 0.0) && (k.theta == 0.0);
+  const bool tc1 = (k.tc == 1.0) && (k.mu == 1.0) && (k.delta == 1.0) && (k.gamma == 0.0) && (k.theta == 0.0) &&
+                   (k.gateDiff != 0);   // the reference's default constants AND switches
   if (canon) return tc1 ? launch2<T, W, true, true>(k, a, nsims, st) : launch2<T, W, true, false>(k, a, nsims, st);
   return tc1 ? launch2<T, W, false, true>(k, a, nsims, st) : launch2<T, W, false, false>(k, a, nsims, st);
 }

@@ -309,7 +309,7 @@ rd_tile_euler(const __grid_constant__ YhK k, const __grid_constant__ TileArgs a)
       double du0 = ((fma(-2.0, uC.x, uw) + uC.y) * k.rx + (fma(-2.0, uC.x, uN.x) + uS.x) * k.ry);
       double du1 = ((fma(-2.0, uC.y, uC.x) + ue) * k.rx + (fma(-2.0, uC.y, uN.y) + uS.y) * k.ry);
       double dv0 = 0.0, dv1 = 0.0;
-      if (k.gateDiff) {
+      if (DEF || k.gateDiff) {   // DEF includes gateDiff == 1: no branch inside the step (see rd_fast.cu)
         const double2 vS = *reinterpret_cast<const double2 *>(iv + cs), vN = *reinterpret_cast<const double2 *>(iv + cn);
         const double vw = le ? vC.y : iv[c - 1], ve = re ? vC.x : iv[c + 2];
         dv0 = ((fma(-2.0, vC.x, vw) + vC.y) * k.rx * k.rscale + (fma(-2.0, vC.x, vN.x) + vS.x) * k.ry * k.rscale);
@@ -432,7 +432,7 @@ int yh_launch_rd_tile_euler(const YhK &k, int tb, const double *u_in, const doub
   if (!yh_rd_fast_supported(k, tb)) return YH_ERR_UNSUPPORTED;
   if (k.row1 <= k.row0) return YH_OK;
   TileArgs a{u_in, v_in, u_out, v_out, nullptr, nullptr, sim_stride, period_d, duration_it, count0, trace, slot};
-  const bool def = is_def(k) && k.tc == 1.0;
+  const bool def = is_def(k) && k.tc == 1.0 && k.gateDiff != 0;
 #define YH_E(TT) (def ? launch_euler<TT, true>(k, a, nsims, st) : launch_euler<TT, false>(k, a, nsims, st))
   switch (tb) {
     case 1: return YH_E(1);
