@@ -82,22 +82,43 @@ def make_params(yh, a):
     return yh.default_params(a.nx, a.ny, scale_L=True, **over)
 
 
+def timing_oracle(oracle_lib):
+    """The plain-C oracle rebuilt for SPEED on this host (SURVEY 8d: gcc -O3 -march=native -fopenmp;
+    contraction allowed -- this build is only timed, parity uses the -ffp-contract=off one).  Built at
+    run time because -march=native must match the box the baseline runs on; falls back to the parity
+    build when no compiler is around."""
+    src = os.path.join(ROOT, "oracle", "yh_oracle.c")
+    out_dir = os.path.join(ROOT, "oracle", "_fast")
+    so = os.path.join(out_dir, "libyh_oracle_fast.so")
+    flags = "-O3 -march=native -fopenmp"
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.run(["gcc"] + flags.split() + ["-fPIC", "-std=c11", "-shared", "-o", so, src, "-lm"],
+                       check=True, capture_output=True, timeout=120)
+        return oracle_lib.Oracle(so), f"gcc {flags}, built on this host"
+    except Exception:
+        return oracle_lib.load(), "gcc -O2 -fopenmp -ffp-contract=off (parity build; no compiler at run time)"
+
+
 def cpu_baseline(a, oracle_lib):
     """Plain-C oracle (OpenMP, all host cores) on a bounded sample of the same workload."""
     from yolohtli_b200 import synth
-    o = oracle_lib.load()
+    o, how = timing_oracle(oracle_lib)
     n = min(a.nx, 4096)
     over = dict(timeIntOrder=1, lap4=0) if a.mode == "euler5" else {}
     p = o.params_default(n, n, scale_L=True, **over)
     u, v = synth.fibrillation_ic(n, n)
-    steps = 24 if a.mode == "euler5" else 4
     o.rd_advance(p, 2, u, v)   # warm-up (page faults, thread pool)
+    t0 = time.perf_counter()
+    o.rd_advance(p, 4, u, v)   # calibration: size the sample for ~12 s of CPU work
+    per_step = (time.perf_counter() - t0) / 4
+    steps = int(max(8, min(4000, 12.0 / max(per_step, 1e-4))))
     t0 = time.perf_counter()
     o.rd_advance(p, steps, u, v)
     dt = time.perf_counter() - t0
     return {"value": n * n * steps / dt / 1e9, "unit": METRIC, "cores": o.threads(), "kind": "port",
             "sample": f"{n}x{n} tile of the same fibrillation IC, {steps} steps, plain-C oracle "
-                      f"(gcc -O2 -fopenmp -ffp-contract=off), wall clock {dt:.2f} s"}
+                      f"({how}), wall clock {dt:.2f} s"}
 
 
 def run_reference(a):
