@@ -123,6 +123,48 @@ def test_sr_step_collectives_over_gloo(tmp_path):
     assert all(os.path.exists(os.path.join(str(tmp_path), f"ok{r}")) for r in range(world))
 
 
+def test_sr_emulation_harness_serves_the_same_collectives():
+    """advance_sr_emulated (the one-process vehicle of tests/test_gpu_sr_slabs.py) answers the three
+    communication points exactly like the torch.distributed driver: ghost rows from the neighbours,
+    tip infos in rank order, element-wise row sums."""
+    from tests import oracle_lib
+    from yolohtli_b200.slab import SlabRunner, advance_sr_emulated
+    oracle = oracle_lib.load()
+    nx, ny, H, world = 16, 45, 7, 3
+    pg = oracle.params_default(nx, ny)
+    glob = np.arange(ny * nx, dtype=np.float64).reshape(ny, nx)
+    runners, seen = [], []
+    for rank in range(world):
+        run = SlabRunner(pg, rank=rank, world=world, halo=H, device=torch.device("cpu"), stepper=lambda *a: None)
+        l = run.lay
+        run.u[run.cur][l.own_lo:l.own_hi] = torch.from_numpy(glob[l.j0:l.j1])
+        run.v[run.cur][l.own_lo:l.own_hi] = torch.from_numpy(-glob[l.j0:l.j1])
+        got = {}
+
+        def fake_steps(nsteps, record, run=run, rank=rank, got=got):
+            yield ("exchange", None)
+            got["u"], got["v"] = run.u[run.cur].clone(), run.v[run.cur].clone()
+            infos = yield ("gather", torch.tensor([float(rank + 1), 10.0 * rank, 0.5], dtype=torch.float64))
+            got["infos"] = torch.stack(infos)
+            rows = torch.zeros(24, dtype=torch.float64)
+            rows[rank::world] = 1.0 + rank
+            yield ("sum", rows)
+            got["rows"] = rows.clone()
+
+        run._sr_steps = fake_steps
+        runners.append(run)
+        seen.append(got)
+    advance_sr_emulated(runners, 1)
+    want_rows = torch.zeros(24, dtype=torch.float64)
+    for r in range(world):
+        want_rows[r::world] = 1.0 + r
+    for run, got in zip(runners, seen):
+        l = run.lay
+        assert torch.equal(got["u"], torch.from_numpy(glob[l.g0:l.g1])) and torch.equal(got["v"], torch.from_numpy(-glob[l.g0:l.g1]))
+        assert got["infos"][:, 0].tolist() == [1.0, 2.0, 3.0]
+        assert torch.equal(got["rows"], want_rows)
+
+
 def test_partition_covers_domain():
     from yolohtli_b200.slab import SlabLayout, partition
     for ny, world in [(16384, 8), (67, 3), (1000, 7)]:
