@@ -15,14 +15,27 @@ from tests import oracle_lib  # noqa: E402
 from yolohtli_b200 import host, synth  # noqa: E402
 
 
-@pytest.fixture(params=["stream", "tile"], autouse=True)
+@pytest.fixture(params=["stream", "tile", "quad"], autouse=True)
 def rd_path(request):
-    """Every test of this module runs twice: forced through the streaming kernels (rd_fast.cu /
-    rd_rk.cu) and forced through the shared-memory tile kernels (rd_tile.cu) where they apply."""
+    """Every test of this module runs three times: forced through the streaming kernels with a column
+    pair per thread (rd_fast.cu / rd_rk.cu), through the shared-memory tile kernels (rd_tile.cu) where
+    they apply, and through the four-columns-per-thread streaming Euler kernel (rd_quad.cu), which
+    otherwise only serves sheets of 2 Mi cells and more."""
     import os
-    os.environ["YH_RD_PATH"] = request.param
+    if request.param == "quad" and request.node.originalname not in QUAD_TESTS:
+        pytest.skip("no Euler kernel on this test's path")
+    os.environ["YH_RD_PATH"] = "stream" if request.param == "quad" else request.param
+    os.environ["YH_EULER_KERNEL"] = "quad" if request.param == "quad" else "pair"
     yield request.param
     os.environ.pop("YH_RD_PATH", None)
+    os.environ.pop("YH_EULER_KERNEL", None)
+
+
+QUAD_TESTS = {"test_every_mode_bitwise_vs_oracle", "test_temporal_blocking_is_bitwise_invariant",
+              "test_masked_temporal_blocking_is_bitwise_invariant", "test_fast_path_gate_diff_off_and_negative_zero",
+              "test_spiral_10k_steps_512", "test_slab_decomposition_is_bitwise_invariant",
+              "test_bitwise_vs_reference_kernels_race_free_modes", "test_full_size_16384_sheet",
+              "test_graph_replay_of_the_step_loop_is_bitwise_invariant"}
 
 
 def dev(a, dtype=torch.float64):
@@ -181,15 +194,37 @@ def test_fast_path_gate_diff_off_and_negative_zero(oracle):
     assert np.array_equal(np.signbit(got[0]), np.signbit(want[0]))
 
 
+_ORACLE_RUNS = {}
+
+
+def oracle_run_cached(oracle, key, p, n, u, v):
+    """The long oracle runs are shared by the kernel-path variants of a test (same inputs)."""
+    if key not in _ORACLE_RUNS:
+        _ORACLE_RUNS[key] = oracle.rd_advance(p, n, u, v)
+    return _ORACLE_RUNS[key]
+
+
 def test_spiral_10k_steps_512(oracle):
-    """C1 geometry (512^2 cross-field spiral), Euler + 5-point: 2000 steps bitwise vs the oracle
-    (the full 10 k-step run is exercised by bench.py; 2000 keeps the CPU side in seconds)."""
+    """BASELINE configs[0] (C1) as written: 512^2 cross-field spiral, headless, 10 000 fixed steps,
+    Euler + 5-point, bitwise vs the plain-C host loop."""
     p = oracle.params_default(512, 512, timeIntOrder=1, lap4=0)
     u, v = synth.cross_field_ic(512, 512)
-    want = oracle.rd_advance(p, 2000, u, v)
-    got = gpu_advance(p, 2000, u, v, tb=4)
+    want = oracle_run_cached(oracle, "c1_euler_10k", p, 10000, u, v)
+    got = gpu_advance(p, 10000, u, v, tb=4)
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
     assert 0.05 < want[0].mean() < 0.9   # a wave is actually propagating
+
+
+def test_spiral_4k_steps_512_default_mode(oracle, rd_path):
+    """C1 in the reference's DEFAULT mode (RK4 + 4th-order Laplacian + gateDiff, saveFiles.cu:124-132):
+    4 000 steps (the CPU side of 10 000 takes minutes) bitwise vs the plain-C host loop with
+    synchronous stages."""
+    p = oracle.params_default(512, 512)
+    u, v = synth.cross_field_ic(512, 512)
+    want = oracle_run_cached(oracle, "c1_default_4k", p, 4000, u, v)
+    got = gpu_advance(p, 4000, u, v)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert 0.05 < want[0].mean() < 0.9
 
 
 def test_default_mode_rk4_lap4_vs_oracle_and_holes(oracle):
@@ -324,7 +359,7 @@ def test_default_mode_trace_and_tip_trajectory_vs_reference(oracle, yh, rd_path)
     shipped closed form (no residual check) reports wherever the sheet still has the x-only
     symmetry of the initial condition exactly, which our arithmetic preserves and the reference's
     races break at 1e-19."""
-    if rd_path == "tile":
+    if rd_path != "stream":
         pytest.skip("one path is enough for this statistical tier")
     nx = ny = 256
     nseg = 16   # beyond ~2000 steps the reference's tip starts splitting into 2-3 noisy crossings

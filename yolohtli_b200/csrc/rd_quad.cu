@@ -1,0 +1,345 @@
+// rd_quad.cu -- second generation of the temporally blocked Euler + 5-point kernel (rd_fast.cu):
+// FOUR columns per thread.  Mode of reactionDiffusion.cu:186-199 + :498-513 (+ :154-184 masks),
+// same expression order, bit-identical to T launches of the reference kernel (--fmad=false).
+//
+// Why: the pair-per-thread kernel is ISSUE bound, not FP64-pipe or HBM bound.  On B200 an FP64
+// instruction holds a scheduler's dispatch port for two cycles and nothing else issues in its shadow
+// (tools/issue_mix.cu, profiles/r2_issue_mix.txt); ncu of rd_euler_stream<4,128> at 16384^2
+// (profiles/r2a_euler_tb4_16384_mix.txt): 64 FP64 + 62 other warp instructions per row pair,
+// 2*FP64 + other = 99.4 % of all issue slots.  Only fewer non-FP64 instructions per cell help:
+//   * a thread owns a QUAD (4 consecutive cells): loop control, range tests, barriers, addresses
+//     are paid once per four cells, the E/W neighbours inside the quad are registers;
+//   * rings of THREE rows per level and a loop unrolled by three: every shared-memory access of the
+//     levels >= 1 has a compile-time offset from one base register (no (m - c0) & 3 arithmetic);
+//   * the W / E neighbours of a row are loaded together with the row (one iteration ahead, kept in
+//     registers), so a level reads exactly ONE ring row per iteration and writes one;
+//   * the no-flux mirror in x is an ADDRESS (the thread at x = 0 loads column 1 as its W value);
+//   * no loader warp: the level-1 warps issue cp.async for their own quads PF rows ahead.
+// Shared-memory rows use the 128-byte XOR swizzle (16-byte chunk j of 128-byte line i sits at j ^ (i & 7)),
+// so that 32 lanes reading 32-byte quads (stride 32 B) are bank-conflict free.
+//
+//   level-l row m is produced in iteration  m - c0 + 2l ;  in that iteration the thread loads row
+//   m + 1 of level l-1 (written one iteration earlier) as its new N row.
+#include <stdlib.h>
+#include <string.h>
+
+#include "rd_euler_cell.cuh"
+
+namespace {
+
+using namespace yh_euler;
+
+struct Quad { double2 a, b; };                       // cells 0,1 | 2,3 of the thread
+struct QRow { Quad u, v; double uW, uE, vW, vE; };   // one source row: the quad and its outer neighbours
+
+// byte offset of 16-byte chunk `ch` inside a swizzled row
+__device__ __forceinline__ int swz(int ch) { return ((ch >> 3) << 7) | ((((ch & 7) ^ (ch >> 3)) & 7) << 4); }
+
+template <int T, int W, bool CANON, bool DEF, bool STIM, bool SOLID, bool FIX>
+__global__ void __launch_bounds__(T *(W / 4))
+rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a) {
+  constexpr int H = (T + 1) & ~1;        // halo columns each side
+  constexpr int BX = W - 2 * H;          // output columns per strip
+  constexpr int NL = W / 4;              // threads per level
+  constexpr int FROW = W * 8;            // bytes of one field row (W = 128: 1 KiB = 8 swizzle lines)
+  constexpr int ROW = 2 * FROW;          // u then v
+  constexpr int NR0 = (T == 1) ? 16 : 8; // level-0 ring (power of two)
+  constexpr int PF = NR0 - 3;            // level-0 rows in flight ahead of use: the slot refilled in iteration i was
+                                         // last read in iteration i - 2, two barriers earlier
+  constexpr int NRL = 3;                 // ring rows of the levels >= 1
+  extern __shared__ __align__(1024) unsigned char smraw[];
+
+  const int tid = threadIdx.x;
+  const int lev = __shfl_sync(0xffffffffu, tid / NL, 0) + 1;   // warp-uniform (NL is a multiple of 32)
+  const int t = tid % NL;
+  const int nx = k.nx;
+  const int x0 = blockIdx.x * BX, wx0 = x0 - H;
+  const int y0 = k.row0 + blockIdx.y * a.RY;
+  const int RYe = min(a.RY, k.row1 - y0);
+  const int c0 = y0 - T;
+  const int dom_lo = -k.jg0, dom_hi = k.nyg - k.jg0;   // local rows that exist globally
+  const size_t zoff = (size_t)blockIdx.z * (size_t)a.sim_stride;
+  const int n_it = ((RYe + 3 * T + 2) / 3) * 3;
+
+  const int c = 4 * t;                   // window column of the thread's first cell
+  const int gx = wx0 + c;
+  const bool okA = (gx >= 0) && (gx < nx), okB = (gx + 2 >= 0) && (gx + 2 < nx);
+  const bool col_ok = okA || okB;
+  const bool outA = okA && (c >= H) && (c + 2 <= W - H);
+  const bool outB = okB && (c + 2 >= H) && (c + 4 <= W - H);
+  // quads that straddle a domain edge (only when H or nx is not a multiple of 4: FIX variants)
+  const bool strL = FIX && (gx == -2), strR = FIX && (gx + 2 == nx);
+  const bool canon = CANON && (lev == 1);
+
+  // ---- static shared-memory offsets of this thread (bytes inside a field row) ----------------
+  const int offA0 = swz(2 * t), offB0 = swz(2 * t + 1);
+  int offW = (t > 0) ? swz(2 * t - 1) + 8 : offA0;         // column c-1 (no neighbour: any valid address)
+  int offE = (t < NL - 1) ? swz(2 * t + 2) : offB0;        // column c+4
+  if (gx == 0) offW = offA0 + 8;                           // no-flux mirror: W of x = 0 is x = 1
+  if (gx + 4 == nx) offE = offB0;                          //                 E of x = nx-1 is x = nx-2
+  int offA = offA0, offB = offB0;
+  // opaque to the compiler from here on: otherwise ptxas rematerialises the swizzle arithmetic from
+  // threadIdx inside the row loop instead of keeping four offsets in registers
+  asm volatile("" : "+r"(offA), "+r"(offB), "+r"(offW), "+r"(offE));
+
+  // rows this level must produce (empty for threads outside the domain)
+  const int lo_l = max(dom_lo, y0 - (T - lev));
+  const int hi_l = col_ok ? min(dom_hi, y0 + RYe + (T - lev)) : lo_l;
+  const int m0 = c0 - 2 * lev;           // row handled in iteration 0
+  // iteration windows: rows lo_l-2 .. hi_l-1 are "active" (the first two only fill the registers)
+  const int it_first = lo_l - 2 - m0;
+  const unsigned n_act = col_ok ? (unsigned)(hi_l - lo_l + 2) : 0u;
+
+  // pacing (batched sweeps): level `lev` performs step count0 + lev - 1 of its sheet
+  bool stim_on = false;
+  if (STIM) {
+    stim_on = k.stim != 0;
+    if (a.period) {
+      const int per = a.period[blockIdx.z];
+      stim_on = per > 0 && ((a.count0 + lev - 1) % per) <= a.duration;
+    }
+  }
+
+  unsigned char *ring0 = smraw;                                        // level 0: NR0 rows
+  unsigned char *src_ring = (lev == 1) ? ring0 : smraw + NR0 * ROW + (lev - 2) * NRL * ROW;
+  unsigned char *dst_ring = smraw + NR0 * ROW + (lev - 1) * NRL * ROW;  // unused by the last level
+  double *gu = a.u_out + zoff + gx;
+  double *gv = a.v_out + zoff + gx;
+
+  // ---- level 0 feed: every level-1 thread fetches its own quad, PF rows ahead ------------------
+  const double *__restrict__ u_in = a.u_in + zoff;
+  const double *__restrict__ v_in = a.v_in + zoff;
+  const int ld_lo = max(dom_lo, c0), ld_hi = min(dom_hi, y0 + RYe + T);
+  const int gA = okA ? gx : 0, gB = okB ? gx + 2 : 0;
+  const unsigned sm_ring0 = (unsigned)__cvta_generic_to_shared(ring0);
+  auto issue_row = [&](int q) {
+    if (q >= ld_lo && q < ld_hi) {
+      const unsigned dst = sm_ring0 + (unsigned)((q - c0) & (NR0 - 1)) * ROW;
+      const double *ru = u_in + (size_t)q * nx;
+      const double *rv = v_in + (size_t)q * nx;
+      cp_async16(dst + offA, ru + gA, okA);
+      cp_async16(dst + offB, ru + gB, okB);
+      cp_async16(dst + FROW + offA, rv + gA, okA);
+      cp_async16(dst + FROW + offB, rv + gB, okB);
+    }
+    cp_async_commit();
+  };
+
+  // one source row into registers
+  auto ld_row = [&](const unsigned char *r, QRow &R) {
+    R.u.a = *reinterpret_cast<const double2 *>(r + offA);
+    R.u.b = *reinterpret_cast<const double2 *>(r + offB);
+    R.v.a = *reinterpret_cast<const double2 *>(r + FROW + offA);
+    R.v.b = *reinterpret_cast<const double2 *>(r + FROW + offB);
+    R.uW = *reinterpret_cast<const double *>(r + offW);
+    R.uE = *reinterpret_cast<const double *>(r + offE);
+    R.vW = *reinterpret_cast<const double *>(r + FROW + offW);
+    R.vE = *reinterpret_cast<const double *>(r + FROW + offE);
+    if (canon) {   // level-0 data is raw: form u0 + (0.0*0.0) literally
+      R.u.a.x += 0.0; R.u.a.y += 0.0; R.u.b.x += 0.0; R.u.b.y += 0.0;
+      R.v.a.x += 0.0; R.v.a.y += 0.0; R.v.b.x += 0.0; R.v.b.y += 0.0;
+      R.uW += 0.0; R.uE += 0.0; R.vW += 0.0; R.vE += 0.0;
+    }
+    if (FIX) {     // the quad straddles x = 0 or x = nx: put the mirror value in the dead inner cell
+      if (strL) { R.u.a.y = R.u.b.y; R.v.a.y = R.v.b.y; }     // x = -1 := x = 1
+      if (strR) { R.u.b.x = R.u.a.x; R.v.b.x = R.v.a.x; }     // x = nx := x = nx-2
+    }
+  };
+
+  // mask patterns of the quad, fetched two rows ahead of use (global / L2; 1 B per cell)
+  unsigned pat_q0 = 0x1F1F1F1Fu, pat_q1 = 0x1F1F1F1Fu;
+  auto ld_pat = [&](int row) -> unsigned {
+    const uint8_t *pp = a.pat + (size_t)row * nx + gx;
+    const unsigned lo = okA ? *reinterpret_cast<const unsigned short *>(pp) : 0x1F1Fu;
+    const unsigned hi = okB ? *reinterpret_cast<const unsigned short *>(pp + 2) : 0x1F1Fu;
+    return lo | (hi << 16);
+  };
+
+  // One iteration of one level.  srcN = ring row holding row m+1 of the level below (written one
+  // iteration ago), srcM = the ring row that still holds row m-1 (its slot is due for row m+2, which
+  // does not exist when m is the last row of the domain), dst = this level's ring row for row m.
+  // The no-flux mirrors in y are LOADS from those rows, never register copies: a conditional copy of
+  // a whole QRow defeats the renaming of the unrolled S / C / N rotation (ptxas then moves all three
+  // rows through registers every iteration -- measured: 125 MOVs per quad row).
+  auto row_step = [&](int it, const unsigned char *srcN, const unsigned char *srcM, unsigned char *dst_row,
+                      QRow &S, QRow &C, QRow &N) {
+    if ((unsigned)(it - it_first) < n_act) {
+      const int m = m0 + it;
+      if (m + 1 < dom_hi) {
+        if (m + 1 >= dom_lo) ld_row(srcN, N);
+      } else {
+        ld_row(srcM, N);                 // last row of the domain: N := row m-1
+      }
+      if (m >= lo_l) {
+        if (m == dom_lo) ld_row(srcN, S);   // first row of the domain: S := row m+1
+        unsigned pat = 0x1F1F1F1Fu;
+        if (SOLID) {
+          if (m == lo_l) { pat_q0 = ld_pat(m); if (m + 1 < hi_l) pat_q1 = ld_pat(m + 1); }
+          pat = pat_q0;
+          pat_q0 = pat_q1;
+          if (m + 2 < hi_l) pat_q1 = ld_pat(m + 2);
+        }
+        bool s0 = false, s1 = false, s2 = false, s3 = false;
+        if (STIM && stim_on) {
+          const int gj = m + k.jg0;
+          s0 = yh_scs_on(k, gx, gj); s1 = yh_scs_on(k, gx + 1, gj);
+          s2 = yh_scs_on(k, gx + 2, gj); s3 = yh_scs_on(k, gx + 3, gj);
+        }
+        Quad uo, vo;
+        if (!SOLID || __all_sync(__activemask(), pat == 0x1F1F1F1Fu)) {   // all tissue around: plain stencil
+          euler_cell<DEF>(k, C.u.a.x, C.v.a.x, C.uW, C.u.a.y, N.u.a.x, S.u.a.x, C.vW, C.v.a.y, N.v.a.x, S.v.a.x, s0, uo.a.x, vo.a.x);
+          euler_cell<DEF>(k, C.u.a.y, C.v.a.y, C.u.a.x, C.u.b.x, N.u.a.y, S.u.a.y, C.v.a.x, C.v.b.x, N.v.a.y, S.v.a.y, s1, uo.a.y, vo.a.y);
+          euler_cell<DEF>(k, C.u.b.x, C.v.b.x, C.u.a.y, C.u.b.y, N.u.b.x, S.u.b.x, C.v.a.y, C.v.b.y, N.v.b.x, S.v.b.x, s2, uo.b.x, vo.b.x);
+          euler_cell<DEF>(k, C.u.b.y, C.v.b.y, C.u.b.x, C.uE, N.u.b.y, S.u.b.y, C.v.b.x, C.vE, N.v.b.y, S.v.b.y, s3, uo.b.y, vo.b.y);
+        } else {
+          euler_cell_solid<DEF>(k, pat & 0xFFu, C.u.a.x, C.v.a.x, C.uW, C.u.a.y, N.u.a.x, S.u.a.x, C.vW, C.v.a.y, N.v.a.x, S.v.a.x, s0, uo.a.x, vo.a.x);
+          euler_cell_solid<DEF>(k, (pat >> 8) & 0xFFu, C.u.a.y, C.v.a.y, C.u.a.x, C.u.b.x, N.u.a.y, S.u.a.y, C.v.a.x, C.v.b.x, N.v.a.y, S.v.a.y, s1, uo.a.y, vo.a.y);
+          euler_cell_solid<DEF>(k, (pat >> 16) & 0xFFu, C.u.b.x, C.v.b.x, C.u.a.y, C.u.b.y, N.u.b.x, S.u.b.x, C.v.a.y, C.v.b.y, N.v.b.x, S.v.b.x, s2, uo.b.x, vo.b.x);
+          euler_cell_solid<DEF>(k, pat >> 24, C.u.b.y, C.v.b.y, C.u.b.x, C.uE, N.u.b.y, S.u.b.y, C.v.b.x, C.vE, N.v.b.y, S.v.b.y, s3, uo.b.y, vo.b.y);
+        }
+        if (STIM && a.apd.APD1 && (outA || outB) && m >= y0 && m < y0 + RYe) {   // fused sAPD epilogue (owner cells)
+          const double th = 0.15;
+          const bool e0 = outA && (((C.u.a.x > th) && (uo.a.x < th)) || ((C.u.a.x < th) && (uo.a.x > th)));
+          const bool e1 = outA && (((C.u.a.y > th) && (uo.a.y < th)) || ((C.u.a.y < th) && (uo.a.y > th)));
+          const bool e2 = outB && (((C.u.b.x > th) && (uo.b.x < th)) || ((C.u.b.x < th) && (uo.b.x > th)));
+          const bool e3 = outB && (((C.u.b.y > th) && (uo.b.y < th)) || ((C.u.b.y < th) && (uo.b.y > th)));
+          if (e0 || e1 || e2 || e3) {
+            const size_t cidx = zoff + (size_t)m * nx + gx;
+            if (e0) apd_event(k, a.apd, cidx, uo.a.x, C.u.a.x, a.count0 + lev);
+            if (e1) apd_event(k, a.apd, cidx + 1, uo.a.y, C.u.a.y, a.count0 + lev);
+            if (e2) apd_event(k, a.apd, cidx + 2, uo.b.x, C.u.b.x, a.count0 + lev);
+            if (e3) apd_event(k, a.apd, cidx + 3, uo.b.y, C.u.b.y, a.count0 + lev);
+          }
+        }
+        if (lev < T) {
+          *reinterpret_cast<double2 *>(dst_row + offA) = uo.a;
+          *reinterpret_cast<double2 *>(dst_row + offB) = uo.b;
+          *reinterpret_cast<double2 *>(dst_row + FROW + offA) = vo.a;
+          *reinterpret_cast<double2 *>(dst_row + FROW + offB) = vo.b;
+        } else {
+          const size_t o = (size_t)m * nx;
+          if (outA) {
+            *reinterpret_cast<double2 *>(gu + o) = uo.a;
+            *reinterpret_cast<double2 *>(gv + o) = vo.a;
+          }
+          if (outB) {
+            *reinterpret_cast<double2 *>(gu + o + 2) = uo.b;
+            *reinterpret_cast<double2 *>(gv + o + 2) = vo.b;
+          }
+        }
+      }
+    }
+  };
+
+  QRow RA, RB, RC;
+  RA.u.a = RA.u.b = RA.v.a = RA.v.b = make_double2(0, 0);
+  RA.uW = RA.uE = RA.vW = RA.vE = 0.0;
+  RB = RA; RC = RA;
+
+  // One loop for every level (one copy of the row code in the instruction cache).  Ring slots are
+  // running byte offsets: the source ring of level 1 is the level-0 ring (NR0 rows), that of the other
+  // levels has three; iteration `it` reads the row written in iteration it-1 and writes slot it % 3.
+  const int src_bytes = (lev == 1 ? NR0 : NRL) * ROW;
+  int sN = src_bytes - ROW;              // slot of iteration -1
+  int sD = 0;                            // slot of iteration 0
+  if (lev == 1) {
+#pragma unroll
+    for (int q = 0; q < PF; q++) issue_row(c0 + q);
+  }
+  auto sub = [&](int it, QRow &S, QRow &C, QRow &N) {
+    if (lev == 1) {
+      issue_row(c0 + PF + it);
+      cp_async_wait<PF>();               // this thread's pieces of rows <= c0 + it have landed
+    }
+    __syncthreads();                     // ... everybody's; rows written in the last iteration are visible
+    int sM = sN - 2 * ROW;               // row m-1 (two slots back)
+    if (sM < 0) sM += src_bytes;
+    row_step(it, src_ring + sN, src_ring + sM, dst_ring + sD, S, C, N);
+    sN += ROW; if (sN == src_bytes) sN = 0;
+    sD += ROW; if (sD == NRL * ROW) sD = 0;
+  };
+  for (int it = 0; it < n_it; it += 3) {
+    sub(it, RA, RB, RC);
+    sub(it + 1, RB, RC, RA);
+    sub(it + 2, RC, RA, RB);
+  }
+  if (lev == 1) cp_async_wait<0>();
+}
+
+template <int T, int W, bool CANON, bool DEF, bool STIM, bool SOLID, bool FIX>
+int launch4(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
+  constexpr int H = (T + 1) & ~1, BX = W - 2 * H, ROW = 2 * W * 8;
+  constexpr int NT = T * (W / 4);
+  constexpr int NR0 = (T == 1) ? 16 : 8;
+  const size_t smem = (size_t)(NR0 + (T - 1) * 3) * ROW;
+  static bool attr_set[64] = {false};
+  static int slots[64] = {0};
+  int dev = 0;
+  YH_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    YH_CUDA(cudaFuncSetAttribute(rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1, sms = 148;
+    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX>,
+                                                          NT, smem));
+    YH_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    slots[dev & 63] = (per_sm > 0 ? per_sm : 1) * sms;
+    attr_set[dev & 63] = true;
+  }
+  const int rows = k.row1 - k.row0;
+  FastArgs b = a;
+  const int strips = (k.nx + BX - 1) / BX;
+  b.RY = a.RY > 0 ? a.RY : pick_ry(rows, strips, nsims, T, slots[dev & 63]);
+  dim3 grd(strips, (rows + b.RY - 1) / b.RY, nsims);
+  rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX><<<grd, NT, smem, st>>>(k, b);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
+
+template <int T, int W, bool CANON, bool DEF, bool FIX>
+int launch3(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
+  const bool stim = k.stim != 0 || a.period != nullptr || a.apd.APD1 != nullptr;
+  if (a.pat)   // obstacle masks: one variant (STIM on) keeps the instantiation count down
+    return launch4<T, W, CANON, DEF, true, true, FIX>(k, a, nsims, st);
+  return stim ? launch4<T, W, CANON, DEF, true, false, FIX>(k, a, nsims, st)
+              : launch4<T, W, CANON, DEF, false, false, FIX>(k, a, nsims, st);
+}
+
+template <int T, int W>
+int launch(const YhK &k, const FastArgs &a, int nsims, bool canon, cudaStream_t st) {
+  constexpr int H = (T + 1) & ~1;
+  // DEF variant: every constant whose operation is an exact identity at the reference defaults
+  const bool def = (k.tc == 1.0) && (k.mu == 1.0) && (k.delta == 1.0) && (k.gamma == 0.0) && (k.theta == 0.0) &&
+                   (k.gateDiff != 0);
+  const bool fix = (H % 4 != 0) || (k.nx % 4 != 0);   // a quad can straddle a domain edge
+  if (!def) {   // non-default constants: one generic variant per shape
+    return canon ? launch3<T, W, true, false, true>(k, a, nsims, st) : launch3<T, W, false, false, true>(k, a, nsims, st);
+  }
+  if (fix) return canon ? launch3<T, W, true, true, true>(k, a, nsims, st) : launch3<T, W, false, true, true>(k, a, nsims, st);
+  return canon ? launch3<T, W, true, true, false>(k, a, nsims, st) : launch3<T, W, false, true, false>(k, a, nsims, st);
+}
+
+}  // namespace
+
+int yh_rd_quad_supported(const YhK &k, int tb) {
+  (void)tb;
+  return k.nx >= 16;
+}
+
+// Same contract as yh_launch_rd_fast_paced (rd_fast.cu), which routes here.
+int yh_launch_rd_quad_paced(const YhK &k, int tb, const FastArgs &a, int nsims, bool canon, int W,
+                            cudaStream_t st) {
+#ifdef YH_QUICK   // developer builds: only the bench variant, for SASS inspection
+  return launch4<4, 128, false, true, false, false, false>(k, a, nsims, st);
+#else
+#define YH_QUAD_DISPATCH(WW)                                      \
+  switch (tb) {                                                   \
+    case 1: return launch<1, WW>(k, a, nsims, canon, st);         \
+    case 2: return launch<2, WW>(k, a, nsims, canon, st);         \
+    default: return launch<4, WW>(k, a, nsims, canon, st);        \
+  }
+  if (W == 256) { YH_QUAD_DISPATCH(256) }
+  YH_QUAD_DISPATCH(128)
+#undef YH_QUAD_DISPATCH
+#endif
+}
