@@ -23,6 +23,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "rd_euler_cell.cuh"
 
 namespace {
@@ -31,6 +33,26 @@ using namespace yh_euler;
 
 struct Quad { double2 a, b; };                       // cells 0,1 | 2,3 of the thread
 struct QRow { Quad u, v; double uW, uE, vW, vE; };   // one source row: the quad and its outer neighbours
+
+// shared-memory accesses by 32-bit shared-window address + compile-time offset: the rings are addressed
+// as base register + immediate (C++ pointers made ptxas rebuild the window base and add it to every
+// offset in every iteration: 13 integer instructions per row)
+template <int IMM>
+__device__ __forceinline__ double2 lds128(unsigned a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(IMM));
+  return v;
+}
+template <int IMM>
+__device__ __forceinline__ double lds64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(IMM));
+  return v;
+}
+template <int IMM>
+__device__ __forceinline__ void sts128(unsigned a, const double2 &v) {
+  asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(IMM), "d"(v.x), "d"(v.y) : "memory");
+}
 
 // byte offset of 16-byte chunk `ch` inside a swizzled row
 __device__ __forceinline__ int swz(int ch) { return ((ch >> 3) << 7) | ((((ch & 7) ^ (ch >> 3)) & 7) << 4); }
@@ -100,41 +122,49 @@ rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a)
     }
   }
 
-  unsigned char *ring0 = smraw;                                        // level 0: NR0 rows
-  unsigned char *src_ring = (lev == 1) ? ring0 : smraw + NR0 * ROW + (lev - 2) * NRL * ROW;
-  unsigned char *dst_ring = smraw + NR0 * ROW + (lev - 1) * NRL * ROW;  // unused by the last level
-  double *gu = a.u_out + zoff + gx;
-  double *gv = a.v_out + zoff + gx;
+  const unsigned sm_ring0 = (unsigned)__cvta_generic_to_shared(smraw);   // level 0: NR0 rows
+  const unsigned src_ring = (lev == 1) ? sm_ring0 : sm_ring0 + NR0 * ROW + (lev - 2) * NRL * ROW;
+  const unsigned dst_ring = sm_ring0 + NR0 * ROW + (lev - 1) * NRL * ROW;  // unused by the last level
+  // this thread's addresses inside slot 0 of its source / destination ring
+  const unsigned aA = src_ring + offA, aB = src_ring + offB, aW = src_ring + offW, aE = src_ring + offE;
+  const unsigned dA = dst_ring + offA, dB = dst_ring + offB;
+  // output row pointers of the last level, advanced one row per computed row (no 64-bit multiply per row)
+  double *gu = a.u_out + zoff + gx + (ptrdiff_t)lo_l * nx;
+  double *gv = a.v_out + zoff + gx + (ptrdiff_t)lo_l * nx;
 
   // ---- level 0 feed: every level-1 thread fetches its own quad, PF rows ahead ------------------
   const double *__restrict__ u_in = a.u_in + zoff;
   const double *__restrict__ v_in = a.v_in + zoff;
   const int ld_lo = max(dom_lo, c0), ld_hi = min(dom_hi, y0 + RYe + T);
-  const int gA = okA ? gx : 0, gB = okB ? gx + 2 : 0;
-  const unsigned sm_ring0 = (unsigned)__cvta_generic_to_shared(ring0);
-  auto issue_row = [&](int q) {
+  // running source pointers (row q, column gx).  For a dead pair of an edge quad the address lies up to
+  // 16 bytes outside the row; it is never dereferenced (cp.async with src-size 0 reads nothing).
+  const double *pu = u_in + gx + (ptrdiff_t)c0 * nx;
+  const double *pv = v_in + gx + (ptrdiff_t)c0 * nx;
+  int szA = okA ? 16 : 0, szB = okB ? 16 : 0;   // cp.async src-size: 0 = zero fill, nothing read
+  asm volatile("" : "+r"(szA), "+r"(szB));      // (kept in registers: ptxas otherwise recomputes okA / okB per row)
+  auto issue_row = [&](int q) {      // called with q = c0, c0+1, ... in order
     if (q >= ld_lo && q < ld_hi) {
       const unsigned dst = sm_ring0 + (unsigned)((q - c0) & (NR0 - 1)) * ROW;
-      const double *ru = u_in + (size_t)q * nx;
-      const double *rv = v_in + (size_t)q * nx;
-      cp_async16(dst + offA, ru + gA, okA);
-      cp_async16(dst + offB, ru + gB, okB);
-      cp_async16(dst + FROW + offA, rv + gA, okA);
-      cp_async16(dst + FROW + offB, rv + gB, okB);
+      cp_async16s(dst + offA, pu, szA);
+      cp_async16s(dst + offB, pu + 2, szB);
+      cp_async16s(dst + FROW + offA, pv, szA);
+      cp_async16s(dst + FROW + offB, pv + 2, szB);
     }
+    pu += nx; pv += nx;
     cp_async_commit();
   };
 
-  // one source row into registers
-  auto ld_row = [&](const unsigned char *r, QRow &R) {
-    R.u.a = *reinterpret_cast<const double2 *>(r + offA);
-    R.u.b = *reinterpret_cast<const double2 *>(r + offB);
-    R.v.a = *reinterpret_cast<const double2 *>(r + FROW + offA);
-    R.v.b = *reinterpret_cast<const double2 *>(r + FROW + offB);
-    R.uW = *reinterpret_cast<const double *>(r + offW);
-    R.uE = *reinterpret_cast<const double *>(r + offE);
-    R.vW = *reinterpret_cast<const double *>(r + FROW + offW);
-    R.vE = *reinterpret_cast<const double *>(r + FROW + offE);
+  // one source row into registers: base addresses + compile-time offset
+  auto ld_row = [&](auto Ic, unsigned rA, unsigned rB, unsigned rW, unsigned rE, QRow &R) {
+    constexpr int I = decltype(Ic)::value;
+    R.u.a = lds128<I>(rA);
+    R.u.b = lds128<I>(rB);
+    R.v.a = lds128<I + FROW>(rA);
+    R.v.b = lds128<I + FROW>(rB);
+    R.uW = lds64<I>(rW);
+    R.uE = lds64<I>(rE);
+    R.vW = lds64<I + FROW>(rW);
+    R.vE = lds64<I + FROW>(rE);
     if (canon) {   // level-0 data is raw: form u0 + (0.0*0.0) literally
       R.u.a.x += 0.0; R.u.a.y += 0.0; R.u.b.x += 0.0; R.u.b.y += 0.0;
       R.v.a.x += 0.0; R.v.a.y += 0.0; R.v.b.x += 0.0; R.v.b.y += 0.0;
@@ -144,6 +174,10 @@ rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a)
       if (strL) { R.u.a.y = R.u.b.y; R.v.a.y = R.v.b.y; }     // x = -1 := x = 1
       if (strR) { R.u.b.x = R.u.a.x; R.v.b.x = R.v.a.x; }     // x = nx := x = nx-2
     }
+  };
+  // ... at a run-time slot offset (level 1, and the rare rows off the fast path)
+  auto ld_row_dyn = [&](int sb, QRow &R) {
+    ld_row(std::integral_constant<int, 0>{}, aA + sb, aB + sb, aW + sb, aE + sb, R);
   };
 
   // mask patterns of the quad, fetched two rows ahead of use (global / L2; 1 B per cell)
@@ -155,49 +189,66 @@ rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a)
     return lo | (hi << 16);
   };
 
+  // "plain" iterations: the row is computed and neither it nor its N row touches a domain edge in y
+  const int pl_lo = max(lo_l, dom_lo + 1), pl_hi = min(hi_l, dom_hi - 1);
+  const int it_p0 = pl_lo - m0;
+  const unsigned n_plain = (col_ok && pl_hi > pl_lo) ? (unsigned)(pl_hi - pl_lo) : 0u;
+
   // One iteration of one level.  srcN = ring row holding row m+1 of the level below (written one
   // iteration ago), srcM = the ring row that still holds row m-1 (its slot is due for row m+2, which
   // does not exist when m is the last row of the domain), dst = this level's ring row for row m.
   // The no-flux mirrors in y are LOADS from those rows, never register copies: a conditional copy of
   // a whole QRow defeats the renaming of the unrolled S / C / N rotation (ptxas then moves all three
   // rows through registers every iteration -- measured: 125 MOVs per quad row).
-  auto row_step = [&](int it, const unsigned char *srcN, const unsigned char *srcM, unsigned char *dst_row,
-                      QRow &S, QRow &C, QRow &N) {
-    if ((unsigned)(it - it_first) < n_act) {
+  auto row_step = [&](auto Jc, int it, int srcN, int srcM, QRow &S, QRow &C, QRow &N) {
+    constexpr int J = decltype(Jc)::value;
+    const bool plain = (unsigned)(it - it_p0) < n_plain;
+    bool comp = plain;
+    if (plain) {
+      if (lev == 1) ld_row_dyn(srcN, N);
+      else ld_row(std::integral_constant<int, ((J + 2) % NRL) * ROW>{}, aA, aB, aW, aE, N);
+    } else if ((unsigned)(it - it_first) < n_act) {   // register fill, first / last row of the domain
       const int m = m0 + it;
       if (m + 1 < dom_hi) {
-        if (m + 1 >= dom_lo) ld_row(srcN, N);
+        if (m + 1 >= dom_lo) ld_row_dyn(srcN, N);
       } else {
-        ld_row(srcM, N);                 // last row of the domain: N := row m-1
+        ld_row_dyn(srcM, N);             // last row of the domain: N := row m-1
       }
       if (m >= lo_l) {
-        if (m == dom_lo) ld_row(srcN, S);   // first row of the domain: S := row m+1
-        unsigned pat = 0x1F1F1F1Fu;
-        if (SOLID) {
-          if (m == lo_l) { pat_q0 = ld_pat(m); if (m + 1 < hi_l) pat_q1 = ld_pat(m + 1); }
-          pat = pat_q0;
-          pat_q0 = pat_q1;
-          if (m + 2 < hi_l) pat_q1 = ld_pat(m + 2);
-        }
-        bool s0 = false, s1 = false, s2 = false, s3 = false;
-        if (STIM && stim_on) {
-          const int gj = m + k.jg0;
-          s0 = yh_scs_on(k, gx, gj); s1 = yh_scs_on(k, gx + 1, gj);
-          s2 = yh_scs_on(k, gx + 2, gj); s3 = yh_scs_on(k, gx + 3, gj);
-        }
-        Quad uo, vo;
-        if (!SOLID || __all_sync(__activemask(), pat == 0x1F1F1F1Fu)) {   // all tissue around: plain stencil
-          euler_cell<DEF>(k, C.u.a.x, C.v.a.x, C.uW, C.u.a.y, N.u.a.x, S.u.a.x, C.vW, C.v.a.y, N.v.a.x, S.v.a.x, s0, uo.a.x, vo.a.x);
-          euler_cell<DEF>(k, C.u.a.y, C.v.a.y, C.u.a.x, C.u.b.x, N.u.a.y, S.u.a.y, C.v.a.x, C.v.b.x, N.v.a.y, S.v.a.y, s1, uo.a.y, vo.a.y);
-          euler_cell<DEF>(k, C.u.b.x, C.v.b.x, C.u.a.y, C.u.b.y, N.u.b.x, S.u.b.x, C.v.a.y, C.v.b.y, N.v.b.x, S.v.b.x, s2, uo.b.x, vo.b.x);
-          euler_cell<DEF>(k, C.u.b.y, C.v.b.y, C.u.b.x, C.uE, N.u.b.y, S.u.b.y, C.v.b.x, C.vE, N.v.b.y, S.v.b.y, s3, uo.b.y, vo.b.y);
-        } else {
-          euler_cell_solid<DEF>(k, pat & 0xFFu, C.u.a.x, C.v.a.x, C.uW, C.u.a.y, N.u.a.x, S.u.a.x, C.vW, C.v.a.y, N.v.a.x, S.v.a.x, s0, uo.a.x, vo.a.x);
-          euler_cell_solid<DEF>(k, (pat >> 8) & 0xFFu, C.u.a.y, C.v.a.y, C.u.a.x, C.u.b.x, N.u.a.y, S.u.a.y, C.v.a.x, C.v.b.x, N.v.a.y, S.v.a.y, s1, uo.a.y, vo.a.y);
-          euler_cell_solid<DEF>(k, (pat >> 16) & 0xFFu, C.u.b.x, C.v.b.x, C.u.a.y, C.u.b.y, N.u.b.x, S.u.b.x, C.v.a.y, C.v.b.y, N.v.b.x, S.v.b.x, s2, uo.b.x, vo.b.x);
-          euler_cell_solid<DEF>(k, pat >> 24, C.u.b.y, C.v.b.y, C.u.b.x, C.uE, N.u.b.y, S.u.b.y, C.v.b.x, C.vE, N.v.b.y, S.v.b.y, s3, uo.b.y, vo.b.y);
-        }
-        if (STIM && a.apd.APD1 && (outA || outB) && m >= y0 && m < y0 + RYe) {   // fused sAPD epilogue (owner cells)
+        comp = true;
+        if (m == dom_lo) ld_row_dyn(srcN, S);   // first row of the domain: S := row m+1
+      }
+    }
+    if (comp) {
+      unsigned pat = 0x1F1F1F1Fu;
+      if (SOLID) {
+        const int m = m0 + it;
+        if (m == lo_l) { pat_q0 = ld_pat(m); if (m + 1 < hi_l) pat_q1 = ld_pat(m + 1); }
+        pat = pat_q0;
+        pat_q0 = pat_q1;
+        if (m + 2 < hi_l) pat_q1 = ld_pat(m + 2);
+      }
+      bool s0 = false, s1 = false, s2 = false, s3 = false;
+      if (STIM && stim_on) {
+        const int gj = m0 + it + k.jg0;
+        s0 = yh_scs_on(k, gx, gj); s1 = yh_scs_on(k, gx + 1, gj);
+        s2 = yh_scs_on(k, gx + 2, gj); s3 = yh_scs_on(k, gx + 3, gj);
+      }
+      Quad uo, vo;
+      if (!SOLID || __all_sync(__activemask(), pat == 0x1F1F1F1Fu)) {   // all tissue around: plain stencil
+        euler_cell<DEF>(k, C.u.a.x, C.v.a.x, C.uW, C.u.a.y, N.u.a.x, S.u.a.x, C.vW, C.v.a.y, N.v.a.x, S.v.a.x, s0, uo.a.x, vo.a.x);
+        euler_cell<DEF>(k, C.u.a.y, C.v.a.y, C.u.a.x, C.u.b.x, N.u.a.y, S.u.a.y, C.v.a.x, C.v.b.x, N.v.a.y, S.v.a.y, s1, uo.a.y, vo.a.y);
+        euler_cell<DEF>(k, C.u.b.x, C.v.b.x, C.u.a.y, C.u.b.y, N.u.b.x, S.u.b.x, C.v.a.y, C.v.b.y, N.v.b.x, S.v.b.x, s2, uo.b.x, vo.b.x);
+        euler_cell<DEF>(k, C.u.b.y, C.v.b.y, C.u.b.x, C.uE, N.u.b.y, S.u.b.y, C.v.b.x, C.vE, N.v.b.y, S.v.b.y, s3, uo.b.y, vo.b.y);
+      } else {
+        euler_cell_solid<DEF>(k, pat & 0xFFu, C.u.a.x, C.v.a.x, C.uW, C.u.a.y, N.u.a.x, S.u.a.x, C.vW, C.v.a.y, N.v.a.x, S.v.a.x, s0, uo.a.x, vo.a.x);
+        euler_cell_solid<DEF>(k, (pat >> 8) & 0xFFu, C.u.a.y, C.v.a.y, C.u.a.x, C.u.b.x, N.u.a.y, S.u.a.y, C.v.a.x, C.v.b.x, N.v.a.y, S.v.a.y, s1, uo.a.y, vo.a.y);
+        euler_cell_solid<DEF>(k, (pat >> 16) & 0xFFu, C.u.b.x, C.v.b.x, C.u.a.y, C.u.b.y, N.u.b.x, S.u.b.x, C.v.a.y, C.v.b.y, N.v.b.x, S.v.b.x, s2, uo.b.x, vo.b.x);
+        euler_cell_solid<DEF>(k, pat >> 24, C.u.b.y, C.v.b.y, C.u.b.x, C.uE, N.u.b.y, S.u.b.y, C.v.b.x, C.vE, N.v.b.y, S.v.b.y, s3, uo.b.y, vo.b.y);
+      }
+      if (STIM && a.apd.APD1 && (outA || outB)) {   // fused sAPD epilogue (owner cells)
+        const int m = m0 + it;
+        if (m >= y0 && m < y0 + RYe) {
           const double th = 0.15;
           const bool e0 = outA && (((C.u.a.x > th) && (uo.a.x < th)) || ((C.u.a.x < th) && (uo.a.x > th)));
           const bool e1 = outA && (((C.u.a.y > th) && (uo.a.y < th)) || ((C.u.a.y < th) && (uo.a.y > th)));
@@ -211,22 +262,22 @@ rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a)
             if (e3) apd_event(k, a.apd, cidx + 3, uo.b.y, C.u.b.y, a.count0 + lev);
           }
         }
-        if (lev < T) {
-          *reinterpret_cast<double2 *>(dst_row + offA) = uo.a;
-          *reinterpret_cast<double2 *>(dst_row + offB) = uo.b;
-          *reinterpret_cast<double2 *>(dst_row + FROW + offA) = vo.a;
-          *reinterpret_cast<double2 *>(dst_row + FROW + offB) = vo.b;
-        } else {
-          const size_t o = (size_t)m * nx;
-          if (outA) {
-            *reinterpret_cast<double2 *>(gu + o) = uo.a;
-            *reinterpret_cast<double2 *>(gv + o) = vo.a;
-          }
-          if (outB) {
-            *reinterpret_cast<double2 *>(gu + o + 2) = uo.b;
-            *reinterpret_cast<double2 *>(gv + o + 2) = vo.b;
-          }
+      }
+      if (lev < T) {
+        sts128<(J % NRL) * ROW>(dA, uo.a);
+        sts128<(J % NRL) * ROW>(dB, uo.b);
+        sts128<(J % NRL) * ROW + FROW>(dA, vo.a);
+        sts128<(J % NRL) * ROW + FROW>(dB, vo.b);
+      } else {               // rows are computed in order lo_l, lo_l+1, ...: running pointers
+        if (outA) {
+          *reinterpret_cast<double2 *>(gu) = uo.a;
+          *reinterpret_cast<double2 *>(gv) = vo.a;
         }
+        if (outB) {
+          *reinterpret_cast<double2 *>(gu + 2) = uo.b;
+          *reinterpret_cast<double2 *>(gv + 2) = vo.b;
+        }
+        gu += nx; gv += nx;
       }
     }
   };
@@ -236,32 +287,31 @@ rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a)
   RA.uW = RA.uE = RA.vW = RA.vE = 0.0;
   RB = RA; RC = RA;
 
-  // One loop for every level (one copy of the row code in the instruction cache).  Ring slots are
-  // running byte offsets: the source ring of level 1 is the level-0 ring (NR0 rows), that of the other
-  // levels has three; iteration `it` reads the row written in iteration it-1 and writes slot it % 3.
-  const int src_bytes = (lev == 1 ? NR0 : NRL) * ROW;
-  int sN = src_bytes - ROW;              // slot of iteration -1
-  int sD = 0;                            // slot of iteration 0
+  // One loop for every level (one copy of the row code in the instruction cache).  Iteration `it`
+  // reads the row the level below wrote in iteration it-1 and writes slot it % 3 of its own ring.  The
+  // loop is unrolled by three, so for the 3-row rings every slot is a compile-time constant; only level
+  // 1, whose source is the NR0-row level-0 ring, computes a (warp-uniform) slot.
   if (lev == 1) {
 #pragma unroll
     for (int q = 0; q < PF; q++) issue_row(c0 + q);
   }
-  auto sub = [&](int it, QRow &S, QRow &C, QRow &N) {
+  auto sub = [&](auto Jc, int it0, QRow &S, QRow &C, QRow &N) {
+    constexpr int J = decltype(Jc)::value;
+    const int it = it0 + J;
+    int sN = ((J + 2) % NRL) * ROW, sM = (J % NRL) * ROW;
     if (lev == 1) {
       issue_row(c0 + PF + it);
       cp_async_wait<PF>();               // this thread's pieces of rows <= c0 + it have landed
+      sN = ((it - 1) & (NR0 - 1)) * ROW;
+      sM = ((it - 3) & (NR0 - 1)) * ROW;
     }
     __syncthreads();                     // ... everybody's; rows written in the last iteration are visible
-    int sM = sN - 2 * ROW;               // row m-1 (two slots back)
-    if (sM < 0) sM += src_bytes;
-    row_step(it, src_ring + sN, src_ring + sM, dst_ring + sD, S, C, N);
-    sN += ROW; if (sN == src_bytes) sN = 0;
-    sD += ROW; if (sD == NRL * ROW) sD = 0;
+    row_step(Jc, it, sN, sM, S, C, N);
   };
   for (int it = 0; it < n_it; it += 3) {
-    sub(it, RA, RB, RC);
-    sub(it + 1, RB, RC, RA);
-    sub(it + 2, RC, RA, RB);
+    sub(std::integral_constant<int, 0>{}, it, RA, RB, RC);
+    sub(std::integral_constant<int, 1>{}, it, RB, RC, RA);
+    sub(std::integral_constant<int, 2>{}, it, RC, RA, RB);
   }
   if (lev == 1) cp_async_wait<0>();
 }
