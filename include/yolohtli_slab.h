@@ -1,0 +1,97 @@
+/*
+ * yolohtli_slab.h -- C ABI of the multi-GPU row-slab driver (libyolohtli_b200.so, csrc/slab.cu).
+ *
+ * The reference is single-GPU: its host is one C++ loop, display() (main.cu:862-1043), around
+ * reactionDiffusion_wrapper + swapSoA (main.cu:879-882).  This is that loop for an nx x ny sheet cut
+ * into contiguous row slabs, one slab per GPU: a slab stores its owned rows plus `halo`
+ * ghost rows per side, steps its EDGE BANDS first on a high-priority stream, pushes the fresh edge rows
+ * straight into the neighbours' ghost rows (NVLink peer stores from a kernel, followed by a release of a
+ * sequence number in the neighbour's flag word) while the INTERIOR rows -- which never read a ghost --
+ * are still computing on the main stream.  No host involvement on the data path, no NCCL, no Python.
+ *
+ * Two ways to place slabs:
+ *   one process per GPU   yh_slab_create on every rank; yh_slab_export writes an opaque handle (CUDA IPC
+ *                         handles of the state block and the flag words); the host moves the handles of
+ *                         the two neighbours by whatever it has (MPI_Sendrecv, torch.distributed, a
+ *                         file) and passes them to yh_slab_connect.
+ *   one process, N GPUs   yh_slab_group_create: creates, peer-enables and connects N slabs; the group
+ *                         calls drive all of them from one host thread, like display() drives one.
+ *
+ * N slabs == one sheet BIT FOR BIT (tests/test_gpu_slab_driver.py, tests/slab_driver.cu).
+ * Every entry point returns a status of yolohtli_abi.h (YH_OK == 0).
+ */
+#ifndef YOLOHTLI_SLAB_H
+#define YOLOHTLI_SLAB_H
+
+#include "yolohtli_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct yh_slab yh_slab;
+typedef struct yh_slab_group yh_slab_group;
+
+#define YH_SLAB_HANDLE_BYTES 256
+
+/* Rows [*j0, *j1) owned by `rank`: as even as possible, remainder to the low ranks. */
+int yh_slab_partition(int ny_global, int world, int rank, int *j0, int *j1);
+
+/* p_global describes the WHOLE sheet (ny == ny_global, jg0 == 0).  halo >= timeIntOrder ghost rows per
+ * side (Euler: halo = time steps per exchange, 1 / 2 / 4).  The slab allocates its state on `device`. */
+int yh_slab_create(yh_slab **out, const yh_params *p_global, int rank, int world, int halo, int device);
+int yh_slab_destroy(yh_slab *s);
+/* global row ranges: owned [*j0, *j1), stored (ghosts included) [*g0, *g1) */
+int yh_slab_layout(const yh_slab *s, int *j0, int *j1, int *g0, int *g1);
+
+/* ---- wiring ------------------------------------------------------------------------------------ */
+int yh_slab_export(yh_slab *s, void *handle /* YH_SLAB_HANDLE_BYTES */);
+/* handles of ranks rank-1 / rank+1 made by yh_slab_export in ANOTHER process (NULL at the sheet edges) */
+int yh_slab_connect(yh_slab *s, const void *handle_up, const void *handle_down);
+/* neighbours living in THIS process (same or peer-accessible device) */
+int yh_slab_connect_local(yh_slab *s, yh_slab *up, yh_slab *down);
+
+/* ---- state ------------------------------------------------------------------------------------- */
+/* Host rows -> device (asynchronous on the slab's main stream; pinned memory overlaps).  with_ghosts = 0:
+ * u_h / v_h hold the owned rows, the ghost rows are fetched from the neighbours by the next advance;
+ * with_ghosts = 1: they hold the stored rows [g0, g1). */
+int yh_slab_set_state(yh_slab *s, const double *u_h, const double *v_h, int with_ghosts);
+/* owned rows -> host; returns after the copy has completed */
+int yh_slab_get_state(yh_slab *s, double *u_h, double *v_h);
+/* obstacle mask (1 = tissue, main.cu:676-680) of the stored rows [g0, g1) */
+int yh_slab_set_solid(yh_slab *s, const uint8_t *mask_h);
+void *yh_slab_device_u(yh_slab *s);   /* current state buffers, ny_local x nx, stored rows */
+void *yh_slab_device_v(yh_slab *s);
+
+/* ---- stepping ---------------------------------------------------------------------------------- */
+/* nsteps x {reactionDiffusion_wrapper; swapSoA} on this slab, asynchronous.  Every rank must make the
+ * same call.  tb_steps: Euler time steps per HBM pass and per exchange (0 = halo). */
+int yh_slab_advance(yh_slab *s, int nsteps, int tb_steps);
+/* waits for the slab's streams; YH_ERR_CUDA if a neighbour never signalled (flag wait timed out) */
+int yh_slab_sync(yh_slab *s);
+/* sum of the owned cells' bit patterns (uint64 views) mod 2^64: order independent, so the sum over the
+ * ranks is the same number for every decomposition of the same sheet */
+int yh_slab_checksum(yh_slab *s, unsigned long long *sum_u, unsigned long long *sum_v);
+/* the reference's whole use on one slab with HOST buffers of the owned rows: upload, nsteps, download */
+int yh_slab_run_host(yh_slab *s, const double *u_in_h, const double *v_in_h, double *u_out_h,
+                     double *v_out_h, int nsteps, int tb_steps);
+
+/* ---- one process, several devices --------------------------------------------------------------- */
+/* devices[r] holds slab r (the same device may appear more than once: test vehicle on one GPU). */
+int yh_slab_group_create(yh_slab_group **out, const yh_params *p_global, int nslabs, const int *devices,
+                         int halo);
+int yh_slab_group_destroy(yh_slab_group *g);
+yh_slab *yh_slab_group_member(yh_slab_group *g, int rank);
+/* whole-sheet host arrays (nx * ny doubles) */
+int yh_slab_group_set_state(yh_slab_group *g, const double *u_h, const double *v_h);
+int yh_slab_group_get_state(yh_slab_group *g, double *u_h, double *v_h);
+int yh_slab_group_set_solid(yh_slab_group *g, const uint8_t *mask_h);
+int yh_slab_group_advance(yh_slab_group *g, int nsteps, int tb_steps);
+int yh_slab_group_sync(yh_slab_group *g);
+int yh_slab_group_run_host(yh_slab_group *g, const double *u_in_h, const double *v_in_h,
+                           double *u_out_h, double *v_out_h, int nsteps, int tb_steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLOHTLI_SLAB_H */

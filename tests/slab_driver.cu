@@ -1,0 +1,106 @@
+// slab_driver.cu -- TEST: a C++ host (no Python, no torch) that drives the monodomain step on N row
+// slabs through include/yolohtli_slab.h, the way a maintainer of the reference's main.cu would reach
+// several GPUs, and checks N slabs == one sheet BIT FOR BIT against yh_sim (single device path).
+//
+//   yh_slab_driver <nx> <ny> <nslabs> <nsteps> <mode: euler|rk4lap4|eulerholes> [ndev]
+//
+// Slab r lives on device r % ndev (ndev = 1: every slab on one GPU, the peers are then the same
+// device and the flag protocol, streams and graphs are exercised exactly as across NVLink).
+// Prints one line "slab_driver PASS ..." or "slab_driver FAIL ..."; exit status 0 / 1.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../include/yolohtli_slab.h"
+
+#define CHECK(call)                                                              \
+  do {                                                                           \
+    int rc__ = (call);                                                           \
+    if (rc__ != YH_OK) {                                                         \
+      printf("slab_driver FAIL %s -> %d: %s\n", #call, rc__, yh_last_error());   \
+      return 1;                                                                  \
+    }                                                                            \
+  } while (0)
+
+// a few plane waves broken by a cross-field: something that moves everywhere, any size
+static void initial_state(int nx, int ny, std::vector<double> &u, std::vector<double> &v) {
+  for (int j = 0; j < ny; j++)
+    for (int i = 0; i < nx; i++) {
+      const size_t c = (size_t)j * nx + i;
+      const int bx = (i * 8) / nx, by = (j * 8) / ny;
+      u[c] = ((bx + by) % 3 == 0 && (i % 97) < 40) ? 1.0 : 0.0;
+      v[c] = ((bx * 3 + by) % 4 == 0 && (j % 89) < 45) ? 0.9 : 0.05 * ((i + 2 * j) % 7);
+    }
+}
+
+int main(int argc, char **argv) {
+  const int nx = argc > 1 ? atoi(argv[1]) : 512, ny = argc > 2 ? atoi(argv[2]) : 512;
+  const int nslabs = argc > 3 ? atoi(argv[3]) : 2, nsteps = argc > 4 ? atoi(argv[4]) : 203;
+  const char *mode = argc > 5 ? argv[5] : "euler";
+  int ndev = argc > 6 ? atoi(argv[6]) : 1;
+  if (yh_device_count() < 1) { printf("slab_driver FAIL no CUDA device\n"); return 1; }
+  if (ndev > yh_device_count()) ndev = yh_device_count();
+
+  yh_params p;
+  CHECK(yh_params_default(&p, nx, ny, 0, 1));
+  const bool holes = strcmp(mode, "eulerholes") == 0;
+  if (strncmp(mode, "euler", 5) == 0) { p.timeIntOrder = 1; p.lap4 = 0; }
+  if (holes) p.solidSwitch = 1;
+  const size_t n = (size_t)nx * ny;
+  std::vector<double> u0(n), v0(n), ua(n), va(n), ub(n), vb(n);
+  initial_state(nx, ny, u0, v0);
+  std::vector<uint8_t> mask(n, 1);
+  if (holes)
+    for (int j = 0; j < ny; j++)
+      for (int i = 0; i < nx; i++) {
+        const int dx = i % 61 - 30, dy = j % 53 - 26;
+        if (dx * dx + dy * dy < 90) { mask[(size_t)j * nx + i] = 0; u0[(size_t)j * nx + i] = 0.0; v0[(size_t)j * nx + i] = 0.0; }
+      }
+
+  // (a) one sheet, one device: the headless single-GPU driver
+  yh_sim *sim = nullptr;
+  CHECK(yh_sim_create(&sim, &p, 1, 0));
+  if (holes) CHECK(yh_sim_set_solid(sim, mask.data()));
+  CHECK(yh_sim_run_host(sim, u0.data(), v0.data(), ua.data(), va.data(), nsteps, 4));
+  CHECK(yh_sim_destroy(sim));
+
+  // (b) the same sheet on nslabs row slabs
+  std::vector<int> devs(nslabs);
+  for (int r = 0; r < nslabs; r++) devs[r] = r % ndev;
+  yh_slab_group *g = nullptr;
+  const int halo = 4;
+  CHECK(yh_slab_group_create(&g, &p, nslabs, devs.data(), halo));
+  if (holes) CHECK(yh_slab_group_set_solid(g, mask.data()));
+  // in two calls, so that a run continues from device-resident state with valid ghosts, and with an
+  // odd remainder so that the tail blocks (T = 2, 1) are exercised too
+  const int first = nsteps / 3;
+  CHECK(yh_slab_group_set_state(g, u0.data(), v0.data()));
+  CHECK(yh_slab_group_advance(g, first, 0));
+  if (getenv("YH_SLAB_DRIVER_SYNC")) CHECK(yh_slab_group_sync(g));
+  CHECK(yh_slab_group_advance(g, nsteps - first, 0));
+  CHECK(yh_slab_group_get_state(g, ub.data(), vb.data()));
+  unsigned long long su = 0, sv = 0;
+  for (int r = 0; r < nslabs; r++) {
+    unsigned long long a = 0, b = 0;
+    CHECK(yh_slab_checksum(yh_slab_group_member(g, r), &a, &b));
+    su += a; sv += b;
+  }
+  CHECK(yh_slab_group_destroy(g));
+
+  unsigned long long wu = 0, wv = 0;
+  for (size_t c = 0; c < n; c++) {
+    unsigned long long x, y;
+    memcpy(&x, &ua[c], 8); memcpy(&y, &va[c], 8);
+    wu += x; wv += y;
+  }
+  const bool same = memcmp(ua.data(), ub.data(), n * sizeof(double)) == 0 && memcmp(va.data(), vb.data(), n * sizeof(double)) == 0;
+  double moved = 0.0;
+  for (size_t c = 0; c < n; c++) moved += (ua[c] - u0[c]) * (ua[c] - u0[c]);
+  const bool ok = same && su == wu && sv == wv && moved > 1e-3;
+  printf("slab_driver %s %dx%d %s nslabs=%d ndev=%d nsteps=%d bitwise=%d checksum=%016llx/%016llx (sheet %016llx/%016llx) moved=%.3g\n",
+         ok ? "PASS" : "FAIL", nx, ny, mode, nslabs, ndev, nsteps, (int)same, su, sv, wu, wv, moved);
+  return ok ? 0 : 1;
+}

@@ -11,9 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def header_symbols():
-    txt = open(os.path.join(ROOT, "include", "yolohtli_abi.h")).read()
-    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(yh_[a-z0-9_]+)\s*\(", txt)))
+    syms = set()
+    for h in ("yolohtli_abi.h", "yolohtli_slab.h", "yolohtli_io.h"):
+        txt = open(os.path.join(ROOT, "include", h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        syms |= set(re.findall(r"\b(yh_[a-z0-9_]+)\s*\(", txt))
+    return sorted(syms)
 
 
 def test_library_exports_every_declared_symbol(yh):
@@ -22,7 +25,7 @@ def test_library_exports_every_declared_symbol(yh):
     syms = header_symbols()
     assert len(syms) >= 30
     for s in syms:
-        assert hasattr(l, s), f"{s} declared in include/yolohtli_abi.h but not exported"
+        assert hasattr(l, s), f"{s} declared in include/*.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
     assert l.yh_abi_version() == 1
 

@@ -142,6 +142,37 @@ SIGNATURES = {
     "yh_sim_device_v": (_vp, [_vp]),
 }
 
+# include/yolohtli_slab.h -- multi-GPU row-slab driver (csrc/slab.cu)
+_ull = C.c_ulonglong
+SIGNATURES.update({
+    "yh_slab_partition": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "yh_slab_create": (_i, [C.POINTER(_vp), _P, _i, _i, _i, _i]),
+    "yh_slab_destroy": (_i, [_vp]),
+    "yh_slab_layout": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "yh_slab_export": (_i, [_vp, _vp]),
+    "yh_slab_connect": (_i, [_vp, _vp, _vp]),
+    "yh_slab_connect_local": (_i, [_vp, _vp, _vp]),
+    "yh_slab_set_state": (_i, [_vp, _vp, _vp, _i]),
+    "yh_slab_get_state": (_i, [_vp, _vp, _vp]),
+    "yh_slab_set_solid": (_i, [_vp, _vp]),
+    "yh_slab_device_u": (_vp, [_vp]),
+    "yh_slab_device_v": (_vp, [_vp]),
+    "yh_slab_advance": (_i, [_vp, _i, _i]),
+    "yh_slab_sync": (_i, [_vp]),
+    "yh_slab_checksum": (_i, [_vp, C.POINTER(_ull), C.POINTER(_ull)]),
+    "yh_slab_run_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "yh_slab_group_create": (_i, [C.POINTER(_vp), _P, _i, C.POINTER(_i), _i]),
+    "yh_slab_group_destroy": (_i, [_vp]),
+    "yh_slab_group_member": (_vp, [_vp, _i]),
+    "yh_slab_group_set_state": (_i, [_vp, _vp, _vp]),
+    "yh_slab_group_get_state": (_i, [_vp, _vp, _vp]),
+    "yh_slab_group_set_solid": (_i, [_vp, _vp]),
+    "yh_slab_group_advance": (_i, [_vp, _i, _i]),
+    "yh_slab_group_sync": (_i, [_vp]),
+    "yh_slab_group_run_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+})
+SLAB_HANDLE_BYTES = 256
+
 # include/yolohtli_io.h -- host-side data formats (no GPU needed)
 SIGNATURES.update({
     "yh_io_run_params_default": (_i, [_RP, _i, _i]),

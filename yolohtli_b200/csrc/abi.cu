@@ -9,6 +9,7 @@
 #include "yh_common.cuh"
 
 static thread_local char g_err[512] = "";
+thread_local int yh_preload_only = 0;   // yh_common.cuh, YH_LAUNCH
 
 void yh_set_error(const char *fmt, ...) {
   va_list ap;
@@ -330,7 +331,7 @@ int yh_advance_whole(const yh_params *p, const YhK &k, int nsteps, int tb, int c
   if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cudaGetLastError();
   int nch = nsteps / YH_GRAPH_CHUNK;
   YH_CUDA(cudaGetDevice(&dev));
-  if (whole && cap == cudaStreamCaptureStatusNone && nch >= 3 && dev < YH_MAX_DEV &&
+  if (whole && !yh_preload_only && cap == cudaStreamCaptureStatusNone && nch >= 3 && dev < YH_MAX_DEV &&
       yh_graphs_enabled((long long)p->nx * p->ny)) {
     cudaStream_t gs;
     rc = graph_stream(dev, &gs);

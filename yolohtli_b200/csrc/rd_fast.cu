@@ -221,8 +221,8 @@ int launch3(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   const int strips = (k.nx + BX - 1) / BX;
   b.RY = a.RY > 0 ? a.RY : pick_ry(rows, strips, nsims, T, slots[dev & 63]);
   dim3 grd(strips, (rows + b.RY - 1) / b.RY, nsims);
-  rd_euler_stream<T, W, CANON, TC1, STIM, SOLID><<<grd, NT, smem, st>>>(k, b);
-  YH_LAUNCH_CHECK();
+  auto kfn = rd_euler_stream<T, W, CANON, TC1, STIM, SOLID>;
+  YH_LAUNCH(kfn, grd, NT, smem, st, k, b);
   return YH_OK;
 }
 
@@ -287,8 +287,7 @@ int yh_rd_fast_solid_supported(const YhK &k, int tb) {
 int yh_rd_solid_patterns(const YhK &k, const uint8_t *solid, uint8_t *pat, cudaStream_t st) {
   const long long n = (long long)k.nx * k.ny;
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  solid_pattern_kernel<<<blocks, 256, 0, st>>>(k, solid, pat);
-  YH_LAUNCH_CHECK();
+  YH_LAUNCH(solid_pattern_kernel, blocks, 256, 0, st, k, solid, pat);
   return YH_OK;
 }
 

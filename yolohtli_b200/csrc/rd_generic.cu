@@ -278,8 +278,7 @@ int yh_launch_rd_generic(const YhK &k, const double *u_in, const double *v_in, d
     a.jhi = min(hi, k.row1 + ext);
     if (a.jhi <= a.jlo) continue;
     dim3 blk(32, 8), grd((k.nx + 31) / 32, (a.jhi - a.jlo + 7) / 8);
-    rd_stage_kernel<<<grd, blk, 0, st>>>(k, a);
-    YH_LAUNCH_CHECK();
+    YH_LAUNCH(rd_stage_kernel, grd, blk, 0, st, k, a);
   }
   return YH_OK;
 }

@@ -341,8 +341,8 @@ int launch4(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   const int strips = (k.nx + BX - 1) / BX;
   b.RY = a.RY > 0 ? a.RY : pick_ry(rows, strips, nsims, T, slots[dev & 63]);
   dim3 grd(strips, (rows + b.RY - 1) / b.RY, nsims);
-  rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX><<<grd, NT, smem, st>>>(k, b);
-  YH_LAUNCH_CHECK();
+  auto kfn = rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX>;
+  YH_LAUNCH(kfn, grd, NT, smem, st, k, b);
   return YH_OK;
 }
 

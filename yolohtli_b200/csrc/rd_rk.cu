@@ -422,8 +422,8 @@ int launch2(const YhK &k, RkArgs a, cudaStream_t st) {
   const char *force_ry = getenv("YH_RK_RY");
   a.RY = force_ry ? atoi(force_ry) : pick_ry_rk(rows, strips, K, slots[dev & 63]);
   dim3 grd(strips, (rows + a.RY - 1) / a.RY);
-  rd_rk_stream<K, W, LAP4, SOLID, DEF, FAST><<<grd, NT, smem, st>>>(k, a);
-  YH_LAUNCH_CHECK();
+  auto kfn = rd_rk_stream<K, W, LAP4, SOLID, DEF, FAST>;
+  YH_LAUNCH(kfn, grd, NT, smem, st, k, a);
   return YH_OK;
 }
 

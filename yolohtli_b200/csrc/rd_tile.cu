@@ -360,8 +360,8 @@ int launch_rk(const YhK &k, const TileArgs &a, cudaStream_t st) {
   YH_CUDA(cudaGetDevice(&dev));
   if (!done[dev & 63]) { int rc = set_smem(rd_tile_rk<K, LAP4, DEF, FAST>, smem); if (rc) return rc; done[dev & 63] = true; }
   dim3 grd((k.nx + TB - 1) / TB, (k.row1 - k.row0 + TB - 1) / TB);
-  rd_tile_rk<K, LAP4, DEF, FAST><<<grd, NTHR, smem, st>>>(k, a);
-  YH_LAUNCH_CHECK();
+  auto kfn = rd_tile_rk<K, LAP4, DEF, FAST>;
+  YH_LAUNCH(kfn, grd, NTHR, smem, st, k, a);
   return YH_OK;
 }
 
@@ -374,8 +374,8 @@ int launch_euler(const YhK &k, const TileArgs &a, int nsims, cudaStream_t st) {
   YH_CUDA(cudaGetDevice(&dev));
   if (!done[dev & 63]) { int rc = set_smem(rd_tile_euler<T, DEF>, smem); if (rc) return rc; done[dev & 63] = true; }
   dim3 grd((k.nx + TB - 1) / TB, (k.row1 - k.row0 + TB - 1) / TB, nsims);
-  rd_tile_euler<T, DEF><<<grd, EulerTile<T>::NT, smem, st>>>(k, a);
-  YH_LAUNCH_CHECK();
+  auto kfn = rd_tile_euler<T, DEF>;
+  YH_LAUNCH(kfn, grd, EulerTile<T>::NT, smem, st, k, a);
   return YH_OK;
 }
 

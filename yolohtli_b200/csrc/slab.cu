@@ -1,0 +1,783 @@
+// slab.cu -- multi-GPU row-slab driver behind include/yolohtli_slab.h: the reference's host loop
+// {reactionDiffusion_wrapper; swapSoA} (main.cu:879-882) for a sheet cut into contiguous row slabs,
+// one per GPU.  Host code is C++ like the reference's; the data path is kernels only:
+//
+//   edge stream (high priority)   wait interior(k-1) | step top band, bottom band | EXCHANGE(k)
+//   main stream                   wait edge(k-1)     | step interior rows
+//
+// EXCHANGE is one kernel: it copies this slab's fresh first / last `halo` owned rows straight into the
+// neighbours' ghost rows (16-byte stores through peer mappings = NVLink), the last CTA to finish
+// releases the block's sequence number into the neighbours' flag words (st.release.sys) and then
+// acquires the two numbers the neighbours release into ours.  The sequence counter lives in device
+// memory, so no launch argument changes from block to block and pairs of blocks replay from a CUDA
+// graph.  Write-after-read safety: a rank cannot reach exchange k before it has acquired its
+// neighbour's exchange k-1, which the neighbour issued after the kernels that read the ghost rows
+// exchange k overwrites.
+//
+// Interior rows are >= halo rows away from the slab edges: they never read a ghost row and overlap
+// the exchange.  One HBM pass per block and region (Euler: T <= halo time steps per pass; RK: one
+// time step), so no pass of one region reads rows another region is writing.
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <vector>
+
+#include "../../include/yolohtli_slab.h"
+#include "yh_common.cuh"
+
+namespace {
+
+constexpr int FLAG_FROM_UP = 0, FLAG_FROM_DOWN = 1, FLAG_STATUS = 2, FLAG_SEQ = 3, FLAG_DONE = 4;
+constexpr int FLAG_WORDS = 64;   // 256 bytes
+constexpr unsigned HANDLE_MAGIC = 0x59485342u;   // "YHSB"
+
+struct SlabHandle {
+  unsigned magic;
+  int rank, world, device, own_lo, own_hi, ny_local, nx, pid;
+  unsigned long long base_off;           // offset of the slab's block inside the exported allocation
+  unsigned long long off[5];             // u0 u1 v0 v1 flags inside the block
+  cudaIpcMemHandle_t mem;
+};
+static_assert(sizeof(SlabHandle) <= YH_SLAB_HANDLE_BYTES, "handle too large");
+
+struct Peer {
+  bool present;
+  double *u[2], *v[2];
+  int *flags;
+  int own_lo, own_hi;
+  void *ipc_base;                        // cudaIpcOpenMemHandle mapping to close, or NULL
+};
+
+struct XchgArgs {
+  const double *src_u, *src_v;           // this slab's buffer (stored rows)
+  double *dst[4];                        // up.u up.v down.u down.v: first ghost row to write, or NULL
+  long long src_off[2];                  // element offset of the rows sent up / down
+  long long n;                           // doubles per field and direction (halo * nx)
+  int *up_flag, *dn_flag;                // flag words to release into (in the neighbours' memory)
+  int *flags;                            // this slab's flag block
+};
+
+__device__ __forceinline__ void st_release_sys(int *p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Peer stores of the fresh edge rows, then release / acquire of the block's sequence number.
+__global__ void __launch_bounds__(256) slab_exchange_kernel(const __grid_constant__ XchgArgs a) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthr = (long long)gridDim.x * blockDim.x;
+  const bool vec = ((a.n & 1) == 0) && (((a.src_off[0] | a.src_off[1]) & 1) == 0);
+  for (int seg = 0; seg < 4; seg++) {
+    double *d = a.dst[seg];
+    if (!d) continue;
+    const double *s = ((seg & 1) ? a.src_v : a.src_u) + a.src_off[seg >> 1];
+    if (vec && ((reinterpret_cast<unsigned long long>(d) | reinterpret_cast<unsigned long long>(s)) & 15) == 0) {
+      const long long n2 = a.n >> 1;
+      for (long long i = tid; i < n2; i += nthr)
+        reinterpret_cast<double2 *>(d)[i] = reinterpret_cast<const double2 *>(s)[i];
+    } else {
+      for (long long i = tid; i < a.n; i += nthr) d[i] = s[i];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  unsigned *done = reinterpret_cast<unsigned *>(a.flags + FLAG_DONE);
+  if (atomicAdd(done, 1u) != gridDim.x - 1) return;
+  // last CTA: every CTA's rows are out (each fenced before it counted itself)
+  *done = 0;
+  const int seq = a.flags[FLAG_SEQ] + 1;
+  __threadfence_system();
+  if (a.up_flag) st_release_sys(a.up_flag, seq);
+  if (a.dn_flag) st_release_sys(a.dn_flag, seq);
+  // a neighbour that never signals must not hang the GPU: ~4 s, then the status word says so
+  const long long t0 = clock64();
+  for (int w = 0; w < 2; w++) {
+    if (!(w == 0 ? a.up_flag : a.dn_flag)) continue;
+    const int *f = a.flags + (w == 0 ? FLAG_FROM_UP : FLAG_FROM_DOWN);
+    while (ld_acquire_sys(f) < seq) {
+      if (clock64() - t0 > 8000000000ll) { a.flags[FLAG_STATUS] = 1; break; }
+      __nanosleep(100);
+    }
+  }
+  a.flags[FLAG_SEQ] = seq;
+  __threadfence_system();
+}
+
+// Sum of the bit patterns of the owned cells mod 2^64 (order independent: one number per sheet, whatever
+// the decomposition).
+__global__ void slab_checksum_kernel(const unsigned long long *u, const unsigned long long *v, long long n,
+                                     unsigned long long *out) {
+  unsigned long long su = 0, sv = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    su += u[i]; sv += v[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    su += __shfl_xor_sync(0xffffffffu, su, o);
+    sv += __shfl_xor_sync(0xffffffffu, sv, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, su); atomicAdd(out + 1, sv); }
+}
+
+struct DevGuard {
+  int prev;
+  explicit DevGuard(int d) { cudaGetDevice(&prev); cudaSetDevice(d); }
+  ~DevGuard() { cudaSetDevice(prev); }
+};
+
+struct GraphSlot {
+  cudaGraphExec_t exec;
+  int n, cur, raw;
+};
+
+}  // namespace
+
+struct yh_slab {
+  yh_params pg, p;                       // whole sheet / this slab's stored rows
+  int rank, world, halo, device, K;
+  int j0, j1, g0, g1, ny_local, own_lo, own_hi, nx;
+  bool fast;                             // temporally blocked Euler path
+  char *block;                           // one allocation: u0 u1 v0 v1 flags
+  size_t block_bytes, off[5];
+  double *u[2], *v[2];
+  int *flags;
+  int cur;
+  uint8_t *solid, *pat;
+  const uint8_t *solid_arg;
+  int solid_flags;
+  Peer up, down;
+  cudaStream_t main, edge;
+  cudaEvent_t ev_int, ev_edge, ev_fork;
+  bool raw, ghosts_valid, connected;
+  long long count;
+  unsigned long long *sum_d;
+  GraphSlot graphs[4];
+  int band;
+};
+
+struct yh_slab_group {
+  std::vector<yh_slab *> m;
+};
+
+namespace {
+
+int launch_exchange(yh_slab *s, int buf, cudaStream_t st) {
+  XchgArgs a;
+  memset(&a, 0, sizeof(a));
+  const long long row = s->nx;
+  a.src_u = s->u[buf]; a.src_v = s->v[buf];
+  a.n = (long long)s->halo * row;
+  a.flags = s->flags;
+  if (s->up.present) {     // my first halo owned rows are the upper neighbour's lower ghosts
+    a.src_off[0] = (long long)s->own_lo * row;
+    a.dst[0] = s->up.u[buf] + (long long)s->up.own_hi * row;
+    a.dst[1] = s->up.v[buf] + (long long)s->up.own_hi * row;
+    a.up_flag = s->up.flags + FLAG_FROM_DOWN;
+  }
+  if (s->down.present) {   // my last halo owned rows are the lower neighbour's upper ghosts
+    a.src_off[1] = (long long)(s->own_hi - s->halo) * row;
+    a.dst[2] = s->down.u[buf] + (long long)(s->down.own_lo - s->halo) * row;
+    a.dst[3] = s->down.v[buf] + (long long)(s->down.own_lo - s->halo) * row;
+    a.dn_flag = s->down.flags + FLAG_FROM_UP;
+  }
+  const long long pieces = a.n / 2 > 0 ? a.n / 2 : 1;
+  int blocks = (int)((pieces + 255) / 256);
+  if (blocks > 32) blocks = 32;
+  if (blocks < 1) blocks = 1;
+  slab_exchange_kernel<<<blocks, 256, 0, st>>>(a);
+  YH_LAUNCH_CHECK();
+  return YH_OK;
+}
+
+int rd_rows(yh_slab *s, int n, int c, int o, int r0, int r1, cudaStream_t st) {
+  if (r1 <= r0) return YH_OK;
+  int inB = 0;
+  const int flags = (s->raw ? 0 : YH_RD_INPUT_CANONICAL) | s->solid_flags;
+  int rc = yh_rd_advance(&s->p, n, s->fast ? n : 1, flags, s->u[c], s->v[c], s->u[o], s->v[o], s->solid_arg,
+                         0, s->nx / 2, s->pg.ny / 2, r0, r1, &inB, st);
+  if (rc != YH_OK) return rc;
+  if (!inB) { yh_set_error("slab block was not a single pass"); return YH_ERR_UNSUPPORTED; }
+  return YH_OK;
+}
+
+bool has_neighbours(const yh_slab *s) { return s->up.present || s->down.present; }
+
+// Load the code of every kernel a block of n steps will launch on this slab (the three row ranges may
+// take different kernels: tiles for the bands, a streaming kernel for the interior), for raw and for
+// library-written input, without launching anything (YH_LAUNCH, yh_common.cuh).
+int preload_block(yh_slab *s, int n) {
+  const int B = s->band;
+  const int top1 = s->up.present ? s->own_lo + B : s->own_lo;
+  const int bot0 = s->down.present ? s->own_hi - B : s->own_hi;
+  const bool raw0 = s->raw;
+  int rc = YH_OK;
+  yh_preload_only = 1;
+  for (int raw = 0; raw < 2 && rc == YH_OK; raw++) {
+    s->raw = raw != 0;
+    rc = rd_rows(s, n, 0, 1, s->own_lo, top1, s->main);
+    if (rc == YH_OK) rc = rd_rows(s, n, 0, 1, bot0, s->own_hi, s->main);
+    if (rc == YH_OK) rc = rd_rows(s, n, 0, 1, top1, bot0, s->main);
+  }
+  yh_preload_only = 0;
+  s->raw = raw0;
+  if (rc != YH_OK) return rc;
+  cudaFuncAttributes fa;
+  YH_CUDA(cudaFuncGetAttributes(&fa, slab_exchange_kernel));
+  return YH_OK;
+}
+
+// time steps of the next block
+int block_steps(const yh_slab *s, int left, int tb) {
+  if (!s->fast) return 1;
+  int cap = s->halo < left ? s->halo : left;
+  const int want = tb ? tb : 4;
+  if (want < cap) cap = want;
+  int n = 1;
+  while (2 * n <= cap && 2 * n <= 4) n *= 2;
+  return n;
+}
+
+int advance_begin(yh_slab *s) {
+  if (s->world > 1 && !s->connected) { yh_set_error("yh_slab_advance before yh_slab_connect"); return YH_ERR_INVALID_ARG; }
+  YH_CUDA(cudaEventRecord(s->ev_int, s->main));
+  YH_CUDA(cudaEventRecord(s->ev_edge, s->main));
+  if (has_neighbours(s) && !s->ghosts_valid) {   // ghost rows of the current state from the neighbours
+    YH_CUDA(cudaStreamWaitEvent(s->edge, s->ev_int, 0));
+    int rc = launch_exchange(s, s->cur, s->edge);
+    if (rc != YH_OK) return rc;
+    YH_CUDA(cudaEventRecord(s->ev_edge, s->edge));
+    s->ghosts_valid = true;
+  }
+  return YH_OK;
+}
+
+// one block of n time steps: state cur -> cur^1
+int advance_block(yh_slab *s, int n) {
+  const int c = s->cur, o = c ^ 1;
+  int rc;
+  if (!has_neighbours(s)) {
+    rc = rd_rows(s, n, c, o, s->own_lo, s->own_hi, s->main);
+    if (rc != YH_OK) return rc;
+  } else {
+    const int B = s->band;
+    const int top0 = s->own_lo, top1 = s->up.present ? s->own_lo + B : s->own_lo;
+    const int bot0 = s->down.present ? s->own_hi - B : s->own_hi, bot1 = s->own_hi;
+    YH_CUDA(cudaStreamWaitEvent(s->edge, s->ev_int, 0));     // interior(k-1)
+    rc = rd_rows(s, n, c, o, top0, top1, s->edge);
+    if (rc != YH_OK) return rc;
+    rc = rd_rows(s, n, c, o, bot0, bot1, s->edge);
+    if (rc != YH_OK) return rc;
+    rc = launch_exchange(s, o, s->edge);
+    if (rc != YH_OK) return rc;
+    YH_CUDA(cudaStreamWaitEvent(s->main, s->ev_edge, 0));    // edge(k-1)
+    rc = rd_rows(s, n, c, o, top1, bot0, s->main);
+    if (rc != YH_OK) return rc;
+    YH_CUDA(cudaEventRecord(s->ev_int, s->main));
+    YH_CUDA(cudaEventRecord(s->ev_edge, s->edge));
+  }
+  s->cur = o;
+  s->raw = false;
+  s->count += n;
+  return YH_OK;
+}
+
+int advance_end(yh_slab *s) {
+  YH_CUDA(cudaStreamWaitEvent(s->main, s->ev_edge, 0));
+  return YH_OK;
+}
+
+// Two blocks (the ping-pong returns to the same buffers) captured once per {n, parity} and replayed.
+int graph_pair(yh_slab *s, int n, cudaGraphExec_t *out) {
+  for (auto &g : s->graphs)
+    if (g.exec && g.n == n && g.cur == s->cur && g.raw == 0) { *out = g.exec; return YH_OK; }
+  GraphSlot *slot = &s->graphs[0];
+  for (auto &g : s->graphs)
+    if (!g.exec) { slot = &g; break; }
+  if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+  const int cur0 = s->cur;
+  const long long count0 = s->count;
+  cudaGraph_t graph = nullptr;
+  YH_CUDA(cudaStreamBeginCapture(s->main, cudaStreamCaptureModeThreadLocal));
+  int rc = cudaEventRecord(s->ev_fork, s->main) == cudaSuccess ? YH_OK : YH_ERR_CUDA;
+  if (rc == YH_OK) rc = cudaStreamWaitEvent(s->edge, s->ev_fork, 0) == cudaSuccess ? YH_OK : YH_ERR_CUDA;
+  if (rc == YH_OK) rc = advance_begin(s);
+  if (rc == YH_OK) rc = advance_block(s, n);
+  if (rc == YH_OK) rc = advance_block(s, n);
+  if (rc == YH_OK) rc = advance_end(s);
+  cudaError_t ce = cudaStreamEndCapture(s->main, &graph);
+  s->cur = cur0; s->count = count0;      // the capture launched nothing
+  if (rc != YH_OK || ce != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc == YH_OK) { yh_set_error("graph capture of the slab block pair failed"); rc = YH_ERR_CUDA; }
+    return rc;
+  }
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) { cudaGetLastError(); yh_set_error("cudaGraphInstantiate failed"); return YH_ERR_CUDA; }
+  slot->exec = exec; slot->n = n; slot->cur = cur0; slot->raw = 0;
+  *out = exec;
+  return YH_OK;
+}
+
+bool graphs_wanted() {
+  const char *f = getenv("YH_SLAB_GRAPHS");
+  return !(f && f[0] == '0');
+}
+
+// The whole run of one slab or, in lock step, of all slabs of a group (breadth first per block, so no
+// slab's queue runs ahead of a neighbour whose work is not enqueued yet).
+int advance_all(yh_slab *const *m, int count, int nsteps, int tb) {
+  int rc;
+  // every kernel of the run resident before the first exchange kernel can be waiting for a neighbour
+  for (int left = nsteps; left > 0;) {
+    const int n = block_steps(m[0], left, tb);
+    for (int q = 0; q < count; q++) {
+      DevGuard g(m[q]->device);
+      rc = preload_block(m[q], n);
+      if (rc != YH_OK) return rc;
+    }
+    left -= (left / n) * n;
+  }
+  for (int q = 0; q < count; q++) {
+    DevGuard g(m[q]->device);
+    rc = advance_begin(m[q]);
+    if (rc != YH_OK) return rc;
+  }
+  int left = nsteps;
+  while (left > 0) {
+    const int n = block_steps(m[0], left, tb);
+    const int same = left / n;             // consecutive blocks of this length
+    int plain = same;
+    // steady state from graphs: two plain blocks first (raw input, first use of the kernel variants)
+    if (graphs_wanted() && same >= 8 && has_neighbours(m[0])) plain = 2 + (same - 2) % 2;
+    for (int b = 0; b < plain; b++) {
+      for (int q = 0; q < count; q++) {
+        DevGuard g(m[q]->device);
+        rc = advance_block(m[q], n);
+        if (rc != YH_OK) return rc;
+      }
+      if (getenv("YH_SLAB_DEBUG_SYNC"))    // debugging aid: host and devices in lock step
+        for (int q = 0; q < count; q++) { cudaStreamSynchronize(m[q]->edge); cudaStreamSynchronize(m[q]->main); }
+    }
+    const int pairs = (same - plain) / 2;
+    if (pairs > 0) {
+      std::vector<cudaGraphExec_t> ex(count, nullptr);
+      bool ok = true;
+      for (int q = 0; q < count; q++) {
+        DevGuard g(m[q]->device);
+        rc = advance_end(m[q]);            // join the edge stream: the graph runs on main
+        if (rc != YH_OK) return rc;
+        if (graph_pair(m[q], n, &ex[q]) != YH_OK) ok = false;
+      }
+      if (ok) {
+        for (int b = 0; b < pairs; b++)
+          for (int q = 0; q < count; q++) {
+            DevGuard g(m[q]->device);
+            YH_CUDA(cudaGraphLaunch(ex[q], m[q]->main));
+          }
+        for (int q = 0; q < count; q++) {
+          DevGuard g(m[q]->device);
+          m[q]->count += (long long)2 * n * pairs;
+          rc = advance_begin(m[q]);        // events of the plain schedule again
+          if (rc != YH_OK) return rc;
+        }
+      } else {                             // capture refused: plain launches
+        for (int b = 0; b < 2 * pairs; b++)
+          for (int q = 0; q < count; q++) {
+            DevGuard g(m[q]->device);
+            rc = advance_block(m[q], n);
+            if (rc != YH_OK) return rc;
+          }
+      }
+    }
+    left -= same * n;
+  }
+  for (int q = 0; q < count; q++) {
+    DevGuard g(m[q]->device);
+    rc = advance_end(m[q]);
+    if (rc != YH_OK) return rc;
+  }
+  return YH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yh_slab_partition(int ny_global, int world, int rank, int *j0, int *j1) {
+  if (!j0 || !j1 || world < 1 || rank < 0 || rank >= world || ny_global < world) {
+    yh_set_error("yh_slab_partition: bad arguments");
+    return YH_ERR_INVALID_ARG;
+  }
+  const int base = ny_global / world, rem = ny_global % world;
+  *j0 = rank * base + (rank < rem ? rank : rem);
+  *j1 = *j0 + base + (rank < rem ? 1 : 0);
+  return YH_OK;
+}
+
+int yh_slab_create(yh_slab **out, const yh_params *pg, int rank, int world, int halo, int device) {
+  int rc = yh_check_device();
+  if (rc != YH_OK) return rc;
+  YH_REQUIRE(out && pg, "null pointer");
+  YH_REQUIRE(pg->jg0 == 0 && pg->ny_global == pg->ny, "p_global must describe the whole sheet");
+  YH_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
+  YH_REQUIRE(device >= 0 && device < yh_device_count(), "no such device");
+  YH_REQUIRE(pg->timeIntOrder == 1 || pg->timeIntOrder == 2 || pg->timeIntOrder == 4, "timeIntOrder must be 1, 2 or 4");
+  YH_REQUIRE(halo >= pg->timeIntOrder && halo >= 1, "halo must be >= timeIntOrder");
+  if (world > 1 && pg->anisotropy && pg->neumannBC && !pg->solidSwitch) {
+    // the anisotropic no-flux corner terms read rows j+-2 at the x edges (reactionDiffusion.cu:290-304)
+    yh_set_error("anisotropy with no-flux boundaries is not supported on row slabs");
+    return YH_ERR_UNSUPPORTED;
+  }
+  DevGuard g(device);
+  yh_slab *s = new yh_slab();
+  memset(&s->up, 0, sizeof(Peer)); memset(&s->down, 0, sizeof(Peer));
+  memset(s->graphs, 0, sizeof(s->graphs));
+  s->pg = *pg; s->rank = rank; s->world = world; s->halo = halo; s->device = device;
+  s->K = pg->timeIntOrder; s->nx = pg->nx;
+  yh_slab_partition(pg->ny, world, rank, &s->j0, &s->j1);
+  if (world > 1 && s->j1 - s->j0 < 2 * halo) {
+    delete s;
+    yh_set_error("slab thinner than two halos");
+    return YH_ERR_INVALID_ARG;
+  }
+  s->g0 = s->j0 - halo > 0 ? s->j0 - halo : 0;
+  s->g1 = s->j1 + halo < pg->ny ? s->j1 + halo : pg->ny;
+  s->ny_local = s->g1 - s->g0;
+  s->own_lo = s->j0 - s->g0; s->own_hi = s->j1 - s->g0;
+  s->p = *pg; s->p.ny = s->ny_local; s->p.ny_global = pg->ny; s->p.jg0 = s->g0;
+  const int own = s->j1 - s->j0;
+  int B = own / 4 < 128 ? own / 4 : 128;
+  if (B < halo) B = halo;
+  s->band = B;
+  YhK k = yh_make_k(&s->p);
+  s->fast = pg->solidSwitch ? yh_rd_fast_solid_supported(k, 1) != 0 : yh_rd_fast_supported(k, 1) != 0;
+  const size_t arr = (((size_t)s->ny_local * s->nx * sizeof(double)) + 255) & ~(size_t)255;
+  for (int q = 0; q < 4; q++) s->off[q] = arr * q;
+  s->off[4] = arr * 4;
+  s->block_bytes = arr * 4 + FLAG_WORDS * sizeof(int);
+  if (cudaMalloc(&s->block, s->block_bytes) != cudaSuccess) {
+    yh_set_error("yh_slab_create: cudaMalloc of %zu bytes failed", s->block_bytes);
+    cudaGetLastError();
+    delete s;
+    return YH_ERR_CUDA;
+  }
+  cudaMemset(s->block, 0, s->block_bytes);
+  s->u[0] = reinterpret_cast<double *>(s->block + s->off[0]);
+  s->u[1] = reinterpret_cast<double *>(s->block + s->off[1]);
+  s->v[0] = reinterpret_cast<double *>(s->block + s->off[2]);
+  s->v[1] = reinterpret_cast<double *>(s->block + s->off[3]);
+  s->flags = reinterpret_cast<int *>(s->block + s->off[4]);
+  s->cur = 0; s->solid = nullptr; s->pat = nullptr; s->solid_arg = nullptr; s->solid_flags = 0;
+  s->raw = true; s->ghosts_valid = false; s->connected = (world == 1); s->count = 0;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = greatest priority (numerically lowest)
+  cudaStreamCreateWithPriority(&s->main, cudaStreamNonBlocking, lo);
+  cudaStreamCreateWithPriority(&s->edge, cudaStreamNonBlocking, hi);
+  cudaEventCreateWithFlags(&s->ev_int, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&s->ev_edge, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
+  cudaMalloc(&s->sum_d, 2 * sizeof(unsigned long long));
+  cudaDeviceSynchronize();
+  if (cudaGetLastError() != cudaSuccess) { yh_set_error("yh_slab_create: stream / event setup failed"); return YH_ERR_CUDA; }
+  *out = s;
+  return YH_OK;
+}
+
+int yh_slab_destroy(yh_slab *s) {
+  if (!s) return YH_OK;
+  DevGuard g(s->device);
+  cudaStreamSynchronize(s->main);
+  cudaStreamSynchronize(s->edge);
+  for (auto &gr : s->graphs)
+    if (gr.exec) cudaGraphExecDestroy(gr.exec);
+  if (s->up.ipc_base) cudaIpcCloseMemHandle(s->up.ipc_base);
+  if (s->down.ipc_base) cudaIpcCloseMemHandle(s->down.ipc_base);
+  cudaFree(s->block); cudaFree(s->solid); cudaFree(s->pat); cudaFree(s->sum_d);
+  cudaStreamDestroy(s->main); cudaStreamDestroy(s->edge);
+  cudaEventDestroy(s->ev_int); cudaEventDestroy(s->ev_edge); cudaEventDestroy(s->ev_fork);
+  cudaGetLastError();
+  delete s;
+  return YH_OK;
+}
+
+int yh_slab_layout(const yh_slab *s, int *j0, int *j1, int *g0, int *g1) {
+  YH_REQUIRE(s != nullptr, "null slab");
+  if (j0) *j0 = s->j0;
+  if (j1) *j1 = s->j1;
+  if (g0) *g0 = s->g0;
+  if (g1) *g1 = s->g1;
+  return YH_OK;
+}
+
+int yh_slab_export(yh_slab *s, void *handle) {
+  YH_REQUIRE(s && handle, "null pointer");
+  DevGuard g(s->device);
+  SlabHandle h;
+  memset(&h, 0, sizeof(h));
+  h.magic = HANDLE_MAGIC; h.rank = s->rank; h.world = s->world; h.device = s->device;
+  h.own_lo = s->own_lo; h.own_hi = s->own_hi; h.ny_local = s->ny_local; h.nx = s->nx; h.pid = (int)getpid();
+  for (int q = 0; q < 5; q++) h.off[q] = s->off[q];
+  // the IPC handle names the ALLOCATION the block lives in; cudaMalloc may place a block inside a larger
+  // reservation, so the offset from the allocation base travels with it (driver entry point resolved at
+  // run time: the library has no link-time dependency on libcuda)
+  typedef int (*GetRange)(unsigned long long *, size_t *, unsigned long long);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  h.base_off = 0;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn) {
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (reinterpret_cast<GetRange>(fn)(&base, &size, (unsigned long long)(uintptr_t)s->block) == 0)
+      h.base_off = (unsigned long long)(uintptr_t)s->block - base;
+  } else {
+    cudaGetLastError();
+  }
+  YH_CUDA(cudaIpcGetMemHandle(&h.mem, s->block));
+  memset(handle, 0, YH_SLAB_HANDLE_BYTES);
+  memcpy(handle, &h, sizeof(h));
+  return YH_OK;
+}
+
+static int open_peer(yh_slab *s, const void *handle, Peer *p, int expect_rank) {
+  SlabHandle h;
+  memcpy(&h, handle, sizeof(h));
+  YH_REQUIRE(h.magic == HANDLE_MAGIC, "not a slab handle");
+  YH_REQUIRE(h.rank == expect_rank && h.world == s->world && h.nx == s->nx, "handle of the wrong rank / sheet");
+  void *base = nullptr;
+  YH_CUDA(cudaIpcOpenMemHandle(&base, h.mem, cudaIpcMemLazyEnablePeerAccess));
+  char *blk = static_cast<char *>(base) + h.base_off;
+  p->present = true; p->ipc_base = base;
+  p->u[0] = reinterpret_cast<double *>(blk + h.off[0]); p->u[1] = reinterpret_cast<double *>(blk + h.off[1]);
+  p->v[0] = reinterpret_cast<double *>(blk + h.off[2]); p->v[1] = reinterpret_cast<double *>(blk + h.off[3]);
+  p->flags = reinterpret_cast<int *>(blk + h.off[4]);
+  p->own_lo = h.own_lo; p->own_hi = h.own_hi;
+  return YH_OK;
+}
+
+int yh_slab_connect(yh_slab *s, const void *handle_up, const void *handle_down) {
+  YH_REQUIRE(s != nullptr, "null slab");
+  YH_REQUIRE((handle_up != nullptr) == (s->rank > 0), "handle_up must be given exactly when rank > 0");
+  YH_REQUIRE((handle_down != nullptr) == (s->rank < s->world - 1), "handle_down must be given exactly when rank < world-1");
+  DevGuard g(s->device);
+  int rc;
+  if (handle_up && (rc = open_peer(s, handle_up, &s->up, s->rank - 1)) != YH_OK) return rc;
+  if (handle_down && (rc = open_peer(s, handle_down, &s->down, s->rank + 1)) != YH_OK) return rc;
+  s->connected = true;
+  return YH_OK;
+}
+
+static int local_peer(yh_slab *s, yh_slab *o, Peer *p) {
+  if (o->device != s->device) {
+    int rc = yh_enable_peer_access(o->device);
+    if (rc != YH_OK) return rc;
+  }
+  p->present = true; p->ipc_base = nullptr;
+  p->u[0] = o->u[0]; p->u[1] = o->u[1]; p->v[0] = o->v[0]; p->v[1] = o->v[1];
+  p->flags = o->flags; p->own_lo = o->own_lo; p->own_hi = o->own_hi;
+  return YH_OK;
+}
+
+int yh_slab_connect_local(yh_slab *s, yh_slab *up, yh_slab *down) {
+  YH_REQUIRE(s != nullptr, "null slab");
+  YH_REQUIRE((up != nullptr) == (s->rank > 0) && (down != nullptr) == (s->rank < s->world - 1),
+             "neighbours must be given exactly where they exist");
+  YH_REQUIRE((!up || up->rank == s->rank - 1) && (!down || down->rank == s->rank + 1), "wrong neighbour rank");
+  DevGuard g(s->device);
+  int rc;
+  if (up && (rc = local_peer(s, up, &s->up)) != YH_OK) return rc;
+  if (down && (rc = local_peer(s, down, &s->down)) != YH_OK) return rc;
+  s->connected = true;
+  return YH_OK;
+}
+
+int yh_slab_set_state(yh_slab *s, const double *u_h, const double *v_h, int with_ghosts) {
+  YH_REQUIRE(s && u_h && v_h, "null pointer");
+  DevGuard g(s->device);
+  const size_t row = (size_t)s->nx;
+  const size_t first = with_ghosts ? 0 : (size_t)s->own_lo;
+  const size_t rows = with_ghosts ? (size_t)s->ny_local : (size_t)(s->own_hi - s->own_lo);
+  YH_CUDA(cudaMemcpyAsync(s->u[s->cur] + first * row, u_h, rows * row * sizeof(double), cudaMemcpyHostToDevice, s->main));
+  YH_CUDA(cudaMemcpyAsync(s->v[s->cur] + first * row, v_h, rows * row * sizeof(double), cudaMemcpyHostToDevice, s->main));
+  s->raw = true;
+  s->ghosts_valid = with_ghosts != 0 || s->world == 1;
+  return YH_OK;
+}
+
+int yh_slab_get_state(yh_slab *s, double *u_h, double *v_h) {
+  YH_REQUIRE(s && u_h && v_h, "null pointer");
+  DevGuard g(s->device);
+  const size_t row = (size_t)s->nx, rows = (size_t)(s->own_hi - s->own_lo);
+  YH_CUDA(cudaMemcpyAsync(u_h, s->u[s->cur] + (size_t)s->own_lo * row, rows * row * sizeof(double), cudaMemcpyDeviceToHost, s->main));
+  YH_CUDA(cudaMemcpyAsync(v_h, s->v[s->cur] + (size_t)s->own_lo * row, rows * row * sizeof(double), cudaMemcpyDeviceToHost, s->main));
+  return yh_slab_sync(s);
+}
+
+int yh_slab_set_solid(yh_slab *s, const uint8_t *mask_h) {
+  YH_REQUIRE(s && mask_h, "null pointer");
+  DevGuard g(s->device);
+  const size_t n = (size_t)s->ny_local * s->nx;
+  if (!s->solid) YH_CUDA(cudaMalloc(&s->solid, n));
+  YH_CUDA(cudaMemcpyAsync(s->solid, mask_h, n, cudaMemcpyHostToDevice, s->main));
+  s->solid_arg = s->solid; s->solid_flags = 0;
+  YhK k = yh_make_k(&s->p);
+  if (yh_rd_fast_solid_supported(k, 1)) {   // masked Euler: neighbourhood patterns once (the mask is fixed)
+    if (!s->pat) YH_CUDA(cudaMalloc(&s->pat, n));
+    int rc = yh_rd_solid_patterns(k, s->solid, s->pat, s->main);
+    if (rc != YH_OK) return rc;
+    s->solid_arg = s->pat; s->solid_flags = YH_RD_SOLID_IS_PATTERNS;
+  }
+  YH_CUDA(cudaStreamSynchronize(s->main));
+  return YH_OK;
+}
+
+void *yh_slab_device_u(yh_slab *s) { return s ? s->u[s->cur] : nullptr; }
+void *yh_slab_device_v(yh_slab *s) { return s ? s->v[s->cur] : nullptr; }
+
+int yh_slab_advance(yh_slab *s, int nsteps, int tb_steps) {
+  YH_REQUIRE(s && nsteps >= 0, "bad arguments");
+  YH_REQUIRE(tb_steps == 0 || tb_steps == 1 || tb_steps == 2 || tb_steps == 4, "tb_steps must be 0, 1, 2 or 4");
+  YH_REQUIRE(!s->pg.solidSwitch || s->solid_arg, "solidSwitch set: call yh_slab_set_solid first");
+  if (nsteps == 0) return YH_OK;
+  return advance_all(&s, 1, nsteps, tb_steps);
+}
+
+int yh_slab_sync(yh_slab *s) {
+  YH_REQUIRE(s != nullptr, "null slab");
+  DevGuard g(s->device);
+  YH_CUDA(cudaStreamSynchronize(s->edge));
+  YH_CUDA(cudaStreamSynchronize(s->main));
+  int f[8] = {0};
+  YH_CUDA(cudaMemcpy(f, s->flags, sizeof(f), cudaMemcpyDeviceToHost));
+  if (f[FLAG_STATUS] != 0) {
+    yh_set_error("slab %d: a neighbour never released its halo rows (flag wait timed out; from_up %d from_down %d "
+                 "own sequence %d arrivals %d); ghost rows are stale", s->rank, f[FLAG_FROM_UP], f[FLAG_FROM_DOWN],
+                 f[FLAG_SEQ], f[FLAG_DONE]);
+    return YH_ERR_CUDA;
+  }
+  return YH_OK;
+}
+
+int yh_slab_checksum(yh_slab *s, unsigned long long *sum_u, unsigned long long *sum_v) {
+  YH_REQUIRE(s && sum_u && sum_v, "null pointer");
+  DevGuard g(s->device);
+  YH_CUDA(cudaMemsetAsync(s->sum_d, 0, 2 * sizeof(unsigned long long), s->main));
+  const long long n = (long long)(s->own_hi - s->own_lo) * s->nx;
+  const size_t o = (size_t)s->own_lo * s->nx;
+  slab_checksum_kernel<<<148 * 4, 256, 0, s->main>>>(reinterpret_cast<const unsigned long long *>(s->u[s->cur] + o),
+                                                     reinterpret_cast<const unsigned long long *>(s->v[s->cur] + o), n, s->sum_d);
+  YH_LAUNCH_CHECK();
+  unsigned long long h[2] = {0, 0};
+  YH_CUDA(cudaMemcpyAsync(h, s->sum_d, sizeof(h), cudaMemcpyDeviceToHost, s->main));
+  YH_CUDA(cudaStreamSynchronize(s->main));
+  *sum_u = h[0]; *sum_v = h[1];
+  return YH_OK;
+}
+
+int yh_slab_run_host(yh_slab *s, const double *u_in_h, const double *v_in_h, double *u_out_h, double *v_out_h,
+                     int nsteps, int tb_steps) {
+  int rc = yh_slab_set_state(s, u_in_h, v_in_h, 0);
+  if (rc != YH_OK) return rc;
+  rc = yh_slab_advance(s, nsteps, tb_steps);
+  if (rc != YH_OK) return rc;
+  return yh_slab_get_state(s, u_out_h, v_out_h);
+}
+
+// ---- one process, several devices ----------------------------------------------------------------
+int yh_slab_group_create(yh_slab_group **out, const yh_params *pg, int nslabs, const int *devices, int halo) {
+  YH_REQUIRE(out && pg && devices && nslabs >= 1, "bad arguments");
+  yh_slab_group *g = new yh_slab_group();
+  int rc = YH_OK;
+  for (int r = 0; r < nslabs && rc == YH_OK; r++) {
+    yh_slab *s = nullptr;
+    rc = yh_slab_create(&s, pg, r, nslabs, halo, devices[r]);
+    if (rc == YH_OK) g->m.push_back(s);
+  }
+  for (int r = 0; r < nslabs && rc == YH_OK; r++)
+    rc = yh_slab_connect_local(g->m[r], r > 0 ? g->m[r - 1] : nullptr, r < nslabs - 1 ? g->m[r + 1] : nullptr);
+  if (rc != YH_OK) { yh_slab_group_destroy(g); return rc; }
+  *out = g;
+  return YH_OK;
+}
+
+int yh_slab_group_destroy(yh_slab_group *g) {
+  if (!g) return YH_OK;
+  for (yh_slab *s : g->m) {          // nobody may still be writing into a block that is about to go
+    DevGuard d(s->device);
+    cudaStreamSynchronize(s->main); cudaStreamSynchronize(s->edge);
+  }
+  for (yh_slab *s : g->m) yh_slab_destroy(s);
+  delete g;
+  return YH_OK;
+}
+
+yh_slab *yh_slab_group_member(yh_slab_group *g, int rank) {
+  return (g && rank >= 0 && rank < (int)g->m.size()) ? g->m[rank] : nullptr;
+}
+
+int yh_slab_group_set_state(yh_slab_group *g, const double *u_h, const double *v_h) {
+  YH_REQUIRE(g && u_h && v_h, "null pointer");
+  for (yh_slab *s : g->m) {
+    const size_t o = (size_t)s->g0 * s->nx;
+    int rc = yh_slab_set_state(s, u_h + o, v_h + o, 1);
+    if (rc != YH_OK) return rc;
+  }
+  return YH_OK;
+}
+
+int yh_slab_group_get_state(yh_slab_group *g, double *u_h, double *v_h) {
+  YH_REQUIRE(g && u_h && v_h, "null pointer");
+  for (yh_slab *s : g->m) {          // all copies in flight, then the waits
+    DevGuard d(s->device);
+    const size_t row = (size_t)s->nx, rows = (size_t)(s->own_hi - s->own_lo), o = (size_t)s->j0 * row;
+    YH_CUDA(cudaMemcpyAsync(u_h + o, s->u[s->cur] + (size_t)s->own_lo * row, rows * row * sizeof(double), cudaMemcpyDeviceToHost, s->main));
+    YH_CUDA(cudaMemcpyAsync(v_h + o, s->v[s->cur] + (size_t)s->own_lo * row, rows * row * sizeof(double), cudaMemcpyDeviceToHost, s->main));
+  }
+  return yh_slab_group_sync(g);
+}
+
+int yh_slab_group_set_solid(yh_slab_group *g, const uint8_t *mask_h) {
+  YH_REQUIRE(g && mask_h, "null pointer");
+  for (yh_slab *s : g->m) {
+    int rc = yh_slab_set_solid(s, mask_h + (size_t)s->g0 * s->nx);
+    if (rc != YH_OK) return rc;
+  }
+  return YH_OK;
+}
+
+int yh_slab_group_advance(yh_slab_group *g, int nsteps, int tb_steps) {
+  YH_REQUIRE(g && nsteps >= 0, "bad arguments");
+  YH_REQUIRE(tb_steps == 0 || tb_steps == 1 || tb_steps == 2 || tb_steps == 4, "tb_steps must be 0, 1, 2 or 4");
+  if (nsteps == 0) return YH_OK;
+  for (yh_slab *s : g->m)
+    YH_REQUIRE(!s->pg.solidSwitch || s->solid_arg, "solidSwitch set: call yh_slab_group_set_solid first");
+  return advance_all(g->m.data(), (int)g->m.size(), nsteps, tb_steps);
+}
+
+int yh_slab_group_sync(yh_slab_group *g) {
+  YH_REQUIRE(g != nullptr, "null group");
+  int rc = YH_OK;
+  for (yh_slab *s : g->m) {
+    int r = yh_slab_sync(s);
+    if (r != YH_OK) rc = r;
+  }
+  return rc;
+}
+
+int yh_slab_group_run_host(yh_slab_group *g, const double *u_in_h, const double *v_in_h, double *u_out_h,
+                           double *v_out_h, int nsteps, int tb_steps) {
+  int rc = yh_slab_group_set_state(g, u_in_h, v_in_h);
+  if (rc != YH_OK) return rc;
+  rc = yh_slab_group_advance(g, nsteps, tb_steps);
+  if (rc != YH_OK) return rc;
+  return yh_slab_group_get_state(g, u_out_h, v_out_h);
+}
+
+}  // extern "C"

@@ -62,6 +62,24 @@ int yh_check_device(void);   // YH_OK or YH_ERR_NO_DEVICE
 
 #define YH_LAUNCH_CHECK() YH_CUDA(cudaGetLastError())
 
+// Kernel launch of the RD step path, or -- in PRELOAD mode -- only the load of the kernel's code.
+// CUDA loads a kernel lazily at its first launch and that load can wait until the device is idle.  The
+// slab driver keeps a kernel resident that waits for a neighbour slab (csrc/slab.cu); a first launch of
+// some RD kernel variant issued by the same host thread meanwhile would block behind it while the
+// neighbour's work is not enqueued yet.  So the driver walks its launch sequence once with
+// yh_preload_only set (no launches, cudaFuncGetAttributes loads the code) before it enqueues anything.
+extern thread_local int yh_preload_only;
+#define YH_LAUNCH(kfn, grd, blk, smem, st, ...)                    \
+  do {                                                             \
+    if (yh_preload_only) {                                         \
+      cudaFuncAttributes fa__;                                     \
+      YH_CUDA(cudaFuncGetAttributes(&fa__, kfn));                  \
+    } else {                                                       \
+      kfn<<<grd, blk, smem, st>>>(__VA_ARGS__);                    \
+      YH_LAUNCH_CHECK();                                           \
+    }                                                              \
+  } while (0)
+
 // internal workspace (per device, grown on demand, abi.cu)
 int yh_workspace(size_t bytes, void **ptr, int slot);
 

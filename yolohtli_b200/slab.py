@@ -424,3 +424,126 @@ def advance_sr_emulated(runners, nsteps, records=None):
                 total += q[1]
             for q in reqs:
                 q[1].copy_(total)
+
+
+# ---------------------------------------------------------------------------------------------------
+# ctypes mirrors of the C++ multi-GPU driver (include/yolohtli_slab.h, csrc/slab.cu).  The partition,
+# the overlap schedule, the NVLink halo exchange and the graph replay all live in the library; Python
+# only moves the 256-byte handles between processes (any transport) and owns the host buffers.
+# ---------------------------------------------------------------------------------------------------
+def _hostptr(a):
+    """numpy array or (pinned) torch CPU tensor -> void*"""
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous()
+        return C.c_void_p(a.data_ptr())
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Slab:
+    """One row slab of an nx x ny sheet on one GPU (yh_slab)."""
+
+    def __init__(self, p_global, rank, world, halo=4, device=0):
+        from ._lib import lib
+        self._lib = lib()
+        self._h = C.c_void_p()
+        host.check(self._lib.yh_slab_create(C.byref(self._h), C.byref(p_global), rank, world, halo, device))
+        self.rank, self.world, self.nx = rank, world, p_global.nx
+        j0, j1, g0, g1 = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        host.check(self._lib.yh_slab_layout(self._h, C.byref(j0), C.byref(j1), C.byref(g0), C.byref(g1)))
+        self.j0, self.j1, self.g0, self.g1 = j0.value, j1.value, g0.value, g1.value
+
+    def export(self):
+        from ._lib import SLAB_HANDLE_BYTES
+        buf = C.create_string_buffer(SLAB_HANDLE_BYTES)
+        host.check(self._lib.yh_slab_export(self._h, buf))
+        return buf.raw
+
+    def connect(self, handle_up, handle_down):
+        host.check(self._lib.yh_slab_connect(self._h, handle_up, handle_down))
+
+    def connect_over(self, all_gather_bytes):
+        """all_gather_bytes(my_bytes) -> list of every rank's bytes (torch.distributed, MPI, ...)."""
+        everyone = all_gather_bytes(self.export())
+        self.connect(everyone[self.rank - 1] if self.rank > 0 else None,
+                     everyone[self.rank + 1] if self.rank < self.world - 1 else None)
+
+    def set_state(self, u_rows, v_rows, with_ghosts=False):
+        host.check(self._lib.yh_slab_set_state(self._h, _hostptr(u_rows), _hostptr(v_rows), int(with_ghosts)))
+
+    def get_state(self, out=None):
+        import numpy as np
+        if out is None:
+            out = (np.empty((self.j1 - self.j0, self.nx)), np.empty((self.j1 - self.j0, self.nx)))
+        host.check(self._lib.yh_slab_get_state(self._h, _hostptr(out[0]), _hostptr(out[1])))
+        return out
+
+    def set_solid(self, mask_rows):
+        import numpy as np
+        m = np.ascontiguousarray(mask_rows, dtype=np.uint8)
+        assert m.shape == (self.g1 - self.g0, self.nx)
+        host.check(self._lib.yh_slab_set_solid(self._h, m.ctypes.data_as(C.c_void_p)))
+
+    def advance(self, nsteps, tb=0):
+        host.check(self._lib.yh_slab_advance(self._h, nsteps, tb))
+
+    def sync(self):
+        host.check(self._lib.yh_slab_sync(self._h))
+
+    def checksum(self):
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        host.check(self._lib.yh_slab_checksum(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def run_host(self, u_in, v_in, u_out, v_out, nsteps, tb=0):
+        host.check(self._lib.yh_slab_run_host(self._h, _hostptr(u_in), _hostptr(v_in), _hostptr(u_out),
+                                              _hostptr(v_out), nsteps, tb))
+
+    def close(self):
+        if self._h:
+            self._lib.yh_slab_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class SlabGroup:
+    """N slabs driven by one process (yh_slab_group): devices[r] holds slab r."""
+
+    def __init__(self, p_global, devices, halo=4):
+        from ._lib import lib
+        self._lib = lib()
+        self._h = C.c_void_p()
+        self.n = len(devices)
+        self.shape = (p_global.ny, p_global.nx)
+        arr = (C.c_int * self.n)(*devices)
+        host.check(self._lib.yh_slab_group_create(C.byref(self._h), C.byref(p_global), self.n, arr, halo))
+
+    def set_state(self, u, v):
+        host.check(self._lib.yh_slab_group_set_state(self._h, _hostptr(u), _hostptr(v)))
+
+    def set_solid(self, mask):
+        import numpy as np
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        host.check(self._lib.yh_slab_group_set_solid(self._h, m.ctypes.data_as(C.c_void_p)))
+
+    def advance(self, nsteps, tb=0):
+        host.check(self._lib.yh_slab_group_advance(self._h, nsteps, tb))
+
+    def get_state(self):
+        import numpy as np
+        u, v = np.empty(self.shape), np.empty(self.shape)
+        host.check(self._lib.yh_slab_group_get_state(self._h, _hostptr(u), _hostptr(v)))
+        return u, v
+
+    def checksum(self):
+        su = sv = 0
+        for r in range(self.n):
+            a, b = C.c_ulonglong(), C.c_ulonglong()
+            host.check(self._lib.yh_slab_checksum(C.c_void_p(self._lib.yh_slab_group_member(self._h, r)),
+                                                  C.byref(a), C.byref(b)))
+            su, sv = (su + a.value) % (1 << 64), (sv + b.value) % (1 << 64)
+        return su, sv
+
+    def close(self):
+        if self._h:
+            self._lib.yh_slab_group_destroy(self._h)
+            self._h = C.c_void_p()
