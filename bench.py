@@ -8,7 +8,9 @@ reactionDiffusion.cu), row-slab sharded over N GPUs with halo exchange ("scaling
 the sheet is fixed, N grows).  At N = 1 the whole sheet (8 GiB of FP64 state with its
 ping-pong copy) lives on one B200 -- far larger than L2, so no flush is needed between steps.
 
-One bench "step" = --substeps time steps of the whole sheet.
+One bench "step" = --substeps x N time steps of the whole sheet (N = number of GPUs, so that the timed
+region stays about a second at N = 8).  The step loop runs in the C++ slab driver of the library
+(include/yolohtli_slab.h); Python only moves the 256-byte IPC handles at start-up.
 
   python bench.py                                   # N=1
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
@@ -126,16 +128,67 @@ def cpu_baseline(a, oracle_lib):
                       f"({how}), wall clock {dt:.2f} s"}
 
 
+WORKLOAD = ("BASELINE configs[3]: {nx}x{ny} fibrillation sheet, reference default ionic model, standard PDE mode, "
+            "no-flux boundaries, {mode}")
+# extra single-GPU measurements printed beside the headline ("modes"): name -> (nx, mode, tb, time steps)
+MODES = {
+    "euler5_tb1_8192": (8192, "euler5", 1, 32),      # one time step per HBM pass: the HBM-bound form of the step
+    "rk4lap4_8192": (8192, "rk4lap4", 0, 12),        # the reference's DEFAULT mode (saveFiles.cu:124-132) on a large sheet
+    "rk4lap4_512": (512, "rk4lap4", 0, 2048),        # ... and on its default 512^2 sheet (BASELINE configs[0])
+    "euler5_512": (512, "euler5", 4, 8192),
+}
+FP64_PER_UPDATE = {"euler5": (8, 24), "rk4lap4": (36, 316)}   # (DFMA, DADD + DMUL) warp-lane instructions per cell update
+
+
+def workload_config(a):
+    """The keys that define the workload: identical in the `ours` and `reference` arms."""
+    return {"workload": WORKLOAD.format(nx=a.nx, ny=a.ny, mode=a.mode), "mode": a.mode, "nx": a.nx, "ny": a.ny}
+
+
+def mode_params(params_default, nx, ny, mode):
+    over = dict(timeIntOrder=1, lap4=0) if mode == "euler5" else {}
+    return params_default(nx, ny, scale_L=True, **over)
+
+
+def fp64_peak():
+    """FP64 instruction issue peaks of this GPU (tools/fp64_peak.cu, ~0.3 s): warp-lane instructions / s
+    for DFMA and for separate DMUL / DADD."""
+    exe = os.path.join(ROOT, "tools", "bin", "fp64_peak")
+    try:
+        if not os.path.exists(exe):
+            os.makedirs(os.path.dirname(exe), exist_ok=True)
+            subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", exe,
+                            os.path.join(ROOT, "tools", "fp64_peak.cu")], check=True, capture_output=True, timeout=120)
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+        best = {}
+        for line in out.splitlines():
+            d = json.loads(line)
+            for k, v in d.items():
+                best[k] = max(best.get(k, 0.0), v["Ginstr_per_s"] * 1e9)
+        return {"dfma_per_s": best["fp64_dfma"], "dmul_dadd_per_s": best["fp64_dmul_dadd"],
+                "source": "measured now (tools/fp64_peak.cu)"}
+    except Exception as e:   # noqa: BLE001
+        return {"dfma_per_s": 16.99e12, "dmul_dadd_per_s": 18.6e12,
+                "source": f"fallback: round-2 measurement on this pool (tools/fp64_peak.cu could not run: {e})"}
+
+
+def fp64_fraction(mode, updates_per_s, pk):
+    """Share of the FP64 issue time the arithmetic of the step needs (exact, contraction-free build)."""
+    fma, other = FP64_PER_UPDATE[mode]
+    return updates_per_s * (fma / pk["dfma_per_s"] + other / pk["dmul_dadd_per_s"])
+
+
 def run_reference(a):
     """--impl reference: the UNMODIFIED reference kernels (reactionDiffusion_wrapper + swapSoA,
-    main.cu:879-882) built headless for sm_100 with the reference's default flags, one GPU."""
+    main.cu:879-882) built headless for sm_100 with the reference's default flags, one GPU.  Nothing of
+    libyolohtli_b200.so is loaded in this arm: parameters come from the oracle's restatement of
+    parameterSetup(), the initial condition from numpy."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from tests import oracle_lib
-    from yolohtli_b200 import synth
-    import yolohtli_b200 as yh
-    p = make_params(yh, a)
+    from yolohtli_b200 import synth   # numpy only
+    o = oracle_lib.load()
     have_gpu = False
     try:
         import torch
@@ -145,44 +198,79 @@ def run_reference(a):
     base = {"metric": METRIC, "unit": METRIC, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference"}
-    cfg = {"workload": f"{a.nx}x{a.ny} fibrillation sheet, {a.mode}, {a.substeps} time steps per bench step",
-           "mode": a.mode, "nx": a.nx, "ny": a.ny, "substeps": a.substeps}
+    cfg = workload_config(a)
     if have_gpu and os.path.exists(oracle_lib.REF_SO):
         ref = oracle_lib.Reference(nofma=False)
-        ref.init(p)
+
+        def ref_rate(n, mode, nsteps, reps):
+            ref.init(mode_params(o.params_default, n, n, mode))
+            u, v = synth.fibrillation_ic(n, n) if n >= 1024 else synth.cross_field_ic(n, n)
+            ref.rd_run(u, v, 2, copy_back=False)
+            ms = [ref.rd_run(u, v, nsteps, copy_back=False)[2] for _ in range(reps)]
+            return n * n * nsteps * reps / (sum(ms) / 1e3) / 1e9, sum(ms) / reps
+
+        ref.init(mode_params(o.params_default, a.nx, a.ny, a.mode))
         u, v = synth.fibrillation_ic(a.nx, a.ny)
-        sub = max(1, a.substeps // 4)   # bounded sample per step: the reference is several times slower
         for _ in range(max(a.warmup, 1)):
             ref.rd_run(u, v, 2, copy_back=False)
-        ms = []
-        for _ in range(a.steps):
-            _, _, t = ref.rd_run(u, v, sub, copy_back=False)
-            ms.append(t)
+        ms = [ref.rd_run(u, v, a.substeps, copy_back=False)[2] for _ in range(a.steps)]
         tot = sum(ms) / 1e3
-        val = a.nx * a.ny * sub * a.steps / tot / 1e9
-        cfg["note"] = ("reference's own CUDA kernels (oracle/_ref/libyhref.so, nvcc -arch sm_100 -O3, default "
-                       "fmad), kernel-only loop {reactionDiffusion_wrapper; swapSoA}, single GPU (the reference "
-                       "has no multi-GPU path); timed with CUDA events inside the harness")
+        val = a.nx * a.ny * a.substeps * a.steps / tot / 1e9
+        del u, v
+        modes = {}
+        if not a.no_modes:
+            for name, (n, mode, _tb, nsteps) in MODES.items():
+                ns = max(4, nsteps // 4)
+                r, ms1 = ref_rate(n, mode, ns, 2)
+                modes[name] = {"value": r, "unit": METRIC, "ms_per_time_step": ms1 / ns}
         out = dict(base, value=val, ms_per_step=tot / a.steps * 1e3, config=cfg,
+                   impl_config={"substeps": a.substeps,
+                                "note": "reference's own CUDA kernels (oracle/_ref/libyhref.so: the reference's .cu files compiled "
+                                        "in place by oracle/build_ref.sh, nvcc -arch sm_100 -O3, default fmad), kernel-only loop "
+                                        "{reactionDiffusion_wrapper; swapSoA}, single GPU at every --gpus N (the reference has no "
+                                        "multi-GPU path and no CPU path); timed with CUDA events inside the harness"},
                    cpu_baseline={"value": val, "unit": METRIC, "cores": 0, "kind": "reference",
-                                 "sample": f"{sub} reference time steps per bench step on the GPU; state resident in HBM"},
+                                 "sample": f"{a.substeps} reference time steps per bench step on the GPU; state resident in HBM"},
                    e2e={"value": val, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                   gpu_launches=0)
+                   modes=modes, gpu_launches=0)
     else:
         cb = cpu_baseline(a, oracle_lib)
-        cfg["note"] = "oracle/_ref or GPU not available: plain-C oracle port on the host cores"
-        out = dict(base, value=cb["value"], ms_per_step=None, config=cfg, cpu_baseline=cb,
+        out = dict(base, value=cb["value"], ms_per_step=None, config=cfg,
+                   impl_config={"note": "oracle/_ref or GPU not available: plain-C oracle port on the host cores"},
+                   cpu_baseline=cb,
                    e2e={"value": cb["value"], "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                    gpu_launches=0)
     print(json.dumps(out), flush=True)
+
+
+def measure_mode(yh, torch, n, mode, tb, nsteps):
+    """One extra single-GPU measurement through the C ABI (yh_rd_advance), state resident in HBM."""
+    from yolohtli_b200 import host, synth
+    p = mode_params(yh.default_params, n, n, mode)
+    u0, v0 = synth.fibrillation_ic(n, n) if n >= 1024 else synth.cross_field_ic(n, n)
+    uA, vA = torch.as_tensor(u0).cuda(), torch.as_tensor(v0).cuda()
+    uB, vB = torch.zeros_like(uA), torch.zeros_like(vA)
+    ru, rv = host.rd_advance(p, max(4, (nsteps // 8) & ~3), uA, vA, uB, vB, tb_steps=tb)
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ou, ov = (uB, vB) if ru is uA else (uA, vA)
+        ru, rv = host.rd_advance(p, nsteps, ru, rv, ou, ov, tb_steps=tb, flags=host.RD_INPUT_CANONICAL)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1)
+        best = t if best is None else min(best, t)
+    return n * n * nsteps / (best / 1e3) / 1e9, best / nsteps
 
 
 def run_ours(a):
     import torch
     import torch.distributed as dist
     import yolohtli_b200 as yh
-    from yolohtli_b200 import host, synth
-    from yolohtli_b200.slab import SlabRunner
+    from yolohtli_b200 import synth
+    from yolohtli_b200.slab import Slab
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- yolohtli_b200 has no CPU fallback")
@@ -194,125 +282,152 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     yh.load_library()
-    p = make_params(yh, a)
-    T = a.tb
+    p = mode_params(yh.default_params, a.nx, a.ny, a.mode)
+    T = a.tb if a.mode == "euler5" else 1
     halo = T if a.mode == "euler5" else 4
-    run = SlabRunner(p, rank=rank, world=world, halo=halo, device=dev, transport=a.transport)
-    lay = run.lay
-    u0, v0 = synth.fibrillation_ic(a.nx, a.ny, rows=(lay.g0, lay.g1))
-    run.u[run.cur].copy_(torch.as_tensor(u0))
-    run.v[run.cur].copy_(torch.as_tensor(v0))
+    # a bench step = substeps time steps; scaled with N so that the timed region stays ~1 s at N = 8
+    substeps = a.substeps * world
+
+    # ---- the C++ slab driver (include/yolohtli_slab.h): one slab per rank, wired over CUDA IPC -------
+    slab = Slab(p, rank, world, halo=halo, device=local)
+
+    def gather_bytes(b):
+        t = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [x.cpu().numpy().tobytes() for x in out]
+
+    if world > 1:
+        slab.connect_over(gather_bytes)
+    u0, v0 = synth.fibrillation_ic(a.nx, a.ny, rows=(slab.g0, slab.g1))
+    slab.set_state(u0, v0, with_ghosts=True)
+    slab.sync()
     del u0, v0
     cells_total = a.nx * a.ny
+    st = slab.stream()
 
     def barrier():
+        slab.sync()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def global_checksum():
+        cu, cv = slab.checksum()
+        parts = [(cu, cv)]
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, (cu, cv))
+        return sum(q[0] for q in parts) % (1 << 64), sum(q[1] for q in parts) % (1 << 64)
+
     # ---- device-resident throughput ----------------------------------------------------
     for _ in range(a.warmup):
-        run.advance(a.substeps, tb=T)
+        slab.advance(substeps, T)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record()
+    e0.record(st)
     for _ in range(a.steps):
-        run.advance(a.substeps, tb=T)
-    e1.record()
+        slab.advance(substeps, T)
+    e1.record(st)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     clocks = sampler.stop() if sampler else None
-    value = cells_total * a.substeps * a.steps / (ms / 1e3) / 1e9
-    # one launch per T time steps (Euler, temporally blocked) or per time step (fused RK4 + lap4 kernel)
-    passes = -(-a.substeps // T) if a.mode == "euler5" else a.substeps
-    launches = passes * a.steps
+    value = cells_total * substeps * a.steps / (ms / 1e3) / 1e9
+    steps_done = substeps * (a.warmup + a.steps)
+    chk = global_checksum()
+    # kernels of this rank in the timed region: one pass per T time steps (Euler) or per step (RK); with
+    # neighbours a pass is {one or two bands on the edge stream, the exchange kernel, the interior}
+    passes = -(-substeps // T) if a.mode == "euler5" else substeps
+    per_pass = 1 if world == 1 else (2 + (1 if 0 < rank < world - 1 else 0) + 1)
+    launches = passes * a.steps * per_pass
 
-    # ---- end to end: pinned host -> device, substeps, device -> pinned host --------------
-    own = lay.j1 - lay.j0
+    # ---- end to end through the C ABI: pinned host -> device, time steps, device -> pinned host --------
+    own = slab.j1 - slab.j0
     hu = torch.empty((own, a.nx), dtype=torch.float64).pin_memory()
     hv = torch.empty((own, a.nx), dtype=torch.float64).pin_memory()
-    uo, vo = run.owned()
-    hu.copy_(uo)
-    hv.copy_(vo)
+    slab.get_state(out=(hu, hv))
     e2e_steps = max(1, min(a.steps, 2))
-
-    def e2e_once(n=None):
-        uo_, vo_ = run.owned()
-        uo_.copy_(hu, non_blocking=True)
-        vo_.copy_(hv, non_blocking=True)
-        run.count = 0   # host data again: first pass treats it as raw
-        run.advance(n or a.e2e_substeps, tb=T)
-        uo2, vo2 = run.owned()
-        hu.copy_(uo2, non_blocking=True)
-        hv.copy_(vo2, non_blocking=True)
-
-    e2e_once(a.substeps)
+    slab.run_host(hu, hv, hu, hv, 4 * T, T)                 # warm-up of the copy path
     barrier()
-    e0.record()
+    e0.record(st)
     for _ in range(e2e_steps):
-        e2e_once()
-    e1.record()
+        slab.run_host(hu, hv, hu, hv, a.e2e_substeps, T)    # yh_slab_run_host: H2D, steps (halo exchange included), D2H
+    e1.record(st)
     barrier()
     ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_val = cells_total * a.e2e_substeps * e2e_steps / (float(ms2.item()) / 1e3) / 1e9
-    checksum = float(hu.sum().item())
+    chk2 = global_checksum()
+    slab.close()
+    del hu, hv
 
     if rank == 0:
         peak, peak_src, _ = peaks()
-        # dominant kernel = the only kernel in the timed region; per-launch duration from the events above
-        per_launch_ms = ms / launches
-        cells_local = (lay.j1 - lay.j0) * a.nx
-        steps_per_launch = T if a.mode == "euler5" else 1.0 / (passes / a.substeps)
-        achieved = BYTES_PER_UPDATE * cells_local * steps_per_launch / (per_launch_ms / 1e3) / 1e9
+        per_launch_ms = ms / (passes * a.steps)      # duration of one pass over the slab (its kernels overlap)
+        cells_local = own * a.nx
+        achieved = BYTES_PER_UPDATE * cells_local * T / (per_launch_ms / 1e3) / 1e9
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tfile):
             traffic = json.load(open(tfile)).get(f"{a.mode}_tb{T}_{a.nx}x{a.ny}_n{world}")
+        pk64 = fp64_peak()
+        kernel = ("rd_euler_quad" if T == 4 else "rd_euler_stream") if a.mode == "euler5" else "rd_rk_stream"
+        roof = {"bound": "hbm" if (a.mode == "euler5" and T == 1) else "fp64", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "kernel": kernel, "peak_source": peak_src,
+                "hbm_actual_frac": (traffic / (per_launch_ms / 1e3) / 1e9 / peak) if traffic else None,
+                "fp64_frac": fp64_fraction(a.mode, value * 1e9 / world, pk64), "fp64_peak": pk64,
+                "note": f"achieved = algorithmic 32 B per cell-update x {T} time step(s) per pass / pass duration (CUDA events), so "
+                        f"temporal blocking lets frac exceed 1; hbm_actual_frac = measured DRAM bytes per pass (ncu, profiles/) / "
+                        f"pass duration / peak; fp64_frac = share of the FP64 issue time the step's {sum(FP64_PER_UPDATE[a.mode])} "
+                        f"FP64 instructions per update need at the measured issue peaks (the binding roof for T >= 2 and for RK4)"}
+        modes = {}
+        if world == 1 and not a.no_modes:
+            for name, (n, mode, tb, nsteps) in MODES.items():
+                r, ms1 = measure_mode(yh, torch, n, mode, tb, nsteps)
+                modes[name] = {"value": r, "unit": METRIC, "ms_per_time_step": ms1,
+                               "hbm_algorithmic_frac": r * BYTES_PER_UPDATE / peak,
+                               "fp64_frac": fp64_fraction(mode, r * 1e9, pk64)}
         from tests import oracle_lib
         cb = cpu_baseline(a, oracle_lib) if world == 1 and not a.no_cpu_baseline else None
         out = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": f"BASELINE configs[3]: {a.nx}x{a.ny} fibrillation sheet, reference default ionic "
-                            f"model, standard PDE mode, {a.mode}, row-slab sharded over {world} GPU(s); "
-                            f"{a.substeps} time steps per bench step, {T} time steps per HBM pass",
-                "mode": a.mode, "nx": a.nx, "ny": a.ny, "substeps": a.substeps, "tb_steps": T,
-                "parallelism": f"slab{world}", "halo_rows": halo, "halo_transport": run.transport,
+            "config": workload_config(a),
+            "impl_config": {
+                "substeps": substeps, "tb_steps": T, "parallelism": f"slab{world}", "halo_rows": halo,
+                "driver": "C++ row-slab driver (include/yolohtli_slab.h): one slab per rank, CUDA-IPC peer mappings, halo rows by "
+                          "NVLink peer stores + release/acquire flags from one exchange kernel, CUDA-graph replay of block pairs",
                 "l2": "inputs (>= 1 GiB per array per GPU) are larger than the 126 MB L2; no flush needed",
                 "arithmetic": "FP64, no FMA contraction (bit-identical to the plain-C oracle)",
-                "checksum_u": checksum,
+                "checksum": {"what": "sum of the uint64 views of all cells mod 2^64 over all ranks (order independent: equal "
+                                     "for every N)", "time_steps": steps_done, "u": f"{chk[0]:016x}", "v": f"{chk[1]:016x}",
+                             "after_e2e_u": f"{chk2[0]:016x}"},
             },
             "e2e": {"value": e2e_val, "unit": METRIC, "h2d_bytes_per_step": 16 * cells_total,
                     "d2h_bytes_per_step": 16 * cells_total, "steps": e2e_steps,
                     "time_steps_per_call": a.e2e_substeps,
-                    "note": "each e2e step = whole state pinned host -> HBM, e2e-substeps time steps (halo exchange "
-                            "included), whole state HBM -> pinned host: the reference's use (upload once, main.cu:470; "
-                            "run; download, main.cu:519)"},
+                    "note": "each e2e step = yh_slab_run_host on every rank: owned rows pinned host -> HBM, ghost rows from the "
+                            "neighbours, e2e-substeps time steps (halo exchange included), owned rows HBM -> pinned host: the "
+                            "reference's use (upload once, main.cu:470; run; download, main.cu:519)"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "rd_euler_stream" if a.mode == "euler5" else "rd_rk_stream",
-                         "peak_source": peak_src,
-                         "note": f"algorithmic 32 B per cell-update x {steps_per_launch:g} step(s) per launch; "
-                                 f"temporal blocking lets frac exceed 1"},
+            "roofline": roof,
+            "modes": modes,
             "clocks": clocks,
         }
         if cb:
             out["cpu_baseline"] = cb
         print(json.dumps(out), flush=True)
-    run.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -428,8 +543,8 @@ def main():
     ap.add_argument("--tb", type=int, default=4, help="time steps per HBM pass (1, 2, 4)")
     ap.add_argument("--substeps", type=int, default=64, help="time steps per bench step")
     ap.add_argument("--e2e-substeps", type=int, default=1024, help="time steps per host->device->host call")
-    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="halo exchange: NVLink peer stores (CUDA IPC) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-modes", action="store_true", help="skip the extra single-GPU mode measurements")
     ap.add_argument("--workload", default="sheet", choices=["sheet", "sweep"],
                     help="sheet: configs[3], one large sheet in row slabs (default, the headline); "
                          "sweep: configs[4], 32 independent 512^2 paced simulations per GPU")

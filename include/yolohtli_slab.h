@@ -62,6 +62,9 @@ int yh_slab_get_state(yh_slab *s, double *u_h, double *v_h);
 int yh_slab_set_solid(yh_slab *s, const uint8_t *mask_h);
 void *yh_slab_device_u(yh_slab *s);   /* current state buffers, ny_local x nx, stored rows */
 void *yh_slab_device_v(yh_slab *s);
+/* the slab's main stream (cudaStream_t): every call above is ordered on it, so events recorded on it
+ * bracket the slab's work (bench.py times with CUDA events on this stream) */
+void *yh_slab_stream(yh_slab *s);
 
 /* ---- stepping ---------------------------------------------------------------------------------- */
 /* nsteps x {reactionDiffusion_wrapper; swapSoA} on this slab, asynchronous.  Every rank must make the

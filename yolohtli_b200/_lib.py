@@ -157,6 +157,7 @@ SIGNATURES.update({
     "yh_slab_set_solid": (_i, [_vp, _vp]),
     "yh_slab_device_u": (_vp, [_vp]),
     "yh_slab_device_v": (_vp, [_vp]),
+    "yh_slab_stream": (_vp, [_vp]),
     "yh_slab_advance": (_i, [_vp, _i, _i]),
     "yh_slab_sync": (_i, [_vp]),
     "yh_slab_checksum": (_i, [_vp, C.POINTER(_ull), C.POINTER(_ull)]),

@@ -640,6 +640,7 @@ int yh_slab_set_solid(yh_slab *s, const uint8_t *mask_h) {
 
 void *yh_slab_device_u(yh_slab *s) { return s ? s->u[s->cur] : nullptr; }
 void *yh_slab_device_v(yh_slab *s) { return s ? s->v[s->cur] : nullptr; }
+void *yh_slab_stream(yh_slab *s) { return s ? (void *)s->main : nullptr; }
 
 int yh_slab_advance(yh_slab *s, int nsteps, int tb_steps) {
   YH_REQUIRE(s && nsteps >= 0, "bad arguments");

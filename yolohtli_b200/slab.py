@@ -490,6 +490,11 @@ class Slab:
     def sync(self):
         host.check(self._lib.yh_slab_sync(self._h))
 
+    def stream(self):
+        """The slab's main stream as a torch ExternalStream (for CUDA-event timing)."""
+        import torch
+        return torch.cuda.ExternalStream(int(self._lib.yh_slab_stream(self._h)))
+
     def checksum(self):
         a, b = C.c_ulonglong(), C.c_ulonglong()
         host.check(self._lib.yh_slab_checksum(self._h, C.byref(a), C.byref(b)))
