@@ -320,6 +320,10 @@ def run_ours(a):
             dist.all_gather_object(parts, (cu, cv))
         return sum(q[0] for q in parts) % (1 << 64), sum(q[1] for q in parts) % (1 << 64)
 
+    # ---- N-invariant record of the result: 64 time steps from the initial condition, then the checksum
+    slab.advance(64, T)
+    chk = global_checksum()
+
     # ---- device-resident throughput ----------------------------------------------------
     for _ in range(a.warmup):
         slab.advance(substeps, T)
@@ -340,8 +344,6 @@ def run_ours(a):
     ms = float(ms.item())
     clocks = sampler.stop() if sampler else None
     value = cells_total * substeps * a.steps / (ms / 1e3) / 1e9
-    steps_done = substeps * (a.warmup + a.steps)
-    chk = global_checksum()
     # kernels of this rank in the timed region: one pass per T time steps (Euler) or per step (RK); with
     # neighbours a pass is {one or two bands on the edge stream, the exchange kernel, the interior}
     passes = -(-substeps // T) if a.mode == "euler5" else substeps
@@ -365,7 +367,6 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_val = cells_total * a.e2e_substeps * e2e_steps / (float(ms2.item()) / 1e3) / 1e9
-    chk2 = global_checksum()
     slab.close()
     del hu, hv
 
@@ -409,8 +410,7 @@ def run_ours(a):
                 "l2": "inputs (>= 1 GiB per array per GPU) are larger than the 126 MB L2; no flush needed",
                 "arithmetic": "FP64, no FMA contraction (bit-identical to the plain-C oracle)",
                 "checksum": {"what": "sum of the uint64 views of all cells mod 2^64 over all ranks (order independent: equal "
-                                     "for every N)", "time_steps": steps_done, "u": f"{chk[0]:016x}", "v": f"{chk[1]:016x}",
-                             "after_e2e_u": f"{chk2[0]:016x}"},
+                                     "for every N)", "time_steps": 64, "u": f"{chk[0]:016x}", "v": f"{chk[1]:016x}"},
             },
             "e2e": {"value": e2e_val, "unit": METRIC, "h2d_bytes_per_step": 16 * cells_total,
                     "d2h_bytes_per_step": 16 * cells_total, "steps": e2e_steps,
