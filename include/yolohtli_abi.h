@@ -106,6 +106,19 @@ const char *yh_last_error(void);             /* thread-local text of the last fa
 int         yh_device_count(void);           /* 0 => every compute call returns YH_ERR_NO_DEVICE */
 int         yh_release_workspace(void);      /* frees internal scratch of this thread's device */
 
+/* Arithmetic flavour of the reaction-diffusion kernels (process-wide; default YH_ARITH_EXACT, or the
+ * environment variable YH_ARITH = exact | fast read at first use).
+ *   EXACT  the reference's expressions operation for operation, no FMA contraction: bit-identical to
+ *          the plain-C oracle and to the reference's kernels built with --fmad=false.
+ *   FAST   the same update with the stencil coefficients combined on the host and FMA chains (the
+ *          reference's shipped build contracts FMAs too, Makefile:9).  About half the FP64 instructions
+ *          in the default RK4 + 4th-order-Laplacian mode.  Differs from EXACT by rounding only; the
+ *          bounds are pinned in tests/test_gpu_arith.py.  Kernels without a FAST variant run EXACT. */
+#define YH_ARITH_EXACT 0
+#define YH_ARITH_FAST  1
+int yh_set_arithmetic(int flavour);
+int yh_get_arithmetic(void);
+
 /* Defaults of parameterSetup() (saveFiles.cu:105-231) for an nx x ny grid with the
  * reference's hx (Lx = 12*(nx-1)/511 keeps hx at its 512-grid value when scale_L != 0).
  * Also applies main.cu:148-158 (dt halved when reduce_sym, rx..fy4 recomputed). */

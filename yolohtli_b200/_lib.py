@@ -90,6 +90,8 @@ SIGNATURES = {
     "yh_last_error": (C.c_char_p, []),
     "yh_device_count": (_i, []),
     "yh_release_workspace": (_i, []),
+    "yh_set_arithmetic": (_i, [_i]),
+    "yh_get_arithmetic": (_i, []),
     "yh_params_default": (_i, [_P, _i, _i, _i, _i]),
     "yh_params_derive": (_i, [_P, _d, _d, _d]),
     "yh_rd_step": (_i, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -59,7 +59,24 @@ int yh_workspace(size_t bytes, void **ptr, int slot) {
   return YH_OK;
 }
 
+static int g_arith = -1;
+int yh_arithmetic(void) {
+  if (g_arith < 0) {
+    const char *f = getenv("YH_ARITH");
+    g_arith = (f && (f[0] == 'f' || f[0] == 'F' || f[0] == '1')) ? YH_ARITH_FAST : YH_ARITH_EXACT;
+  }
+  return g_arith;
+}
+
 extern "C" {
+
+int yh_set_arithmetic(int flavour) {
+  if (flavour != YH_ARITH_EXACT && flavour != YH_ARITH_FAST) { yh_set_error("yh_set_arithmetic: unknown flavour"); return YH_ERR_INVALID_ARG; }
+  g_arith = flavour;
+  yh_graphs_release();   // captured step loops hold kernels of the other flavour
+  return YH_OK;
+}
+int yh_get_arithmetic(void) { return yh_arithmetic(); }
 
 int yh_abi_version(void) { return YH_ABI_VERSION; }
 const char *yh_last_error(void) { return g_err; }

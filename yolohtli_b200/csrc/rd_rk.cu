@@ -446,10 +446,22 @@ int yh_rd_rk_supported(const YhK &k) {
   return 1;
 }
 
+int yh_rd_rkq_supported(const YhK &k);   // rd_rkq.cu: four columns per thread, exact | fast arithmetic
+int yh_launch_rd_rkq(const YhK &k, int arith, const double *u_in, const double *v_in, double *u_out, double *v_out,
+                     double *vtu, double *vtv, cudaStream_t st);
+
 int yh_launch_rd_rk(const YhK &k, const double *u_in, const double *v_in, double *u_out,
                     double *v_out, double *vtu, double *vtv, const uint8_t *solid, cudaStream_t st) {
   if (!yh_rd_rk_supported(k)) return YH_ERR_UNSUPPORTED;
   if (k.row1 <= k.row0) return YH_OK;
+  {   // the reference's default mode on sheets that fill the machine: rd_rkq.cu; YH_RK_KERNEL = quad | pair overrides
+    const char *kern = getenv("YH_RK_KERNEL");
+    const long long cells_ = (long long)k.nx * (k.row1 - k.row0);
+    const bool quad = kern ? (kern[0] == 'q') : (cells_ >= (1ll << 21));
+    if (quad && yh_rd_rkq_supported(k))
+      return yh_launch_rd_rkq(k, yh_arithmetic(), u_in, v_in, u_out, v_out, (vtu && k.gateDiff) ? vtu : nullptr,
+                              (vtu && k.gateDiff) ? vtv : nullptr, st);
+  }
   RkArgs a{u_in, v_in, u_out, v_out, vtu, vtv, solid, 0, 0.0, 0.0, 0.0, 0.0};
   {
     volatile double q4 = k.qx4 + k.qy4;          // volatile: every product is rounded to double here

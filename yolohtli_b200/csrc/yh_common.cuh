@@ -136,7 +136,8 @@ int yh_advect_bfecc_device_c(const yh_params *p, const double *u_in, const doubl
                              double *v_out, const double *sr_state, double *adv_x, double *adv_y,
                              const uint8_t *solid, cudaStream_t st);
 
-int yh_graphs_enabled(long long cells);   // abi.cu: YH_GRAPHS = 0 | 1 override, else small sheets only
+int yh_graphs_enabled(long long cells);
+int yh_arithmetic(void);   // abi.cu: YH_ARITH_EXACT | YH_ARITH_FAST (yh_set_arithmetic, or YH_ARITH = exact | fast)   // abi.cu: YH_GRAPHS = 0 | 1 override, else small sheets only
 
 // ---- device helpers --------------------------------------------------------------------
 // Neumann mirror index (the rule of coord_i/coord_j, helper_functions.cu:69-79).
