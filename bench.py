@@ -132,6 +132,7 @@ WORKLOAD = ("BASELINE configs[3]: {nx}x{ny} fibrillation sheet, reference defaul
             "no-flux boundaries, {mode}")
 # extra single-GPU measurements printed beside the headline ("modes"): name -> (nx, mode, tb, time steps)
 MODES = {
+    "euler5_tb4_16384_fast": (16384, "euler5", 4, 64),   # the headline workload in the FAST arithmetic flavour
     "euler5_tb1_8192": (8192, "euler5", 1, 32),      # one time step per HBM pass: the HBM-bound form of the step
     "rk4lap4_8192": (8192, "rk4lap4", 0, 12),        # the reference's DEFAULT mode (saveFiles.cu:124-132) on a large sheet
     "rk4lap4_8192_fast": (8192, "rk4lap4", 0, 12),   # ... in the FAST arithmetic flavour (yh_set_arithmetic, tests/test_gpu_arith.py)

@@ -299,7 +299,7 @@ int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const doub
                             const int *period_d, int duration_it, int count0, int canon_in,
                             cudaStream_t st, const YhApd *apd, const uint8_t *pat) {
   if (!(pat ? yh_rd_fast_solid_supported(k, tb) : yh_rd_fast_supported(k, tb))) return YH_ERR_UNSUPPORTED;
-  FastArgs a{u_in, v_in, u_out, v_out, 0, sim_stride, period_d, duration_it, count0, {}, pat};
+  FastArgs a{u_in, v_in, u_out, v_out, 0, sim_stride, period_d, duration_it, count0, {}, pat, 0, 0, 0, 0, 0, 0, 0, 0};
   if (apd) a.apd = *apd; else memset(&a.apd, 0, sizeof(a.apd));
   const int rows = k.row1 - k.row0;
   if (rows <= 0) return YH_OK;

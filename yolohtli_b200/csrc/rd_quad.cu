@@ -57,7 +57,7 @@ __device__ __forceinline__ void sts128(unsigned a, const double2 &v) {
 // byte offset of 16-byte chunk `ch` inside a swizzled row
 __device__ __forceinline__ int swz(int ch) { return ((ch >> 3) << 7) | ((((ch & 7) ^ (ch >> 3)) & 7) << 4); }
 
-template <int T, int W, bool CANON, bool DEF, bool STIM, bool SOLID, bool FIX>
+template <int T, int W, bool CANON, bool DEF, bool STIM, bool SOLID, bool FIX, int ARITH>
 __global__ void __launch_bounds__(T *(W / 4))
 rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a) {
   constexpr int H = (T + 1) & ~1;        // halo columns each side
@@ -235,7 +235,12 @@ rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a)
         s2 = yh_scs_on(k, gx + 2, gj); s3 = yh_scs_on(k, gx + 3, gj);
       }
       Quad uo, vo;
-      if (!SOLID || __all_sync(__activemask(), pat == 0x1F1F1F1Fu)) {   // all tissue around: plain stencil
+      if (ARITH == 1) {   // FAST flavour (instantiated without stimulus and masks only)
+        euler_cell_fast<DEF>(k, a, C.u.a.x, C.v.a.x, C.uW, C.u.a.y, N.u.a.x, S.u.a.x, C.vW, C.v.a.y, N.v.a.x, S.v.a.x, uo.a.x, vo.a.x);
+        euler_cell_fast<DEF>(k, a, C.u.a.y, C.v.a.y, C.u.a.x, C.u.b.x, N.u.a.y, S.u.a.y, C.v.a.x, C.v.b.x, N.v.a.y, S.v.a.y, uo.a.y, vo.a.y);
+        euler_cell_fast<DEF>(k, a, C.u.b.x, C.v.b.x, C.u.a.y, C.u.b.y, N.u.b.x, S.u.b.x, C.v.a.y, C.v.b.y, N.v.b.x, S.v.b.x, uo.b.x, vo.b.x);
+        euler_cell_fast<DEF>(k, a, C.u.b.y, C.v.b.y, C.u.b.x, C.uE, N.u.b.y, S.u.b.y, C.v.b.x, C.vE, N.v.b.y, S.v.b.y, uo.b.y, vo.b.y);
+      } else if (!SOLID || __all_sync(__activemask(), pat == 0x1F1F1F1Fu)) {   // all tissue around: plain stencil
         euler_cell<DEF>(k, C.u.a.x, C.v.a.x, C.uW, C.u.a.y, N.u.a.x, S.u.a.x, C.vW, C.v.a.y, N.v.a.x, S.v.a.x, s0, uo.a.x, vo.a.x);
         euler_cell<DEF>(k, C.u.a.y, C.v.a.y, C.u.a.x, C.u.b.x, N.u.a.y, S.u.a.y, C.v.a.x, C.v.b.x, N.v.a.y, S.v.a.y, s1, uo.a.y, vo.a.y);
         euler_cell<DEF>(k, C.u.b.x, C.v.b.x, C.u.a.y, C.u.b.y, N.u.b.x, S.u.b.x, C.v.a.y, C.v.b.y, N.v.b.x, S.v.b.x, s2, uo.b.x, vo.b.x);
@@ -316,7 +321,7 @@ rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a)
   if (lev == 1) cp_async_wait<0>();
 }
 
-template <int T, int W, bool CANON, bool DEF, bool STIM, bool SOLID, bool FIX>
+template <int T, int W, bool CANON, bool DEF, bool STIM, bool SOLID, bool FIX, int ARITH = 0>
 int launch4(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   constexpr int H = (T + 1) & ~1, BX = W - 2 * H, ROW = 2 * W * 8;
   constexpr int NT = T * (W / 4);
@@ -327,10 +332,10 @@ int launch4(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    YH_CUDA(cudaFuncSetAttribute(rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX>,
+    YH_CUDA(cudaFuncSetAttribute(rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX, ARITH>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1, sms = 148;
-    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX>,
+    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX, ARITH>,
                                                           NT, smem));
     YH_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     slots[dev & 63] = (per_sm > 0 ? per_sm : 1) * sms;
@@ -341,7 +346,7 @@ int launch4(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   const int strips = (k.nx + BX - 1) / BX;
   b.RY = a.RY > 0 ? a.RY : pick_ry(rows, strips, nsims, T, slots[dev & 63]);
   dim3 grd(strips, (rows + b.RY - 1) / b.RY, nsims);
-  auto kfn = rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX>;
+  auto kfn = rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX, ARITH>;
   YH_LAUNCH(kfn, grd, NT, smem, st, k, b);
   return YH_OK;
 }
@@ -351,8 +356,15 @@ int launch3(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   const bool stim = k.stim != 0 || a.period != nullptr || a.apd.APD1 != nullptr;
   if (a.pat)   // obstacle masks: one variant (STIM on) keeps the instantiation count down
     return launch4<T, W, CANON, DEF, true, true, FIX>(k, a, nsims, st);
-  return stim ? launch4<T, W, CANON, DEF, true, false, FIX>(k, a, nsims, st)
-              : launch4<T, W, CANON, DEF, false, false, FIX>(k, a, nsims, st);
+  if (stim) return launch4<T, W, CANON, DEF, true, false, FIX>(k, a, nsims, st);
+  if (yh_arithmetic() == YH_ARITH_FAST) {   // masks and the stimulus stay exact
+    FastArgs b = a;
+    const double rs = k.gateDiff ? k.rscale : 0.0;
+    b.uH = k.tc * k.rx; b.uV = k.tc * k.ry; b.uC = 1.0 - 2.0 * k.tc * (k.rx + k.ry); b.uT = k.tc * k.dt;
+    b.vH = rs * b.uH; b.vV = rs * b.uV; b.vC = 1.0 - 2.0 * k.tc * rs * (k.rx + k.ry); b.vT = k.tc * k.dt * k.eps;
+    return launch4<T, W, CANON, DEF, false, false, FIX, 1>(k, b, nsims, st);
+  }
+  return launch4<T, W, CANON, DEF, false, false, FIX>(k, a, nsims, st);
 }
 
 template <int T, int W>
@@ -380,7 +392,7 @@ int yh_rd_quad_supported(const YhK &k, int tb) {
 int yh_launch_rd_quad_paced(const YhK &k, int tb, const FastArgs &a, int nsims, bool canon, int W,
                             cudaStream_t st) {
 #ifdef YH_QUICK   // developer builds: only the bench variant, for SASS inspection
-  return launch4<4, 128, false, true, false, false, false>(k, a, nsims, st);
+  return launch4<4, 128, false, true, false, false, false, 0>(k, a, nsims, st);
 #else
 #define YH_QUAD_DISPATCH(WW)                                      \
   switch (tb) {                                                   \

@@ -455,6 +455,8 @@ int yh_slab_create(yh_slab **out, const yh_params *pg, int rank, int world, int 
   s->p = *pg; s->p.ny = s->ny_local; s->p.ny_global = pg->ny; s->p.jg0 = s->g0;
   const int own = s->j1 - s->j0;
   int B = own / 4 < 128 ? own / 4 : 128;
+  if (const char *f = getenv("YH_SLAB_BAND")) B = atoi(f);   // tuning hook
+  if (B > own / 2) B = own / 2;
   if (B < halo) B = halo;
   s->band = B;
   YhK k = yh_make_k(&s->p);
