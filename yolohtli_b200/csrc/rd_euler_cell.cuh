@@ -182,5 +182,24 @@ static inline int pick_ry(int rows, int strips, int nsims, int T, int slots) {
   return best_ry;
 }
 
+// Chunk height of the four-columns-per-thread kernels (rd_quad.cu, rd_rkq.cu).  Measured on B200
+// (tools/gpu_ry.sh, 16384 columns): a grid that is ONE full wave is the worst case -- every CTA is in the
+// same phase, nothing fills in behind the first CTA that finishes (2048 rows: RY = 512, 0.93 wave:
+// 338 Gcell/s; RY = 128, 3.7 waves: 372) -- and the rows of pipeline fill cost less than full rows (not every
+// level is active).  Score = RY / (RY + 2*depth) * w / (w + 1/4), w = CTAs / resident slots.
+static inline int pick_ry_waves(int rows, int strips, int nsims, int depth, int slots) {
+  int best_ry = rows;
+  double best = -1.0;
+  for (int C = 1; C <= rows; C++) {
+    const int ry = (rows + C - 1) / C;
+    if (ry > 512) continue;
+    if (ry < 16 && C > 1) break;
+    const int chunks = (rows + ry - 1) / ry;
+    const double w = (double)strips * chunks * nsims / (double)slots;
+    const double eff = (double)ry / (double)(ry + 2 * depth) * w / (w + 0.25);
+    if (eff > best + 1e-9) { best = eff; best_ry = ry; }
+  }
+  return best_ry;
+}
 
 }  // namespace yh_euler

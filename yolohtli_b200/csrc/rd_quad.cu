@@ -344,7 +344,7 @@ int launch4(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   const int rows = k.row1 - k.row0;
   FastArgs b = a;
   const int strips = (k.nx + BX - 1) / BX;
-  b.RY = a.RY > 0 ? a.RY : pick_ry(rows, strips, nsims, T, slots[dev & 63]);
+  b.RY = a.RY > 0 ? a.RY : pick_ry_waves(rows, strips, nsims, T, slots[dev & 63]);
   dim3 grd(strips, (rows + b.RY - 1) / b.RY, nsims);
   auto kfn = rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX, ARITH>;
   YH_LAUNCH(kfn, grd, NT, smem, st, k, b);

@@ -419,7 +419,7 @@ int launch_q(const YhK &k, RkqArgs a, cudaStream_t st) {
   const int rows = k.row1 - k.row0;
   const int strips = (k.nx + BX - 1) / BX;
   const char *force_ry = getenv("YH_RK_RY");
-  a.RY = force_ry ? atoi(force_ry) : pick_ry(rows, strips, 1, 4, slots[dev & 63]);
+  a.RY = force_ry ? atoi(force_ry) : pick_ry_waves(rows, strips, 1, 4, slots[dev & 63]);
   dim3 grd(strips, (rows + a.RY - 1) / a.RY);
   YH_LAUNCH(kfn, grd, NT, smem, st, k, a);
   return YH_OK;
