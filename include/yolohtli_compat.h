@@ -14,6 +14,40 @@ typedef struct stateVar { REAL *u, *v; } stateVar;
 typedef struct advVar { REAL *x, *y; } advVar;
 typedef struct sliceVar { REAL *ux, *uy, *ut, *vx, *vy, *vt; } sliceVar;
 typedef struct vec5dyn { float x, y, vx, vy, t; } vec5dyn;
+/* Layout of the reference's run-parameter block (typeDefinition.cuh:35-125).  The reference keeps ONE
+ * global of this type, `paramVar param` (main.cu:37, `extern` in helper_functions.cu:17), filled by
+ * parameterSetup() and main.cu:148-158 before the first wrapper call.  The shim reads the scalars of the
+ * hot path from that global when the host program defines it, so main.cu links against
+ * libyolohtli_shim.so WITHOUT SOURCE CHANGES (the cudaMemcpyToSymbol block of main.cu:309-402 then
+ * fills __constant__ symbols nobody reads).  Field order and types must match the reference's. */
+typedef struct paramVar {
+  bool animate, saveEveryIt, plotTip, recordTip, plotContour, recordContour, stimulate, apdContour,
+       plotTimeSeries, recordTimeSeries, reduceSym, reduceSymStart, clock, counterclock, firstIterTip,
+       firstIterContour, firstFPS;
+  bool solidSwitch, neumannBC, gateDiff, anisotropy, tipGrad;
+  int lap4, contourMode, timeIntOrder, tipAlgorithm;
+  bool load, save;
+  int nx, ny, memSize;
+  REAL Lx, Ly, hx, hy, dt, diff_par, diff_per, Dxx, Dyy, Dxy, rx, ry, rxy, rbx, rby, rscale, invdx, invdy, sample;
+  int count;
+  REAL physicalTime, physicalTimeLim;
+  int startRecTime;
+  REAL stimPeriod, stimDuration, stimMag;
+  bool fibThreshold, fibTerminated;
+  int leapShocks, eSize;
+  int2 point;
+  int nc;
+  REAL rdomTrapz, rdomStim, rdomAPD, stcx, stcy;
+  float2 pointStim;
+  int savePackage;
+  float tiempo;
+  REAL degrad, boundaryVal, qx4, qy4, fx4, fy4;
+  int itPerFrame, tipOffsetX, tipOffsetY;
+  float minVarColor, maxVarColor;
+  int wnx, wny;
+  float uMax, uMin, vMax, vMin, tipx, tipy;
+  REAL contourThresh1, contourThresh2, contourThresh3, Uth, tc, alpha, beta, gamma, delta, eps, mu, theta;
+} paramVar;
 #endif
 
 /* The reference's wrappers (hostPrototypes.h:22-57), implemented by the shim. */
@@ -47,7 +81,9 @@ void get_rgba_wrapper(size_t pitch, dim3 grid2D, dim3 block2D, int ncol, REAL *f
                       unsigned int *plot_rba_data, unsigned int *cmap_rgba_data, bool *lines);
 void swapSoA(stateVar *A, stateVar *B);
 
-/* New: replaces the ~45 cudaMemcpyToSymbol calls of main.cu:309-402. */
+/* Explicit configuration for hosts that do not define the reference's global `paramVar param`
+ * (replaces the ~45 cudaMemcpyToSymbol calls of main.cu:309-402).  When the host
+ * program DOES define `param`, no call is needed: every wrapper reads it (weak reference). */
 struct yh_params;
 extern "C" int yh_shim_configure(const struct yh_params *p);
 extern "C" int yh_shim_last_status(void);

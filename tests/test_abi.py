@@ -43,6 +43,68 @@ def test_shim_exports_reference_signatures():
     assert "_Z25reactionDiffusion_wrapperm4dim3S_8stateVarS0_S0_S0_bPbbPdb4int2" in out
 
 
+REFERENCE_WRAPPERS = [   # mangled names of hostPrototypes.h:22-57 as the reference's translation units export them
+    "_Z25reactionDiffusion_wrapperm4dim3S_8stateVarS0_S0_S0_bPbbPdb4int2",
+    "_Z11tip_wrapperm4dim3S_8stateVarS0_S0_dibPbPiP7vec5dyn",
+    "_Z13slice_wrapperm4dim3S_8stateVar8sliceVarS1_bb6advVariPbPiP7vec5dyni",
+    "_Z17Cxy_field_wrapperm4dim3S_6advVar5REAL3S1_Pb",
+    "_Z18advFDBFECC_wrapperm4dim3S_8stateVarS0_6advVarS0_S0_S0_Pb",
+    "_Z12solve_matrix5REAL3S_Pd",
+    "_Z13trapz_wrapper4dim3S_8sliceVarS0_8stateVarPdS2_PiP7vec5dyni",
+    "_Z18singleCell_wrapperm4dim3S_8stateVariPdS1_4int2",
+    "_Z12sAPD_wrapperm4dim3S_iPdS0_S0_S0_S0_S0_S0_S0_PbS1_b",
+    "_Z16countour_wrapperm4dim3S_PdS0_PbS1_PiP6float3fi",
+    "_Z7swapSoAP8stateVarS0_",
+]
+
+
+def test_shim_exports_the_full_mangled_set_of_the_reference():
+    """Every wrapper symbol of the reference's own translation units (nm of oracle/_ref/libyhref.so when it is
+    built here, else the recorded list) is exported by libyolohtli_shim.so under the SAME mangled name, and the
+    shim refers to the reference's global `param` weakly (zero-source-change link)."""
+    from yolohtli_b200 import _lib
+    import subprocess
+    from tests import oracle_lib
+    shim = subprocess.check_output(["nm", "-D", _lib.SHIM_PATH]).decode()
+    exported = {l.split()[-1] for l in shim.splitlines() if " T " in l}
+    want = set(REFERENCE_WRAPPERS)
+    if os.path.exists(oracle_lib.REF_SO):
+        ref = subprocess.check_output(["nm", "-D", "--defined-only", oracle_lib.REF_SO]).decode()
+        ref_syms = {l.split()[-1] for l in ref.splitlines()
+                    if " T _Z" in l and ("wrapper" in l or "solve_matrix" in l or "swapSoA" in l)}
+        assert ref_syms == want, "the recorded list is out of date with the reference build"
+    assert want <= exported, want - exported
+    assert "_Z16get_rgba_wrapperm4dim3S_iPdPjS1_Pb" in exported          # main.cu:1633 (GL translation unit)
+    assert any(l.split()[-2:] == ["w", "param"] for l in shim.splitlines()), "weak reference to `param` missing"
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference headers")
+def test_compat_paramvar_layout_matches_the_reference(tmp_path):
+    """include/yolohtli_compat.h re-declares paramVar (typeDefinition.cuh:35-125); the shim reads the
+    reference's global through it, so size and field offsets must be identical."""
+    import subprocess
+    body = """
+#include <cstdio>
+#include <cstddef>
+int main() {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(paramVar), offsetof(paramVar, solidSwitch),
+         offsetof(paramVar, lap4), offsetof(paramVar, nx), offsetof(paramVar, dt), offsetof(paramVar, invdy),
+         offsetof(paramVar, point), offsetof(paramVar, qx4), offsetof(paramVar, tipOffsetX), offsetof(paramVar, tipx),
+         offsetof(paramVar, theta));
+  return 0;
+}
+"""
+    outs = []
+    for name, head in (("ours", f'#include "{ROOT}/include/yolohtli_compat.h"\n'),
+                       ("ref", '#include <cuda_runtime.h>\n#include "/root/reference/typeDefinition.cuh"\n')):
+        src = tmp_path / f"{name}.cu"
+        src.write_text(head.replace("\\n", "\n") + body.replace("\\\\n", "\\n"))
+        exe = tmp_path / name
+        subprocess.check_call(["nvcc", "-o", str(exe), str(src)], stderr=subprocess.DEVNULL)
+        outs.append(subprocess.check_output([str(exe)]).decode().split())
+    assert outs[0] == outs[1], outs
+
+
 def test_params_default_matches_oracle(yh, oracle):
     for nx, ny, rs, sc in [(512, 512, 0, 0), (512, 512, 1, 0), (1024, 1024, 0, 1), (500, 300, 0, 1)]:
         a = yh.default_params(nx, ny, bool(rs), bool(sc))

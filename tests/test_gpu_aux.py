@@ -320,6 +320,19 @@ def test_reference_launch_api_through_the_shim(oracle):
         assert nt.value == len(want) and tips[:nt.value].tobytes() == want.tobytes()
 
 
+@pytest.mark.parametrize("args", ["256 60 default", "512 40 euler", "200 30 default"])
+def test_shim_zero_source_change_link(args):
+    """tests/shim_main.cu: a program that defines the reference's global `paramVar param` like main.cu:37 and
+    never calls yh_shim_configure -- the wrappers read `param` (weak reference) -- bitwise == the C ABI."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "yolohtli_b200", "lib", "yh_shim_main")
+    assert os.path.exists(exe), "build the library first"
+    r = subprocess.run([exe] + args.split(), capture_output=True, text=True, timeout=300)
+    print(r.stdout.strip())
+    assert r.returncode == 0 and "shim_main PASS" in r.stdout, r.stdout + r.stderr
+
+
 def test_symmetry_reduction_step_loop(oracle, yh):
     """C3 (scaled down): the display() symmetry-reduction loop (main.cu:894-954) in the headless
     driver == the same loop composed from oracle pieces, bit for bit: fields, (c, phi) history."""

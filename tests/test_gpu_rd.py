@@ -303,6 +303,29 @@ def test_slab_generic_rk4_rows(oracle):
         assert np.array_equal(got[1][l.own_lo:l.own_hi], want[1][l.j0:l.j1])
 
 
+@pytest.mark.parametrize("order,nsteps", [(1, 3), (4, 1), (2, 2)])
+def test_anisotropic_slab_rows_bitwise(oracle, order, nsteps):
+    """Anisotropy + no-flux boundaries on a ROW RANGE: the corner corrections at x = 0 / x = nx-1 read rows
+    j +- 2 (reactionDiffusion.cu:290-304), so a stage consumes two ghost rows; the slab result must equal the
+    whole-sheet result bit for bit, and a slab with too few ghost rows must be refused, not computed wrong."""
+    nx, ny = 96, 120
+    p = oracle.params_default(nx, ny, timeIntOrder=order, lap4=0, anisotropy=1)
+    p.rxy, p.rbx, p.rby = 0.013, 0.21, 0.19          # a non-trivial diffusion tensor
+    u, v = rand_fields(nx, ny, seed=9)
+    wu, wv = oracle.rd_advance(p, nsteps, u, v)
+    lo, hi = 40, 90
+    H = 2 * order * nsteps                            # two rows per stage and step
+    q = p.copy()
+    q.ny, q.ny_global, q.jg0 = hi - lo + 2 * H, ny, lo - H
+    gu, gv = gpu_advance(q, nsteps, u[lo - H:hi + H], v[lo - H:hi + H], rows=(H, H + hi - lo))
+    assert np.array_equal(gu[H:H + hi - lo], wu[lo:hi]) and np.array_equal(gv[H:H + hi - lo], wv[lo:hi])
+    # half the ghost rows: refused
+    Hs = order * nsteps
+    q.ny, q.jg0 = hi - lo + 2 * Hs, lo - Hs
+    with pytest.raises(Exception):
+        gpu_advance(q, nsteps, u[lo - Hs:hi + Hs], v[lo - Hs:hi + Hs], rows=(Hs, Hs + hi - lo))
+
+
 @pytest.mark.skipif(not oracle_lib.have_reference(), reason="oracle/_ref not built")
 def test_bitwise_vs_reference_kernels_race_free_modes(oracle):
     """T1 tier: Euler + lap4=0, every boundary/mask branch the reference defines, against the

@@ -6,6 +6,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "yh_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -38,6 +41,19 @@ int yh_check_device(void) {
 #define YH_MAX_DEV 32
 static void *g_ws[YH_MAX_DEV][YH_WS_SLOTS];
 static size_t g_ws_sz[YH_MAX_DEV][YH_WS_SLOTS];
+static std::mutex g_ws_mutex;
+// bumped whenever a slot is (re)allocated or freed: captured step loops hold workspace addresses, their
+// cache key carries the generation they were captured under (every thread's cache goes stale at once)
+static std::atomic<unsigned long long> g_ws_generation{1};
+unsigned long long yh_workspace_generation(void) { return g_ws_generation.load(); }
+// launch epochs of the ordered-compaction kernels (tip.cu, contour.cu): process-wide, so that two host
+// threads sharing the per-device look-back words never produce the same epoch
+unsigned yh_next_epoch(void) {
+  static std::atomic<unsigned> e{0};
+  unsigned v;
+  do { v = (e.fetch_add(1) + 1) & 0xFFFFFFu; } while (v == 0);   // zero-initialised words must never look current
+  return v;
+}
 
 void yh_graphs_release(void);
 
@@ -45,7 +61,9 @@ int yh_workspace(size_t bytes, void **ptr, int slot) {
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
   if (dev >= YH_MAX_DEV || slot >= YH_WS_SLOTS) return YH_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
   if (g_ws_sz[dev][slot] < bytes) {
+    g_ws_generation++;
     if (g_ws[dev][slot]) {
       YH_CUDA(cudaDeviceSynchronize());
       YH_CUDA(cudaFree(g_ws[dev][slot]));
@@ -93,7 +111,9 @@ int yh_release_workspace(void) {
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
   YH_CUDA(cudaDeviceSynchronize());
-  yh_graphs_release();   // captured graphs hold workspace addresses
+  yh_graphs_release();   // captured graphs hold workspace addresses (other threads' caches: see the generation)
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  g_ws_generation++;
   for (int s = 0; s < YH_WS_SLOTS; s++) {
     if (g_ws[dev][s]) YH_CUDA(cudaFree(g_ws[dev][s]));
     g_ws[dev][s] = nullptr; g_ws_sz[dev][s] = 0;
@@ -165,7 +185,7 @@ int yh_rd_step(const yh_params *p, const double *u_in, const double *v_in, doubl
                int stim_mouse, int point_x, int point_y, int row0, int row1, void *stream) {
   int rc = yh_check_device();
   if (rc != YH_OK) return rc;
-  rc = validate_rd(p, u_in, v_in, u_out, v_out, solid, row0, row1, p ? p->timeIntOrder : 1);
+  rc = validate_rd(p, u_in, v_in, u_out, v_out, solid, row0, row1, p ? p->timeIntOrder * yh_rd_radius(p) : 1);
   if (rc != YH_OK) return rc;
   YH_REQUIRE(u_in != u_out && v_in != v_out, "in-place step is not supported (neighbours are read)");
   YH_REQUIRE((velTan_u == nullptr) == (velTan_v == nullptr), "velTan_u / velTan_v must both be set or NULL");
@@ -205,7 +225,7 @@ static int advance_plain(const AdvanceCtx &x, int nsteps, int &canon, double *&c
     int T = 1;
     if (x.pat || yh_rd_fast_supported(k, 1)) { T = x.tb; while (T > left) T >>= 1; }
     // rows that must be valid after this pass so that the remaining steps stay exact
-    const int ext = (left - T) * K;
+    const int ext = (left - T) * K * yh_rd_radius(p);
     k.row0 = x.row0 - ext > dom_lo ? x.row0 - ext : dom_lo;
     k.row1 = x.row1 + ext < dom_hi ? x.row1 + ext : dom_hi;
     if (k.row0 < 0) k.row0 = 0;
@@ -242,11 +262,15 @@ static int advance_plain(const AdvanceCtx &x, int nsteps, int &canon, double *&c
 #define YH_GRAPH_CHUNK 64
 #define YH_GRAPH_CACHE 8
 
-struct GraphKey {
+struct GraphKey {   // compared with memcmp: no padding anywhere (asserted below), zeroed before it is filled
   yh_params p;
   int stim, px, py, tb, row0, row1;
   const void *cu, *cv, *nu, *nv, *solid, *pat;
+  unsigned long long ws_generation;
+  long long arith;
 };
+static_assert(sizeof(yh_params) == 16 * 4 + 27 * 8, "yh_params must not contain padding");
+static_assert(sizeof(GraphKey) == sizeof(yh_params) + 6 * 4 + 6 * 8 + 16, "GraphKey must not contain padding");
 struct GraphEntry {
   GraphKey key;
   cudaGraphExec_t exec;
@@ -282,6 +306,8 @@ static GraphKey graph_key(const AdvanceCtx &x, const double *cu, const double *c
   key.p = *x.p; key.stim = x.k.stim; key.px = x.k.px; key.py = x.k.py; key.tb = x.tb;
   key.row0 = x.row0; key.row1 = x.row1;
   key.cu = cu; key.cv = cv; key.nu = nu; key.nv = nv; key.solid = x.solid; key.pat = x.pat;
+  key.ws_generation = yh_workspace_generation();
+  key.arith = yh_arithmetic();
   return key;
 }
 
@@ -393,7 +419,7 @@ int yh_rd_advance(const yh_params *p, int nsteps, int tb_steps, int flags, doubl
   YH_REQUIRE(nsteps >= 0 && result_in_B, "bad nsteps / result_in_B");
   YH_REQUIRE(tb_steps >= 0 && tb_steps <= 4 && tb_steps != 3, "tb_steps must be 0 (auto), 1, 2 or 4");
   rc = validate_rd(p, uA, vA, uB, vB, solid, row0, row1,
-                   nsteps * (p ? p->timeIntOrder : 1));
+                   nsteps * (p ? p->timeIntOrder * yh_rd_radius(p) : 1));
   if (rc != YH_OK) return rc;
   YhK k = yh_make_k(p);
   k.stim = stim_mouse != 0; k.px = point_x; k.py = point_y;

@@ -154,7 +154,6 @@ extern "C" int yh_contour(const yh_params *p, const double *field1, const double
   YH_REQUIRE(mode == 1 || field1, "modes 2 and 3 need field1");
   YH_REQUIRE(capacity >= 0, "negative capacity");
   YH_REQUIRE(p->jg0 == 0 && p->ny_global == p->ny, "contour extraction works on a whole sheet");
-  static thread_local unsigned epoch = 0;
   YhK k = yh_make_k(p);
   cudaStream_t st = (cudaStream_t)stream;
   const long long ncell = (long long)p->nx * p->ny;
@@ -162,8 +161,7 @@ extern "C" int yh_contour(const yh_params *p, const double *field1, const double
   unsigned long long *state = nullptr;
   rc = yh_workspace(((size_t)nchunks + 1) * sizeof(unsigned long long), (void **)&state, 3);
   if (rc != YH_OK) return rc;
-  epoch = (epoch + 1) & 0xFFFFFFu;
-  if (epoch == 0) epoch = 1;
+  const unsigned epoch = yh_next_epoch();
   if (contour_plot) YH_CUDA(cudaMemsetAsync(contour_plot, 0, (size_t)ncell, st));   // :268
   ContourArgs a{field1, field2, stimArea, contour_plot, contour_count, contour_vector, capacity, mode,
                 (float)physical_time, thresh1, thresh2, thresh3, {state, epoch, nchunks}};

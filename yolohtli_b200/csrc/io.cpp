@@ -238,8 +238,18 @@ int yh_io_params_read_csv(const char *path, yh_run_params *rp) {
   // saveFiles.cu:640 reads dt as written; main.cu:148 halves it again when reduceSym
   if (rp->reduceSym) rp->k.dt = 0.5 * rp->k.dt;
   rp->k.ny_global = rp->k.ny; rp->k.jg0 = 0;
-  // the derived scalars come back with 6 decimals: recompute them (main.cu:148-155 does so too)
-  return yh_params_derive(&rp->k, rp->Dxx, rp->Dyy, rp->Dxy);
+  // main.cu:148-155 recomputes rx, ry, rxy, qx4, qy4, fx4, fy4 after loadParamValues and KEEPS rbx, rby, invdx,
+  // invdy as the 6-decimal values read from the file; a restart here is bit-compatible with that
+  yh_params *k = &rp->k;
+  k->rx = k->dt * rp->Dxx / (k->hx * k->hx);
+  k->ry = k->dt * rp->Dyy / (k->hy * k->hy);
+  k->rxy = 2.0 * rp->Dxy * k->dt / (4.0 * k->hx * k->hy);
+  k->qx4 = k->dt * rp->Dyy / (k->hy * k->hy * 12.0);
+  k->qy4 = k->dt * rp->Dxx / (k->hx * k->hx * 12.0);
+  k->fx4 = k->dt / 12.0;
+  k->fy4 = k->dt / 12.0;
+  rp->startRecTime = (double)(int)rp->startRecTime;   // saveFiles.cu:656: (int)
+  return YH_OK;
 }
 
 // print2D2column, printFunctions.cu:58-79

@@ -273,7 +273,10 @@ int yh_launch_rd_generic(const YhK &k, const double *u_in, const double *v_in, d
     a.solid = solid;
     a.a_next = a.last ? 0.0 : ki[s + 1];
     a.w = w[s];
-    const int ext = K - 1 - s;   // later stages read one more ring of this stage's output
+    // later stages read `rad` more rows of this stage's output per remaining stage (rad = 2 for the
+    // anisotropic no-flux corner terms, reactionDiffusion.cu:290-304)
+    const int rad = (k.anisotropy && k.neumannBC && !k.solidSwitch) ? 2 : 1;
+    const int ext = rad * (K - 1 - s);
     a.jlo = max(lo, k.row0 - ext);
     a.jhi = min(hi, k.row1 + ext);
     if (a.jhi <= a.jlo) continue;

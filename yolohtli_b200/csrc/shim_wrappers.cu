@@ -12,8 +12,32 @@
 #include "../../include/yolohtli_compat.h"
 
 static yh_params g_p;
-static bool g_configured = false;
+static bool g_configured = false;     // yh_shim_configure() was called: the explicit block wins
 static int g_status = YH_OK;
+static double g_con_th[3] = {0.8, 0.85, 0.7};
+static double g_color[2] = {-0.1f, 1.1f};
+
+// The reference's global run-parameter block (main.cu:37).  Weak: the shim also loads into programs that
+// do not have it (then yh_shim_configure is the way in).
+extern paramVar param __attribute__((weak));
+
+// paramVar -> yh_params, field for field what main.cu:309-402 copies into the __constant__ symbols.
+static void from_reference_param(void) {
+  const paramVar &q = param;
+  yh_params p;
+  p.nx = q.nx; p.ny = q.ny; p.ny_global = q.ny; p.jg0 = 0;
+  p.solidSwitch = q.solidSwitch; p.neumannBC = q.neumannBC; p.gateDiff = q.gateDiff; p.anisotropy = q.anisotropy;
+  p.lap4 = q.lap4; p.timeIntOrder = q.timeIntOrder; p.tipGrad = q.tipGrad; p.tipAlgorithm = q.tipAlgorithm;
+  p.tipOffsetX = q.tipOffsetX; p.tipOffsetY = q.tipOffsetY; p.tipx0 = q.tipx; p.tipy0 = q.tipy;   // main.cu:373-376
+  p.dt = q.dt; p.hx = q.hx; p.hy = q.hy; p.Lx = q.Lx; p.Ly = q.Ly;
+  p.rx = q.rx; p.ry = q.ry; p.rxy = q.rxy; p.rbx = q.rbx; p.rby = q.rby; p.rscale = q.rscale;
+  p.qx4 = q.qx4; p.qy4 = q.qy4; p.fx4 = q.fx4; p.fy4 = q.fy4; p.invdx = q.invdx; p.invdy = q.invdy;
+  p.tc = q.tc; p.alpha = q.alpha; p.beta = q.beta; p.gamma = q.gamma; p.delta = q.delta; p.eps = q.eps;
+  p.mu = q.mu; p.theta = q.theta; p.boundaryVal = q.boundaryVal; p.Uth = q.Uth;
+  g_p = p;
+  g_con_th[0] = q.contourThresh1; g_con_th[1] = q.contourThresh2; g_con_th[2] = q.contourThresh3;
+  if (q.minVarColor != q.maxVarColor) { g_color[0] = q.minVarColor; g_color[1] = q.maxVarColor; }
+}
 
 static void note(int rc, const char *what) {
   if (rc == YH_OK) return;
@@ -23,8 +47,13 @@ static void note(int rc, const char *what) {
 }
 static bool ready(const char *what) {
   if (g_configured) return true;
+  if (&param != nullptr) {      // the host is the reference's main.cu (or built like it): read its global,
+    from_reference_param();     // at every call -- it is a few dozen scalars, and always current
+    return true;
+  }
   g_status = YH_ERR_INVALID_ARG;
-  fprintf(stderr, "yolohtli shim: %s called before yh_shim_configure()\n", what);
+  fprintf(stderr, "yolohtli shim: %s called before yh_shim_configure() in a program without the reference's "
+                  "global `paramVar param`\n", what);
   if (getenv("YH_SHIM_ABORT_ON_ERROR")) exit(-1);
   return false;
 }
@@ -121,8 +150,6 @@ void sAPD_wrapper(size_t, dim3, dim3, int count, REAL *uold, REAL *unew, REAL *A
 
 // conTh1_d..conTh3_d and minVarColor_d / maxVarColor_d are __constant__ symbols in the reference
 // (main.cu:378-383, 366-369); defaults of parameterSetup (saveFiles.cu:196-217).
-static double g_con_th[3] = {0.8, 0.85, 0.7};
-static double g_color[2] = {-0.1f, 1.1f};
 extern "C" int yh_shim_set_contour_thresholds(double th1, double th2, double th3) {
   g_con_th[0] = th1; g_con_th[1] = th2; g_con_th[2] = th3;
   return YH_OK;

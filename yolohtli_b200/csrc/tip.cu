@@ -236,7 +236,6 @@ extern "C" int yh_tip_track_rows(const yh_params *p, const double *u_past, const
   YH_REQUIRE(row0 >= 0 && row0 < row1 && row1 <= p->ny, "bad row range");
   YH_REQUIRE(row1 < p->ny || p->jg0 + p->ny == p->ny_global, "the last row needs the row after it");
   YH_REQUIRE(!p->tipGrad || (p->jg0 == 0 && p->ny == p->ny_global), "tipGrad reads up to two rows away: whole sheets only");
-  static thread_local unsigned epoch = 0;
   YhK k = yh_make_k(p);
   k.row0 = row0; k.row1 = row1;
   const long long ncell = (long long)p->nx * (row1 - row0);
@@ -244,8 +243,7 @@ extern "C" int yh_tip_track_rows(const yh_params *p, const double *u_past, const
   unsigned long long *state = nullptr;
   rc = yh_workspace(((size_t)nchunks + 1) * sizeof(unsigned long long), (void **)&state, 1);
   if (rc != YH_OK) return rc;
-  epoch = (epoch + 1) & 0xFFFFFFu;
-  if (epoch == 0) epoch = 1;   // zero-initialised workspace must never look current
+  const unsigned epoch = yh_next_epoch();
   TipArgs a{u_past, u_present, tip_plot, tip_count, tip_vector, capacity, algorithm,
             (float)physical_time, {state, epoch, nchunks}, nullptr, 0.0, 0};
   tip_kernel<<<nchunks, TIP_THREADS, 0, (cudaStream_t)stream>>>(k, a);

@@ -82,6 +82,8 @@ extern thread_local int yh_preload_only;
 
 // internal workspace (per device, grown on demand, abi.cu)
 int yh_workspace(size_t bytes, void **ptr, int slot);
+unsigned long long yh_workspace_generation(void);
+unsigned yh_next_epoch(void);   // launch epoch of the ordered-compaction kernels, process-wide
 
 // nsteps x {RD step; swapSoA} on (uA,vA) <-> (uB,vB), CUDA-graph replay for small whole sheets
 // (abi.cu).  *last_T (optional) = time steps of the final pass.
@@ -175,6 +177,12 @@ struct YhApd {
   const uint8_t *stimArea;
   int stimulate;
 };
+
+// Rows a stage reads beyond the rows it writes.  1, except for the anisotropic no-flux corner corrections,
+// which read rows j +- 2 at the columns x = 0 and x = nx-1 (reactionDiffusion.cu:290-304).
+static inline int yh_rd_radius(const yh_params *p) {
+  return (p->anisotropy && p->neumannBC && !p->solidSwitch) ? 2 : 1;
+}
 
 // ---- kernel launchers (one per .cu) ------------------------------------------------------
 int yh_launch_rd_generic(const YhK &k, const double *u_in, const double *v_in, double *u_out,

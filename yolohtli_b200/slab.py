@@ -61,7 +61,10 @@ class SlabRunner:
         self.p = self.lay.local_params(p_global)
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.halo = halo
-        self.K = max(1, p_global.timeIntOrder)   # stencil radius consumed per time step
+        # rows consumed per time step: one per stage, two with the anisotropic no-flux corner terms
+        # (reactionDiffusion.cu:290-304 read rows j +- 2 at the x edges)
+        rad = 2 if (p_global.anisotropy and p_global.neumannBC and not p_global.solidSwitch) else 1
+        self.K = max(1, p_global.timeIntOrder) * rad
         self.nx = p_global.nx
         shape = (self.lay.ny_local, self.nx)
         self.u = [torch.zeros(shape, dtype=torch.float64, device=self.device) for _ in range(2)]
