@@ -2,7 +2,7 @@
 counts): opcode -> warp-level instructions executed, FP64 vs everything else, and the issue-slot
 model of DESIGN.md (an FP64 instruction holds the dispatch port two cycles, tools/issue_mix.cu).
 
-  python tools/ncu_mix.py gpurun_out/x.ncu-rep [top=25]
+  python tools/ncu_mix.py gpurun_out/x.ncu-rep | x_source.csv [top=25]
 """
 import csv
 import io
@@ -12,8 +12,11 @@ from collections import Counter
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
-                     capture_output=True, text=True).stdout
+if rep.endswith(".csv"):      # an exported source page (ncu -i x.ncu-rep --page source --csv --print-source sass)
+    txt = open(rep).read()
+else:
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
+                         capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 name = rows[0][1]
 hdr = rows[1]
