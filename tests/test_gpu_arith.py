@@ -129,6 +129,21 @@ def test_fast_flavour_euler_100_steps_within_1e12(oracle, yh, fast, kw, tb):
     assert 0 < eu <= 1e-13 and ev <= 1e-13          # measured 2.4e-15 / 5.3e-15
 
 
+def test_fast_flavour_tile_kernel_25_steps(oracle, yh, fast):
+    """The small-sheet (tile) RK4 + lap4 kernel in the FAST flavour: the reference's default 512^2 sheet."""
+    os.environ["YH_RD_PATH"] = "tile"
+    nx = ny = 512
+    for kw in (dict(), dict(mu=1.1, delta=0.9, gamma=0.05, theta=0.01)):
+        p = oracle.params_default(nx, ny, **kw)
+        u, v = synth.cross_field_ic(nx, ny)
+        u = u + 0.05 * np.sin(0.07 * np.arange(nx))[None, :] * np.cos(0.05 * np.arange(ny))[:, None]
+        want = oracle.rd_advance(p, 25, u, v)
+        got = advance(p, 25, u, v)
+        eu, ev = np.abs(got[0] - want[0]).max(), np.abs(got[1] - want[1]).max()
+        print(f"tile kernel, fast vs exact after 25 steps {kw}: max |du| {eu:.3e}, max |dv| {ev:.3e}")
+        assert 0 < eu <= 1e-14 and ev <= 1e-14
+
+
 def test_fast_flavour_spiral_traces_and_tip(oracle, yh):
     """2000 default-mode steps of a rotating spiral at 512^2 (C1 geometry): electrode traces and the tip
     of the FAST run against the EXACT run."""

@@ -55,14 +55,44 @@ struct TileArgs {
   // z = (u, v) at (k.px, k.py) after s of this launch's steps, s = 0 .. T-1; slot0 = *slot
   double *trace;
   const unsigned long long *slot;
+  // FAST arithmetic flavour of the RK kernel (yh_set_arithmetic; coefficients as in rd_rkq.cu):
+  //   d = cC*C + cH*(W+E) + cV*(N+S) + cQ*(SW+SE+NW+NE) + jC*Jc - jX*(JW+JE) - jY*(JN+JS)
+  double uC, uH, uV, uQ, vC, vH, vV, vQ, jC, jX, jY, neg_eps;
 };
+
+__device__ __forceinline__ double t_flip(double t) {
+  return __hiloint2double(__double2hiint(t) ^ (int)0x80000000, __double2loint(t));
+}
+// currents of the FAST flavour (stimulus off): FMA-contracted forms of t_Isum / t_Iv
+template <bool DEF>
+__device__ __forceinline__ void t_currents_fast(const YhK &k, const TileArgs &a, double u, double v, double &ju, double &jv) {
+  const double mu_u = DEF ? u : k.mu * u;
+  const double ug = DEF ? u : k.delta * (u - k.gamma);
+  ju = t_flip(fma(mu_u * (1.0 - u), u - k.alpha, -(u * v)));
+  const double yv = fma(ug, k.beta - u, -v);
+  jv = a.neg_eps * (DEF ? yv : yv - k.theta);
+}
+template <int F, bool LAP4>
+__device__ __forceinline__ double t_cell_fast(const TileArgs &a, double C, double WE, double NS, double Q, double Jc,
+                                              double JWE, double JNS) {
+  double d = (F == 0 ? a.uC : a.vC) * C;
+  d = fma(F == 0 ? a.uH : a.vH, WE, d);
+  d = fma(F == 0 ? a.uV : a.vV, NS, d);
+  if (LAP4) {
+    d = fma(F == 0 ? a.uQ : a.vQ, Q, d);
+    d = fma(-a.jX, JWE, d);
+    d = fma(-a.jY, JNS, d);
+  }
+  return fma(a.jC, Jc, d);
+}
 
 // ------------------------------------------------------------------------------------------
 // Runge-Kutta tile kernel
 // ------------------------------------------------------------------------------------------
 // FAST: gateDiff on and the live stimulus off at compile time (the reference's default mode): no
 // uniform branches inside a stage, so ptxas schedules the u and v halves as one block (rd_rk.cu).
-template <int K, bool LAP4, bool DEF, bool FAST>
+// ARITH: 0 = exact (the reference's expressions, no contraction), 1 = fast (FAST switches only; see rd_rkq.cu).
+template <int K, bool LAP4, bool DEF, bool FAST, int ARITH = 0>
 __global__ void __launch_bounds__(NTHR, 2)
 rd_tile_rk(const __grid_constant__ YhK k, const __grid_constant__ TileArgs a) {
   constexpr int H = K;                       // halo (K = 2 or 4: even, keeps pairs 16-byte aligned)
@@ -121,26 +151,43 @@ rd_tile_rk(const __grid_constant__ YhK k, const __grid_constant__ TileArgs a) {
 #pragma unroll
   for (int s = 0; s < SLOTS; s++) ru[s] = rv[s] = du[s] = dv[s] = make_double2(0.0, 0.0);
 
+  // Geometry of this thread's pairs, once per launch instead of once per stage and phase (the divisions and
+  // range tests were 40 % of the executed instructions, ncu profiles/r2a_tile_rk_512_mix.txt): cell index,
+  // offsets of the S / N rows (no-flux mirror = index selection inside the tile, helper_functions.cu:69-79),
+  // and a bit per stage: "du of this stage is needed here" (tile minus st+1 outer rings); bit K: output row.
+  int g_c[SLOTS], g_s[SLOTS], g_n[SLOTS];
+  unsigned g_m[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; s++) {
+    const int t = tid + s * NTHR;
+    g_c[s] = 0; g_s[s] = 0; g_n[s] = 0; g_m[s] = 0;
+    if (t >= NPAIR) continue;
+    const int ty = t / NP, tx = 2 * (t % NP);
+    const int gx = gx0 + tx, ly = ly0 + ty;
+    const bool in_dom = gx >= 0 && gx < nx && ly >= dom_lo && ly < dom_hi;
+    g_c[s] = ty * TW + tx;
+    g_s[s] = (ly - 1 < dom_lo) ? TW : -TW;
+    g_n[s] = (ly + 1 >= dom_hi) ? -TW : TW;
+    unsigned m = 0;
+#pragma unroll
+    for (int st = 0; st < K; st++) m |= (in_dom && pair_in_ring(tx, ty, st + 1, TW)) ? (1u << st) : 0u;
+    if (ly >= k.row0 && ly < out_hi) m |= 1u << K;
+    // tile-edge pairs (tx == 0 / TW-2) hold one cell outside the ring: its value is never read by a valid
+    // cell, it only must not read outside the tile
+    if ((gx == 0) || (tx == 0)) m |= 1u << (K + 1);
+    if ((gx + 2 == nx) || (tx == TW - 2)) m |= 1u << (K + 2);
+    g_m[s] = m;
+  }
+
 #pragma unroll
   for (int st = 0; st < K; st++) {
-    const int ring = st + 1;   // cells whose du_st is needed: tile minus `ring` outer rings
+    // cells whose du_st is needed: tile minus st+1 outer rings (bit st of g_m)
     // ---- phase A: du, dv of stage st into registers ----------------------------------------
 #pragma unroll
     for (int s = 0; s < SLOTS; s++) {
-      const int t = tid + s * NTHR;
-      if (t >= NPAIR) continue;
-      const int ty = t / NP, tx = 2 * (t % NP);
-      const int gx = gx0 + tx, ly = ly0 + ty;
-      const bool in_dom = gx >= 0 && gx < nx && ly >= dom_lo && ly < dom_hi;
-      const bool in_ring = pair_in_ring(tx, ty, ring, TW);
-      if (!(in_dom && in_ring)) continue;
-      const int c = ty * TW + tx;
-      // no-flux mirror = index selection inside the tile (helper_functions.cu:69-79)
-      const int cs = (ly - 1 < dom_lo) ? c + TW : c - TW;
-      const int cn = (ly + 1 >= dom_hi) ? c - TW : c + TW;
-      // tile-edge pairs (tx == 0 / TW-2) hold one cell outside the ring: its value is never
-      // read by a valid cell, it only must not read outside the tile
-      const bool le = (gx == 0) || (tx == 0), re = (gx + 2 == nx) || (tx == TW - 2);
+      if (!((g_m[s] >> st) & 1u)) continue;
+      const int c = g_c[s], cs = c + g_s[s], cn = c + g_n[s];
+      const bool le = (g_m[s] >> (K + 1)) & 1u, re = (g_m[s] >> (K + 2)) & 1u;
       double d[2][2];
 #pragma unroll
       for (int f = 0; f < 2; f++) {
@@ -150,6 +197,29 @@ rd_tile_rk(const __grid_constant__ YhK k, const __grid_constant__ TileArgs a) {
         const double2 N = *reinterpret_cast<const double2 *>(P + cn);
         const double Wv = le ? C.y : P[c - 1], Ev = re ? C.x : P[c + 2];
         double d0, d1;
+        if (ARITH == 1) {   // FAST flavour: collected coefficients, FMA chains (FAST switches: gateDiff on)
+          const double2 Jc = *reinterpret_cast<const double2 *>(J + c);
+          double q0 = 0.0, q1 = 0.0, jwe0 = 0.0, jwe1 = 0.0, jns0 = 0.0, jns1 = 0.0;
+          const double ns0 = N.x + S.x, ns1 = N.y + S.y;
+          if (LAP4) {
+            const double SWv = le ? S.y : P[cs - 1], SEv = re ? S.x : P[cs + 2];
+            const double NWv = le ? N.y : P[cn - 1], NEv = re ? N.x : P[cn + 2];
+            const double2 Js = *reinterpret_cast<const double2 *>(J + cs);
+            const double2 Jn = *reinterpret_cast<const double2 *>(J + cn);
+            const double JW = le ? Jc.y : J[c - 1], JE = re ? Jc.x : J[c + 2];
+            q0 = (SWv + NWv) + ns1; q1 = ns0 + (SEv + NEv);     // corners of a cell = (N+S) of its two x neighbours
+            jwe0 = JW + Jc.y; jwe1 = Jc.x + JE;
+            jns0 = Jn.x + Js.x; jns1 = Jn.y + Js.y;
+          }
+          if (f == 0) {
+            d[f][0] = t_cell_fast<0, LAP4>(a, C.x, Wv + C.y, ns0, q0, Jc.x, jwe0, jns0);
+            d[f][1] = t_cell_fast<0, LAP4>(a, C.y, C.x + Ev, ns1, q1, Jc.y, jwe1, jns1);
+          } else {
+            d[f][0] = t_cell_fast<1, LAP4>(a, C.x, Wv + C.y, ns0, q0, Jc.x, jwe0, jns0);
+            d[f][1] = t_cell_fast<1, LAP4>(a, C.y, C.x + Ev, ns1, q1, Jc.y, jwe1, jns1);
+          }
+          continue;
+        }
         if (f == 0) {
           d0 = ((fma(-2.0, C.x, Wv) + C.y) * k.rx + (fma(-2.0, C.x, N.x) + S.x) * k.ry);
           d1 = ((fma(-2.0, C.y, C.x) + Ev) * k.rx + (fma(-2.0, C.y, N.y) + S.y) * k.ry);
@@ -183,41 +253,58 @@ rd_tile_rk(const __grid_constant__ YhK k, const __grid_constant__ TileArgs a) {
       }
       du[s] = make_double2(d[0][0], d[0][1]);
       dv[s] = make_double2(d[1][0], d[1][1]);
-      ru[s].x += (ws[st] * du[s].x); ru[s].y += (ws[st] * du[s].y);   // :502-503
-      rv[s].x += (ws[st] * dv[s].x); rv[s].y += (ws[st] * dv[s].y);
+      if (ARITH == 1) {
+        ru[s].x = fma(ws[st], du[s].x, ru[s].x); ru[s].y = fma(ws[st], du[s].y, ru[s].y);
+        rv[s].x = fma(ws[st], dv[s].x, rv[s].x); rv[s].y = fma(ws[st], dv[s].y, rv[s].y);
+      } else {
+        ru[s].x += (ws[st] * du[s].x); ru[s].y += (ws[st] * du[s].y);   // :502-503
+        rv[s].x += (ws[st] * dv[s].x); rv[s].y += (ws[st] * dv[s].y);
+      }
     }
     __syncthreads();   // every read of the stage-st state is done
     // ---- phase B: stage st+1 state and currents, or the final update -----------------------
 #pragma unroll
     for (int s = 0; s < SLOTS; s++) {
-      const int t = tid + s * NTHR;
-      if (t >= NPAIR) continue;
-      const int ty = t / NP, tx = 2 * (t % NP);
-      const int gx = gx0 + tx, ly = ly0 + ty;
-      const bool in_dom = gx >= 0 && gx < nx && ly >= dom_lo && ly < dom_hi;
-      const bool in_ring = pair_in_ring(tx, ty, ring, TW);
-      if (!(in_dom && in_ring)) continue;
-      const int c = ty * TW + tx;
+      if (!((g_m[s] >> st) & 1u)) continue;
+      const int c = g_c[s];
       const double2 u0 = *reinterpret_cast<const double2 *>(s_u0 + c);
       const double2 v0 = *reinterpret_cast<const double2 *>(s_v0 + c);
       if (st < K - 1) {
         double2 U, V, ju, jv;
-        U.x = u0.x + (ki[st + 1] * du[s].x); U.y = u0.y + (ki[st + 1] * du[s].y);   // :117-118
-        V.x = v0.x + (ki[st + 1] * dv[s].x); V.y = v0.y + (ki[st + 1] * dv[s].y);
-        const int gj = ly + k.jg0;
-        ju.x = t_Isum<DEF, FAST>(k, U.x, V.x, FAST ? false : yh_scs(k, gx, gj));
-        ju.y = t_Isum<DEF, FAST>(k, U.y, V.y, FAST ? false : yh_scs(k, gx + 1, gj));
-        jv.x = t_Iv<DEF>(k, U.x, V.x);
-        jv.y = t_Iv<DEF>(k, U.y, V.y);
+        if (ARITH == 1) {
+          U.x = fma(ki[st + 1], du[s].x, u0.x); U.y = fma(ki[st + 1], du[s].y, u0.y);
+          V.x = fma(ki[st + 1], dv[s].x, v0.x); V.y = fma(ki[st + 1], dv[s].y, v0.y);
+          t_currents_fast<DEF>(k, a, U.x, V.x, ju.x, jv.x);
+          t_currents_fast<DEF>(k, a, U.y, V.y, ju.y, jv.y);
+        } else {
+          U.x = u0.x + (ki[st + 1] * du[s].x); U.y = u0.y + (ki[st + 1] * du[s].y);   // :117-118
+          V.x = v0.x + (ki[st + 1] * dv[s].x); V.y = v0.y + (ki[st + 1] * dv[s].y);
+          bool s0 = false, s1 = false;
+          if (!FAST) {   // live stimulus: global coordinates of the pair from its tile index
+            const int t = tid + s * NTHR;
+            const int gx = gx0 + 2 * (t % NP), gj = ly0 + t / NP + k.jg0;
+            s0 = yh_scs(k, gx, gj); s1 = yh_scs(k, gx + 1, gj);
+          }
+          ju.x = t_Isum<DEF, FAST>(k, U.x, V.x, s0);
+          ju.y = t_Isum<DEF, FAST>(k, U.y, V.y, s1);
+          jv.x = t_Iv<DEF>(k, U.x, V.x);
+          jv.y = t_Iv<DEF>(k, U.y, V.y);
+        }
         *reinterpret_cast<double2 *>(s_U + c) = U;
         *reinterpret_cast<double2 *>(s_V + c) = V;
         *reinterpret_cast<double2 *>(s_Ju + c) = ju;
         *reinterpret_cast<double2 *>(s_Jv + c) = jv;
-      } else if (ly >= k.row0 && ly < out_hi) {   // ring == H here: exactly the output tile
+      } else if ((g_m[s] >> K) & 1u) {   // ring == H here: exactly the output tile
         double2 uo, vo;   // :512-513
-        uo.x = u0.x + k.tc * ru[s].x; uo.y = u0.y + k.tc * ru[s].y;
-        vo.x = v0.x + k.tc * rv[s].x; vo.y = v0.y + k.tc * rv[s].y;
-        const size_t o = (size_t)ly * nx + gx;
+        if (ARITH == 1) {
+          uo.x = fma(k.tc, ru[s].x, u0.x); uo.y = fma(k.tc, ru[s].y, u0.y);
+          vo.x = fma(k.tc, rv[s].x, v0.x); vo.y = fma(k.tc, rv[s].y, v0.y);
+        } else {
+          uo.x = u0.x + k.tc * ru[s].x; uo.y = u0.y + k.tc * ru[s].y;
+          vo.x = v0.x + k.tc * rv[s].x; vo.y = v0.y + k.tc * rv[s].y;
+        }
+        const int t = tid + s * NTHR;
+        const size_t o = (size_t)(ly0 + t / NP) * nx + (gx0 + 2 * (t % NP));
         *reinterpret_cast<double2 *>(a.u_out + o) = uo;
         *reinterpret_cast<double2 *>(a.v_out + o) = vo;
         if (a.vtu && gd) {   // :551-552
@@ -351,16 +438,16 @@ int set_smem(KernelT kern, size_t smem) {
   return YH_OK;
 }
 
-template <int K, bool LAP4, bool DEF, bool FAST>
+template <int K, bool LAP4, bool DEF, bool FAST, int ARITH = 0>
 int launch_rk(const YhK &k, const TileArgs &a, cudaStream_t st) {
   constexpr int TW = TB + 2 * K;
   const size_t smem = (size_t)6 * TW * TW * sizeof(double);
   static bool done[64] = {false};
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
-  if (!done[dev & 63]) { int rc = set_smem(rd_tile_rk<K, LAP4, DEF, FAST>, smem); if (rc) return rc; done[dev & 63] = true; }
+  auto kfn = rd_tile_rk<K, LAP4, DEF, FAST, ARITH>;
+  if (!done[dev & 63]) { int rc = set_smem(kfn, smem); if (rc) return rc; done[dev & 63] = true; }
   dim3 grd((k.nx + TB - 1) / TB, (k.row1 - k.row0 + TB - 1) / TB);
-  auto kfn = rd_tile_rk<K, LAP4, DEF, FAST>;
   YH_LAUNCH(kfn, grd, NTHR, smem, st, k, a);
   return YH_OK;
 }
@@ -410,8 +497,16 @@ int yh_launch_rd_tile_rk(const YhK &k, const double *u_in, const double *v_in, d
   TileArgs a{u_in, v_in, u_out, v_out, vtu, vtv, 0, nullptr, 0, 0, nullptr, nullptr};
   const bool lap4 = k.lap4 != 0, def = is_def(k);
 #define YH_T(KK, L) (def ? launch_rk<KK, L, true, false>(k, a, st) : launch_rk<KK, L, false, false>(k, a, st))
-  if (k.timeIntOrder == 4 && lap4 && k.gateDiff && !k.stim)   // the reference's default mode
+  if (k.timeIntOrder == 4 && lap4 && k.gateDiff && !k.stim) {   // the reference's default mode
+    if (yh_arithmetic() == YH_ARITH_FAST) {
+      const double q = k.qx4 + k.qy4;
+      a.uH = k.rx - 2.0 * q; a.uV = k.ry - 2.0 * q; a.uC = -2.0 * (k.rx + k.ry) + 4.0 * q; a.uQ = q;
+      a.vH = k.rscale * a.uH; a.vV = k.rscale * a.uV; a.vC = k.rscale * a.uC; a.vQ = k.rscale * a.uQ;
+      a.jX = k.fx4; a.jY = k.fy4; a.jC = 2.0 * (k.fx4 + k.fy4) - k.dt; a.neg_eps = -k.eps;
+      return def ? launch_rk<4, true, true, true, 1>(k, a, st) : launch_rk<4, true, false, true, 1>(k, a, st);
+    }
     return def ? launch_rk<4, true, true, true>(k, a, st) : launch_rk<4, true, false, true>(k, a, st);
+  }
   if (k.timeIntOrder == 4) return lap4 ? YH_T(4, true) : YH_T(4, false);
   return lap4 ? YH_T(2, true) : YH_T(2, false);
 #undef YH_T
