@@ -57,7 +57,9 @@ __device__ __forceinline__ void sts128(unsigned a, const double2 &v) {
 // byte offset of 16-byte chunk `ch` inside a swizzled row
 __device__ __forceinline__ int swz(int ch) { return ((ch >> 3) << 7) | ((((ch & 7) ^ (ch >> 3)) & 7) << 4); }
 
-template <int T, int W, bool CANON, bool DEF, bool STIM, bool SOLID, bool FIX, int ARITH>
+// FLAV: bit 0 = FAST arithmetic (yh_set_arithmetic), bit 1 = level-0 rows by TMA bulk copies + mbarriers instead of
+// per-thread cp.async (YH_EULER_FEED = tma | cpasync; the A/B is in DESIGN.md).
+template <int T, int W, bool CANON, bool DEF, bool STIM, bool SOLID, bool FIX, int FLAV>
 __global__ void __launch_bounds__(T *(W / 4))
 rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a) {
   constexpr int H = (T + 1) & ~1;        // halo columns each side
@@ -94,15 +96,22 @@ rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a)
   const bool canon = CANON && (lev == 1);
 
   // ---- static shared-memory offsets of this thread (bytes inside a field row) ----------------
-  const int offA0 = swz(2 * t), offB0 = swz(2 * t + 1);
-  int offW = (t > 0) ? swz(2 * t - 1) + 8 : offA0;         // column c-1 (no neighbour: any valid address)
-  int offE = (t < NL - 1) ? swz(2 * t + 2) : offB0;        // column c+4
-  if (gx == 0) offW = offA0 + 8;                           // no-flux mirror: W of x = 0 is x = 1
-  if (gx + 4 == nx) offE = offB0;                          //                 E of x = nx-1 is x = nx-2
-  int offA = offA0, offB = offB0;
+  // offA / offB: the thread's own quad in a swizzled row (every store, and the loads of the levels >= 2);
+  // srcA / srcB / srcW / srcE: where this level READS its quad and the outer neighbours.  With the TMA feed
+  // (FLAV & 2) the level-0 rows are plain row-major copies of the sheet (a bulk copy cannot swizzle a 1-KiB
+  // row), so level 1 reads at 32-byte stride -- a 2-way bank conflict on a quarter of the kernel's loads.
+  constexpr bool TMA = (FLAV & 2) != 0;
+  constexpr int ARITH = FLAV & 1;
+  const bool lin = TMA && lev == 1;
+  int offA = swz(2 * t), offB = swz(2 * t + 1);
+  int srcA = lin ? 32 * t : offA, srcB = lin ? 32 * t + 16 : offB;
+  int srcW = (t > 0) ? (lin ? 32 * t - 8 : swz(2 * t - 1) + 8) : srcA;   // column c-1 (no neighbour: any valid address)
+  int srcE = (t < NL - 1) ? (lin ? 32 * t + 32 : swz(2 * t + 2)) : srcB;  // column c+4
+  if (gx == 0) srcW = srcA + 8;                            // no-flux mirror: W of x = 0 is x = 1
+  if (gx + 4 == nx) srcE = srcB;                           //                 E of x = nx-1 is x = nx-2
   // opaque to the compiler from here on: otherwise ptxas rematerialises the swizzle arithmetic from
-  // threadIdx inside the row loop instead of keeping four offsets in registers
-  asm volatile("" : "+r"(offA), "+r"(offB), "+r"(offW), "+r"(offE));
+  // threadIdx inside the row loop instead of keeping the offsets in registers
+  asm volatile("" : "+r"(offA), "+r"(offB), "+r"(srcA), "+r"(srcB), "+r"(srcW), "+r"(srcE));
 
   // rows this level must produce (empty for threads outside the domain)
   const int lo_l = max(dom_lo, y0 - (T - lev));
@@ -126,7 +135,7 @@ rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a)
   const unsigned src_ring = (lev == 1) ? sm_ring0 : sm_ring0 + NR0 * ROW + (lev - 2) * NRL * ROW;
   const unsigned dst_ring = sm_ring0 + NR0 * ROW + (lev - 1) * NRL * ROW;  // unused by the last level
   // this thread's addresses inside slot 0 of its source / destination ring
-  const unsigned aA = src_ring + offA, aB = src_ring + offB, aW = src_ring + offW, aE = src_ring + offE;
+  const unsigned aA = src_ring + srcA, aB = src_ring + srcB, aW = src_ring + srcW, aE = src_ring + srcE;
   const unsigned dA = dst_ring + offA, dB = dst_ring + offB;
   // output row pointers of the last level, advanced one row per computed row (no 64-bit multiply per row)
   double *gu = a.u_out + zoff + gx + (ptrdiff_t)lo_l * nx;
@@ -142,7 +151,40 @@ rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a)
   const double *pv = v_in + gx + (ptrdiff_t)c0 * nx;
   int szA = okA ? 16 : 0, szB = okB ? 16 : 0;   // cp.async src-size: 0 = zero fill, nothing read
   asm volatile("" : "+r"(szA), "+r"(szB));      // (kept in registers: ptxas otherwise recomputes okA / okB per row)
+  // TMA feed: one thread per CTA moves a whole level-0 row (the strip's columns that exist, u then v) with two
+  // bulk copies that complete on the row slot's mbarrier
+  const unsigned sm_bar = sm_ring0 + (NR0 + (T - 1) * NRL) * ROW;       // NR0 mbarriers behind the rings
+  const int tx0 = max(wx0, 0), tx1 = min(wx0 + W, nx);                   // columns of this strip inside the sheet
+  const unsigned t_bytes = (unsigned)(tx1 - tx0) * 8u, t_dst = (unsigned)(tx0 - wx0) * 8u;
+  const double *tu = u_in + tx0 + (ptrdiff_t)c0 * nx;
+  const double *tv = v_in + tx0 + (ptrdiff_t)c0 * nx;
+  if (TMA) {
+    if (tid == 0) {
+#pragma unroll
+      for (int q = 0; q < NR0; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm_bar + 8u * q));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
   auto issue_row = [&](int q) {      // called with q = c0, c0+1, ... in order
+    if (TMA) {
+      if (tid == 0) {
+        const unsigned slot = (unsigned)((q - c0) & (NR0 - 1));
+        const unsigned dst = sm_ring0 + slot * ROW + t_dst, bar = sm_bar + 8u * slot;
+        if (q >= ld_lo && q < ld_hi) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * t_bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst), "l"(tu), "r"(t_bytes), "r"(bar) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst + FROW), "l"(tv), "r"(t_bytes), "r"(bar) : "memory");
+        } else {   // a row that does not exist (above / below the sheet, past the chunk): the slot's phase still
+                   // advances, so that phase parity == use count of the slot for every row
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        }
+      }
+      tu += nx; tv += nx;
+      return;
+    }
     if (q >= ld_lo && q < ld_hi) {
       const unsigned dst = sm_ring0 + (unsigned)((q - c0) & (NR0 - 1)) * ROW;
       cp_async16s(dst + offA, pu, szA);
@@ -152,6 +194,15 @@ rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a)
     }
     pu += nx; pv += nx;
     cp_async_commit();
+  };
+  // wait until level-0 row q has landed (TMA feed: the row slot's mbarrier, phase = use count of the slot)
+  auto wait_row = [&](int q) {
+    if (q >= ld_lo && q < ld_hi) {
+      const unsigned bar = sm_bar + 8u * (unsigned)((q - c0) & (NR0 - 1));
+      const unsigned parity = (unsigned)(((q - c0) / NR0) & 1);
+      asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                   " @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n }" ::"r"(bar), "r"(parity) : "memory");
+    }
   };
 
   // one source row into registers: base addresses + compile-time offset
@@ -306,7 +357,8 @@ rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a)
     int sN = ((J + 2) % NRL) * ROW, sM = (J % NRL) * ROW;
     if (lev == 1) {
       issue_row(c0 + PF + it);
-      cp_async_wait<PF>();               // this thread's pieces of rows <= c0 + it have landed
+      if (TMA) wait_row(c0 + it - 1);    // the row this iteration reads
+      else cp_async_wait<PF>();          // this thread's pieces of rows <= c0 + it have landed
       sN = ((it - 1) & (NR0 - 1)) * ROW;
       sM = ((it - 3) & (NR0 - 1)) * ROW;
     }
@@ -318,24 +370,24 @@ rd_euler_quad(const __grid_constant__ YhK k, const __grid_constant__ FastArgs a)
     sub(std::integral_constant<int, 1>{}, it, RB, RC, RA);
     sub(std::integral_constant<int, 2>{}, it, RC, RA, RB);
   }
-  if (lev == 1) cp_async_wait<0>();
+  if (lev == 1 && !TMA) cp_async_wait<0>();
 }
 
-template <int T, int W, bool CANON, bool DEF, bool STIM, bool SOLID, bool FIX, int ARITH = 0>
+template <int T, int W, bool CANON, bool DEF, bool STIM, bool SOLID, bool FIX, int FLAV = 0>
 int launch4(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   constexpr int H = (T + 1) & ~1, BX = W - 2 * H, ROW = 2 * W * 8;
   constexpr int NT = T * (W / 4);
   constexpr int NR0 = (T == 1) ? 16 : 8;
-  const size_t smem = (size_t)(NR0 + (T - 1) * 3) * ROW;
+  const size_t smem = (size_t)(NR0 + (T - 1) * 3) * ROW + ((FLAV & 2) ? 8 * NR0 : 0);
   static bool attr_set[64] = {false};
   static int slots[64] = {0};
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    YH_CUDA(cudaFuncSetAttribute(rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX, ARITH>,
+    YH_CUDA(cudaFuncSetAttribute(rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX, FLAV>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1, sms = 148;
-    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX, ARITH>,
+    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX, FLAV>,
                                                           NT, smem));
     YH_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     slots[dev & 63] = (per_sm > 0 ? per_sm : 1) * sms;
@@ -346,7 +398,7 @@ int launch4(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   const int strips = (k.nx + BX - 1) / BX;
   b.RY = a.RY > 0 ? a.RY : pick_ry_waves(rows, strips, nsims, T, slots[dev & 63]);
   dim3 grd(strips, (rows + b.RY - 1) / b.RY, nsims);
-  auto kfn = rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX, ARITH>;
+  auto kfn = rd_euler_quad<T, W, CANON, DEF, STIM, SOLID, FIX, FLAV>;
   YH_LAUNCH(kfn, grd, NT, smem, st, k, b);
   return YH_OK;
 }
@@ -357,14 +409,22 @@ int launch3(const YhK &k, const FastArgs &a, int nsims, cudaStream_t st) {
   if (a.pat)   // obstacle masks: one variant (STIM on) keeps the instantiation count down
     return launch4<T, W, CANON, DEF, true, true, FIX>(k, a, nsims, st);
   if (stim) return launch4<T, W, CANON, DEF, true, false, FIX>(k, a, nsims, st);
+  // level-0 feed.  Measured A/B (B200, Gcell/s, cp.async vs TMA bulk copies): T = 1 (HBM-bound) 176 vs 185,
+  // T = 2 332 vs 320, T = 4 (issue-bound) 410 vs 379 -- the bulk copy frees the load issue slots of the
+  // memory-bound kernel, but its row-major rows cost level 1 a 2-way bank conflict, which the issue-bound
+  // kernels feel.  Default: TMA for T = 1, cp.async otherwise; YH_EULER_FEED = tma | cpasync overrides.
+  static const int feed = [] { const char *f = getenv("YH_EULER_FEED"); return !f ? -1 : (f[0] == 't' ? 1 : 0); }();
+  const bool tma = feed < 0 ? (T == 1) : feed == 1;
   if (yh_arithmetic() == YH_ARITH_FAST) {   // masks and the stimulus stay exact
     FastArgs b = a;
     const double rs = k.gateDiff ? k.rscale : 0.0;
     b.uH = k.tc * k.rx; b.uV = k.tc * k.ry; b.uC = 1.0 - 2.0 * k.tc * (k.rx + k.ry); b.uT = k.tc * k.dt;
     b.vH = rs * b.uH; b.vV = rs * b.uV; b.vC = 1.0 - 2.0 * k.tc * rs * (k.rx + k.ry); b.vT = k.tc * k.dt * k.eps;
-    return launch4<T, W, CANON, DEF, false, false, FIX, 1>(k, b, nsims, st);
+    return tma ? launch4<T, W, CANON, DEF, false, false, FIX, 3>(k, b, nsims, st)
+               : launch4<T, W, CANON, DEF, false, false, FIX, 1>(k, b, nsims, st);
   }
-  return launch4<T, W, CANON, DEF, false, false, FIX>(k, a, nsims, st);
+  return tma ? launch4<T, W, CANON, DEF, false, false, FIX, 2>(k, a, nsims, st)
+             : launch4<T, W, CANON, DEF, false, false, FIX>(k, a, nsims, st);
 }
 
 template <int T, int W>
