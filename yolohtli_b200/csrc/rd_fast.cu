@@ -317,7 +317,9 @@ int yh_launch_rd_fast_paced(const YhK &k, int tb, const double *u_in, const doub
   // four columns per thread (rd_quad.cu) for sheets that fill the machine; YH_EULER_KERNEL = quad | pair overrides
   const char *kern = getenv("YH_EULER_KERNEL");
   // measured (B200, 16384^2 / 8192^2, Gcell/s): T = 4 quad 410 vs pair 361; T = 2 332 vs 346; T = 1 185 (TMA feed) vs 160
-  const bool quad = kern ? (kern[0] == 'q') : (tb != 2 && cells >= (1ll << 21));
+  // batched paced sheets with the fused APD epilogue (C5): pair 167 vs quad 153 -- stays on the pair kernel
+  const bool paced = nsims > 1 || period_d != nullptr || apd != nullptr;
+  const bool quad = kern ? (kern[0] == 'q') : (tb != 2 && !paced && cells >= (1ll << 21));
   if (quad && k.nx >= 16) return yh_launch_rd_quad_paced(k, tb, a, nsims, canon, W == 256 ? 256 : 128, st);
 #define YH_FAST_DISPATCH(WW)                                     \
   switch (tb) {                                                  \
