@@ -137,6 +137,7 @@ MODES = {
     "rk4lap4_8192": (8192, "rk4lap4", 0, 12),        # the reference's DEFAULT mode (saveFiles.cu:124-132) on a large sheet
     "rk4lap4_8192_fast": (8192, "rk4lap4", 0, 12),   # ... in the FAST arithmetic flavour (yh_set_arithmetic, tests/test_gpu_arith.py)
     "rk4lap4_512": (512, "rk4lap4", 0, 2048),        # ... and on its default 512^2 sheet (BASELINE configs[0])
+    "rk4lap4_512_fast": (512, "rk4lap4", 0, 2048),
     "euler5_512": (512, "euler5", 4, 8192),
 }
 FP64_PER_UPDATE = {"euler5": (8, 24), "rk4lap4": (36, 316)}   # (DFMA, DADD + DMUL) warp-lane instructions per cell update

@@ -494,6 +494,8 @@ int yh_launch_rd_tile_rk(const YhK &k, const double *u_in, const double *v_in, d
                          double *v_out, double *vtu, double *vtv, cudaStream_t st) {
   if (!yh_rd_tile_rk_supported(k)) return YH_ERR_UNSUPPORTED;
   if (k.row1 <= k.row0) return YH_OK;
+  // default switches (gate diffusion on, live stimulus off): the marching kernel, one tile per SM (rd_tile_march.cu)
+  if (yh_rd_tile_march_supported(k)) return yh_launch_rd_tile_march(k, u_in, v_in, u_out, v_out, vtu, vtv, st);
   TileArgs a{u_in, v_in, u_out, v_out, vtu, vtv, 0, nullptr, 0, 0, nullptr, nullptr};
   const bool lap4 = k.lap4 != 0, def = is_def(k);
 #define YH_T(KK, L) (def ? launch_rk<KK, L, true, false>(k, a, st) : launch_rk<KK, L, false, false>(k, a, st))

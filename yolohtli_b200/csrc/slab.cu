@@ -3,7 +3,7 @@
 // one per GPU.  Host code is C++ like the reference's; the data path is kernels only:
 //
 //   edge stream (high priority)   wait interior(k-1) | step top band, bottom band | EXCHANGE(k)
-//   main stream                   wait edge(k-1)     | step interior rows
+//   main stream                   wait bands(k-1)    | step interior rows
 //
 // EXCHANGE is one kernel: it copies this slab's fresh first / last `halo` owned rows straight into the
 // neighbours' ghost rows (16-byte stores through peer mappings = NVLink), the last CTA to finish
@@ -152,7 +152,7 @@ struct yh_slab {
   int solid_flags;
   Peer up, down;
   cudaStream_t main, edge;
-  cudaEvent_t ev_int, ev_edge, ev_fork;
+  cudaEvent_t ev_int, ev_edge, ev_fork, ev_band;
   bool raw, ghosts_valid, connected;
   long long count;
   unsigned long long *sum_d;
@@ -246,6 +246,7 @@ int advance_begin(yh_slab *s) {
   if (s->world > 1 && !s->connected) { yh_set_error("yh_slab_advance before yh_slab_connect"); return YH_ERR_INVALID_ARG; }
   YH_CUDA(cudaEventRecord(s->ev_int, s->main));
   YH_CUDA(cudaEventRecord(s->ev_edge, s->main));
+  YH_CUDA(cudaEventRecord(s->ev_band, s->main));
   if (has_neighbours(s) && !s->ghosts_valid) {   // ghost rows of the current state from the neighbours
     YH_CUDA(cudaStreamWaitEvent(s->edge, s->ev_int, 0));
     int rc = launch_exchange(s, s->cur, s->edge);
@@ -272,9 +273,14 @@ int advance_block(yh_slab *s, int n) {
     if (rc != YH_OK) return rc;
     rc = rd_rows(s, n, c, o, bot0, bot1, s->edge);
     if (rc != YH_OK) return rc;
+    // the interior of block k reads band rows in state k-1 and overwrites rows the bands of block k-1 read:
+    // it depends on those BAND kernels, not on the exchange behind them (whose wait for the neighbours would
+    // otherwise sit on the interior's critical path); only the next bands need the exchanged ghost rows, and
+    // they follow the exchange in stream order
+    YH_CUDA(cudaStreamWaitEvent(s->main, s->ev_band, 0));    // bands(k-1)
+    YH_CUDA(cudaEventRecord(s->ev_band, s->edge));           // bands(k)
     rc = launch_exchange(s, o, s->edge);
     if (rc != YH_OK) return rc;
-    YH_CUDA(cudaStreamWaitEvent(s->main, s->ev_edge, 0));    // edge(k-1)
     rc = rd_rows(s, n, c, o, top1, bot0, s->main);
     if (rc != YH_OK) return rc;
     YH_CUDA(cudaEventRecord(s->ev_int, s->main));
@@ -486,6 +492,7 @@ int yh_slab_create(yh_slab **out, const yh_params *pg, int rank, int world, int 
   cudaEventCreateWithFlags(&s->ev_int, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&s->ev_edge, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&s->ev_band, cudaEventDisableTiming);
   cudaMalloc(&s->sum_d, 2 * sizeof(unsigned long long));
   cudaDeviceSynchronize();
   if (cudaGetLastError() != cudaSuccess) { yh_set_error("yh_slab_create: stream / event setup failed"); return YH_ERR_CUDA; }
@@ -504,7 +511,7 @@ int yh_slab_destroy(yh_slab *s) {
   if (s->down.ipc_base) cudaIpcCloseMemHandle(s->down.ipc_base);
   cudaFree(s->block); cudaFree(s->solid); cudaFree(s->pat); cudaFree(s->sum_d);
   cudaStreamDestroy(s->main); cudaStreamDestroy(s->edge);
-  cudaEventDestroy(s->ev_int); cudaEventDestroy(s->ev_edge); cudaEventDestroy(s->ev_fork);
+  cudaEventDestroy(s->ev_int); cudaEventDestroy(s->ev_edge); cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_band);
   cudaGetLastError();
   delete s;
   return YH_OK;
