@@ -75,9 +75,17 @@ int yh_slab_sync(yh_slab *s);
 /* sum of the owned cells' bit patterns (uint64 views) mod 2^64: order independent, so the sum over the
  * ranks is the same number for every decomposition of the same sheet */
 int yh_slab_checksum(yh_slab *s, unsigned long long *sum_u, unsigned long long *sum_v);
-/* the reference's whole use on one slab with HOST buffers of the owned rows: upload, nsteps, download */
+/* the reference's whole use on one slab with HOST buffers of the owned rows: upload, nsteps, download
+ * (main.cu:470 ... 519).  The copies are hidden behind the time steps: the rows travel in chunks, the first
+ * blocks of time steps run on a chunk while the next one is in flight, the last blocks while the previous
+ * chunk is on its way back (skewed chunk boundaries + edge wedges caught up with one halo exchange per level,
+ * csrc/slab.cu); bit-identical to set_state / advance / get_state.  Pinned host memory is what makes the
+ * copies asynchronous.  Every rank must make the same call.  YH_SLAB_PIPE=0: plain schedule. */
 int yh_slab_run_host(yh_slab *s, const double *u_in_h, const double *v_in_h, double *u_out_h,
                      double *v_out_h, int nsteps, int tb_steps);
+/* blocks of time steps per chunk the pipelined schedule of yh_slab_run_host would use for such a call
+ * (0: the plain schedule -- run too short, slab too small, masks) */
+int yh_slab_pipeline_levels(const yh_slab *s, int nsteps, int tb_steps);
 
 /* ---- one process, several devices --------------------------------------------------------------- */
 /* devices[r] holds slab r (the same device may appear more than once: test vehicle on one GPU). */

@@ -2,7 +2,11 @@
 // slabs through include/yolohtli_slab.h, the way a maintainer of the reference's main.cu would reach
 // several GPUs, and checks N slabs == one sheet BIT FOR BIT against yh_sim (single device path).
 //
-//   yh_slab_driver <nx> <ny> <nslabs> <nsteps> <mode: euler|rk4lap4|eulerholes> [ndev]
+//   yh_slab_driver <nx> <ny> <nslabs> <nsteps> <mode: euler|rk4lap4|eulerholes> [ndev] [pipe]
+//
+// pipe: the slabs run through yh_slab_group_run_host (host buffers in, steps, host buffers out; the copies
+// hidden behind the time steps by skewed chunks and edge wedges) in two calls; FAIL unless the pipelined
+// schedule was really taken.
 //
 // Slab r lives on device r % ndev (ndev = 1: every slab on one GPU, the peers are then the same
 // device and the flag protocol, streams and graphs are exercised exactly as across NVLink).
@@ -41,6 +45,7 @@ int main(int argc, char **argv) {
   const int nslabs = argc > 3 ? atoi(argv[3]) : 2, nsteps = argc > 4 ? atoi(argv[4]) : 203;
   const char *mode = argc > 5 ? argv[5] : "euler";
   int ndev = argc > 6 ? atoi(argv[6]) : 1;
+  const bool pipe = argc > 7 && strcmp(argv[7], "pipe") == 0;
   if (yh_device_count() < 1) { printf("slab_driver FAIL no CUDA device\n"); return 1; }
   if (ndev > yh_device_count()) ndev = yh_device_count();
 
@@ -77,11 +82,19 @@ int main(int argc, char **argv) {
   // in two calls, so that a run continues from device-resident state with valid ghosts, and with an
   // odd remainder so that the tail blocks (T = 2, 1) are exercised too
   const int first = nsteps / 3;
-  CHECK(yh_slab_group_set_state(g, u0.data(), v0.data()));
-  CHECK(yh_slab_group_advance(g, first, 0));
-  if (getenv("YH_SLAB_DRIVER_SYNC")) CHECK(yh_slab_group_sync(g));
-  CHECK(yh_slab_group_advance(g, nsteps - first, 0));
-  CHECK(yh_slab_group_get_state(g, ub.data(), vb.data()));
+  int levels = -1;
+  if (pipe) {
+    std::vector<double> ut(n), vt(n);
+    levels = yh_slab_pipeline_levels(yh_slab_group_member(g, 0), nsteps - first, 0);
+    CHECK(yh_slab_group_run_host(g, u0.data(), v0.data(), ut.data(), vt.data(), first, 0));
+    CHECK(yh_slab_group_run_host(g, ut.data(), vt.data(), ub.data(), vb.data(), nsteps - first, 0));
+  } else {
+    CHECK(yh_slab_group_set_state(g, u0.data(), v0.data()));
+    CHECK(yh_slab_group_advance(g, first, 0));
+    if (getenv("YH_SLAB_DRIVER_SYNC")) CHECK(yh_slab_group_sync(g));
+    CHECK(yh_slab_group_advance(g, nsteps - first, 0));
+    CHECK(yh_slab_group_get_state(g, ub.data(), vb.data()));
+  }
   unsigned long long su = 0, sv = 0;
   for (int r = 0; r < nslabs; r++) {
     unsigned long long a = 0, b = 0;
@@ -99,7 +112,8 @@ int main(int argc, char **argv) {
   const bool same = memcmp(ua.data(), ub.data(), n * sizeof(double)) == 0 && memcmp(va.data(), vb.data(), n * sizeof(double)) == 0;
   double moved = 0.0;
   for (size_t c = 0; c < n; c++) moved += (ua[c] - u0[c]) * (ua[c] - u0[c]);
-  const bool ok = same && su == wu && sv == wv && moved > 1e-3;
+  const bool ok = same && su == wu && sv == wv && moved > 1e-3 && (!pipe || levels > 0);
+  if (pipe) printf("slab_driver pipelined run_host: %d levels per chunk\n", levels);
   printf("slab_driver %s %dx%d %s nslabs=%d ndev=%d nsteps=%d bitwise=%d checksum=%016llx/%016llx (sheet %016llx/%016llx) moved=%.3g\n",
          ok ? "PASS" : "FAIL", nx, ny, mode, nslabs, ndev, nsteps, (int)same, su, sv, wu, wv, moved);
   return ok ? 0 : 1;

@@ -31,6 +31,18 @@ def test_cpp_host_drives_slabs_bitwise(args):
     assert r.returncode == 0 and "slab_driver PASS" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("args", ["256 1024 1 203 euler", "256 1024 2 203 euler", "256 1200 3 171 euler", "128 1024 4 150 euler",
+                                  "256 1024 2 61 rk4lap4", "256 1100 3 47 rk4lap4", "2048 4096 2 403 euler"])
+def test_cpp_host_pipelined_run_host_bitwise(args):
+    """yh_slab_group_run_host with the copies hidden behind the time steps (skewed chunks, edge wedges caught up
+    with one exchange per level): host buffers in -> steps -> host buffers out, bit-identical to one sheet."""
+    assert os.path.exists(DRIVER), "build the library first (make -C yolohtli_b200/csrc)"
+    ndev = str(min(torch.cuda.device_count(), int(args.split()[2])))
+    r = subprocess.run([DRIVER] + args.split() + [ndev, "pipe"], capture_output=True, text=True, timeout=300)
+    print(r.stdout.strip())
+    assert r.returncode == 0 and "slab_driver PASS" in r.stdout and "levels per chunk" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("mode,n,world,steps", [("euler", 384, 2, 100), ("euler", 384, 3, 64), ("rk4lap4", 256, 2, 25),
                                                ("rk2", 256, 3, 12), ("euler_holes", 512, 2, 80)])
 def test_slab_group_vs_oracle(oracle, yh, mode, n, world, steps):

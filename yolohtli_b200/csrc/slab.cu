@@ -151,13 +151,15 @@ struct yh_slab {
   const uint8_t *solid_arg;
   int solid_flags;
   Peer up, down;
-  cudaStream_t main, edge;
+  cudaStream_t main, edge, copy;         // copy: host <-> device chunks of the pipelined yh_slab_run_host
+  std::vector<cudaEvent_t> ev_chunk;     // per chunk: rows arrived (H2D) / rows final (D2H may start)
   cudaEvent_t ev_int, ev_edge, ev_fork, ev_band;
   bool raw, ghosts_valid, connected;
   long long count;
   unsigned long long *sum_d;
   GraphSlot graphs[4];
   int band;
+  std::vector<cudaEvent_t> tl;           // YH_SLAB_TIMELINE: t0, then 5 events per block (see timeline_dump)
 };
 
 struct yh_slab_group {
@@ -165,6 +167,51 @@ struct yh_slab_group {
 };
 
 namespace {
+
+// YH_SLAB_TIMELINE=<path prefix>: the plain (graph-free) schedule with timing events around every kernel of the
+// first 48 blocks of a run, written to <prefix>.<rank> -- the per-rank timeline the profiles/ directory keeps
+// (no nsys in this image).  Per block: bands start / bands end / exchange end on the edge stream, interior
+// start / interior end on the main stream, microseconds since the start of the run.
+const char *timeline_prefix() {
+  const char *e = getenv("YH_SLAB_TIMELINE");
+  return (e && e[0]) ? e : nullptr;
+}
+constexpr int TL_BLOCKS = 48;
+void tl_mark(yh_slab *s, cudaStream_t st) {
+  if (!timeline_prefix() || s->tl.size() >= 1 + 5 * TL_BLOCKS) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  s->tl.push_back(e);
+}
+void timeline_dump(yh_slab *s) {
+  if (!timeline_prefix() || s->tl.size() < 6) return;
+  cudaStreamSynchronize(s->edge); cudaStreamSynchronize(s->main);
+  char path[512];
+  snprintf(path, sizeof(path), "%s.%d", timeline_prefix(), s->rank);
+  FILE *f = fopen(path, "w");
+  if (f) {
+    fprintf(f, "# slab %d of %d, rows [%d, %d), band %d rows; us since the start of the run\n", s->rank, s->world, s->j0, s->j1, s->band);
+    fprintf(f, "# block  bands_start  bands_end  exchange_end  interior_start  interior_end\n");
+    for (size_t b = 0; 1 + 5 * (b + 1) <= s->tl.size(); b++) {
+      fprintf(f, "%3zu", b);
+      for (int q = 0; q < 5; q++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s->tl[0], s->tl[1 + 5 * b + q]);
+        fprintf(f, " %10.1f", ms * 1e3);
+      }
+      fprintf(f, "\n");
+    }
+    fclose(f);
+  }
+  for (cudaEvent_t e : s->tl) cudaEventDestroy(e);
+  s->tl.clear();
+}
+// YH_SLAB_WAIT=exchange: the round-1 dependency (interior waits for the whole edge chain of the previous block), A/B
+bool wait_for_exchange() {
+  static const bool v = [] { const char *e = getenv("YH_SLAB_WAIT"); return e && e[0] == 'e'; }();
+  return v;
+}
 
 int launch_exchange(yh_slab *s, int buf, cudaStream_t st) {
   XchgArgs a;
@@ -194,10 +241,14 @@ int launch_exchange(yh_slab *s, int buf, cudaStream_t st) {
   return YH_OK;
 }
 
+int rd_rows_raw(yh_slab *s, int n, int c, int o, int r0, int r1, bool raw, cudaStream_t st);
 int rd_rows(yh_slab *s, int n, int c, int o, int r0, int r1, cudaStream_t st) {
+  return rd_rows_raw(s, n, c, o, r0, r1, s->raw, st);
+}
+int rd_rows_raw(yh_slab *s, int n, int c, int o, int r0, int r1, bool raw, cudaStream_t st) {
   if (r1 <= r0) return YH_OK;
   int inB = 0;
-  const int flags = (s->raw ? 0 : YH_RD_INPUT_CANONICAL) | s->solid_flags;
+  const int flags = (raw ? 0 : YH_RD_INPUT_CANONICAL) | s->solid_flags;
   int rc = yh_rd_advance(&s->p, n, s->fast ? n : 1, flags, s->u[c], s->v[c], s->u[o], s->v[o], s->solid_arg,
                          0, s->nx / 2, s->pg.ny / 2, r0, r1, &inB, st);
   if (rc != YH_OK) return rc;
@@ -269,6 +320,7 @@ int advance_block(yh_slab *s, int n) {
     const int top0 = s->own_lo, top1 = s->up.present ? s->own_lo + B : s->own_lo;
     const int bot0 = s->down.present ? s->own_hi - B : s->own_hi, bot1 = s->own_hi;
     YH_CUDA(cudaStreamWaitEvent(s->edge, s->ev_int, 0));     // interior(k-1)
+    tl_mark(s, s->edge);
     rc = rd_rows(s, n, c, o, top0, top1, s->edge);
     if (rc != YH_OK) return rc;
     rc = rd_rows(s, n, c, o, bot0, bot1, s->edge);
@@ -277,12 +329,16 @@ int advance_block(yh_slab *s, int n) {
     // it depends on those BAND kernels, not on the exchange behind them (whose wait for the neighbours would
     // otherwise sit on the interior's critical path); only the next bands need the exchanged ghost rows, and
     // they follow the exchange in stream order
-    YH_CUDA(cudaStreamWaitEvent(s->main, s->ev_band, 0));    // bands(k-1)
+    YH_CUDA(cudaStreamWaitEvent(s->main, wait_for_exchange() ? s->ev_edge : s->ev_band, 0));    // bands(k-1)
     YH_CUDA(cudaEventRecord(s->ev_band, s->edge));           // bands(k)
+    tl_mark(s, s->edge);
     rc = launch_exchange(s, o, s->edge);
     if (rc != YH_OK) return rc;
+    tl_mark(s, s->edge);
+    tl_mark(s, s->main);
     rc = rd_rows(s, n, c, o, top1, bot0, s->main);
     if (rc != YH_OK) return rc;
+    tl_mark(s, s->main);
     YH_CUDA(cudaEventRecord(s->ev_int, s->main));
     YH_CUDA(cudaEventRecord(s->ev_edge, s->edge));
   }
@@ -334,7 +390,7 @@ int graph_pair(yh_slab *s, int n, cudaGraphExec_t *out) {
 
 bool graphs_wanted() {
   const char *f = getenv("YH_SLAB_GRAPHS");
-  return !(f && f[0] == '0');
+  return !(f && f[0] == '0') && !timeline_prefix();
 }
 
 // The whole run of one slab or, in lock step, of all slabs of a group (breadth first per block, so no
@@ -355,6 +411,7 @@ int advance_all(yh_slab *const *m, int count, int nsteps, int tb) {
     DevGuard g(m[q]->device);
     rc = advance_begin(m[q]);
     if (rc != YH_OK) return rc;
+    if (has_neighbours(m[q]) && m[q]->tl.empty()) tl_mark(m[q], m[q]->main);
   }
   int left = nsteps;
   while (left > 0) {
@@ -410,6 +467,234 @@ int advance_all(yh_slab *const *m, int count, int nsteps, int tb) {
     rc = advance_end(m[q]);
     if (rc != YH_OK) return rc;
   }
+  if (timeline_prefix())
+    for (int q = 0; q < count; q++) {
+      DevGuard g(m[q]->device);
+      if (m[q]->tl.size() >= 1 + 5 * TL_BLOCKS) timeline_dump(m[q]);
+    }
+  return YH_OK;
+}
+
+
+// ---- yh_slab_run_host with the copies hidden behind the time steps ----------------------------------------
+// Host -> device, nsteps, device -> host is what a caller of the reference does (main.cu:470 ... 519).  The
+// copies of a 16384^2 sheet take 2 x 75 ms over PCIe against 730 ms of time steps on one GPU, and 2 x 35 ms
+// against 100 ms on each of 8 GPUs that share the host's memory -- so the owned rows travel in C chunks and
+// the time steps start on a chunk as soon as it has arrived (and end on a chunk while the others still run):
+//
+//   level b = state after b blocks of n time steps; a block needs h = n * timeIntOrder rows of the previous
+//   level on either side.  Chunk c at level b covers rows [X_c - h*b, X_{c+1} - h*b): every level the
+//   boundaries move UP by h rows, so block (c, b) reads only (c, b-1) and (c-1, b-1) -- chunks that arrived
+//   EARLIER.  Prologue: after chunk c has arrived it runs P blocks (while chunk c+1 is in flight).  The rows
+//   of a slab edge that faces a neighbour cannot follow without the neighbour's rows: that edge recedes by h
+//   rows per level and the wedge left behind (h*P rows) is caught up afterwards, level by level with one
+//   halo exchange each, like ordinary blocks on a few rows.  Then all rows are at level P and the run
+//   continues with whole-slab blocks (advance_all).  Epilogue: the mirror image -- chunk after chunk runs
+//   its last E blocks and its rows start their way back to the host while the next chunk computes; the edge
+//   wedges are finished last.
+// Every cell update is the same function of the same inputs as in the plain schedule: results are bit-identical
+// (tests/slab_driver.cu `pipe` mode, tests/test_gpu_slab_driver.py).  YH_SLAB_PIPE=0 switches it off.
+struct PipePlan {
+  int n, h, B, P, E, C, S;
+};
+
+int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+
+bool plan_pipeline(const yh_slab *s, int nsteps, int tb, PipePlan *pl) {
+  if (env_int("YH_SLAB_PIPE", 1) == 0) return false;
+  if (s->solid_arg) return false;                        // masks: plain schedule (untested here)
+  const int n = block_steps(s, nsteps, tb);
+  const int h = n * s->K;
+  if (h > s->halo || nsteps < n) return false;
+  const int own = s->own_hi - s->own_lo;
+  // every rank must reach the same plan on its own (one exchange per wedge level on both sides of a slab
+  // boundary): chunk count and level count come from the SMALLEST slab height of the partition, not from this slab's
+  const int own_min = s->pg.ny / s->world;
+  int C = env_int("YH_SLAB_PIPE_CHUNKS", own_min >= 8192 ? 8 : 4);
+  if (C < 2 || own_min < 64 * C) return false;
+  const int S = (own + C - 1) / C;
+  if (own - (C - 1) * S < 1) return false;
+  // blocks a chunk runs while the next chunk is in flight: copy time of a chunk / time of one block on it.
+  // Euler (4 steps per block at ~370 Gcell/s) against ~50 GB/s of pinned copies: ~28; RK4: ~10
+  int P = env_int("YH_SLAB_PIPE_LEVELS", s->fast ? 28 : 10);
+  const int cap = ((own_min + C - 1) / C - 16) / (2 * h);   // chunk 0 keeps >= 16 rows: S - h*P (shift) - h*P (wedge)
+  if (P > cap) P = cap;
+  const int B = nsteps / n;
+  if (P > (B - 1) / 2) P = (B - 1) / 2;
+  if (P < 2) return false;
+  pl->n = n; pl->h = h; pl->B = B; pl->P = P; pl->E = P; pl->C = C; pl->S = S;
+  return true;
+}
+
+// rows of chunk c at (relative) level b >= 1
+void pipe_region(const yh_slab *s, const PipePlan &pl, int c, int b, int *r0, int *r1) {
+  const int X0 = s->own_lo + c * pl.S;
+  const int X1 = (c == pl.C - 1) ? s->own_hi : s->own_lo + (c + 1) * pl.S;
+  *r0 = (c == 0) ? (s->up.present ? s->own_lo + pl.h * b : s->own_lo) : X0 - pl.h * b;
+  *r1 = (c == pl.C - 1) ? (s->down.present ? s->own_hi - pl.h * b : s->own_hi) : X1 - pl.h * b;
+}
+
+// levels 1 .. L of every chunk, chunk-major; base = buffer that holds level 0.  wait_chunks: the prologue (chunk
+// c waits for its rows); done_chunks: the epilogue (rows of chunk c at level L go home once they are final).
+int pipe_chunks(yh_slab *s, const PipePlan &pl, int L, int base, bool raw0, bool prologue, double *u_out_h, double *v_out_h) {
+  const size_t row = (size_t)s->nx;
+  for (int c = 0; c < pl.C; c++) {
+    if (prologue) YH_CUDA(cudaStreamWaitEvent(s->main, s->ev_chunk[c], 0));
+    for (int b = 1; b <= L; b++) {
+      int r0, r1;
+      pipe_region(s, pl, c, b, &r0, &r1);
+      int rc = rd_rows_raw(s, pl.n, (base + b - 1) & 1, (base + b) & 1, r0, r1, raw0 && b == 1, s->main);
+      if (rc != YH_OK) return rc;
+    }
+    if (!prologue) {
+      int r0, r1;
+      pipe_region(s, pl, c, L, &r0, &r1);
+      YH_CUDA(cudaEventRecord(s->ev_chunk[c], s->main));
+      YH_CUDA(cudaStreamWaitEvent(s->copy, s->ev_chunk[c], 0));
+      const int fb = (base + L) & 1;
+      const size_t ho = (size_t)(r0 - s->own_lo) * row, bytes = (size_t)(r1 - r0) * row * sizeof(double);
+      YH_CUDA(cudaMemcpyAsync(u_out_h + ho, s->u[fb] + (size_t)r0 * row, bytes, cudaMemcpyDeviceToHost, s->copy));
+      YH_CUDA(cudaMemcpyAsync(v_out_h + ho, s->v[fb] + (size_t)r0 * row, bytes, cudaMemcpyDeviceToHost, s->copy));
+    }
+  }
+  return YH_OK;
+}
+
+// wedge catch-up, level j of L (all slabs of the call in lock step): exchange of the level j-1 edge rows, then the
+// top / bottom wedge rows [lo, lo + h*j) / [hi - h*j, hi) go from level j-1 to j.
+int pipe_wedge_level(yh_slab *s, const PipePlan &pl, int j, int base, bool raw0) {
+  if (!has_neighbours(s)) return YH_OK;
+  int rc = launch_exchange(s, (base + j - 1) & 1, s->main);
+  if (rc != YH_OK) return rc;
+  const bool raw = raw0 && j == 1;
+  if (s->up.present) {
+    rc = rd_rows_raw(s, pl.n, (base + j - 1) & 1, (base + j) & 1, s->own_lo, s->own_lo + pl.h * j, raw, s->main);
+    if (rc != YH_OK) return rc;
+  }
+  if (s->down.present) {
+    rc = rd_rows_raw(s, pl.n, (base + j - 1) & 1, (base + j) & 1, s->own_hi - pl.h * j, s->own_hi, raw, s->main);
+    if (rc != YH_OK) return rc;
+  }
+  return YH_OK;
+}
+
+int pipe_preload(yh_slab *s, const PipePlan &pl) {
+  // code of every kernel variant the chunk and wedge passes can take, loaded before any exchange kernel waits
+  int rc = YH_OK;
+  yh_preload_only = 1;
+  for (int raw = 0; raw < 2 && rc == YH_OK; raw++) {
+    int r0, r1;
+    for (int c = 0; c < pl.C && rc == YH_OK; c++) {
+      pipe_region(s, pl, c, 1, &r0, &r1);
+      rc = rd_rows_raw(s, pl.n, 0, 1, r0, r1, raw != 0, s->main);
+      pipe_region(s, pl, c, pl.P, &r0, &r1);
+      if (rc == YH_OK) rc = rd_rows_raw(s, pl.n, 0, 1, r0, r1, raw != 0, s->main);
+    }
+    for (int j = 1; j <= pl.P && rc == YH_OK; j++)
+      rc = rd_rows_raw(s, pl.n, 0, 1, s->own_lo, s->own_lo + pl.h * j, raw != 0, s->main);
+  }
+  yh_preload_only = 0;
+  if (rc != YH_OK) return rc;
+  cudaFuncAttributes fa;
+  YH_CUDA(cudaFuncGetAttributes(&fa, slab_exchange_kernel));
+  return YH_OK;
+}
+
+// u_in / u_out ...: per slab, the host arrays of its OWNED rows
+int run_host_pipelined(yh_slab *const *m, int count, const double *const *u_in, const double *const *v_in,
+                       double *const *u_out, double *const *v_out, int nsteps, int tb, bool *done) {
+  *done = false;
+  PipePlan pl;
+  if (!plan_pipeline(m[0], nsteps, tb, &pl)) return YH_OK;
+  for (int q = 1; q < count; q++) {       // one plan for all slabs of the call (lock step): the most restrictive
+    PipePlan o;
+    if (!plan_pipeline(m[q], nsteps, tb, &o) || o.n != pl.n || o.C != pl.C) return YH_OK;
+    if (o.P < pl.P) { pl.P = o.P; pl.E = o.P; }
+  }
+  int rc;
+  std::vector<int> base(count);
+  for (int q = 0; q < count; q++) {
+    yh_slab *s = m[q];
+    DevGuard g(s->device);
+    if (s->world > 1 && !s->connected) { yh_set_error("yh_slab_run_host before yh_slab_connect"); return YH_ERR_INVALID_ARG; }
+    while ((int)s->ev_chunk.size() < pl.C) {
+      cudaEvent_t e;
+      YH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      s->ev_chunk.push_back(e);
+    }
+    rc = pipe_preload(s, pl);
+    if (rc != YH_OK) return rc;
+    // ---- host -> device, chunk by chunk (the copy stream follows everything enqueued on main so far) ----
+    YH_CUDA(cudaEventRecord(s->ev_fork, s->main));
+    YH_CUDA(cudaStreamWaitEvent(s->copy, s->ev_fork, 0));
+    const size_t row = (size_t)s->nx;
+    for (int c = 0; c < pl.C; c++) {
+      const int X0 = s->own_lo + c * pl.S, X1 = (c == pl.C - 1) ? s->own_hi : X0 + pl.S;
+      const size_t ho = (size_t)(X0 - s->own_lo) * row, bytes = (size_t)(X1 - X0) * row * sizeof(double);
+      YH_CUDA(cudaMemcpyAsync(s->u[s->cur] + (size_t)X0 * row, u_in[q] + ho, bytes, cudaMemcpyHostToDevice, s->copy));
+      YH_CUDA(cudaMemcpyAsync(s->v[s->cur] + (size_t)X0 * row, v_in[q] + ho, bytes, cudaMemcpyHostToDevice, s->copy));
+      YH_CUDA(cudaEventRecord(s->ev_chunk[c], s->copy));
+    }
+    base[q] = s->cur;
+  }
+  // ---- prologue: P levels per chunk, then the wedges ----
+  for (int q = 0; q < count; q++) {
+    DevGuard g(m[q]->device);
+    rc = pipe_chunks(m[q], pl, pl.P, base[q], true, true, nullptr, nullptr);
+    if (rc != YH_OK) return rc;
+  }
+  for (int j = 1; j <= pl.P; j++)
+    for (int q = 0; q < count; q++) {
+      DevGuard g(m[q]->device);
+      rc = pipe_wedge_level(m[q], pl, j, base[q], true);
+      if (rc != YH_OK) return rc;
+    }
+  for (int q = 0; q < count; q++) {
+    yh_slab *s = m[q];
+    s->cur = (base[q] + pl.P) & 1; s->raw = false; s->ghosts_valid = false; s->count += (long long)pl.P * pl.n;
+  }
+  // ---- whole-slab blocks ----
+  const int mid = nsteps - (pl.P + pl.E) * pl.n;
+  if (mid > 0) {
+    rc = advance_all(m, count, mid, tb);
+    if (rc != YH_OK) return rc;
+  }
+  // ---- epilogue: E levels per chunk with its rows leaving as soon as they are final, then the wedges ----
+  for (int q = 0; q < count; q++) {
+    DevGuard g(m[q]->device);
+    base[q] = m[q]->cur;
+    rc = pipe_chunks(m[q], pl, pl.E, base[q], false, false, u_out[q], v_out[q]);
+    if (rc != YH_OK) return rc;
+  }
+  for (int j = 1; j <= pl.E; j++)
+    for (int q = 0; q < count; q++) {
+      DevGuard g(m[q]->device);
+      rc = pipe_wedge_level(m[q], pl, j, base[q], false);
+      if (rc != YH_OK) return rc;
+    }
+  for (int q = 0; q < count; q++) {
+    yh_slab *s = m[q];
+    DevGuard g(s->device);
+    const int fb = (base[q] + pl.E) & 1;
+    const size_t row = (size_t)s->nx;
+    YH_CUDA(cudaEventRecord(s->ev_fork, s->main));
+    YH_CUDA(cudaStreamWaitEvent(s->copy, s->ev_fork, 0));
+    for (int w = 0; w < 2; w++) {
+      if (!(w == 0 ? s->up.present : s->down.present)) continue;
+      const int r0 = w == 0 ? s->own_lo : s->own_hi - pl.h * pl.E, r1 = r0 + pl.h * pl.E;
+      const size_t ho = (size_t)(r0 - s->own_lo) * row, bytes = (size_t)(r1 - r0) * row * sizeof(double);
+      YH_CUDA(cudaMemcpyAsync(u_out[q] + ho, s->u[fb] + (size_t)r0 * row, bytes, cudaMemcpyDeviceToHost, s->copy));
+      YH_CUDA(cudaMemcpyAsync(v_out[q] + ho, s->v[fb] + (size_t)r0 * row, bytes, cudaMemcpyDeviceToHost, s->copy));
+    }
+    s->cur = fb; s->ghosts_valid = false; s->count += (long long)pl.E * pl.n;
+    // main joins the copy stream: later work on this slab follows the copies
+    YH_CUDA(cudaEventRecord(s->ev_fork, s->copy));
+    YH_CUDA(cudaStreamWaitEvent(s->main, s->ev_fork, 0));
+  }
+  *done = true;
   return YH_OK;
 }
 
@@ -489,6 +774,7 @@ int yh_slab_create(yh_slab **out, const yh_params *pg, int rank, int world, int 
   cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = greatest priority (numerically lowest)
   cudaStreamCreateWithPriority(&s->main, cudaStreamNonBlocking, lo);
   cudaStreamCreateWithPriority(&s->edge, cudaStreamNonBlocking, hi);
+  cudaStreamCreateWithPriority(&s->copy, cudaStreamNonBlocking, lo);
   cudaEventCreateWithFlags(&s->ev_int, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&s->ev_edge, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
@@ -510,7 +796,8 @@ int yh_slab_destroy(yh_slab *s) {
   if (s->up.ipc_base) cudaIpcCloseMemHandle(s->up.ipc_base);
   if (s->down.ipc_base) cudaIpcCloseMemHandle(s->down.ipc_base);
   cudaFree(s->block); cudaFree(s->solid); cudaFree(s->pat); cudaFree(s->sum_d);
-  cudaStreamDestroy(s->main); cudaStreamDestroy(s->edge);
+  cudaStreamDestroy(s->main); cudaStreamDestroy(s->edge); cudaStreamDestroy(s->copy);
+  for (cudaEvent_t e : s->ev_chunk) cudaEventDestroy(e);
   cudaEventDestroy(s->ev_int); cudaEventDestroy(s->ev_edge); cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_band);
   cudaGetLastError();
   delete s;
@@ -693,11 +980,22 @@ int yh_slab_checksum(yh_slab *s, unsigned long long *sum_u, unsigned long long *
 
 int yh_slab_run_host(yh_slab *s, const double *u_in_h, const double *v_in_h, double *u_out_h, double *v_out_h,
                      int nsteps, int tb_steps) {
-  int rc = yh_slab_set_state(s, u_in_h, v_in_h, 0);
+  YH_REQUIRE(s && u_in_h && v_in_h && u_out_h && v_out_h && nsteps >= 0, "bad arguments");
+  YH_REQUIRE(tb_steps == 0 || tb_steps == 1 || tb_steps == 2 || tb_steps == 4, "tb_steps must be 0, 1, 2 or 4");
+  bool done = false;
+  int rc = run_host_pipelined(&s, 1, &u_in_h, &v_in_h, &u_out_h, &v_out_h, nsteps, tb_steps, &done);
+  if (rc != YH_OK) return rc;
+  if (done) return yh_slab_sync(s);
+  rc = yh_slab_set_state(s, u_in_h, v_in_h, 0);
   if (rc != YH_OK) return rc;
   rc = yh_slab_advance(s, nsteps, tb_steps);
   if (rc != YH_OK) return rc;
   return yh_slab_get_state(s, u_out_h, v_out_h);
+}
+
+int yh_slab_pipeline_levels(const yh_slab *s, int nsteps, int tb_steps) {
+  PipePlan pl;
+  return (s && nsteps > 0 && plan_pipeline(s, nsteps, tb_steps, &pl)) ? pl.P : 0;
 }
 
 // ---- one process, several devices ----------------------------------------------------------------
@@ -783,6 +1081,21 @@ int yh_slab_group_sync(yh_slab_group *g) {
 
 int yh_slab_group_run_host(yh_slab_group *g, const double *u_in_h, const double *v_in_h, double *u_out_h,
                            double *v_out_h, int nsteps, int tb_steps) {
+  YH_REQUIRE(g && u_in_h && v_in_h && u_out_h && v_out_h && nsteps >= 0, "bad arguments");
+  YH_REQUIRE(tb_steps == 0 || tb_steps == 1 || tb_steps == 2 || tb_steps == 4, "tb_steps must be 0, 1, 2 or 4");
+  {
+    const size_t nsl = g->m.size();
+    std::vector<const double *> ui(nsl), vi(nsl);
+    std::vector<double *> uo(nsl), vo(nsl);
+    for (size_t q = 0; q < nsl; q++) {
+      const size_t o = (size_t)g->m[q]->j0 * g->m[q]->nx;
+      ui[q] = u_in_h + o; vi[q] = v_in_h + o; uo[q] = u_out_h + o; vo[q] = v_out_h + o;
+    }
+    bool done = false;
+    int rc = run_host_pipelined(g->m.data(), (int)nsl, ui.data(), vi.data(), uo.data(), vo.data(), nsteps, tb_steps, &done);
+    if (rc != YH_OK) return rc;
+    if (done) return yh_slab_group_sync(g);
+  }
   int rc = yh_slab_group_set_state(g, u_in_h, v_in_h);
   if (rc != YH_OK) return rc;
   rc = yh_slab_group_advance(g, nsteps, tb_steps);
