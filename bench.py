@@ -139,6 +139,8 @@ MODES = {
     "rk4lap4_512": (512, "rk4lap4", 0, 2048),        # ... and on its default 512^2 sheet (BASELINE configs[0])
     "rk4lap4_512_fast": (512, "rk4lap4", 0, 2048),
     "euler5_512": (512, "euler5", 4, 8192),
+    "euler5_holes_1024": (1024, "euler5holes", 4, 2000),   # BASELINE configs[1]: blood-vessel obstacle masks, fibrillation IC
+    "rk4_holes_1024": (1024, "rk4holes", 0, 500),          # ... in the reference's default time integrator (no lap4 in the mask branch)
 }
 FP64_PER_UPDATE = {"euler5": (8, 24), "rk4lap4": (36, 316)}   # (DFMA, DADD + DMUL) warp-lane instructions per cell update
 
@@ -149,8 +151,20 @@ def workload_config(a):
 
 
 def mode_params(params_default, nx, ny, mode):
-    over = dict(timeIntOrder=1, lap4=0) if mode == "euler5" else {}
+    over = dict(timeIntOrder=1, lap4=0) if mode.startswith("euler5") else {}
+    if mode.endswith("holes"):
+        over["solidSwitch"] = 1
     return params_default(nx, ny, scale_L=True, **over)
+
+
+def mode_inputs(synth, n, mode):
+    """Initial condition (and obstacle mask) of a `modes` measurement: identical in both arms."""
+    u, v = synth.fibrillation_ic(n, n) if n >= 1024 else synth.cross_field_ic(n, n)
+    mask = None
+    if mode.endswith("holes"):
+        mask = synth.hole_mask(n, seed=1)
+        u, v = u * mask, v * mask
+    return u, v, mask
 
 
 def fp64_peak():
@@ -207,9 +221,9 @@ def run_reference(a):
 
         def ref_rate(n, mode, nsteps, reps):
             ref.init(mode_params(o.params_default, n, n, mode))
-            u, v = synth.fibrillation_ic(n, n) if n >= 1024 else synth.cross_field_ic(n, n)
-            ref.rd_run(u, v, 2, copy_back=False)
-            ms = [ref.rd_run(u, v, nsteps, copy_back=False)[2] for _ in range(reps)]
+            u, v, mask = mode_inputs(synth, n, mode)
+            ref.rd_run(u, v, 2, solid=mask, copy_back=False)
+            ms = [ref.rd_run(u, v, nsteps, solid=mask, copy_back=False)[2] for _ in range(reps)]
             return n * n * nsteps * reps / (sum(ms) / 1e3) / 1e9, sum(ms) / reps
 
         ref.init(mode_params(o.params_default, a.nx, a.ny, a.mode))
@@ -252,17 +266,18 @@ def measure_mode(yh, torch, n, mode, tb, nsteps):
     """One extra single-GPU measurement through the C ABI (yh_rd_advance), state resident in HBM."""
     from yolohtli_b200 import host, synth
     p = mode_params(yh.default_params, n, n, mode)
-    u0, v0 = synth.fibrillation_ic(n, n) if n >= 1024 else synth.cross_field_ic(n, n)
+    u0, v0, mask = mode_inputs(synth, n, mode)
+    solid = torch.as_tensor(mask).cuda() if mask is not None else None
     uA, vA = torch.as_tensor(u0).cuda(), torch.as_tensor(v0).cuda()
     uB, vB = torch.zeros_like(uA), torch.zeros_like(vA)
-    ru, rv = host.rd_advance(p, max(4, (nsteps // 8) & ~3), uA, vA, uB, vB, tb_steps=tb)
+    ru, rv = host.rd_advance(p, max(4, (nsteps // 8) & ~3), uA, vA, uB, vB, tb_steps=tb, solid=solid)
     torch.cuda.synchronize()
     best = None
     for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         ou, ov = (uB, vB) if ru is uA else (uA, vA)
-        ru, rv = host.rd_advance(p, nsteps, ru, rv, ou, ov, tb_steps=tb, flags=host.RD_INPUT_CANONICAL)
+        ru, rv = host.rd_advance(p, nsteps, ru, rv, ou, ov, tb_steps=tb, flags=host.RD_INPUT_CANONICAL, solid=solid)
         e1.record()
         torch.cuda.synchronize()
         t = e0.elapsed_time(e1)
@@ -405,7 +420,7 @@ def run_ours(a):
                                "hbm_algorithmic_frac": r * BYTES_PER_UPDATE / peak,
                                "arithmetic": "fast (coefficients combined, FMA chains; rounding-level differences, "
                                              "tests/test_gpu_arith.py)" if fast else "exact"}
-                if not fast:
+                if not fast and mode in FP64_PER_UPDATE:
                     modes[name]["fp64_frac"] = fp64_fraction(mode, r * 1e9, pk64)
         from tests import oracle_lib
         cb = cpu_baseline(a, oracle_lib) if world == 1 and not a.no_cpu_baseline else None

@@ -102,6 +102,15 @@ int yh_slab_group_sync(yh_slab_group *g);
 int yh_slab_group_run_host(yh_slab_group *g, const double *u_in_h, const double *v_in_h,
                            double *u_out_h, double *v_out_h, int nsteps, int tb_steps);
 
+/* ---- symmetry-reduction mode on the slabs of a group (display()'s reduceSym branch, main.cu:894-954) ----
+ * Every step: ghost exchange, RD + velTan, tips, the 12 phase-condition integrals (row sums per slab, added over
+ * the slabs, closed in the single-sheet order), the host 3x3 solve, BFECC in the moving frame -- bit for bit
+ * yh_sim_run_sr on the whole sheet.  The group must have been created with halo >= timeIntOrder + 3.
+ * c_phi_h (optional): 6 doubles per step, (c, phi) as pushed to clist / philist.  yh_slab_group_sr_state reads
+ * or sets (c, phi); setting restarts the step count (the first step solves twice, main.cu:910-921). */
+int yh_slab_group_advance_sr(yh_slab_group *g, int nsteps, double *c_phi_h);
+int yh_slab_group_sr_state(yh_slab_group *g, double c[3], double phi[3], int set);
+
 #ifdef __cplusplus
 }
 #endif

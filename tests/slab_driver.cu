@@ -2,7 +2,11 @@
 // slabs through include/yolohtli_slab.h, the way a maintainer of the reference's main.cu would reach
 // several GPUs, and checks N slabs == one sheet BIT FOR BIT against yh_sim (single device path).
 //
-//   yh_slab_driver <nx> <ny> <nslabs> <nsteps> <mode: euler|rk4lap4|eulerholes> [ndev] [pipe]
+//   yh_slab_driver <nx> <ny> <nslabs> <nsteps> <mode: euler|rk4lap4|eulerholes|sr> [ndev] [pipe]
+//
+// sr: the symmetry-reduction branch of display() (main.cu:894-954) -- yh_slab_group_advance_sr on nslabs slabs
+// against yh_sim_run_sr on one sheet: fields AND the (c, phi) record bit for bit, starting from a spiral that
+// the program grows itself (cross-field initial condition, 3000 Euler steps).
 //
 // pipe: the slabs run through yh_slab_group_run_host (host buffers in, steps, host buffers out; the copies
 // hidden behind the time steps by skewed chunks and edge wedges) in two calls; FAIL unless the pipelined
@@ -14,8 +18,10 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 
+#include <chrono>
 #include <vector>
 
 #include "../include/yolohtli_slab.h"
@@ -40,6 +46,56 @@ static void initial_state(int nx, int ny, std::vector<double> &u, std::vector<do
     }
 }
 
+// symmetry-reduction mode: N slabs vs one sheet, fields and the (c, phi) history
+static int run_sr(int nx, int ny, int nslabs, int nsteps, int ndev) {
+  yh_params pe, p;
+  CHECK(yh_params_default(&pe, nx, ny, 0, 0));
+  pe.timeIntOrder = 1; pe.lap4 = 0;
+  const size_t n = (size_t)nx * ny;
+  std::vector<double> u0(n), v0(n), ua(n), va(n), ub(n), vb(n), reca((size_t)6 * nsteps), recb((size_t)6 * nsteps);
+  yh_sim *sim = nullptr;
+  CHECK(yh_sim_create(&sim, &pe, 1, 0));
+  CHECK(yh_sim_cross_field_ic(sim));
+  CHECK(yh_sim_run(sim, 3000, 4, nullptr));
+  CHECK(yh_sim_get_state(sim, u0.data(), v0.data()));
+  CHECK(yh_sim_destroy(sim));
+  CHECK(yh_params_default(&p, nx, ny, 1, 0));      // reduce_sym: dt halved, default RK4 + lap4 (main.cu:148-158)
+  p.tipx0 = nx / 2; p.tipy0 = ny / 2;
+  if (p.tipOffsetX > nx / 3) { p.tipOffsetX = nx / 3; p.tipOffsetY = ny / 3; }
+  // (a) one sheet
+  CHECK(yh_sim_create(&sim, &p, 1, 0));
+  CHECK(yh_sim_set_state(sim, u0.data(), v0.data()));
+  auto t0 = std::chrono::steady_clock::now();
+  CHECK(yh_sim_run_sr(sim, nsteps, reca.data()));
+  const double us_sheet = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / nsteps;
+  CHECK(yh_sim_get_state(sim, ua.data(), va.data()));
+  CHECK(yh_sim_destroy(sim));
+  // (b) nslabs slabs, timeIntOrder + 3 ghost rows
+  std::vector<int> devs(nslabs);
+  for (int r = 0; r < nslabs; r++) devs[r] = r % ndev;
+  yh_slab_group *g = nullptr;
+  CHECK(yh_slab_group_create(&g, &p, nslabs, devs.data(), p.timeIntOrder + 3));
+  CHECK(yh_slab_group_set_state(g, u0.data(), v0.data()));
+  const int first = nsteps / 2;                     // in two calls: the run continues from resident state
+  CHECK(yh_slab_group_advance_sr(g, first, recb.data()));
+  t0 = std::chrono::steady_clock::now();
+  CHECK(yh_slab_group_advance_sr(g, nsteps - first, recb.data() + (size_t)6 * first));
+  const double us_slabs = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / (nsteps - first);
+  CHECK(yh_slab_group_get_state(g, ub.data(), vb.data()));
+  CHECK(yh_slab_group_destroy(g));
+  const bool same = memcmp(ua.data(), ub.data(), n * sizeof(double)) == 0 && memcmp(va.data(), vb.data(), n * sizeof(double)) == 0;
+  const bool same_rec = memcmp(reca.data(), recb.data(), reca.size() * sizeof(double)) == 0;
+  double moved = 0.0, cmax = 0.0;
+  for (size_t c = 0; c < n; c++) moved += (ua[c] - u0[c]) * (ua[c] - u0[c]);
+  for (size_t q = 0; q < reca.size(); q++) cmax = reca[q] * reca[q] > cmax ? reca[q] * reca[q] : cmax;
+  const bool ok = same && same_rec && moved > 1e-6 && cmax > 0.0 && cmax == cmax;
+  printf("slab_driver %s %dx%d sr nslabs=%d ndev=%d nsteps=%d bitwise_fields=%d bitwise_c_phi=%d moved=%.3g max|c,phi|=%.3g "
+         "us_per_step: sheet %.1f slabs %.1f\n",
+         ok ? "PASS" : "FAIL", nx, ny, nslabs, ndev, nsteps, (int)same, (int)same_rec, moved, cmax > 0 ? sqrt(cmax) : 0.0,
+         us_sheet, us_slabs);
+  return ok ? 0 : 1;
+}
+
 int main(int argc, char **argv) {
   const int nx = argc > 1 ? atoi(argv[1]) : 512, ny = argc > 2 ? atoi(argv[2]) : 512;
   const int nslabs = argc > 3 ? atoi(argv[3]) : 2, nsteps = argc > 4 ? atoi(argv[4]) : 203;
@@ -48,6 +104,7 @@ int main(int argc, char **argv) {
   const bool pipe = argc > 7 && strcmp(argv[7], "pipe") == 0;
   if (yh_device_count() < 1) { printf("slab_driver FAIL no CUDA device\n"); return 1; }
   if (ndev > yh_device_count()) ndev = yh_device_count();
+  if (strcmp(mode, "sr") == 0) return run_sr(nx, ny, nslabs, nsteps, ndev);
 
   yh_params p;
   CHECK(yh_params_default(&p, nx, ny, 0, 1));

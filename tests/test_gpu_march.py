@@ -28,10 +28,11 @@ def dev(a):
     return torch.as_tensor(np.ascontiguousarray(a)).cuda()
 
 
-def advance(p, n, u, v, rows=None):
+def advance(p, n, u, v, rows=None, solid=None):
     uA, vA = dev(u), dev(v)
     uB, vB = torch.zeros_like(uA), torch.zeros_like(vA)
-    ru, rv = host.rd_advance(p, n, uA, vA, uB, vB, rows=rows)
+    ds = torch.as_tensor(np.ascontiguousarray(solid, dtype=np.uint8)).cuda() if solid is not None else None
+    ru, rv = host.rd_advance(p, n, uA, vA, uB, vB, rows=rows, solid=ds)
     torch.cuda.synchronize()
     return ru.cpu().numpy(), rv.cpu().numpy()
 
@@ -123,3 +124,48 @@ def test_march_fast_flavour_25_steps_within_1e14(oracle, yh, kw):
     eu, ev = np.abs(got[0] - want[0]).max(), np.abs(got[1] - want[1]).max()
     print(f"march fast vs exact after 25 steps {kw}: max |du| {eu:.3e}, max |dv| {ev:.3e}")
     assert 0 < eu <= 1e-14 and ev <= 1e-14
+
+
+def random_mask(nx, ny, seed):
+    """Tissue with holes of every local shape: isolated cells, bars, blocks, holes on the sheet's edges."""
+    rng = np.random.default_rng(seed)
+    m = (rng.uniform(size=(ny, nx)) > 0.08).astype(np.uint8)
+    for _ in range(6):
+        j, i = rng.integers(0, ny), rng.integers(0, nx)
+        m[j:j + rng.integers(1, 9), i:i + rng.integers(1, 17)] = 0
+    m[0, :7] = 0
+    m[-1, -5:] = 0
+    m[ny // 2:, 0] = 0
+    return m
+
+
+@pytest.mark.parametrize("nx,ny", [(48, 40), (130, 67), (256, 96), (500, 131), (1024, 300)])
+@pytest.mark.parametrize("kw", [dict(), dict(timeIntOrder=2), dict(mu=1.1, delta=0.9, gamma=0.05, theta=0.01, tc=0.9)])
+def test_march_masks_bitwise_vs_oracle(oracle, nx, ny, kw):
+    """Obstacle masks (C2) on the marching tiles: mask codes derived once per launch, kept in registers."""
+    os.environ["YH_SOLID_RK"] = "march"
+    try:
+        p = oracle.params_default(nx, ny, solidSwitch=1, **kw)
+        mask = random_mask(nx, ny, nx + 7 * ny)
+        u, v = fields(nx, ny, seed=nx)
+        u, v = u * mask, v * mask
+        want = oracle.rd_advance(p, 3, u, v, solid=mask)
+        got = advance(p, 3, u, v, solid=mask)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        assert (got[0][mask == 0] == 0.0).all() and not np.signbit(got[0][mask == 0]).any()
+        os.environ["YH_SOLID_RK"] = "stream"
+        other = advance(p, 3, u, v, solid=mask)
+        assert np.array_equal(got[0], other[0]) and np.array_equal(got[1], other[1])
+        # a slab of the same sheet: rows [lo, hi) with ghost rows, mask rows stored alike
+        os.environ["YH_SOLID_RK"] = "march"
+        if ny >= 60:
+            H = 4
+            wu, wv = oracle.rd_advance(p, 1, u, v, solid=mask)
+            for lo, hi in [(0, 30), (20, ny - 10), (ny - 25, ny)]:
+                g0, g1 = max(0, lo - H), min(ny, hi + H)
+                q = p.copy()
+                q.ny, q.ny_global, q.jg0 = g1 - g0, ny, g0
+                gu, gv = advance(q, 1, u[g0:g1], v[g0:g1], rows=(lo - g0, hi - g0), solid=mask[g0:g1])
+                assert np.array_equal(gu[lo - g0:hi - g0], wu[lo:hi]) and np.array_equal(gv[lo - g0:hi - g0], wv[lo:hi]), (lo, hi)
+    finally:
+        os.environ.pop("YH_SOLID_RK", None)

@@ -43,6 +43,17 @@ def test_cpp_host_pipelined_run_host_bitwise(args):
     assert r.returncode == 0 and "slab_driver PASS" in r.stdout and "levels per chunk" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("args", ["256 256 1 40 sr", "256 256 2 60 sr", "256 384 3 40 sr", "512 512 2 100 sr"])
+def test_cpp_host_symmetry_reduction_on_slabs(args):
+    """yh_slab_group_advance_sr: display()'s symmetry-reduction branch on row slabs from a C++ host -- fields and the
+    (c, phi) record bit for bit those of yh_sim_run_sr on one sheet, from a spiral the program grows itself."""
+    assert os.path.exists(DRIVER), "build the library first (make -C yolohtli_b200/csrc)"
+    ndev = str(min(torch.cuda.device_count(), int(args.split()[2])))
+    r = subprocess.run([DRIVER] + args.split() + [ndev], capture_output=True, text=True, timeout=300)
+    print(r.stdout.strip())
+    assert r.returncode == 0 and "slab_driver PASS" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("mode,n,world,steps", [("euler", 384, 2, 100), ("euler", 384, 3, 64), ("rk4lap4", 256, 2, 25),
                                                ("rk2", 256, 3, 12), ("euler_holes", 512, 2, 80)])
 def test_slab_group_vs_oracle(oracle, yh, mode, n, world, steps):

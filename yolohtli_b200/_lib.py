@@ -173,6 +173,9 @@ SIGNATURES.update({
     "yh_slab_group_advance": (_i, [_vp, _i, _i]),
     "yh_slab_group_sync": (_i, [_vp]),
     "yh_slab_group_run_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "yh_slab_pipeline_levels": (_i, [_vp, _i, _i]),
+    "yh_slab_group_advance_sr": (_i, [_vp, _i, _vp]),
+    "yh_slab_group_sr_state": (_i, [_vp, _vp, _vp, _i]),
 })
 SLAB_HANDLE_BYTES = 256
 

@@ -172,6 +172,9 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
   if (g == 0) { lo_g = max(dom_lo, y0 - K); hi_g = min(dom_hi, y0 + RYe + K); }
   else { lo_g = max(dom_lo, y0 - (K - 1 - st)); hi_g = min(dom_hi, y0 + RYe + (K - 1 - st)); }
   if (!col_ok) hi_g = lo_g;
+  // lanes of this warp that take part in the row steps (out-of-domain columns of an edge strip never do): the
+  // participants of the warp vote in s_step.  All 32 lanes are here: the loader warp left above, groups are whole warps.
+  const unsigned col_lanes = __ballot_sync(0xffffffffu, col_ok);
   const int m_shift = (g == 0) ? 1 : 1 + 2 * g;   // row m = it + c0 - m_shift
 
   const double q4 = a.q4, m2q = a.m2q, mrs2q4 = a.mrs2q4, rsq = a.rsq;
@@ -249,13 +252,17 @@ rd_rk_stream(const __grid_constant__ YhK k, const __grid_constant__ RkArgs a) {
     const double *pc = Ak + slot * ROWA;
     unsigned codes = 0;
     if (SOLID) codes = *reinterpret_cast<const unsigned *>(Cr + ((m - c0) & (NR0 - 1)) * W + c);
+    // a warp whose 64 cells and all their neighbours are tissue (code (1,2,1) on both axes, sc = 1 -- the bulk of a
+    // sheet with compact obstacles) takes the plain stencil: the same expression bit for bit, without the selects
+    constexpr unsigned FULL1 = 1u | (2u << 2) | (1u << 4) | (1u << 6) | (2u << 8) | (1u << 10) | (1u << 12);
+    const bool masked = SOLID && !__all_sync(col_lanes, codes == (FULL1 | (FULL1 << 16)));
     double du[2], dv[2];
 #pragma unroll
     for (int f = 0; f < 2; f++) {   // f = 0: u with Ju, f = 1: v with Jv
       const double2 Cc = f ? C.v : C.u, Ss = f ? S.v : S.u, Nn = f ? N.v : N.u;
       const double Wv = f ? C.vw : C.uw, Ev = f ? C.ve : C.ue;
       double d0, d1;
-      if (SOLID) {   // reactionDiffusion.cu:171-180
+      if (SOLID && masked) {   // reactionDiffusion.cu:171-180
         // The coefficient triples are exact 0 / 1 / 2 and only four occur per axis for a tissue cell:
         // (1,2,1), (2,2,0), (0,2,2), (0,0,0).  Each equals -- bit for bit, for finite fields -- the
         // plain stencil fma(-2, c, A) + B on substituted neighbours (table in rd_fast.cu), which
@@ -461,6 +468,15 @@ int yh_launch_rd_rk(const YhK &k, const double *u_in, const double *v_in, double
     if (quad && yh_rd_rkq_supported(k))
       return yh_launch_rd_rkq(k, yh_arithmetic(), u_in, v_in, u_out, v_out, (vtu && k.gateDiff) ? vtu : nullptr,
                               (vtu && k.gateDiff) ? vtv : nullptr, st);
+  }
+  {   // obstacle masks (C2: 1024^2 + holes): the marching tiles, which derive a cell's mask code once per launch and
+      // keep it in a register, on the sheets the tile kernels serve.  Measured (B200, RK4 + holes, us per step, march |
+      // this kernel): 512^2 14.0 | 18.6, 1024^2 53.5 | 49.2, 4096^2 876 | 624; YH_SOLID_RK = march | stream overrides
+    const char *kern = getenv("YH_SOLID_RK");
+    const long long cells_ = (long long)k.nx * (k.row1 - k.row0);
+    const bool march = kern ? (kern[0] == 'm') : (yh_rd_prefer_tile(cells_) != 0);
+    if (march && k.solidSwitch && solid && k.gateDiff && !k.stim && yh_rd_tile_march_solid_supported(k))
+      return yh_launch_rd_tile_march_solid(k, u_in, v_in, u_out, v_out, vtu, vtv, solid, st);
   }
   RkArgs a{u_in, v_in, u_out, v_out, vtu, vtv, solid, 0, 0.0, 0.0, 0.0, 0.0};
   {

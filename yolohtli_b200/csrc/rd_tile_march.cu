@@ -19,6 +19,12 @@
 // mirror is an address adjustment of the row load.
 //
 // Same expressions, same bits as rd_tile.cu / rd_rk.cu / the plain-C oracle in the EXACT flavour.
+//
+// Code size matters here: the stage over R rows is unrolled (~1.4 K instructions, two copies: with / without the next
+// stage state), eight warps run through it a few hundred cycles apart, and every further copy measured SLOWER than
+// the work it saved -- rows dealt 6/5 to the warps so that the four schedulers carry 11 instead of 12 rows (a second
+// pair of instantiations: 13.1 -> 14.3 us), a plain-stencil copy for all-tissue warps of the masked kernel
+// (14.0 -> 15.1 us at 512^2).  Both were dropped (profiles/r2d_tile_march_probe.txt).
 #include <stdlib.h>
 
 #include "yh_common.cuh"
@@ -31,6 +37,7 @@ constexpr int ROWS_MAX = 48;           // tile rows a CTA can hold (band + 2 hal
 struct MarchArgs {
   const double *u_in, *v_in;
   double *u_out, *v_out, *vtu, *vtv;
+  const uint8_t *solid;                // SOLID variants: 1 = tissue (main.cu:676-680), local rows
   int sw, bh;                          // strip width (outputs per tile row, even), band height
   // FAST arithmetic flavour (yh_set_arithmetic; coefficients as in rd_rkq.cu / rd_tile.cu):
   //   d = cC*C + cH*(W+E) + cV*(N+S) + cQ*(SW+SE+NW+NE) + jC*Jc - jX*(JW+JE) - jY*(JN+JS)
@@ -113,6 +120,45 @@ __device__ __forceinline__ void pair_du_exact(const YhK &k, double m2q, double q
   o1 = d1 - k.dt * Jc.y;
 }
 
+// Obstacle masks (reactionDiffusion.cu:154-184), as in rd_rk.cu: the six stencil coefficients of a cell depend only
+// on the mask of the cell and of its four (mirrored) neighbours -- packed once per launch into 13 bits per cell
+// (cxx cxy cxz cyx cyy cyz, 2 bits each, values 0 / 1 / 2, and sc) and kept in a register of the thread that owns
+// the cell for all stages.  The coefficient triples are exact 0 / 1 / 2 and only (1,2,1), (2,2,0), (0,2,2), (0,0,0)
+// occur per axis for a tissue cell; each equals -- bit for bit, for finite fields -- the plain stencil
+// fma(-2, c, A) + B on substituted neighbours (table in rd_fast.cu).  The mask branch has no 4th-order terms (:184).
+__device__ __forceinline__ unsigned m_solid_code(bool sc, bool sw, bool se, bool sn, bool ss) {
+  const unsigned cxx = (sw && se) && (sw && sc) ? 1u : ((sw && sc) ? 2u : 0u);
+  const unsigned cxy = sc ? ((sw || se) ? 2u : 0u) : 0u;
+  const unsigned cxz = (sw && se) && (sc && se) ? 1u : ((sc && se) ? 2u : 0u);
+  const unsigned cyx = (sn && ss) && (sn && sc) ? 1u : ((sn && sc) ? 2u : 0u);
+  const unsigned cyy = sc ? ((sn || ss) ? 2u : 0u) : 0u;
+  const unsigned cyz = (sn && ss) && (sc && ss) ? 1u : ((sc && ss) ? 2u : 0u);
+  return cxx | (cxy << 2) | (cxz << 4) | (cyx << 6) | (cyy << 8) | (cyz << 10) | ((sc ? 1u : 0u) << 12);
+}
+__device__ __forceinline__ double m_axis(unsigned cL, unsigned cC, double c, double L, double R) {
+  const bool both = cL == 1u;
+  const double t = (cL == 2u) ? L : R;
+  const double r = fma(-2.0, c, both ? L : t + t) + (both ? R : 0.0);
+  return cC ? r : 0.0;
+}
+template <int F>
+__device__ __forceinline__ void pair_du_solid(const YhK &k, unsigned codes, const Row4 &S, const Row4 &C, const Row4 &N,
+                                              const Row4 &Jc, double &o0, double &o1) {
+  const unsigned k0 = codes & 0xFFFFu, k1 = codes >> 16;   // reactionDiffusion.cu:171-180
+  const double x0 = m_axis(k0 & 3u, (k0 >> 2) & 3u, C.x, C.w, C.y), y0 = m_axis((k0 >> 6) & 3u, (k0 >> 8) & 3u, C.x, N.x, S.x);
+  const double x1 = m_axis(k1 & 3u, (k1 >> 2) & 3u, C.y, C.x, C.e), y1 = m_axis((k1 >> 6) & 3u, (k1 >> 8) & 3u, C.y, N.y, S.y);
+  double d0, d1;
+  if (F == 0) {
+    d0 = (x0 * k.rx + y0 * k.ry);
+    d1 = (x1 * k.rx + y1 * k.ry);
+  } else {
+    d0 = (x0 * k.rx * k.rscale + y0 * k.ry * k.rscale);
+    d1 = (x1 * k.rx * k.rscale + y1 * k.ry * k.rscale);
+  }
+  o0 = d0 - k.dt * Jc.x;
+  o1 = d1 - k.dt * Jc.y;
+}
+
 template <int F, bool LAP4>
 __device__ __forceinline__ void pair_du_fast(const MarchArgs &a, const Row4 &S, const Row4 &C, const Row4 &N, const Row4 &Js,
                                              const Row4 &Jc, const Row4 &Jn, double &o0, double &o1) {
@@ -149,9 +195,10 @@ struct MarchCtx {
 // are predicated (rows outside the stage's ring or outside the domain produce values nobody reads), so ptxas
 // can issue the loads of row j+1 under the arithmetic of row j -- with a branch per row the LDS latency
 // and the tail of every row's dependency chain were exposed (2 warps per scheduler cannot hide them).
-template <int K, bool LAP4, bool DEF, int ARITH, int R, bool LAST>
+template <int K, bool LAP4, bool DEF, int ARITH, int R, bool SOLID, bool LAST>
 __device__ __forceinline__ void march_stage(const YhK &k, const MarchArgs &a, const MarchCtx &c, const double2 (&u0)[R],
-                                            const double2 (&v0)[R], double2 (&ru)[R], double2 (&rv)[R]) {
+                                            const double2 (&v0)[R], double2 (&ru)[R], double2 (&rv)[R],
+                                            const unsigned (&codes)[R]) {
   Row4 Su, Cu, Nu, Sv, Cv, Nv, Sju, Cju, Nju, Sjv, Cjv, Njv;
   Sju = Cju = Nju = Sjv = Cjv = Njv = Row4{0.0, 0.0, 0.0, 0.0};
   {
@@ -183,8 +230,13 @@ __device__ __forceinline__ void march_stage(const YhK &k, const MarchArgs &a, co
       ru[j].x = fma(c.wst, du0, ru[j].x); ru[j].y = fma(c.wst, du1, ru[j].y);
       rv[j].x = fma(c.wst, dv0, rv[j].x); rv[j].y = fma(c.wst, dv1, rv[j].y);
     } else {
-      pair_du_exact<0, LAP4>(k, c.m2qu, c.q4u, Su, Cu, Nu, Sju, Cju, Nju, du0, du1);
-      pair_du_exact<1, LAP4>(k, c.m2qv, c.q4v, Sv, Cv, Nv, Sjv, Cjv, Njv, dv0, dv1);
+      if (SOLID) {
+        pair_du_solid<0>(k, codes[j], Su, Cu, Nu, Cju, du0, du1);
+        pair_du_solid<1>(k, codes[j], Sv, Cv, Nv, Cjv, dv0, dv1);
+      } else {
+        pair_du_exact<0, LAP4>(k, c.m2qu, c.q4u, Su, Cu, Nu, Sju, Cju, Nju, du0, du1);
+        pair_du_exact<1, LAP4>(k, c.m2qv, c.q4v, Sv, Cv, Nv, Sjv, Cjv, Njv, dv0, dv1);
+      }
       ru[j].x += (c.wst * du0); ru[j].y += (c.wst * du1);   // :502-503
       rv[j].x += (c.wst * dv0); rv[j].y += (c.wst * dv1);
     }
@@ -216,12 +268,17 @@ __device__ __forceinline__ void march_stage(const YhK &k, const MarchArgs &a, co
         uo.x = u0[j].x + k.tc * ru[j].x; uo.y = u0[j].y + k.tc * ru[j].y;
         vo.x = v0[j].x + k.tc * rv[j].x; vo.y = v0[j].y + k.tc * rv[j].y;
       }
+      const bool sc0 = !SOLID || ((codes[j] >> 12) & 1u), sc1 = !SOLID || ((codes[j] >> 28) & 1u);
+      if (SOLID) {   // :521-522 masked cells are exactly 0.0
+        uo.x = sc0 ? uo.x : 0.0; uo.y = sc1 ? uo.y : 0.0;
+        vo.x = sc0 ? vo.x : 0.0; vo.y = sc1 ? vo.y : 0.0;
+      }
       const size_t o = c.o + (size_t)j * k.nx;
       *reinterpret_cast<double2 *>(a.u_out + o) = uo;
       *reinterpret_cast<double2 *>(a.v_out + o) = vo;
-      if (a.vtu) {   // :551-552
-        *reinterpret_cast<double2 *>(a.vtu + o) = make_double2(ru[j].x / k.dt, ru[j].y / k.dt);
-        *reinterpret_cast<double2 *>(a.vtv + o) = make_double2(rv[j].x / k.dt, rv[j].y / k.dt);
+      if (a.vtu) {   // :551-552, :529-530
+        *reinterpret_cast<double2 *>(a.vtu + o) = make_double2(sc0 ? ru[j].x / k.dt : 0.0, sc1 ? ru[j].y / k.dt : 0.0);
+        *reinterpret_cast<double2 *>(a.vtv + o) = make_double2(sc0 ? rv[j].x / k.dt : 0.0, sc1 ? rv[j].y / k.dt : 0.0);
       }
     }
     Su = Cu; Cu = Nu; Sv = Cv; Cv = Nv;
@@ -231,7 +288,7 @@ __device__ __forceinline__ void march_stage(const YhK &k, const MarchArgs &a, co
 
 // K = 2 | 4 stages; switches of the reference's default mode compiled in (gateDiff on, live stimulus off).
 // ARITH: 0 = exact, 1 = fast.  R = rows per warp.
-template <int K, bool LAP4, bool DEF, int ARITH, int R>
+template <int K, bool LAP4, bool DEF, int ARITH, int R, bool SOLID>
 __global__ void __launch_bounds__(LANES * (ROWS_MAX / R), 1)
 rd_tile_march(const __grid_constant__ YhK k, const __grid_constant__ MarchArgs a) {
   constexpr int H = K;
@@ -260,12 +317,24 @@ rd_tile_march(const __grid_constant__ YhK k, const __grid_constant__ MarchArgs a
 
   // ---- u0, v0 of the thread's cells; stage-0 state and currents into the ping half ----------------------
   double2 u0[R], v0[R], ru[R], rv[R];
+  unsigned codes[R];
 #pragma unroll
   for (int j = 0; j < R; j++) {
     const int t = r0 + j;
     u0[j] = v0[j] = ru[j] = rv[j] = make_double2(0.0, 0.0);
+    codes[j] = 0u;
     if (t >= t_lo && t <= t_hi && in_x) {
       const size_t o = (size_t)(ly0 + t) * nx + gx;
+      if (SOLID && t >= 1 && t <= twy - 2) {   // ring-0 rows are inputs only: no code needed, no mask row beyond the tile read
+        const int ly = ly0 + t, gj = ly + k.jg0;
+        const uint8_t *mc = a.solid + (size_t)ly * nx;
+        const uint8_t *mS = a.solid + (size_t)(yh_mir(gj - 1, k.nyg) - k.jg0) * nx;   // S = j-1 (:149)
+        const uint8_t *mN = a.solid + (size_t)(yh_mir(gj + 1, k.nyg) - k.jg0) * nx;   // N = j+1 (:150)
+        const bool c0m = mc[gx] != 0, c1m = mc[gx + 1] != 0;
+        const bool w0 = mc[yh_mir(gx - 1, nx)] != 0, e1 = mc[yh_mir(gx + 2, nx)] != 0;
+        codes[j] = m_solid_code(c0m, w0, c1m, mN[gx] != 0, mS[gx] != 0) |
+                   (m_solid_code(c1m, c0m, e1, mN[gx + 1] != 0, mS[gx + 1] != 0) << 16);
+      }
       u0[j] = *reinterpret_cast<const double2 *>(a.u_in + o);
       v0[j] = *reinterpret_cast<const double2 *>(a.v_in + o);
       const double Ux = u0[j].x + 0.0, Uy = u0[j].y + 0.0, Vx = v0[j].x + 0.0, Vy = v0[j].y + 0.0;   // u0 + (0.0*0.0)
@@ -301,8 +370,8 @@ rd_tile_march(const __grid_constant__ YhK k, const __grid_constant__ MarchArgs a
     if (jlo < R && jhi >= 0 && jlo <= jhi) {
       MarchCtx c{cur, nxt, wst, kin, q4u, m2qu, q4v, m2qv, jlo, jhi, jm_lo, jm_hi, in_x, out_x, padL, padR,
                  (size_t)(ly0 + r0) * nx + gx};
-      if (st < K - 1) march_stage<K, LAP4, DEF, ARITH, R, false>(k, a, c, u0, v0, ru, rv);
-      else march_stage<K, LAP4, DEF, ARITH, R, true>(k, a, c, u0, v0, ru, rv);
+      if (st < K - 1) march_stage<K, LAP4, DEF, ARITH, R, SOLID, false>(k, a, c, u0, v0, ru, rv, codes);
+      else march_stage<K, LAP4, DEF, ARITH, R, SOLID, true>(k, a, c, u0, v0, ru, rv, codes);
     }
     if (st < K - 1) __syncthreads();
   }
@@ -332,13 +401,13 @@ void pick_tiling(int nx, int rows, int K, int nsm, int *sw_out, int *bh_out) {
   }
 }
 
-template <int K, bool LAP4, bool DEF, int ARITH, int R>
+template <int K, bool LAP4, bool DEF, int ARITH, int R, bool SOLID = false>
 int launch_march(const YhK &k, MarchArgs &a, cudaStream_t st) {
   static bool done[64] = {false};
   static int nsm[64] = {0};
   int dev = 0;
   YH_CUDA(cudaGetDevice(&dev));
-  auto kfn = rd_tile_march<K, LAP4, DEF, ARITH, R>;
+  auto kfn = rd_tile_march<K, LAP4, DEF, ARITH, R, SOLID>;
   if (!done[dev & 63]) {
     YH_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     YH_CUDA(cudaDeviceGetAttribute(&nsm[dev & 63], cudaDevAttrMultiProcessorCount, dev));
@@ -360,14 +429,33 @@ int launch_march(const YhK &k, MarchArgs &a, cudaStream_t st) {
 
 }  // namespace
 
+// solidSwitch: only through yh_launch_rd_tile_march_solid (the caller must hold the mask)
 int yh_rd_tile_march_supported(const YhK &k) {
+  if (k.solidSwitch) return 0;
+  return yh_rd_tile_march_solid_supported(k);
+}
+
+int yh_rd_tile_march_solid_supported(const YhK &k) {
   if (k.timeIntOrder != 2 && k.timeIntOrder != 4) return 0;
-  if (!k.neumannBC || k.solidSwitch || k.anisotropy) return 0;
+  if (!k.neumannBC || k.anisotropy) return 0;
   if (!k.gateDiff || k.stim) return 0;
   if ((k.nx & 1) || k.nx < 8 || k.nyg < 4) return 0;
   const char *f = getenv("YH_TILE_RK");   // march | cell (A/B, tests)
   if (f && f[0] == 'c') return 0;
   return 1;
+}
+
+// Obstacle masks: the exact flavour only (the mask coefficients are the reference's expressions), RK2 / RK4.
+int yh_launch_rd_tile_march_solid(const YhK &k, const double *u_in, const double *v_in, double *u_out, double *v_out,
+                                  double *vtu, double *vtv, const uint8_t *solid, cudaStream_t st) {
+  if (!k.solidSwitch || !solid || !yh_rd_tile_march_solid_supported(k)) return YH_ERR_UNSUPPORTED;
+  if (k.row1 <= k.row0) return YH_OK;
+  MarchArgs a{};
+  a.u_in = u_in; a.v_in = v_in; a.u_out = u_out; a.v_out = v_out; a.vtu = vtu; a.vtv = vtv; a.solid = solid;
+  const bool def = (k.mu == 1.0) && (k.delta == 1.0) && (k.gamma == 0.0) && (k.theta == 0.0);
+  if (k.timeIntOrder == 4)
+    return def ? launch_march<4, false, true, 0, 6, true>(k, a, st) : launch_march<4, false, false, 0, 6, true>(k, a, st);
+  return def ? launch_march<2, false, true, 0, 6, true>(k, a, st) : launch_march<2, false, false, 0, 6, true>(k, a, st);
 }
 
 int yh_launch_rd_tile_march(const YhK &k, const double *u_in, const double *v_in, double *u_out, double *v_out,

@@ -159,11 +159,19 @@ struct yh_slab {
   unsigned long long *sum_d;
   GraphSlot graphs[4];
   int band;
+  // symmetry-reduction mode (yh_slab_group_advance_sr): tangent field, frame velocity, tip list, row sums
+  double *sr_vt[2], *sr_adv[2], *sr_rows;
+  int *sr_tip_count;
+  yh_tip *sr_tip_vec;
+  int sr_tip_cap;
   std::vector<cudaEvent_t> tl;           // YH_SLAB_TIMELINE: t0, then 5 events per block (see timeline_dump)
 };
 
 struct yh_slab_group {
   std::vector<yh_slab *> m;
+  double c[3] = {0.0, 0.0, 0.0}, phi[3] = {0.0, 0.0, 0.0};   // frame velocity and phase (main.cu:902-938)
+  long long sr_count = 0;
+  std::vector<double> sr_part, sr_sum;
 };
 
 namespace {
@@ -770,6 +778,8 @@ int yh_slab_create(yh_slab **out, const yh_params *pg, int rank, int world, int 
   s->flags = reinterpret_cast<int *>(s->block + s->off[4]);
   s->cur = 0; s->solid = nullptr; s->pat = nullptr; s->solid_arg = nullptr; s->solid_flags = 0;
   s->raw = true; s->ghosts_valid = false; s->connected = (world == 1); s->count = 0;
+  s->sr_vt[0] = s->sr_vt[1] = s->sr_adv[0] = s->sr_adv[1] = s->sr_rows = nullptr;
+  s->sr_tip_count = nullptr; s->sr_tip_vec = nullptr; s->sr_tip_cap = 0;
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = greatest priority (numerically lowest)
   cudaStreamCreateWithPriority(&s->main, cudaStreamNonBlocking, lo);
@@ -796,6 +806,8 @@ int yh_slab_destroy(yh_slab *s) {
   if (s->up.ipc_base) cudaIpcCloseMemHandle(s->up.ipc_base);
   if (s->down.ipc_base) cudaIpcCloseMemHandle(s->down.ipc_base);
   cudaFree(s->block); cudaFree(s->solid); cudaFree(s->pat); cudaFree(s->sum_d);
+  cudaFree(s->sr_vt[0]); cudaFree(s->sr_vt[1]); cudaFree(s->sr_adv[0]); cudaFree(s->sr_adv[1]); cudaFree(s->sr_rows);
+  cudaFree(s->sr_tip_count); cudaFree(s->sr_tip_vec);
   cudaStreamDestroy(s->main); cudaStreamDestroy(s->edge); cudaStreamDestroy(s->copy);
   for (cudaEvent_t e : s->ev_chunk) cudaEventDestroy(e);
   cudaEventDestroy(s->ev_int); cudaEventDestroy(s->ev_edge); cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_band);
@@ -1101,6 +1113,165 @@ int yh_slab_group_run_host(yh_slab_group *g, const double *u_in_h, const double 
   rc = yh_slab_group_advance(g, nsteps, tb_steps);
   if (rc != YH_OK) return rc;
   return yh_slab_group_get_state(g, u_out_h, v_out_h);
+}
+
+// ---- symmetry-reduction (co-moving frame) steps on the slabs of a group ("SR mode") ----------
+// display()'s reduceSym branch (main.cu:894-954; yh_sim_run_sr on one device) with every kernel on row slabs:
+//   exchange ghosts of (u, v)^n                 timeIntOrder + 3 rows per side (RD radius + BFECC radius)
+//   RD           rows own-3 .. own+3 -> (u*, v*), velTan                          yh_rd_step
+//   tips         owned rows; slabs are contiguous in j, so the LAST tip of the sheet's list (the disc centre)
+//                is the last tip of the highest slab that found one                 yh_tip_track_rows
+//   integrals    row sums of the owned disc rows; tables added over the slabs (one non-zero contributor per
+//                row: exact), closed in the canonical order of the single-sheet pass  yh_sr_integral_rows, _close
+//   solve        3x3 on the host (same text as the reference)                       yh_solve_matrix
+//   BFECC        owned rows of u* -> (u, v)^{n+1} in the frame moving with c         yh_advect_bfecc_cphi_rows
+// The host sees three small results per step (tip counts, the row table, the 12 integrals), as the reference's
+// host sees twelve; everything else stays on the devices.  N slabs == yh_sim_run_sr on the whole sheet, bit for
+// bit (tests/slab_driver.cu, mode sr).  C++ text of yolohtli_b200/slab.py::SlabRunner._sr_steps.
+static int sr_alloc_slab(yh_slab *s) {
+  if (s->sr_rows) return YH_OK;
+  const size_t n = (size_t)s->ny_local * s->nx * sizeof(double);
+  for (int q = 0; q < 2; q++) {
+    YH_CUDA(cudaMalloc(&s->sr_vt[q], n));
+    YH_CUDA(cudaMalloc(&s->sr_adv[q], n));
+    YH_CUDA(cudaMemsetAsync(s->sr_vt[q], 0, n, s->main));     // velTan and the advection field start at zero (main.cu:431-434)
+    YH_CUDA(cudaMemsetAsync(s->sr_adv[q], 0, n, s->main));
+  }
+  s->sr_tip_cap = 65536;
+  YH_CUDA(cudaMalloc(&s->sr_tip_count, sizeof(int)));
+  YH_CUDA(cudaMalloc(&s->sr_tip_vec, (size_t)s->sr_tip_cap * sizeof(yh_tip)));
+  YH_CUDA(cudaMemsetAsync(s->sr_tip_count, 0, sizeof(int), s->main));
+  YH_CUDA(cudaMalloc(&s->sr_rows, (size_t)12 * yh_sr_disc_slots(&s->p) * sizeof(double)));
+  return YH_OK;
+}
+
+int yh_slab_group_sr_state(yh_slab_group *g, double c[3], double phi[3], int set) {
+  YH_REQUIRE(g && c && phi, "null pointer");
+  for (int q = 0; q < 3; q++) {
+    if (set) { g->c[q] = c[q]; g->phi[q] = phi[q]; }
+    else { c[q] = g->c[q]; phi[q] = g->phi[q]; }
+  }
+  if (set) g->sr_count = 0;
+  return YH_OK;
+}
+
+int yh_slab_group_advance_sr(yh_slab_group *g, int nsteps, double *c_phi_h) {
+  YH_REQUIRE(g && nsteps >= 0, "bad arguments");
+  const int count = (int)g->m.size();
+  int rc;
+  for (yh_slab *s : g->m) {
+    YH_REQUIRE(s->world == 1 || s->halo >= s->K + 3, "symmetry-reduction steps need timeIntOrder + 3 ghost rows");
+    YH_REQUIRE(!s->pg.solidSwitch || s->solid_arg, "solidSwitch set: call yh_slab_group_set_solid first");
+    DevGuard d(s->device);
+    rc = sr_alloc_slab(s);
+    if (rc != YH_OK) return rc;
+  }
+  const yh_params *pg = &g->m[0]->pg;
+  const size_t tbl = (size_t)12 * yh_sr_disc_slots(&g->m[0]->p);
+  g->sr_part.resize(tbl); g->sr_sum.resize(tbl);
+  double I[12];
+  const bool dbg = getenv("YH_SR_DEBUG") != nullptr;
+  for (int it = 0; it < nsteps; it++) {
+    if (dbg) { fprintf(stderr, "sr step %d (count %lld) c = %g %g %g\n", it, g->sr_count, g->c[0], g->c[1], g->c[2]); fflush(stderr); }
+    if (count > 1)
+      for (yh_slab *s : g->m) {
+        DevGuard d(s->device);
+        rc = launch_exchange(s, s->cur, s->main);
+        if (rc != YH_OK) return rc;
+      }
+    for (yh_slab *s : g->m) {
+      DevGuard d(s->device);
+      const int c = s->cur, o = c ^ 1;
+      const int r0 = s->own_lo - 3 > 0 ? s->own_lo - 3 : 0, r1 = s->own_hi + 3 < s->ny_local ? s->own_hi + 3 : s->ny_local;
+      rc = yh_rd_step(&s->p, s->u[c], s->v[c], s->u[o], s->v[o], s->sr_vt[0], s->sr_vt[1], s->solid_arg, 0,
+                      s->nx / 2, s->pg.ny / 2, r0, r1, s->main);
+      if (rc != YH_OK) return rc;
+    }
+    // tips.  Slabs on the SAME device (the one-GPU test vehicle) share that device's look-back scratch of the
+    // ordered compaction (yh_workspace), so their tip kernels must not overlap: one slab per device at a time.
+    // The last tip of the concatenated list = the disc centre (count == 0 or no tip anywhere: the set centre, B3).
+    float cx = (float)pg->tipx0, cy = (float)pg->tipy0;
+    {
+      std::vector<int> ntips(count, -1);
+      std::vector<yh_tip> last(count);
+      int left = count;
+      while (left > 0) {
+        std::vector<int> wave, devs;
+        for (int q = 0; q < count; q++) {
+          yh_slab *s = g->m[q];
+          bool busy = ntips[q] >= 0;
+          for (int d : devs) busy = busy || d == s->device;
+          if (busy) continue;
+          DevGuard d(s->device);
+          rc = yh_tip_track_rows(&s->p, s->u[s->cur ^ 1], s->u[s->cur], nullptr, s->sr_tip_count, s->sr_tip_vec, s->sr_tip_cap,
+                                 s->p.dt * (double)g->sr_count, s->p.tipAlgorithm, s->own_lo, s->own_hi, s->main);
+          if (rc != YH_OK) return rc;
+          wave.push_back(q); devs.push_back(s->device);
+        }
+        for (int q : wave) {
+          yh_slab *s = g->m[q];
+          DevGuard d(s->device);
+          int n = 0;
+          YH_CUDA(cudaMemcpyAsync(&n, s->sr_tip_count, sizeof(int), cudaMemcpyDeviceToHost, s->main));
+          YH_CUDA(cudaStreamSynchronize(s->main));
+          if (n > s->sr_tip_cap) { yh_set_error("tip list overflow on slab %d", s->rank); return YH_ERR_INVALID_ARG; }
+          if (n > 0) {
+            YH_CUDA(cudaMemcpyAsync(&last[q], s->sr_tip_vec + (n - 1), sizeof(yh_tip), cudaMemcpyDeviceToHost, s->main));
+            YH_CUDA(cudaStreamSynchronize(s->main));
+          }
+          ntips[q] = n;
+          left--;
+        }
+      }
+      if (g->sr_count != 0)
+        for (int q = 0; q < count; q++)      // rank order = ascending j: the last non-empty list wins
+          if (ntips[q] > 0) { cx = last[q].x; cy = last[q].y; }
+    }
+    if (c_phi_h)
+      for (int q = 0; q < 3; q++) { c_phi_h[6 * it + q] = g->c[q]; c_phi_h[6 * it + 3 + q] = g->phi[q]; }   // main.cu:902-903
+    const int passes = g->sr_count == 0 ? 2 : 1;                       // first step: main.cu:910-921
+    for (int k = 0; k < passes; k++) {
+      for (yh_slab *s : g->m) {
+        DevGuard d(s->device);
+        rc = yh_sr_integral_rows(&s->p, s->u[s->cur], s->v[s->cur], s->sr_vt[0], s->sr_vt[1], s->sr_adv[0], s->sr_adv[1],
+                                 cx, cy, s->own_lo, s->own_hi, s->sr_rows, s->main);
+        if (rc != YH_OK) return rc;
+      }
+      for (size_t q = 0; q < tbl; q++) g->sr_sum[q] = 0.0;
+      for (yh_slab *s : g->m) {
+        DevGuard d(s->device);
+        YH_CUDA(cudaMemcpyAsync(g->sr_part.data(), s->sr_rows, tbl * sizeof(double), cudaMemcpyDeviceToHost, s->main));
+        YH_CUDA(cudaStreamSynchronize(s->main));
+        for (size_t q = 0; q < tbl; q++) g->sr_sum[q] += g->sr_part[q];
+      }
+      {
+        yh_slab *s = g->m[0];
+        DevGuard d(s->device);
+        if (count > 1) YH_CUDA(cudaMemcpyAsync(s->sr_rows, g->sr_sum.data(), tbl * sizeof(double), cudaMemcpyHostToDevice, s->main));
+        rc = yh_sr_integrals_close(&s->p, s->sr_rows, I, s->main);
+        if (rc != YH_OK) return rc;
+      }
+      yh_solve_matrix(g->c, g->phi, I, g->c);                           // main.cu:913 / 926
+      if (passes == 2 && k == 0)
+        for (yh_slab *s : g->m) {
+          DevGuard d(s->device);
+          rc = yh_cxy_field(&s->p, s->sr_adv[0], s->sr_adv[1], g->c, g->phi, s->solid_arg, s->main);
+          if (rc != YH_OK) return rc;
+        }
+    }
+    for (yh_slab *s : g->m) {
+      DevGuard d(s->device);
+      const int c = s->cur, o = c ^ 1;
+      // u^{n+1} = BFECC(u*) in the frame moving with (c, phi); lands in the `c` buffers (main.cu:930-932)
+      rc = yh_advect_bfecc_cphi_rows(&s->p, s->u[o], s->v[o], s->u[c], s->v[c], g->c, g->phi, s->sr_adv[0], s->sr_adv[1],
+                                     s->solid_arg, s->own_lo, s->own_hi, s->main);
+      if (rc != YH_OK) return rc;
+      s->count++; s->raw = false; s->ghosts_valid = false;
+    }
+    for (int q = 0; q < 3; q++) g->phi[q] = g->phi[q] + g->c[q] * pg->dt;   // main.cu:936-938
+    g->sr_count++;
+  }
+  return yh_slab_group_sync(g);
 }
 
 }  // extern "C"

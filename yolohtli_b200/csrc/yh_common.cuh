@@ -218,6 +218,9 @@ int yh_launch_rd_tile_rk(const YhK &k, const double *u_in, const double *v_in, d
 int yh_rd_tile_march_supported(const YhK &k);   // rd_tile_march.cu (YH_TILE_RK = march | cell overrides)
 int yh_launch_rd_tile_march(const YhK &k, const double *u_in, const double *v_in, double *u_out,
                             double *v_out, double *vtu, double *vtv, cudaStream_t st);
+int yh_rd_tile_march_solid_supported(const YhK &k);   // ... with obstacle masks (RK2 / RK4, exact flavour)
+int yh_launch_rd_tile_march_solid(const YhK &k, const double *u_in, const double *v_in, double *u_out, double *v_out,
+                                  double *vtu, double *vtv, const uint8_t *solid, cudaStream_t st);
 // trace / slot (optional): the electrode (k.px, k.py) of every sheet is recorded at each of the tb
 // levels into trace[2*((*slot + s)*nsims + z)]; yh_slot_bump advances the device-resident slot.
 int yh_launch_rd_tile_euler(const YhK &k, int tb, const double *u_in, const double *v_in, double *u_out,

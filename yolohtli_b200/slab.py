@@ -536,6 +536,13 @@ class SlabGroup:
     def advance(self, nsteps, tb=0):
         host.check(self._lib.yh_slab_group_advance(self._h, nsteps, tb))
 
+    def advance_sr(self, nsteps):
+        """Symmetry-reduction steps (yh_slab_group_advance_sr); returns the (c, phi) record, nsteps x 6."""
+        import numpy as np
+        rec = np.zeros((nsteps, 6))
+        host.check(self._lib.yh_slab_group_advance_sr(self._h, nsteps, _hostptr(rec)))
+        return rec
+
     def get_state(self):
         import numpy as np
         u, v = np.empty(self.shape), np.empty(self.shape)
