@@ -56,6 +56,26 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self._stop_ev = index, [], threading.Event()
 
     def run(self):
+        # NVML in-process (a sample every ~10 ms); nvidia-smi subprocesses (~0.2 s each) only as the fallback
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = [(getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),),
+                    (getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),),
+                    (getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),),
+                    (getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),)]
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop_ev.is_set():
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = get_reasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.rows.append([str(sm), str(mx), f"{pw:.1f}"] + ["Active" if (r & b[0]) else "Not Active" for b in bits])
+                self._stop_ev.wait(0.01)
+            return
+        except Exception:
+            pass
         while not self._stop_ev.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",

@@ -307,7 +307,16 @@ static GraphKey graph_key(const AdvanceCtx &x, const double *cu, const double *c
   key.row0 = x.row0; key.row1 = x.row1;
   key.cu = cu; key.cv = cv; key.nu = nu; key.nv = nv; key.solid = x.solid; key.pat = x.pat;
   key.ws_generation = yh_workspace_generation();
-  key.arith = yh_arithmetic();
+  // the kernel-selection switches the launchers read from the environment (A/B hooks, tests) are part of what a
+  // captured graph froze: a cached graph must not outlive a change of any of them
+  unsigned long long h = 1469598103934665603ull;   // FNV-1a over "NAME=value;"
+  for (const char *name : {"YH_RD_PATH", "YH_TILE_RK", "YH_EULER_KERNEL", "YH_RK_KERNEL", "YH_SOLID_RK", "YH_EULER_FEED",
+                           "YH_MARCH_TILING", "YH_MARCH_R", "YH_FAST_W", "YH_RK_W"}) {
+    const char *v = getenv(name);
+    for (const char *c = v ? v : ""; *c; c++) h = (h ^ (unsigned char)*c) * 1099511628211ull;
+    h = (h ^ 0x3bu) * 1099511628211ull;
+  }
+  key.arith = (long long)yh_arithmetic() | (long long)((h >> 8) << 8);
   return key;
 }
 
