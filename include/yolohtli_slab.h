@@ -86,6 +86,16 @@ int yh_slab_run_host(yh_slab *s, const double *u_in_h, const double *v_in_h, dou
 /* blocks of time steps per chunk the pipelined schedule of yh_slab_run_host would use for such a call
  * (0: the plain schedule -- run too short, slab too small, masks) */
 int yh_slab_pipeline_levels(const yh_slab *s, int nsteps, int tb_steps);
+/* The same plan as host arithmetic, no device needed (tests/test_slab_pipeline_plan.py checks its invariants on the
+ * CPU): slab `rank` of `world` slabs of an ny_global-row sheet, `halo` ghost rows, fast = the temporally blocked
+ * Euler path.  plan[8] = {time steps per block, halo rows per block h, blocks, levels per chunk P, chunks C, chunk
+ * height S, first owned LOCAL row, one past the last}; returns P (0: plain schedule).  _region: LOCAL rows
+ * [rows[0], rows[1]) of `chunk` at `level` (1 .. P): boundaries move up by h rows per level, an edge that faces a
+ * neighbour recedes by h rows per level. */
+int yh_slab_pipeline_plan(int ny_global, int world, int rank, int halo, int timeIntOrder, int fast, int nsteps,
+                          int tb_steps, int plan[8]);
+int yh_slab_pipeline_region(int ny_global, int world, int rank, int halo, int timeIntOrder, int fast, int nsteps,
+                            int tb_steps, int chunk, int level, int rows[2]);
 
 /* ---- one process, several devices --------------------------------------------------------------- */
 /* devices[r] holds slab r (the same device may appear more than once: test vehicle on one GPU). */

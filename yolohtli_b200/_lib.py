@@ -174,6 +174,8 @@ SIGNATURES.update({
     "yh_slab_group_sync": (_i, [_vp]),
     "yh_slab_group_run_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
     "yh_slab_pipeline_levels": (_i, [_vp, _i, _i]),
+    "yh_slab_pipeline_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "yh_slab_pipeline_region": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "yh_slab_group_advance_sr": (_i, [_vp, _i, _vp]),
     "yh_slab_group_sr_state": (_i, [_vp, _vp, _vp, _i]),
 })

@@ -511,23 +511,47 @@ int env_int(const char *name, int dflt) {
   return (e && e[0]) ? atoi(e) : dflt;
 }
 
-bool plan_pipeline(const yh_slab *s, int nsteps, int tb, PipePlan *pl) {
+// What the plan depends on -- host arithmetic only, so that it can be checked without a device
+// (yh_slab_pipeline_plan / _region, tests/test_slab_pipeline_plan.py).  Rows are LOCAL rows of the slab's arrays.
+struct PipeGeom {
+  bool fast, solid, has_up, has_down;
+  int halo, K, own_lo, own_hi, ny, world;
+};
+
+PipeGeom geom_of(const yh_slab *s) {
+  PipeGeom g;
+  g.fast = s->fast; g.solid = s->solid_arg != nullptr; g.has_up = s->rank > 0; g.has_down = s->rank < s->world - 1;
+  g.halo = s->halo; g.K = s->K; g.own_lo = s->own_lo; g.own_hi = s->own_hi; g.ny = s->pg.ny; g.world = s->world;
+  return g;
+}
+
+int block_steps_g(bool fast, int halo, int left, int tb) {   // block_steps without a slab
+  if (!fast) return 1;
+  int cap = halo < left ? halo : left;
+  const int want = tb ? tb : 4;
+  if (want < cap) cap = want;
+  int n = 1;
+  while (2 * n <= cap && 2 * n <= 4) n *= 2;
+  return n;
+}
+
+bool plan_geom(const PipeGeom &g, int nsteps, int tb, PipePlan *pl) {
   if (env_int("YH_SLAB_PIPE", 1) == 0) return false;
-  if (s->solid_arg) return false;                        // masks: plain schedule (untested here)
-  const int n = block_steps(s, nsteps, tb);
-  const int h = n * s->K;
-  if (h > s->halo || nsteps < n) return false;
-  const int own = s->own_hi - s->own_lo;
+  if (g.solid) return false;                             // masks: plain schedule (untested here)
+  const int n = block_steps_g(g.fast, g.halo, nsteps, tb);
+  const int h = n * g.K;
+  if (h > g.halo || nsteps < n) return false;
+  const int own = g.own_hi - g.own_lo;
   // every rank must reach the same plan on its own (one exchange per wedge level on both sides of a slab
   // boundary): chunk count and level count come from the SMALLEST slab height of the partition, not from this slab's
-  const int own_min = s->pg.ny / s->world;
+  const int own_min = g.ny / g.world;
   int C = env_int("YH_SLAB_PIPE_CHUNKS", own_min >= 8192 ? 8 : 4);
   if (C < 2 || own_min < 64 * C) return false;
   const int S = (own + C - 1) / C;
   if (own - (C - 1) * S < 1) return false;
   // blocks a chunk runs while the next chunk is in flight: copy time of a chunk / time of one block on it.
   // Euler (4 steps per block at ~370 Gcell/s) against ~50 GB/s of pinned copies: ~28; RK4: ~10
-  int P = env_int("YH_SLAB_PIPE_LEVELS", s->fast ? 28 : 10);
+  int P = env_int("YH_SLAB_PIPE_LEVELS", g.fast ? 28 : 10);
   const int cap = ((own_min + C - 1) / C - 16) / (2 * h);   // chunk 0 keeps >= 16 rows: S - h*P (shift) - h*P (wedge)
   if (P > cap) P = cap;
   const int B = nsteps / n;
@@ -537,12 +561,18 @@ bool plan_pipeline(const yh_slab *s, int nsteps, int tb, PipePlan *pl) {
   return true;
 }
 
+bool plan_pipeline(const yh_slab *s, int nsteps, int tb, PipePlan *pl) { return plan_geom(geom_of(s), nsteps, tb, pl); }
+
 // rows of chunk c at (relative) level b >= 1
+void region_geom(const PipeGeom &g, const PipePlan &pl, int c, int b, int *r0, int *r1) {
+  const int X0 = g.own_lo + c * pl.S;
+  const int X1 = (c == pl.C - 1) ? g.own_hi : g.own_lo + (c + 1) * pl.S;
+  *r0 = (c == 0) ? (g.has_up ? g.own_lo + pl.h * b : g.own_lo) : X0 - pl.h * b;
+  *r1 = (c == pl.C - 1) ? (g.has_down ? g.own_hi - pl.h * b : g.own_hi) : X1 - pl.h * b;
+}
+
 void pipe_region(const yh_slab *s, const PipePlan &pl, int c, int b, int *r0, int *r1) {
-  const int X0 = s->own_lo + c * pl.S;
-  const int X1 = (c == pl.C - 1) ? s->own_hi : s->own_lo + (c + 1) * pl.S;
-  *r0 = (c == 0) ? (s->up.present ? s->own_lo + pl.h * b : s->own_lo) : X0 - pl.h * b;
-  *r1 = (c == pl.C - 1) ? (s->down.present ? s->own_hi - pl.h * b : s->own_hi) : X1 - pl.h * b;
+  region_geom(geom_of(s), pl, c, b, r0, r1);
 }
 
 // levels 1 .. L of every chunk, chunk-major; base = buffer that holds level 0.  wait_chunks: the prologue (chunk
@@ -1003,6 +1033,39 @@ int yh_slab_run_host(yh_slab *s, const double *u_in_h, const double *v_in_h, dou
   rc = yh_slab_advance(s, nsteps, tb_steps);
   if (rc != YH_OK) return rc;
   return yh_slab_get_state(s, u_out_h, v_out_h);
+}
+
+// Host arithmetic of the pipelined schedule for slab `rank` of `world` slabs of an ny_global-row sheet, no device needed.
+static bool geom_from_args(int ny_global, int world, int rank, int halo, int timeIntOrder, int fast, PipeGeom *g) {
+  int j0 = 0, j1 = 0;
+  if (halo < 1 || timeIntOrder < 1 || yh_slab_partition(ny_global, world, rank, &j0, &j1) != YH_OK) return false;
+  const int g0 = j0 - halo > 0 ? j0 - halo : 0;
+  g->fast = fast != 0; g->solid = false; g->has_up = rank > 0; g->has_down = rank < world - 1;
+  g->halo = halo; g->K = timeIntOrder; g->own_lo = j0 - g0; g->own_hi = j1 - g0; g->ny = ny_global; g->world = world;
+  return true;
+}
+
+int yh_slab_pipeline_plan(int ny_global, int world, int rank, int halo, int timeIntOrder, int fast, int nsteps,
+                          int tb_steps, int plan[8]) {
+  PipeGeom g;
+  PipePlan pl;
+  if (!plan || !geom_from_args(ny_global, world, rank, halo, timeIntOrder, fast, &g)) return 0;
+  for (int q = 0; q < 8; q++) plan[q] = 0;
+  if (nsteps <= 0 || !plan_geom(g, nsteps, tb_steps, &pl)) return 0;
+  plan[0] = pl.n; plan[1] = pl.h; plan[2] = pl.B; plan[3] = pl.P; plan[4] = pl.C; plan[5] = pl.S;
+  plan[6] = g.own_lo; plan[7] = g.own_hi;
+  return pl.P;
+}
+
+int yh_slab_pipeline_region(int ny_global, int world, int rank, int halo, int timeIntOrder, int fast, int nsteps,
+                            int tb_steps, int chunk, int level, int rows[2]) {
+  PipeGeom g;
+  PipePlan pl;
+  if (!rows || !geom_from_args(ny_global, world, rank, halo, timeIntOrder, fast, &g)) return YH_ERR_INVALID_ARG;
+  if (nsteps <= 0 || !plan_geom(g, nsteps, tb_steps, &pl) || chunk < 0 || chunk >= pl.C || level < 1 || level > pl.P)
+    return YH_ERR_INVALID_ARG;
+  region_geom(g, pl, chunk, level, &rows[0], &rows[1]);
+  return YH_OK;
 }
 
 int yh_slab_pipeline_levels(const yh_slab *s, int nsteps, int tb_steps) {
