@@ -49,19 +49,32 @@ static void initial_state(int nx, int ny, std::vector<double> &u, std::vector<do
 // symmetry-reduction mode: N slabs vs one sheet, fields and the (c, phi) history
 static int run_sr(int nx, int ny, int nslabs, int nsteps, int ndev) {
   yh_params pe, p;
-  CHECK(yh_params_default(&pe, nx, ny, 0, 0));
+  // the spiral is grown on a sheet of at most 512 x 512 (the reference's default); larger sheets keep that grid
+  // spacing (scale_L) and are tiled with copies of it, the integration disc sits on the copy nearest to the middle
+  const int scale_L = nx > 512 || ny > 512;
+  const int bx = nx > 512 ? 512 : nx, by = ny > 512 ? 512 : ny;
+  if (nx % bx || ny % by) { printf("slab_driver FAIL sr: sheets larger than 512 must be multiples of 512\n"); return 1; }
+  CHECK(yh_params_default(&pe, bx, by, 0, 0));
   pe.timeIntOrder = 1; pe.lap4 = 0;
   const size_t n = (size_t)nx * ny;
   std::vector<double> u0(n), v0(n), ua(n), va(n), ub(n), vb(n), reca((size_t)6 * nsteps), recb((size_t)6 * nsteps);
   yh_sim *sim = nullptr;
-  CHECK(yh_sim_create(&sim, &pe, 1, 0));
-  CHECK(yh_sim_cross_field_ic(sim));
-  CHECK(yh_sim_run(sim, 3000, 4, nullptr));
-  CHECK(yh_sim_get_state(sim, u0.data(), v0.data()));
-  CHECK(yh_sim_destroy(sim));
-  CHECK(yh_params_default(&p, nx, ny, 1, 0));      // reduce_sym: dt halved, default RK4 + lap4 (main.cu:148-158)
-  p.tipx0 = nx / 2; p.tipy0 = ny / 2;
-  if (p.tipOffsetX > nx / 3) { p.tipOffsetX = nx / 3; p.tipOffsetY = ny / 3; }
+  {
+    std::vector<double> us((size_t)bx * by), vs((size_t)bx * by);
+    CHECK(yh_sim_create(&sim, &pe, 1, 0));
+    CHECK(yh_sim_cross_field_ic(sim));
+    CHECK(yh_sim_run(sim, 3000, 4, nullptr));
+    CHECK(yh_sim_get_state(sim, us.data(), vs.data()));
+    CHECK(yh_sim_destroy(sim));
+    for (int j = 0; j < ny; j++)
+      for (int i = 0; i < nx; i++) {
+        u0[(size_t)j * nx + i] = us[(size_t)(j % by) * bx + i % bx];
+        v0[(size_t)j * nx + i] = vs[(size_t)(j % by) * bx + i % bx];
+      }
+  }
+  CHECK(yh_params_default(&p, nx, ny, 1, scale_L));      // reduce_sym: dt halved, default RK4 + lap4 (main.cu:148-158)
+  p.tipx0 = (float)(bx / 2 + bx * ((nx / bx) / 2)); p.tipy0 = (float)(by / 2 + by * ((ny / by) / 2));
+  if (p.tipOffsetX > bx / 3) { p.tipOffsetX = bx / 3; p.tipOffsetY = by / 3; }
   // (a) one sheet
   CHECK(yh_sim_create(&sim, &p, 1, 0));
   CHECK(yh_sim_set_state(sim, u0.data(), v0.data()));

@@ -43,7 +43,7 @@ def test_cpp_host_pipelined_run_host_bitwise(args):
     assert r.returncode == 0 and "slab_driver PASS" in r.stdout and "levels per chunk" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("args", ["256 256 1 40 sr", "256 256 2 60 sr", "256 384 3 40 sr", "512 512 2 100 sr"])
+@pytest.mark.parametrize("args", ["256 256 1 40 sr", "256 256 2 60 sr", "256 384 3 40 sr", "512 512 2 100 sr", "1024 1024 2 30 sr"])
 def test_cpp_host_symmetry_reduction_on_slabs(args):
     """yh_slab_group_advance_sr: display()'s symmetry-reduction branch on row slabs from a C++ host -- fields and the
     (c, phi) record bit for bit those of yh_sim_run_sr on one sheet, from a spiral the program grows itself."""
