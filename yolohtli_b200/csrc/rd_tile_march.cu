@@ -401,6 +401,18 @@ void pick_tiling(int nx, int rows, int K, int nsm, int *sw_out, int *bh_out) {
   }
 }
 
+// the search costs ~10 us of host time: remember the last answers of this thread (a step loop asks for the same one)
+void pick_tiling_memo(int nx, int rows, int stages, int nsm, int *sw_out, int *bh_out) {
+  struct Memo { int nx, rows, stages, nsm, sw, bh; };
+  static thread_local Memo memo[4] = {};
+  static thread_local int memo_next = 0;
+  for (const Memo &m : memo)
+    if (m.nx == nx && m.rows == rows && m.stages == stages && m.nsm == nsm && m.sw > 0) { *sw_out = m.sw; *bh_out = m.bh; return; }
+  pick_tiling(nx, rows, stages, nsm, sw_out, bh_out);
+  memo[memo_next] = Memo{nx, rows, stages, nsm, *sw_out, *bh_out};
+  memo_next = (memo_next + 1) & 3;
+}
+
 template <int K, bool LAP4, bool DEF, int ARITH, int R, bool SOLID = false>
 int launch_march(const YhK &k, MarchArgs &a, cudaStream_t st) {
   static bool done[64] = {false};
@@ -417,7 +429,7 @@ int launch_march(const YhK &k, MarchArgs &a, cudaStream_t st) {
   const char *e = getenv("YH_MARCH_TILING");   // "sw,bh" override (tuning)
   if (!(e && sscanf(e, "%d,%d", &a.sw, &a.bh) == 2 && a.sw > 0 && !(a.sw & 1) && a.sw <= 2 * LANES - 2 * K && a.bh > 0 &&
         a.bh <= ROWS_MAX - 2 * K))
-    pick_tiling(k.nx, rows, K, nsm[dev & 63], &a.sw, &a.bh);
+    pick_tiling_memo(k.nx, rows, K, nsm[dev & 63], &a.sw, &a.bh);
   const int nseg = (a.bh + 2 * K + R - 1) / R;
   dim3 grd((k.nx + a.sw - 1) / a.sw, (rows + a.bh - 1) / a.bh);
   // (programmatic dependent launch -- griddepcontrol.launch_dependents at the top, .wait before the first global

@@ -1233,6 +1233,8 @@ int yh_slab_group_advance_sr(yh_slab_group *g, int nsteps, double *c_phi_h) {
   const size_t tbl = (size_t)12 * yh_sr_disc_slots(&g->m[0]->p);
   g->sr_part.resize(tbl); g->sr_sum.resize(tbl);
   double I[12];
+  std::vector<int> ntips(count, -1), wave, devs;
+  std::vector<yh_tip> last(count);
   const bool dbg = getenv("YH_SR_DEBUG") != nullptr;
   for (int it = 0; it < nsteps; it++) {
     if (dbg) { fprintf(stderr, "sr step %d (count %lld) c = %g %g %g\n", it, g->sr_count, g->c[0], g->c[1], g->c[2]); fflush(stderr); }
@@ -1255,11 +1257,10 @@ int yh_slab_group_advance_sr(yh_slab_group *g, int nsteps, double *c_phi_h) {
     // The last tip of the concatenated list = the disc centre (count == 0 or no tip anywhere: the set centre, B3).
     float cx = (float)pg->tipx0, cy = (float)pg->tipy0;
     {
-      std::vector<int> ntips(count, -1);
-      std::vector<yh_tip> last(count);
+      ntips.assign(count, -1);
       int left = count;
       while (left > 0) {
-        std::vector<int> wave, devs;
+        wave.clear(); devs.clear();
         for (int q = 0; q < count; q++) {
           yh_slab *s = g->m[q];
           bool busy = ntips[q] >= 0;
