@@ -486,9 +486,9 @@ int yh_launch_rd_tile_march(const YhK &k, const double *u_in, const double *v_in
     a.jX = k.fx4; a.jY = k.fy4; a.jC = (lap4 ? 2.0 * (k.fx4 + k.fy4) : 0.0) - k.dt; a.neg_eps = -k.eps;
   }
   // rows per warp, measured at 512^2 (B200, us per step, R = 6 | 4): exact 13.3 | 13.5, fast 10.9 | 10.1
-  static const int rows_env = [] { const char *e = getenv("YH_MARCH_R"); return e ? atoi(e) : 0; }();   // 3 | 4 | 6 (tuning)
+  static const int rows_env = [] { const char *e = getenv("YH_MARCH_R"); return e ? atoi(e) : 0; }();   // 4 | 6 (tuning; 3 rows per warp spilled and was no faster)
   const int rows_per_warp = rows_env ? rows_env : (arith ? 4 : 6);
-#define YH_M(KK, L, D, A) (rows_per_warp == 4 ? launch_march<KK, L, D, A, 4>(k, a, st) : rows_per_warp == 3 ? launch_march<KK, L, D, A, 3>(k, a, st) : launch_march<KK, L, D, A, 6>(k, a, st))
+#define YH_M(KK, L, D, A) (rows_per_warp == 4 ? launch_march<KK, L, D, A, 4>(k, a, st) : launch_march<KK, L, D, A, 6>(k, a, st))
 #define YH_MD(KK, L, A) (def ? YH_M(KK, L, true, A) : YH_M(KK, L, false, A))
 #define YH_ML(KK, A) (lap4 ? YH_MD(KK, true, A) : YH_MD(KK, false, A))
   if (k.timeIntOrder == 4) return arith ? YH_ML(4, 1) : YH_ML(4, 0);
