@@ -215,6 +215,86 @@ def fp64_fraction(mode, updates_per_s, pk):
     return updates_per_s * (fma / pk["dfma_per_s"] + other / pk["dmul_dadd_per_s"])
 
 
+# ---- BASELINE configs[2] (C3: symmetry-reduction step) and configs[4] (C5: batched restitution sweep) as `modes` ----
+SR_STEPS, SWEEP_SHEETS, SWEEP_STEPS = 1000, 32, 600
+
+
+def ours_sr_mode(yh, torch):
+    """C3: 512^2 meandering spiral, every step = RD (RK4 + lap4) + tips + 12 phase-condition integrals + 3x3 solve +
+    BFECC, device-resident loop (yh_sim_run_sr_device); wall clock around the call."""
+    import time
+    nx = 512
+    sim = yh.Sim(yh.default_params(nx, nx, timeIntOrder=1, lap4=0))
+    sim.cross_field_ic()
+    sim.run(12001, tb_steps=4)          # the cross-field initial condition curls into a spiral
+    tips = sim.tips()
+    u0, v0 = sim.get_state()
+    sim.close()
+    tx, ty = (float(tips[-1]["x"]), float(tips[-1]["y"])) if len(tips) else (nx / 2.0, nx / 2.0)
+    sim = yh.Sim(yh.default_params(nx, nx, reduce_sym=True, tipx0=tx, tipy0=ty))
+    sim.set_state(u0, v0)
+    sim.run_sr(2, record=False)
+    sim.run_sr_device(64, record=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sim.run_sr_device(SR_STEPS, record=False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    sim.close()
+    return {"value": nx * nx * SR_STEPS / dt / 1e9, "unit": METRIC, "ms_per_time_step": dt * 1e3 / SR_STEPS,
+            "arithmetic": "exact", "note": "BASELINE configs[2]: one symmetry-reduction step per time step, no host round trip"}
+
+
+def ours_sweep_mode(yh, torch, synth):
+    """C5: 32 paced 512^2 sheets per GPU (of the 256 of configs[4]), Euler + 5-point, sAPD every step."""
+    import time
+    nx = 512
+    p = yh.default_params(nx, nx, timeIntOrder=1, lap4=0)
+    periods = (np.linspace(600.0, 100.0, 256)[:SWEEP_SHEETS] / p.dt).astype(np.int32)
+    area = synth.stim_area_square(nx, nx)
+    sim = yh.Sim(p, n_sims=SWEEP_SHEETS)
+    sim.set_pacing(periods, int(10.0 / p.dt))
+    sim.run_apd(20, stim_area=area)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sim.run_apd(SWEEP_STEPS, stim_area=area)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    sim.close()
+    return {"value": SWEEP_SHEETS * nx * nx * SWEEP_STEPS / dt / 1e9, "unit": METRIC, "ms_per_time_step": dt * 1e3 / SWEEP_STEPS,
+            "arithmetic": "exact", "note": f"BASELINE configs[4]: {SWEEP_SHEETS} sheets per GPU in one batch"}
+
+
+def ref_sr_mode(ref, o, synth):
+    """The reference's own symmetry-reduction loop (main.cu:894-954 through its wrappers) on a spiral grown with its
+    own kernels; the disc centre is the last tip of its own tip kernel."""
+    nx, nsr = 512, 300
+    ref.init(o.params_default(nx, nx, timeIntOrder=1, lap4=0))
+    u, v = synth.cross_field_ic(nx, nx)
+    u1, v1, _ = ref.rd_run(u, v, 12000)
+    u2, v2, _ = ref.rd_run(u1, v1, 1)
+    tips = ref.tip(u2, u1)
+    tx, ty = (float(tips[-1]["x"]), float(tips[-1]["y"])) if len(tips) else (nx / 2.0, nx / 2.0)
+    ref.init(o.params_default(nx, nx, reduce_sym=True, tipx0=tx, tipy0=ty))
+    ref.sr_run(u2, v2, 20)
+    ms = ref.sr_run(u2, v2, nsr)[3]
+    return {"value": nx * nx * nsr / ms / 1e6, "unit": METRIC, "ms_per_time_step": ms / nsr}
+
+
+def ref_sweep_mode(ref, o, synth):
+    """The reference runs one sheet at a time (its contourMode == 1 loop with sAPD every step)."""
+    nx = 512
+    p = o.params_default(nx, nx, timeIntOrder=1, lap4=0)
+    ref.init(p)
+    area = synth.stim_area_square(nx, nx)
+    z = np.zeros((nx, nx))
+    per, dur = int(600.0 / p.dt), int(10.0 / p.dt)
+    ref.apd_run(z, z, 20, per, dur, area)
+    ms = ref.apd_run(z, z, SWEEP_STEPS, per, dur, area)[4]
+    return {"value": nx * nx * SWEEP_STEPS / ms / 1e6, "unit": METRIC, "ms_per_time_step": ms / SWEEP_STEPS,
+            "note": "one sheet at a time"}
+
+
 def run_reference(a):
     """--impl reference: the UNMODIFIED reference kernels (reactionDiffusion_wrapper + swapSoA,
     main.cu:879-882) built headless for sm_100 with the reference's default flags, one GPU.  Nothing of
@@ -262,6 +342,11 @@ def run_reference(a):
                 ns = max(4, nsteps // 4)
                 r, ms1 = ref_rate(n, mode, ns, 2)
                 modes[name] = {"value": r, "unit": METRIC, "ms_per_time_step": ms1 / ns}
+            for name, fn in (("sr_step_512", ref_sr_mode), ("sweep_32x512", ref_sweep_mode)):
+                try:
+                    modes[name] = fn(ref, o, synth)
+                except Exception as e:   # noqa: BLE001 -- an extra measurement must not cost the line
+                    modes[name] = {"error": f"{type(e).__name__}: {e}"}
         out = dict(base, value=val, ms_per_step=tot / a.steps * 1e3, config=cfg,
                    impl_config={"substeps": a.substeps,
                                 "note": "reference's own CUDA kernels (oracle/_ref/libyhref.so: the reference's .cu files compiled "
@@ -442,6 +527,12 @@ def run_ours(a):
                                              "tests/test_gpu_arith.py)" if fast else "exact"}
                 if not fast and mode in FP64_PER_UPDATE:
                     modes[name]["fp64_frac"] = fp64_fraction(mode, r * 1e9, pk64)
+            for name, fn in (("sr_step_512", lambda: ours_sr_mode(yh, torch)),
+                             ("sweep_32x512", lambda: ours_sweep_mode(yh, torch, synth))):
+                try:
+                    modes[name] = fn()
+                except Exception as e:   # noqa: BLE001 -- an extra measurement must not cost the line
+                    modes[name] = {"error": f"{type(e).__name__}: {e}"}
         from tests import oracle_lib
         cb = cpu_baseline(a, oracle_lib) if world == 1 and not a.no_cpu_baseline else None
         out = {
