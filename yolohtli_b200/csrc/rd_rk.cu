@@ -485,8 +485,11 @@ int yh_launch_rd_rk(const YhK &k, const double *u_in, const double *v_in, double
   const char *force_w = getenv("YH_RK_W");
   const long long cells = (long long)k.nx * (k.row1 - k.row0);
   int W = cells >= (1ll << 23) ? 192 : (cells >= (1ll << 21) ? 128 : 64);
-  if (force_w) W = atoi(force_w);
   const bool so = k.solidSwitch != 0;
+  // masks: the widest strips pay earlier (measured, RK4 + holes, us per step, W = 64 | 128 | 192: 1024^2 49.2 | 47.6 | 46.7,
+  // 2048^2 - | 192 | 168)
+  if (so && cells >= (3ll << 18)) W = 192;
+  if (force_w) W = atoi(force_w);
   const bool lap4 = k.lap4 != 0 && !so;   // the mask branch has no 4th-order terms (:184)
 #define YH_RK_W(KK, WW)                                                                       \
   {                                                                                           \
