@@ -119,6 +119,11 @@ int         yh_release_workspace(void);      /* frees internal scratch of this t
 int yh_set_arithmetic(int flavour);
 int yh_get_arithmetic(void);
 
+/* How the small-sheet Runge-Kutta kernel (csrc/rd_tile_march.cu) would cut `rows` x nx outputs into tiles on a device
+ * with n_sm multiprocessors: tiling[0] = strip width (outputs per tile row, even, <= 64 - 2*stages), tiling[1] = band
+ * height (<= 48 - 2*stages).  Host arithmetic, no device needed (tests/test_abi.py checks its invariants). */
+int yh_rd_tile_march_tiling(int nx, int rows, int stages, int n_sm, int tiling[2]);
+
 /* Defaults of parameterSetup() (saveFiles.cu:105-231) for an nx x ny grid with the
  * reference's hx (Lx = 12*(nx-1)/511 keeps hx at its 512-grid value when scale_L != 0).
  * Also applies main.cu:148-158 (dt halved when reduce_sym, rx..fy4 recomputed). */

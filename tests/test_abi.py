@@ -150,3 +150,22 @@ def test_missing_library_fails_loudly(yh, tmp_path):
     from yolohtli_b200 import _lib
     with pytest.raises(_lib.YolohtliError):
         _lib.load_library(str(tmp_path / "nope.so"))
+
+
+def test_march_tiling_invariants():
+    """Host arithmetic of the marching tile kernel's launcher: strips x bands cover the rows, respect the tile's
+    capacity (64 columns, 48 rows, halo = stages on every side) and fill at most one wave where that is possible."""
+    import ctypes as C
+    from yolohtli_b200 import _lib
+    l = _lib.lib()
+    for nx, rows, stages, n_sm in [(512, 512, 4, 148), (256, 256, 4, 148), (640, 37, 4, 148), (8, 8, 2, 148), (768, 768, 4, 148),
+                                   (500, 131, 2, 148), (1024, 1024, 4, 148), (512, 512, 4, 132), (118, 61, 4, 16)]:
+        t = (C.c_int * 2)()
+        assert l.yh_rd_tile_march_tiling(nx, rows, stages, n_sm, t) == 0
+        sw, bh = t[0], t[1]
+        assert sw > 0 and sw % 2 == 0 and sw <= 64 - 2 * stages and 0 < bh <= 48 - 2 * stages, (nx, rows, sw, bh)
+        tiles = -(-nx // sw) * -(-rows // bh)
+        least = -(-nx // (64 - 2 * stages)) * -(-rows // (48 - 2 * stages))     # tiles at full capacity
+        waves, least_waves = -(-tiles // n_sm), -(-least // n_sm)
+        assert waves == least_waves, (nx, rows, stages, n_sm, sw, bh, tiles)
+    assert l.yh_rd_tile_march_tiling(511, 512, 4, 148, (C.c_int * 2)()) != 0      # odd nx: not served

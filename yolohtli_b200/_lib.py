@@ -173,6 +173,7 @@ SIGNATURES.update({
     "yh_slab_group_advance": (_i, [_vp, _i, _i]),
     "yh_slab_group_sync": (_i, [_vp]),
     "yh_slab_group_run_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "yh_rd_tile_march_tiling": (_i, [_i, _i, _i, _i, _vp]),
     "yh_slab_pipeline_levels": (_i, [_vp, _i, _i]),
     "yh_slab_pipeline_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "yh_slab_pipeline_region": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

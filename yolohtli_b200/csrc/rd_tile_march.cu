@@ -441,6 +441,15 @@ int launch_march(const YhK &k, MarchArgs &a, cudaStream_t st) {
 
 }  // namespace
 
+extern "C" int yh_rd_tile_march_tiling(int nx, int rows, int stages, int n_sm, int tiling[2]) {
+  if (!tiling || nx < 8 || (nx & 1) || rows < 1 || (stages != 2 && stages != 4) || n_sm < 1) {
+    yh_set_error("yh_rd_tile_march_tiling: bad arguments");
+    return YH_ERR_INVALID_ARG;
+  }
+  pick_tiling(nx, rows, stages, n_sm, &tiling[0], &tiling[1]);
+  return YH_OK;
+}
+
 // solidSwitch: only through yh_launch_rd_tile_march_solid (the caller must hold the mask)
 int yh_rd_tile_march_supported(const YhK &k) {
   if (k.solidSwitch) return 0;
